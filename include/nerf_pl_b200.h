@@ -1,0 +1,149 @@
+/* nerf_pl_b200 — C ABI of the B200-native volumetric-rendering hot path of kwea123/nerf_pl.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point
+ * cites the reference interface it replaces (paths relative to the reference repository).
+ * All pointers are DEVICE pointers unless the name ends in `_host`.  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  Functions never allocate or
+ * free caller-visible memory and never throw.
+ *
+ * Return value: 0 = ok; negative = invalid argument (NERFB200_E*); positive = cudaError_t.
+ * nerfb200_last_error() returns a thread-local, human-readable description of the last
+ * non-zero return on this thread.
+ */
+#ifndef NERF_PL_B200_H_
+#define NERF_PL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NERFB200_ABI_VERSION 1
+
+#define NERFB200_EINVAL (-1)      /* bad argument value / null pointer            */
+#define NERFB200_EUNSUPPORTED (-2) /* shape outside what the fused kernel supports */
+#define NERFB200_EDEVICE (-3)     /* device is not sm_100 / kernel image missing   */
+
+int nerfb200_abi_version(void);
+const char* nerfb200_last_error(void);
+
+/* ---- weights --------------------------------------------------------------------------
+ * Replaces: the implicit use of the 12 nn.Linear parameter tensors by NeRF.forward
+ * (models/nerf.py:61-81, 83-124).  `params` are the 24 fp32 device tensors of one NeRF in
+ * state_dict order: xyz_encoding_{1..8}.0.{weight,bias}, xyz_encoding_final.{weight,bias},
+ * dir_encoding.0.{weight,bias}, sigma.{weight,bias}, rgb.0.{weight,bias}; weights are
+ * (out,in) row-major as torch stores them.  Produces the fp16/fp32 image the kernels stream
+ * (nerfb200_packed_bytes() bytes, 1024-byte aligned). */
+size_t nerfb200_packed_bytes(void);
+int nerfb200_pack_weights(const float* const params[24], void* packed, void* stream);
+
+/* ---- render_rays -----------------------------------------------------------------------
+ * Replaces: models/rendering.py:58-244 render_rays(models, embeddings, rays, N_samples,
+ * use_disp, perturb, noise_std, N_importance, chunk, white_back, test_time) including the
+ * inner inference() closure (:91-172), sample_pdf (:14-55), the torchsearchsorted call
+ * (:42) and the torch.sort merge (:229).  `chunk` has no equivalent (nothing is chunked).
+ *
+ * rays: (n_rays, 8) fp32 rows [o(3) d(3) near far], row stride `ray_stride` floats.
+ * Random inputs are supplied by the caller so a seeded torch stream can be reproduced:
+ *   perturb_rand (n_rays,N_samples) U[0,1)  — required iff perturb > 0     (:203)
+ *   noise_coarse (n_rays,N_samples) N(0,1)  — required iff noise_std > 0   (:152)
+ *   u_rand       (n_rays,N_importance) U[0,1) — required iff perturb > 0 and N_importance > 0 (:39)
+ *   noise_fine   (n_rays,N_samples+N_importance) N(0,1) — iff noise_std > 0 and N_importance > 0
+ * Outputs (result-dict keys, :209-221, :240-242); fp32:
+ *   rgb_coarse (n,3), depth_coarse (n) — written unless test_time; may be NULL if test_time
+ *   opacity_coarse (n); rgb_fine (n,3), depth_fine (n), opacity_fine (n) iff N_importance > 0
+ * Optional outputs (NULL to skip): z_fine (n, N_samples+N_importance) merged sorted depths,
+ *   weights_coarse (n,N_samples), weights_fine (n,N_samples+N_importance).
+ * Supported shapes: N_samples in {64,128}; N_importance in {0,64,128}; total <= 192.
+ * `status` is a device int32 the kernel sets non-zero on a device-side fault (may be NULL,
+ * then an internal one is used and checked with a synchronising copy). */
+typedef struct nerfb200_render_args {
+  const float* rays;
+  int64_t n_rays;
+  int64_t ray_stride;
+  const void* packed_coarse;
+  const void* packed_fine; /* NULL iff n_importance == 0 */
+  int32_t n_samples;
+  int32_t n_importance;
+  int32_t use_disp;
+  float perturb;
+  float noise_std;
+  int32_t white_back;
+  int32_t test_time;
+  const float* perturb_rand;
+  const float* noise_coarse;
+  const float* u_rand;
+  const float* noise_fine;
+  float* rgb_coarse;
+  float* depth_coarse;
+  float* opacity_coarse;
+  float* rgb_fine;
+  float* depth_fine;
+  float* opacity_fine;
+  float* z_fine;
+  float* weights_coarse;
+  float* weights_fine;
+  int32_t* status;
+  int32_t max_ctas; /* 0 = one CTA per SM */
+} nerfb200_render_args;
+
+int nerfb200_render_rays(const nerfb200_render_args* args, void* stream);
+
+/* Same call with HOST buffers (pageable or pinned): copies rays (and the random inputs that
+ * are non-NULL) to the device, renders, copies the requested outputs back, synchronises.
+ * The packed weight images stay device-resident.  This is the end-to-end entry the
+ * reference's eval.py loop (eval.py:117-123 `.cuda()` ... `.cpu()`) maps to. */
+int nerfb200_render_rays_host(const nerfb200_render_args* host_args, void* stream);
+
+/* ---- NeRF.forward ------------------------------------------------------------------------
+ * Replaces: models/nerf.py:83-124 NeRF.forward(x, sigma_only).  x: (n, x_stride) fp32 rows of
+ * embedded xyz (63) followed, unless sigma_only, by the embedded direction (27).
+ * out: (n,4) [r,g,b,sigma] or (n,1) sigma. */
+int nerfb200_nerf_forward(const float* x, int64_t n, int64_t x_stride, const void* packed,
+                          int32_t sigma_only, float* out, void* stream);
+
+/* ---- Embedding.forward -------------------------------------------------------------------
+ * Replaces: models/nerf.py:21-38.  x: (n,3) -> out: (n, 3 + 6*n_freqs). */
+int nerfb200_embed(const float* x, int64_t n, int32_t n_freqs, float* out, void* stream);
+
+/* ---- searchsorted ------------------------------------------------------------------------
+ * Replaces: torchsearchsorted/src/torchsearchsorted/searchsorted.py:20-53 and
+ * src/cuda/searchsorted_cuda_kernel.cu:83-142.  a: (nrow_a, ncol_a) sorted rows,
+ * v: (nrow_v, ncol_v); nrow_a == nrow_v or one of them is 1 (broadcast).
+ * out: (max(nrow_a,nrow_v), ncol_v) int64.  side_right: 0 = 'left', 1 = 'right'. */
+int nerfb200_searchsorted(const float* a, const float* v, int64_t* out, int64_t nrow_a,
+                          int64_t nrow_v, int32_t ncol_a, int32_t ncol_v, int32_t side_right,
+                          void* stream);
+
+/* ---- sample_pdf --------------------------------------------------------------------------
+ * Replaces: models/rendering.py:14-55 with the random/deterministic u supplied by the caller.
+ * bins (n_rays, n_weights+1), weights (n_rays, n_weights), u (n_rays, n_u) -> out (n_rays, n_u). */
+int nerfb200_sample_pdf(const float* bins, const float* weights, const float* u, int64_t n_rays,
+                        int32_t n_weights, int32_t n_u, float* out, void* stream);
+
+/* ---- volume rendering quadrature ---------------------------------------------------------
+ * Replaces: models/rendering.py:143-170 (inside inference()).  sigmas (n,S), rgbs (n,S,3) or
+ * NULL (weights_only), z_vals (n,S), dirs (n,3), noise (n,S) or NULL.  S % 32 == 0, S <= 192.
+ * weights (n,S) may be NULL; rgb (n,3) / depth (n) ignored when rgbs is NULL; opacity (n). */
+int nerfb200_composite(const float* sigmas, const float* rgbs, const float* z_vals,
+                       const float* dirs, const float* noise, float noise_std, int32_t white_back,
+                       int64_t n_rays, int32_t n_samples, float* weights, float* rgb, float* depth,
+                       float* opacity, void* stream);
+
+/* ---- diagnostics -------------------------------------------------------------------------
+ * Number of kernels this library has launched on the calling process so far (all entry
+ * points).  bench.py reports the delta as `gpu_launches`. */
+int64_t nerfb200_launch_count(void);
+/* One K=64 weight slice of a packed image against a (128,64) fp32 A tile through the tcgen05
+ * engine: d (128, N) with N = 256 for slices 0..33 and 128 for slices 34..38 (csrc/layout.h).
+ * Unit-test hook for the shared-memory / descriptor layout; not part of the reference API. */
+int nerfb200_debug_gemm(const float* a, const void* packed, int32_t slice, float* d, void* stream);
+/* Device properties the launcher uses: SM count of the current device (0 if none). */
+int nerfb200_sm_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERF_PL_B200_H_ */

@@ -1,0 +1,12 @@
+"""nerf_pl_b200 — B200-native (sm_100a) implementation of the volumetric-rendering hot path of
+kwea123/nerf_pl: ``render_rays`` + ``Embedding`` / ``NeRF`` behind the reference's own Python
+signatures, executed by hand-written tcgen05/TMEM CUDA kernels through a C-ABI library
+(``include/nerf_pl_b200.h``).  See DESIGN.md and INTEGRATION.md."""
+from .nerf import Embedding, NeRF, nerf_forward_fused, nerf_forward_torch, nerf_parameters, packed_weights
+from .rendering import render_rays, sample_pdf, searchsorted, volume_render
+
+__all__ = [
+    "Embedding", "NeRF", "render_rays", "sample_pdf", "searchsorted", "volume_render",
+    "nerf_forward_fused", "nerf_forward_torch", "nerf_parameters", "packed_weights",
+]
+__version__ = "0.1.0"

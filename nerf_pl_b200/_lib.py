@@ -1,0 +1,172 @@
+"""Build and load ``libnerf_pl_b200.so`` (the C-ABI library, ``include/nerf_pl_b200.h``).
+
+The library is compiled in-tree with plain ``nvcc`` (no torch headers) so it builds in seconds,
+ships to the GPU box with the repository snapshot and shows up as a loaded in-tree ``.so``.
+There is no CPU fallback: if the library is missing or cannot be loaded every operator in this
+package raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libnerf_pl_b200.so")
+SOURCES = ["capi.cu"]
+HEADERS = ["ptx.cuh", "layout.h", "mlp_engine.cuh", "render_kernel.cuh", "aux_kernels.cuh"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--shared", "-Xcompiler", "-fPIC",
+    "-diag-suppress", "550",
+]
+
+# Every symbol include/nerf_pl_b200.h declares (tests check the library exports all of them).
+EXPORTS = [
+    "nerfb200_abi_version",
+    "nerfb200_last_error",
+    "nerfb200_packed_bytes",
+    "nerfb200_pack_weights",
+    "nerfb200_render_rays",
+    "nerfb200_render_rays_host",
+    "nerfb200_nerf_forward",
+    "nerfb200_embed",
+    "nerfb200_searchsorted",
+    "nerfb200_sample_pdf",
+    "nerfb200_composite",
+    "nerfb200_launch_count",
+    "nerfb200_debug_gemm",
+    "nerfb200_sm_count",
+]
+
+
+class RenderArgs(ctypes.Structure):
+    """Mirror of ``nerfb200_render_args`` (include/nerf_pl_b200.h)."""
+
+    _fields_ = [
+        ("rays", c_void_p),
+        ("n_rays", c_int64),
+        ("ray_stride", c_int64),
+        ("packed_coarse", c_void_p),
+        ("packed_fine", c_void_p),
+        ("n_samples", c_int32),
+        ("n_importance", c_int32),
+        ("use_disp", c_int32),
+        ("perturb", c_float),
+        ("noise_std", c_float),
+        ("white_back", c_int32),
+        ("test_time", c_int32),
+        ("perturb_rand", c_void_p),
+        ("noise_coarse", c_void_p),
+        ("u_rand", c_void_p),
+        ("noise_fine", c_void_p),
+        ("rgb_coarse", c_void_p),
+        ("depth_coarse", c_void_p),
+        ("opacity_coarse", c_void_p),
+        ("rgb_fine", c_void_p),
+        ("depth_fine", c_void_p),
+        ("opacity_fine", c_void_p),
+        ("z_fine", c_void_p),
+        ("weights_coarse", c_void_p),
+        ("weights_fine", c_void_p),
+        ("status", c_void_p),
+        ("max_ctas", c_int32),
+    ]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    deps.append(os.path.join(_HERE, "..", "include", "nerf_pl_b200.h"))
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library for sm_100a (cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def _declare(lib: ctypes.CDLL) -> None:
+    lib.nerfb200_abi_version.restype = c_int32
+    lib.nerfb200_last_error.restype = c_char_p
+    lib.nerfb200_packed_bytes.restype = c_size_t
+    lib.nerfb200_pack_weights.argtypes = [POINTER(c_void_p), c_void_p, c_void_p]
+    lib.nerfb200_render_rays.argtypes = [POINTER(RenderArgs), c_void_p]
+    lib.nerfb200_render_rays_host.argtypes = [POINTER(RenderArgs), c_void_p]
+    lib.nerfb200_nerf_forward.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p]
+    lib.nerfb200_embed.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    lib.nerfb200_searchsorted.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+                                          c_int32, c_int32, c_void_p]
+    lib.nerfb200_sample_pdf.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
+                                        c_void_p, c_void_p]
+    lib.nerfb200_composite.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                       c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p]
+    lib.nerfb200_debug_gemm.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]
+    lib.nerfb200_debug_gemm.restype = c_int32
+    lib.nerfb200_launch_count.restype = c_int64
+    lib.nerfb200_sm_count.restype = c_int32
+    for name in ("nerfb200_pack_weights", "nerfb200_render_rays", "nerfb200_render_rays_host",
+                 "nerfb200_nerf_forward", "nerfb200_embed", "nerfb200_searchsorted",
+                 "nerfb200_sample_pdf", "nerfb200_composite"):
+        getattr(lib, name).restype = c_int32
+
+
+def load() -> ctypes.CDLL:
+    """Load the library (never builds implicitly: build() is the explicit step)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(nerf_pl_b200 has no CPU fallback)")
+            lib = ctypes.CDLL(LIB_PATH)
+            _declare(lib)
+            if lib.nerfb200_abi_version() != 1:
+                raise RuntimeError("libnerf_pl_b200.so ABI version mismatch")
+            _lib = lib
+    return _lib
+
+
+class NerfB200Error(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    """Map the C-ABI return code to the Python exceptions the reference raises
+    (asserts / Exception in searchsorted.py:23-45, RuntimeError from AT_ASSERTM)."""
+    if rc == 0:
+        return
+    msg = load().nerfb200_last_error().decode("utf-8", "replace")
+    if rc in (-1, -2):
+        raise ValueError(f"{what}: {msg}")
+    raise NerfB200Error(f"{what}: {msg} (code {rc})")

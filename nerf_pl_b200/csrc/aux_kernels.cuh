@@ -1,0 +1,353 @@
+// Stand-alone kernels for the individual reference functions on the hot path
+//  and the weight packer.  The render kernel
+// fuses all of them; these entries exist so each row has its own parity test and so callers
+// that use the pieces directly (extract_color_mesh.py:127-140) have a drop-in.
+#pragma once
+#include "render_kernel.cuh"
+
+namespace nerfb200 {
+
+// ------------------------------------------------------------ weight packer
+struct PackParams {
+  const float* p[kNumParams];   // device pointers, order in layout.h
+  uint8_t* out;
+};
+
+// One thread per fp16 element of the slice region, then the fp32 tail.
+__global__ void pack_weights_kernel(const PackParams pp) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n_half = kHalfRegionBytes / 2;
+  if (idx < n_half) {
+    int slice, n, k, N;
+    const long long n256 = static_cast<long long>(kNumSlices256) * 256 * 64;
+    if (idx < n256) {
+      slice = static_cast<int>(idx / (256 * 64));
+      const int rem = static_cast<int>(idx % (256 * 64));
+      n = rem / 64; k = rem % 64; N = 256;
+    } else {
+      const long long j = idx - n256;
+      slice = kNumSlices256 + static_cast<int>(j / (128 * 64));
+      const int rem = static_cast<int>(j % (128 * 64));
+      n = rem / 64; k = rem % 64; N = 128;
+    }
+    // slice -> (weight tensor, input-feature offset, in_features, valid k)
+    const float* W; int ld, koff, kvalid;
+    if (slice == 0) { W = pp.p[0]; ld = 63; koff = 0; kvalid = 63; }
+    else if (slice <= 12) { const int l = 1 + (slice - 1) / 4; W = pp.p[2 * l]; ld = 256; koff = ((slice - 1) % 4) * 64; kvalid = 64; }
+    else if (slice == 13) { W = pp.p[8]; ld = 319; koff = 0; kvalid = 63; }
+    else if (slice <= 17) { W = pp.p[8]; ld = 319; koff = 63 + (slice - 14) * 64; kvalid = 64; }
+    else if (slice <= 29) { const int l = 5 + (slice - 18) / 4; W = pp.p[2 * l]; ld = 256; koff = ((slice - 18) % 4) * 64; kvalid = 64; }
+    else if (slice <= 33) { W = pp.p[16]; ld = 256; koff = (slice - 30) * 64; kvalid = 64; }
+    else if (slice <= 37) { W = pp.p[18]; ld = 283; koff = (slice - 34) * 64; kvalid = 64; }
+    else { W = pp.p[18]; ld = 283; koff = 256; kvalid = 27; }
+    const float v = (k < kvalid) ? W[static_cast<long long>(n) * ld + koff + k] : 0.f;
+    const uint32_t base = (slice < kNumSlices256) ? slice * kSliceBytes256
+                                                   : kOffDir + (slice - kNumSlices256) * kSliceBytes128;
+    (void)N;
+    *reinterpret_cast<__half*>(pp.out + base + sw128_off(n, k)) = __float2half_rn(v);
+    return;
+  }
+  const long long f = idx - n_half;
+  if (f >= kF32Count) return;
+  float* o = reinterpret_cast<float*>(pp.out + kHalfRegionBytes);
+  float v = 0.f;
+  const int i = static_cast<int>(f);
+  if (i < kF32WSigma) {
+    const int l = i / 256, n = i % 256;
+    if (l < 8) v = pp.p[2 * l + 1][n];
+    else if (l == 8) v = pp.p[17][n];
+    else v = (n < 128) ? pp.p[19][n] : 0.f;
+  } else if (i < kF32BSigma) v = pp.p[20][i - kF32WSigma];
+  else if (i < kF32WRgb) v = (i == kF32BSigma) ? pp.p[21][0] : 0.f;
+  else if (i < kF32BRgb) v = pp.p[22][i - kF32WRgb];
+  else if (i < kF32WDirPart) v = (i - kF32BRgb < 3) ? pp.p[23][i - kF32BRgb] : 0.f;
+  else {
+    const int j = i - kF32WDirPart;
+    const int n = j / 28, k = j % 28;
+    v = (k < 27) ? pp.p[18][static_cast<long long>(n) * 283 + 256 + k] : 0.f;
+  }
+  o[i] = v;
+}
+
+// ------------------------------------------------ NeRF.forward (models/nerf.py:83-124)
+struct MlpParams {
+  const float* x;          // (n, x_stride): embedded xyz (63) [+ embedded dir (27)]
+  long long x_stride;
+  long long n;
+  const uint8_t* net;
+  int sigma_only;
+  float* out;              // (n, 4) rgb,sigma  or (n, 1) sigma
+  int* status;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const MlpParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Scratch* sc = reinterpret_cast<Scratch*>(smem + kSmemScratch);
+  Barriers* bars = &sc->bars;
+  if (!engine_setup(smem, bars)) {
+    if (threadIdx.x == 0) atomicExch(p.status, 101);
+    return;
+  }
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long n_tiles = (p.n + 127) / 128;
+  const bool so = p.sigma_only != 0;
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      RingState rs;
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) produce_tile(rs, smem, bars, p.net, so, !so);
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      RingState rs;
+      uint32_t a_phase = 0;
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) mma_tile(rs, a_phase, smem, bars, so, !so);
+    }
+  } else {
+    EpiCtx c;
+    c.smem = smem; c.bars = bars; c.lane = lane;
+    c.row = (warp & 3) * 32 + lane;
+    c.half = warp >> 2;
+    c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    c.d_phase = 0;
+    c.f32 = reinterpret_cast<const float*>(p.net + kHalfRegionBytes);
+    uint8_t* enc = smem + kSmemEnc;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long gi = tile * 128 + c.row;
+      const bool valid = gi < p.n;
+      const float* xr = p.x + (valid ? gi : (p.n - 1)) * p.x_stride;
+      const int k0 = c.half * 32;
+      for (int k = k0; k < k0 + 32; ++k) {
+        const float v = (k < kEncXyz) ? __ldg(xr + k) : 0.f;
+        *reinterpret_cast<__half*>(enc + sw128_off(c.row, k)) = __float2half_rn(v);
+      }
+      float sig_part, rgb_part[3];
+      epi_run_tile(c, so, nullptr, so ? nullptr : xr + kEncXyz, sig_part, rgb_part);
+      sc->sig_part[c.half][c.row] = sig_part;
+      if (!so) {
+        sc->rgb_part[c.half][0][c.row] = rgb_part[0];
+        sc->rgb_part[c.half][1][c.row] = rgb_part[1];
+        sc->rgb_part[c.half][2][c.row] = rgb_part[2];
+      }
+      epi_bar();
+      if (c.half == 0 && valid) {
+        const float sg = sc->sig_part[0][c.row] + sc->sig_part[1][c.row] + __ldg(c.f32 + kF32BSigma);
+        if (so) {
+          p.out[gi] = sg;
+        } else {
+          float4 o;
+          o.x = sigmoid_ref(sc->rgb_part[0][0][c.row] + sc->rgb_part[1][0][c.row] + __ldg(c.f32 + kF32BRgb + 0));
+          o.y = sigmoid_ref(sc->rgb_part[0][1][c.row] + sc->rgb_part[1][1][c.row] + __ldg(c.f32 + kF32BRgb + 1));
+          o.z = sigmoid_ref(sc->rgb_part[0][2][c.row] + sc->rgb_part[1][2][c.row] + __ldg(c.f32 + kF32BRgb + 2));
+          o.w = sg;
+          *reinterpret_cast<float4*>(p.out + gi * 4) = o;
+        }
+      }
+      epi_bar();
+    }
+  }
+  engine_teardown(bars);
+}
+
+// ------------------------------------------------ Embedding.forward (models/nerf.py:21-38)
+// x: (n, 3) -> out: (n, 3 + 6*n_freqs), channel order [x, sin f0 x, cos f0 x, ...].
+__global__ void embed_kernel(const float* __restrict__ x, long long n, int n_freqs,
+                             float* __restrict__ out) {
+  const int C = 3 + 6 * n_freqs;
+  const long long total = n * C;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = idx / C;
+    const int ch = static_cast<int>(idx - r * C);
+    float v;
+    if (ch < 3) {
+      v = x[r * 3 + ch];
+    } else {
+      const int j = ch - 3;
+      const int k = j / 6, fn = (j % 6) / 3, c = j % 3;
+      const float a = __fmul_rn(exp2f(static_cast<float>(k)), x[r * 3 + c]);
+      v = fn ? cosf(a) : sinf(a);
+    }
+    out[idx] = v;
+  }
+}
+
+// ------------------------------------------------ searchsorted (torchsearchsorted)
+// res[r, c] = #{k : a[r,k] <  v[r,c]} (side='left') or #{k : a[r,k] <= v[r,c]} ('right');
+// a or v may have a single row that is broadcast (searchsorted.py:23-35, kernel.cu:83-107).
+__global__ void searchsorted_kernel(const float* __restrict__ a, const float* __restrict__ v,
+                                    long long* __restrict__ res, long long nrow_a, long long nrow_v,
+                                    int ncol_a, int ncol_v, int side_right) {
+  const long long nrow = nrow_a > nrow_v ? nrow_a : nrow_v;
+  const long long total = nrow * ncol_v;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = idx / ncol_v;
+    const int c = static_cast<int>(idx - r * ncol_v);
+    const float* ar = a + (nrow_a == 1 ? 0 : r) * ncol_a;
+    const float val = v[(nrow_v == 1 ? 0 : r) * ncol_v + c];
+    int lo = 0, hi = ncol_a;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const float x = __ldg(ar + mid);
+      const bool go_right = side_right ? (x <= val) : (x < val);
+      if (go_right) lo = mid + 1; else hi = mid;
+    }
+    res[idx] = lo;
+  }
+}
+
+// ------------------------------------------------ sample_pdf (models/rendering.py:14-55)
+// bins (R, nb = nw+1), weights (R, nw), u (R, K) sorted or not; out (R, K).  One warp per ray.
+__global__ void sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights,
+                                  const float* __restrict__ u, long long n_rays, int nw, int K,
+                                  float* __restrict__ out) {
+  extern __shared__ float sh[];
+  const int wpb = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* cdf = sh + warp * (nw + 1);
+  for (long long r = static_cast<long long>(blockIdx.x) * wpb + warp; r < n_rays;
+       r += static_cast<long long>(gridDim.x) * wpb) {
+    const float* w = weights + r * nw;
+    const float* b = bins + r * (nw + 1);
+    float part = 0.f;
+    for (int i = lane; i < nw; i += 32) part += __fadd_rn(w[i], 1e-5f);
+    const float total = warp_sum(part);
+    if (lane == 0) {
+      float run = 0.f;
+      cdf[0] = 0.f;
+      for (int i = 0; i < nw; ++i) {
+        run = __fadd_rn(run, __fdiv_rn(__fadd_rn(w[i], 1e-5f), total));
+        cdf[i + 1] = run;
+      }
+    }
+    __syncwarp();
+    for (int j = lane; j < K; j += 32) {
+      const float uj = u[r * K + j];
+      int lo = 0, hi = nw + 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cdf[mid] <= uj) lo = mid + 1; else hi = mid;
+      }
+      const int below = max(lo - 1, 0), above = min(lo, nw);
+      const float c0 = cdf[below], c1 = cdf[above];
+      float denom = __fsub_rn(c1, c0);
+      if (denom < 1e-5f) denom = 1.f;
+      const float t = __fdiv_rn(__fsub_rn(uj, c0), denom);
+      out[r * K + j] = __fadd_rn(b[below], __fmul_rn(t, __fsub_rn(b[above], b[below])));
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------ volume rendering (models/rendering.py:143-170)
+// sigmas (R,S), rgbs (R,S,3) nullable, z (R,S), dirs (R,3), noise (R,S) nullable.
+// One warp per ray.  S % 32 == 0, S <= 192.
+__global__ void composite_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                 const float* __restrict__ z, const float* __restrict__ dirs,
+                                 const float* __restrict__ noise, float noise_std, int white_back,
+                                 long long n_rays, int S, float* __restrict__ weights,
+                                 float* __restrict__ rgb_out, float* __restrict__ depth_out,
+                                 float* __restrict__ opac_out) {
+  extern __shared__ float sh[];
+  const int wpb = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* base = sh + warp * (6 * S);
+  float *sz = base, *ss = base + S, *sr = base + 2 * S, *sg = base + 3 * S, *sb = base + 4 * S,
+        *sw = base + 5 * S;
+  for (long long r = static_cast<long long>(blockIdx.x) * wpb + warp; r < n_rays;
+       r += static_cast<long long>(gridDim.x) * wpb) {
+    for (int i = lane; i < S; i += 32) {
+      sz[i] = z[r * S + i];
+      ss[i] = sigmas[r * S + i];
+      if (rgbs != nullptr) {
+        sr[i] = rgbs[(r * S + i) * 3 + 0];
+        sg[i] = rgbs[(r * S + i) * 3 + 1];
+        sb[i] = rgbs[(r * S + i) * 3 + 2];
+      }
+    }
+    __syncwarp();
+    const float dx = dirs[r * 3], dy = dirs[r * 3 + 1], dz = dirs[r * 3 + 2];
+    const float dn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const RayOut o = composite_ray(lane, S, sz, ss, sr, sg, sb, noise ? noise + r * S : nullptr,
+                                   noise_std, dn, rgbs != nullptr, sw);
+    __syncwarp();
+    if (weights != nullptr)
+      for (int i = lane; i < S; i += 32) weights[r * S + i] = sw[i];
+    if (lane == 0) {
+      opac_out[r] = o.opac;
+      if (rgbs != nullptr) {
+        const float add = white_back ? __fsub_rn(1.f, o.opac) : 0.f;
+        rgb_out[r * 3 + 0] = o.r + add;
+        rgb_out[r * 3 + 1] = o.g + add;
+        rgb_out[r * 3 + 2] = o.b + add;
+        depth_out[r] = o.depth;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------ diagnostics: one K=64 slice through the engine
+// d[128 x N] = fp16(a[128 x 64]) . slice^T, N = 256 (slices 0..33) or 128 (34..38), read back from
+// TMEM unmodified.  Isolates descriptor / swizzle / TMEM-lane mapping from the layer protocol.
+__global__ void __launch_bounds__(kThreads, 1) gemm_probe_kernel(const float* __restrict__ a,
+                                                                 const uint8_t* __restrict__ blob,
+                                                                 int slice, float* __restrict__ d,
+                                                                 int* status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Scratch* sc = reinterpret_cast<Scratch*>(smem + kSmemScratch);
+  Barriers* bars = &sc->bars;
+  if (!engine_setup(smem, bars)) {
+    if (threadIdx.x == 0) atomicExch(status, 101);
+    return;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool wide = slice < kNumSlices256;
+  const int N = wide ? 256 : 128;
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      const uint32_t full = smem_u32(&bars->full[0]);
+      const uint32_t bytes = wide ? kSliceBytes256 : kSliceBytes128;
+      const uint8_t* src = wide ? blob + static_cast<size_t>(slice) * kSliceBytes256
+                                : blob + kOffDir + static_cast<size_t>(slice - kNumSlices256) * kSliceBytes128;
+      mbar_wait(smem_u32(&bars->empty[0]), 1, 11);
+      mbar_arrive_expect_tx(full, bytes);
+      for (uint32_t c = 0; c < bytes; c += 8192) bulk_g2s(smem_u32(smem + kSmemRing) + c, src + c, 8192, full);
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      mbar_wait(smem_u32(&bars->a_ready), 0, 12);
+      tc_fence_after();
+      mbar_wait(smem_u32(&bars->full[0]), 0, 13);
+      tc_fence_after();
+      const uint64_t adesc = make_desc_sw128(smem_u32(smem + kSmemEnc));
+      const uint64_t bdesc = make_desc_sw128(smem_u32(smem + kSmemRing));
+      for (int j = 0; j < 4; ++j)
+        umma_f16(bars->tmem_base, adesc + 2 * j, bdesc + 2 * j, make_idesc_f16(N), j != 0 ? 1u : 0u);
+      umma_commit(smem_u32(&bars->d_ready));
+    }
+  } else {
+    EpiCtx c;
+    c.smem = smem; c.bars = bars; c.lane = lane;
+    c.row = (warp & 3) * 32 + lane;
+    c.half = warp >> 2;
+    c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    c.d_phase = 0;
+    uint8_t* enc = smem + kSmemEnc;
+    for (int k = c.half * 32; k < c.half * 32 + 32; ++k)
+      *reinterpret_cast<__half*>(enc + sw128_off(c.row, k)) = __float2half_rn(a[c.row * 64 + k]);
+    epi_signal_a(c);
+    epi_wait_d(c);
+    const int ncol = N / 2;
+    for (int cc = 0; cc < ncol; cc += 32) {
+      uint32_t r[32];
+      tmem_ld32(c.tmem_row + c.half * ncol + cc, r);
+      tmem_ld_wait();
+      for (int i = 0; i < 32; ++i) d[c.row * N + c.half * ncol + cc + i] = __uint_as_float(r[i]);
+    }
+  }
+  engine_teardown(bars);
+}
+
+}  // namespace nerfb200

@@ -1,0 +1,389 @@
+// C ABI of libnerf_pl_b200.so (declarations + reference citations: include/nerf_pl_b200.h).
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/nerf_pl_b200.h"
+#include "aux_kernels.cuh"
+
+using namespace nerfb200;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, const char* detail = "") {
+  std::snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+  std::snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
+  return static_cast<int>(e);
+}
+#define CUDA_TRY(expr, where)                          \
+  do {                                                 \
+    cudaError_t e_ = (expr);                           \
+    if (e_ != cudaSuccess) return cuda_fail(e_, where); \
+  } while (0)
+
+struct DeviceInfo {
+  int sm_count = 0;
+  int cc_major = 0;
+  bool attrs_set = false;
+  int* status = nullptr;
+};
+std::mutex g_mu;
+DeviceInfo g_dev[64];
+
+int device_info(DeviceInfo** out) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+  if (dev < 0 || dev >= 64) return fail(NERFB200_EDEVICE, "device ordinal out of range%s");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceInfo& d = g_dev[dev];
+  if (d.sm_count == 0) {
+    CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev), "attr sm");
+    CUDA_TRY(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev), "attr cc");
+  }
+  if (d.cc_major != 10) return fail(NERFB200_EDEVICE, "nerf_pl_b200 needs an sm_100 (B200) device%s");
+  if (!d.attrs_set) {
+    CUDA_TRY(cudaFuncSetAttribute(render_rays_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kSmemTotal)), "smem attr render");
+    CUDA_TRY(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kSmemTotal)), "smem attr mlp");
+    CUDA_TRY(cudaFuncSetAttribute(gemm_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kSmemTotal)), "smem attr probe");
+    CUDA_TRY(cudaMalloc(&d.status, sizeof(int)), "status alloc");
+    CUDA_TRY(cudaMemset(d.status, 0, sizeof(int)), "status memset");
+    d.attrs_set = true;
+  }
+  *out = &d;
+  return 0;
+}
+
+int check_render_shapes(const nerfb200_render_args* a) {
+  if (a == nullptr) return fail(NERFB200_EINVAL, "args is NULL%s");
+  if (a->n_rays < 0) return fail(NERFB200_EINVAL, "n_rays < 0%s");
+  if (a->n_samples != 64 && a->n_samples != 128)
+    return fail(NERFB200_EUNSUPPORTED, "N_samples must be 64 or 128%s");
+  if (a->n_importance != 0 && a->n_importance != 64 && a->n_importance != 128)
+    return fail(NERFB200_EUNSUPPORTED, "N_importance must be 0, 64 or 128%s");
+  if (a->n_samples + a->n_importance > kMaxSf)
+    return fail(NERFB200_EUNSUPPORTED, "N_samples + N_importance must be <= 192%s");
+  if (a->n_rays == 0) return 0;
+  if (!a->rays || !a->packed_coarse) return fail(NERFB200_EINVAL, "rays / packed_coarse is NULL%s");
+  if (a->ray_stride < 8) return fail(NERFB200_EINVAL, "ray_stride < 8%s");
+  if (!a->opacity_coarse) return fail(NERFB200_EINVAL, "opacity_coarse is NULL%s");
+  if (!a->test_time && (!a->rgb_coarse || !a->depth_coarse))
+    return fail(NERFB200_EINVAL, "rgb_coarse / depth_coarse is NULL with test_time=0%s");
+  if (a->n_importance > 0) {
+    if (!a->packed_fine) return fail(NERFB200_EINVAL, "packed_fine is NULL with N_importance>0%s");
+    if (!a->rgb_fine || !a->depth_fine || !a->opacity_fine)
+      return fail(NERFB200_EINVAL, "fine outputs are NULL with N_importance>0%s");
+  }
+  if (a->perturb > 0.f) {
+    if (!a->perturb_rand) return fail(NERFB200_EINVAL, "perturb>0 needs perturb_rand%s");
+    if (a->n_importance > 0 && !a->u_rand) return fail(NERFB200_EINVAL, "perturb>0 needs u_rand%s");
+  }
+  if (a->noise_std > 0.f) {
+    if (!a->noise_coarse) return fail(NERFB200_EINVAL, "noise_std>0 needs noise_coarse%s");
+    if (a->n_importance > 0 && !a->noise_fine) return fail(NERFB200_EINVAL, "noise_std>0 needs noise_fine%s");
+  }
+  if ((reinterpret_cast<uintptr_t>(a->packed_coarse) & 15) ||
+      (reinterpret_cast<uintptr_t>(a->packed_fine) & 15))
+    return fail(NERFB200_EINVAL, "packed images must be 16-byte aligned%s");
+  return 0;
+}
+
+// grow-only device arena for the *_host entry
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0;
+  size_t off = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (base) cudaFree(base);
+    base = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&base, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "arena cudaMalloc");
+    cap = bytes;
+    return 0;
+  }
+  void* take(size_t bytes) {
+    void* p = base + off;
+    off += (bytes + 255) & ~static_cast<size_t>(255);
+    return p;
+  }
+};
+Arena g_arena[64];
+
+}  // namespace
+
+extern "C" {
+
+int nerfb200_abi_version(void) { return NERFB200_ABI_VERSION; }
+const char* nerfb200_last_error(void) { return g_err; }
+size_t nerfb200_packed_bytes(void) { return kPackedBytes; }
+int64_t nerfb200_launch_count(void) { return g_launches.load(); }
+
+int nerfb200_sm_count(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return n;
+}
+
+int nerfb200_pack_weights(const float* const params[24], void* packed, void* stream) {
+  if (!params || !packed) return fail(NERFB200_EINVAL, "pack_weights: NULL argument%s");
+  if (reinterpret_cast<uintptr_t>(packed) & 15) return fail(NERFB200_EINVAL, "packed must be 16-byte aligned%s");
+  PackParams pp;
+  for (int i = 0; i < kNumParams; ++i) {
+    if (!params[i]) return fail(NERFB200_EINVAL, "pack_weights: NULL parameter tensor%s");
+    pp.p[i] = params[i];
+  }
+  pp.out = static_cast<uint8_t*>(packed);
+  const long long total = kHalfRegionBytes / 2 + kF32Count;
+  const int threads = 256;
+  const int blocks = static_cast<int>((total + threads - 1) / threads);
+  pack_weights_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(pp);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "pack_weights launch");
+  return 0;
+}
+
+int nerfb200_render_rays(const nerfb200_render_args* a, void* stream) {
+  int rc = check_render_shapes(a);
+  if (rc) return rc;
+  if (a->n_rays == 0) return 0;
+  if (a->n_rays > 0x7fffffff) return fail(NERFB200_EINVAL, "n_rays too large%s");
+  DeviceInfo* d = nullptr;
+  rc = device_info(&d);
+  if (rc) return rc;
+  RenderParams p;
+  p.rays = a->rays;
+  p.ray_stride = a->ray_stride;
+  p.n_rays = static_cast<int>(a->n_rays);
+  p.net_coarse = static_cast<const uint8_t*>(a->packed_coarse);
+  p.net_fine = static_cast<const uint8_t*>(a->packed_fine);
+  p.n_samples = a->n_samples;
+  p.n_importance = a->n_importance;
+  p.use_disp = a->use_disp;
+  p.perturb = a->perturb;
+  p.noise_std = a->noise_std;
+  p.white_back = a->white_back;
+  p.test_time = a->test_time;
+  p.perturb_rand = a->perturb_rand;
+  p.noise_coarse = a->noise_coarse;
+  p.noise_fine = a->noise_fine;
+  p.u_rand = a->u_rand;
+  p.rgb_coarse = a->rgb_coarse;
+  p.depth_coarse = a->depth_coarse;
+  p.opacity_coarse = a->opacity_coarse;
+  p.rgb_fine = a->rgb_fine;
+  p.depth_fine = a->depth_fine;
+  p.opacity_fine = a->opacity_fine;
+  p.z_fine = a->z_fine;
+  p.weights_coarse = a->weights_coarse;
+  p.weights_fine = a->weights_fine;
+  p.status = a->status ? a->status : d->status;
+  const int n_groups = (p.n_rays + 1) / 2;
+  int ctas = d->sm_count;
+  if (a->max_ctas > 0 && a->max_ctas < ctas) ctas = a->max_ctas;
+  if (n_groups < ctas) ctas = n_groups;
+  render_rays_kernel<false><<<ctas, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "render_rays launch");
+  return 0;
+}
+
+int nerfb200_render_rays_host(const nerfb200_render_args* h, void* stream_v) {
+  int rc = check_render_shapes(h);
+  if (rc) return rc;
+  if (h->n_rays == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+  const size_t n = static_cast<size_t>(h->n_rays);
+  const size_t Sc = h->n_samples, K = h->n_importance, Sf = Sc + K;
+  const size_t fl = sizeof(float);
+  // rays + 4 random inputs + 8 float outputs (+3 optional) + status, each rounded to 256 B
+  size_t need = 16 * 256 + n * fl * (8 + Sc + Sc + K + Sf + 3 + 1 + 1 + 3 + 1 + 1 + Sf + Sc + Sf) + 256;
+  Arena& ar = g_arena[dev];
+  std::lock_guard<std::mutex> lk(g_mu);
+  rc = ar.reserve(need);
+  if (rc) return rc;
+  ar.off = 0;
+  nerfb200_render_args a = *h;
+  a.ray_stride = 8;
+  auto up = [&](const float* src, size_t count, size_t src_stride, size_t width) -> const float* {
+    if (!src) return nullptr;
+    float* dst = static_cast<float*>(ar.take(count * fl));
+    if (src_stride == width) {
+      cudaMemcpyAsync(dst, src, count * fl, cudaMemcpyHostToDevice, stream);
+    } else {
+      cudaMemcpy2DAsync(dst, width * fl, src, src_stride * fl, width * fl, count / width,
+                        cudaMemcpyHostToDevice, stream);
+    }
+    return dst;
+  };
+  a.rays = up(h->rays, n * 8, static_cast<size_t>(h->ray_stride), 8);
+  a.perturb_rand = up(h->perturb_rand, n * Sc, Sc, Sc);
+  a.noise_coarse = up(h->noise_coarse, n * Sc, Sc, Sc);
+  a.u_rand = up(h->u_rand, n * K, K, K);
+  a.noise_fine = up(h->noise_fine, n * Sf, Sf, Sf);
+  auto dn = [&](float* hostp, size_t count) -> float* {
+    return hostp ? static_cast<float*>(ar.take(count * fl)) : nullptr;
+  };
+  a.rgb_coarse = dn(h->rgb_coarse, n * 3);
+  a.depth_coarse = dn(h->depth_coarse, n);
+  a.opacity_coarse = dn(h->opacity_coarse, n);
+  a.rgb_fine = dn(h->rgb_fine, n * 3);
+  a.depth_fine = dn(h->depth_fine, n);
+  a.opacity_fine = dn(h->opacity_fine, n);
+  a.z_fine = dn(h->z_fine, n * Sf);
+  a.weights_coarse = dn(h->weights_coarse, n * Sc);
+  a.weights_fine = dn(h->weights_fine, n * Sf);
+  int* dstatus = static_cast<int*>(ar.take(sizeof(int)));
+  CUDA_TRY(cudaMemsetAsync(dstatus, 0, sizeof(int), stream), "status memset");
+  a.status = dstatus;
+  rc = nerfb200_render_rays(&a, stream);
+  if (rc) return rc;
+  auto back = [&](float* hostp, const float* devp, size_t count) {
+    if (hostp) cudaMemcpyAsync(hostp, devp, count * fl, cudaMemcpyDeviceToHost, stream);
+  };
+  back(h->rgb_coarse, a.rgb_coarse, n * 3);
+  back(h->depth_coarse, a.depth_coarse, n);
+  back(h->opacity_coarse, a.opacity_coarse, n);
+  back(h->rgb_fine, a.rgb_fine, n * 3);
+  back(h->depth_fine, a.depth_fine, n);
+  back(h->opacity_fine, a.opacity_fine, n);
+  back(h->z_fine, a.z_fine, n * Sf);
+  back(h->weights_coarse, a.weights_coarse, n * Sc);
+  back(h->weights_fine, a.weights_fine, n * Sf);
+  int hstatus = 0;
+  CUDA_TRY(cudaMemcpyAsync(&hstatus, dstatus, sizeof(int), cudaMemcpyDeviceToHost, stream), "status copy");
+  CUDA_TRY(cudaStreamSynchronize(stream), "render_rays_host sync");
+  if (hstatus != 0) {
+    std::snprintf(g_err, sizeof(g_err), "render kernel reported device status %d", hstatus);
+    return NERFB200_EDEVICE;
+  }
+  if (h->status) *h->status = hstatus;
+  return 0;
+}
+
+int nerfb200_nerf_forward(const float* x, int64_t n, int64_t x_stride, const void* packed,
+                          int32_t sigma_only, float* out, void* stream) {
+  if (n < 0) return fail(NERFB200_EINVAL, "nerf_forward: n < 0%s");
+  if (n == 0) return 0;
+  if (!x || !packed || !out) return fail(NERFB200_EINVAL, "nerf_forward: NULL argument%s");
+  if (x_stride < (sigma_only ? kEncXyz : kEncXyz + kEncDir))
+    return fail(NERFB200_EINVAL, "nerf_forward: x_stride too small for the input width%s");
+  if (!sigma_only && (reinterpret_cast<uintptr_t>(out) & 15))
+    return fail(NERFB200_EINVAL, "nerf_forward: out must be 16-byte aligned%s");
+  DeviceInfo* d = nullptr;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  MlpParams p;
+  p.x = x; p.x_stride = x_stride; p.n = n;
+  p.net = static_cast<const uint8_t*>(packed);
+  p.sigma_only = sigma_only;
+  p.out = out;
+  p.status = d->status;
+  const long long tiles = (n + 127) / 128;
+  const int ctas = static_cast<int>(tiles < d->sm_count ? tiles : d->sm_count);
+  mlp_forward_kernel<<<ctas, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "nerf_forward launch");
+  return 0;
+}
+
+int nerfb200_embed(const float* x, int64_t n, int32_t n_freqs, float* out, void* stream) {
+  if (n < 0 || n_freqs < 0 || n_freqs > 16) return fail(NERFB200_EINVAL, "embed: bad n / n_freqs%s");
+  if (n == 0) return 0;
+  if (!x || !out) return fail(NERFB200_EINVAL, "embed: NULL argument%s");
+  const long long total = n * (3 + 6 * n_freqs);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  embed_kernel<<<static_cast<int>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(x, n, n_freqs, out);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "embed launch");
+  return 0;
+}
+
+int nerfb200_searchsorted(const float* a, const float* v, int64_t* out, int64_t nrow_a,
+                          int64_t nrow_v, int32_t ncol_a, int32_t ncol_v, int32_t side_right,
+                          void* stream) {
+  if (nrow_a < 0 || nrow_v < 0 || ncol_a < 0 || ncol_v < 0)
+    return fail(NERFB200_EINVAL, "searchsorted: negative size%s");
+  // searchsorted.py:26-29: same number of rows, or one of them has a single row
+  if (nrow_a != nrow_v && nrow_a != 1 && nrow_v != 1)
+    return fail(NERFB200_EINVAL, "searchsorted: a and v need the same number of rows, or 1 row%s");
+  const long long nrow = nrow_a > nrow_v ? nrow_a : nrow_v;
+  const long long total = nrow * ncol_v;
+  if (total == 0) return 0;
+  if (!a && ncol_a > 0) return fail(NERFB200_EINVAL, "searchsorted: a is NULL%s");
+  if (!v || !out) return fail(NERFB200_EINVAL, "searchsorted: NULL argument%s");
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  searchsorted_kernel<<<static_cast<int>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, v, reinterpret_cast<long long*>(out), nrow_a, nrow_v, ncol_a, ncol_v, side_right);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "searchsorted launch");
+  return 0;
+}
+
+int nerfb200_sample_pdf(const float* bins, const float* weights, const float* u, int64_t n_rays,
+                        int32_t n_weights, int32_t n_u, float* out, void* stream) {
+  if (n_rays < 0 || n_weights < 1 || n_u < 0 || n_weights > 4096)
+    return fail(NERFB200_EINVAL, "sample_pdf: bad sizes%s");
+  if (n_rays == 0 || n_u == 0) return 0;
+  if (!bins || !weights || !u || !out) return fail(NERFB200_EINVAL, "sample_pdf: NULL argument%s");
+  const int wpb = 4;
+  const size_t sh = wpb * (n_weights + 1) * sizeof(float);
+  long long blocks = (n_rays + wpb - 1) / wpb;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sample_pdf_kernel<<<static_cast<int>(blocks), wpb * 32, sh, static_cast<cudaStream_t>(stream)>>>(
+      bins, weights, u, n_rays, n_weights, n_u, out);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "sample_pdf launch");
+  return 0;
+}
+
+int nerfb200_composite(const float* sigmas, const float* rgbs, const float* z_vals,
+                       const float* dirs, const float* noise, float noise_std, int32_t white_back,
+                       int64_t n_rays, int32_t S, float* weights, float* rgb, float* depth,
+                       float* opacity, void* stream) {
+  if (n_rays < 0) return fail(NERFB200_EINVAL, "composite: n_rays < 0%s");
+  if (S <= 0 || (S % 32) != 0 || S > kMaxSf) return fail(NERFB200_EUNSUPPORTED, "composite: S must be a multiple of 32, <= 192%s");
+  if (n_rays == 0) return 0;
+  if (!sigmas || !z_vals || !dirs || !opacity) return fail(NERFB200_EINVAL, "composite: NULL argument%s");
+  if (rgbs && (!rgb || !depth)) return fail(NERFB200_EINVAL, "composite: rgb/depth outputs NULL%s");
+  const int wpb = 4;
+  const size_t sh = wpb * 6 * S * sizeof(float);
+  long long blocks = (n_rays + wpb - 1) / wpb;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  composite_kernel<<<static_cast<int>(blocks), wpb * 32, sh, static_cast<cudaStream_t>(stream)>>>(
+      sigmas, rgbs, z_vals, dirs, noise, noise_std, white_back, n_rays, S, weights, rgb, depth, opacity);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "composite launch");
+  return 0;
+}
+
+int nerfb200_debug_gemm(const float* a, const void* packed, int32_t slice, float* d, void* stream) {
+  if (!a || !packed || !d) return fail(NERFB200_EINVAL, "debug_gemm: NULL argument%s");
+  if (slice < 0 || slice >= kNumSlices256 + kNumSlices128) return fail(NERFB200_EINVAL, "debug_gemm: bad slice%s");
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  gemm_probe_kernel<<<1, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(
+      a, static_cast<const uint8_t*>(packed), slice, d, di->status);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "debug_gemm launch");
+  return 0;
+}
+
+}  // extern "C"

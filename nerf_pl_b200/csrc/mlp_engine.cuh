@@ -1,0 +1,331 @@
+// The NeRF MLP (models/nerf.py:83-124) as a warp-specialised tcgen05 tile engine.
+//
+// One CTA owns one 128-row tile of samples at a time:
+//   * warps 0..7  "epilogue" warps.  Warp w reads TMEM lane quadrant (w & 3) and column
+//                 half (w >> 2).  They write the fp16 A operand (encoded input, then
+//                 each layer's activations) into shared memory in the UMMA K-major
+//                 SWIZZLE_128B layout, and do bias/ReLU/heads on the fp32 accumulator.
+//   * warp 8      weight producer: streams the packed K-slices (layout.h) of the
+//                 network through a 4-stage 32 KiB ring with cp.async.bulk + mbarriers.
+//                 It runs ahead of the MMA by up to one full layer.
+//   * warp 9      MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16)
+//                 with the accumulator in TMEM, tcgen05.commit frees ring stages and
+//                 signals "accumulator ready".
+// Layer l+1's MMA reads the A tile that layer l's epilogue wrote, so MMA and epilogue of
+// one tile alternate; the producer keeps the next layer's weights resident meanwhile.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "layout.h"
+#include "ptx.cuh"
+
+namespace nerfb200 {
+
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;   // 256
+constexpr int kProducerWarp = 8;
+constexpr int kMmaWarp = 9;
+constexpr int kThreads = 320;
+constexpr int kStages = 4;
+constexpr int kTmemCols = 256;
+
+constexpr uint32_t kSmemA = 0;                       // [4][128 x 64] fp16  64 KiB
+constexpr uint32_t kSmemEnc = 65536;                 // [128 x 64] fp16     16 KiB
+constexpr uint32_t kSmemRing = 81920;                // 4 x 32 KiB
+constexpr uint32_t kSmemScratch = 212992;            // barriers + per-group scratch
+constexpr uint32_t kSmemTotal = 232448;              // 227 KiB (max opt-in)
+constexpr uint32_t kScratchBytes = kSmemTotal - kSmemScratch;   // 19456
+
+constexpr int kLayersFull = 10;       // L1..L8, final, dir
+constexpr int kLayersSigma = 8;       // L1..L8
+
+struct Barriers {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t a_ready;
+  uint64_t d_ready;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+struct RingState {
+  uint32_t stage = 0, phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++stage == kStages) { stage = 0; phase ^= 1; }
+  }
+};
+
+// ----------------------------------------------------------------- set-up
+// Called by all threads at kernel start.  Returns false (uniformly) on misaligned smem.
+__device__ __forceinline__ bool engine_setup(uint8_t* smem, Barriers* bars) {
+  const int warp = threadIdx.x >> 5;
+  if ((smem_u32(smem) & 1023u) != 0) return false;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(smem_u32(&bars->full[i]), 1);
+      mbar_init(smem_u32(&bars->empty[i]), 1);
+    }
+    mbar_init(smem_u32(&bars->a_ready), kEpiWarps);
+    mbar_init(smem_u32(&bars->d_ready), 1);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return true;
+}
+__device__ __forceinline__ void engine_teardown(Barriers* bars) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(bars->tmem_base, kTmemCols);
+  }
+}
+
+// --------------------------------------------------------------- producer
+// One thread.  Streams the slices of one network for one tile.
+__device__ __forceinline__ void produce_tile(RingState& rs, uint8_t* smem, Barriers* bars,
+                                             const uint8_t* __restrict__ blob, bool sigma_only,
+                                             bool dir_slice) {
+  const int n256 = sigma_only ? kNumSlicesSigmaOnly : kNumSlices256;
+  for (int i = 0; i < n256; ++i) {
+    mbar_wait(smem_u32(&bars->empty[rs.stage]), rs.phase ^ 1, 1);
+    const uint32_t full = smem_u32(&bars->full[rs.stage]);
+    const uint32_t dst = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
+    mbar_arrive_expect_tx(full, kSliceBytes256);
+    const uint8_t* src = blob + static_cast<size_t>(i) * kSliceBytes256;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bulk_g2s(dst + c * 8192, src + c * 8192, 8192, full);
+    rs.advance();
+  }
+  if (!sigma_only) {
+    const int n128 = dir_slice ? 5 : 4;
+    for (int i = 0; i < n128; ++i) {
+      mbar_wait(smem_u32(&bars->empty[rs.stage]), rs.phase ^ 1, 2);
+      const uint32_t full = smem_u32(&bars->full[rs.stage]);
+      const uint32_t dst = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
+      mbar_arrive_expect_tx(full, kSliceBytes128);
+      const uint8_t* src = blob + kOffDir + static_cast<size_t>(i) * kSliceBytes128;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) bulk_g2s(dst + c * 8192, src + c * 8192, 8192, full);
+      rs.advance();
+    }
+  }
+}
+
+// -------------------------------------------------------------------- MMA
+// One thread.  Issues all MMAs of one tile.
+__device__ __forceinline__ void mma_tile(RingState& rs, uint32_t& a_phase, uint8_t* smem,
+                                         Barriers* bars, bool sigma_only, bool dir_slice) {
+  const uint32_t tmem_d = bars->tmem_base;
+  const uint32_t a_base = smem_u32(smem + kSmemA);
+  const uint32_t enc_base = smem_u32(smem + kSmemEnc);
+  const int n_layers = sigma_only ? kLayersSigma : kLayersFull;
+  for (int l = 0; l < n_layers; ++l) {
+    mbar_wait(smem_u32(&bars->a_ready), a_phase, 3);
+    a_phase ^= 1;
+    tc_fence_after();
+    const int n_slices = (l == 0) ? 1 : (l == 4) ? 5 : (l == 9 && dir_slice) ? 5 : 4;
+    const uint32_t idesc = (l == 9) ? make_idesc_f16(128) : make_idesc_f16(256);
+    for (int s = 0; s < n_slices; ++s) {
+      const bool from_enc = (l == 0) || (l == 4 && s == 0) || (l == 9 && s == 4);
+      const int kb = (l == 4) ? s - 1 : s;
+      const uint32_t a_addr = from_enc ? enc_base : a_base + kb * 16384;
+      const uint32_t b_addr = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
+      mbar_wait(smem_u32(&bars->full[rs.stage]), rs.phase, 4);
+      tc_fence_after();
+      const uint64_t adesc = make_desc_sw128(a_addr);
+      const uint64_t bdesc = make_desc_sw128(b_addr);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in the addr field
+        umma_f16(tmem_d, adesc + 2 * j, bdesc + 2 * j, idesc, (s | j) != 0 ? 1u : 0u);
+      }
+      umma_commit(smem_u32(&bars->empty[rs.stage]));
+      rs.advance();
+    }
+    umma_commit(smem_u32(&bars->d_ready));
+  }
+}
+
+// --------------------------------------------------------------- epilogue
+struct EpiCtx {
+  uint8_t* smem;
+  Barriers* bars;
+  const float* __restrict__ f32;   // fp32 region of the current network image
+  uint32_t tmem_row;               // tmem base + (lane quadrant << 16)
+  uint32_t d_phase;
+  int row;                         // 0..127 : tile row == TMEM lane
+  int half;                        // 0/1    : column half
+  int lane;
+};
+
+__device__ __forceinline__ void epi_bar() {   // all 256 epilogue threads
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+__device__ __forceinline__ void epi_signal_a(EpiCtx& c) {
+  fence_proxy_async();
+  tc_fence_before();
+  __syncwarp();
+  if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_ready));
+}
+__device__ __forceinline__ void epi_wait_d(EpiCtx& c) {
+  mbar_wait(smem_u32(&c.bars->d_ready), c.d_phase, 5);
+  c.d_phase ^= 1;
+  tc_fence_after();
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z,
+                                             uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w)
+               : "memory");
+}
+
+// Hidden layer epilogue over this thread's 128 columns: v = act(acc + bias), stored as the
+// next layer's fp16 A operand.  Optionally accumulates the sigma head (models/nerf.py:112).
+template <bool kRelu, bool kSigma, bool kStore>
+__device__ __forceinline__ void epi_hidden(EpiCtx& c, const float* __restrict__ bias,
+                                           const float* __restrict__ wsig, float& sig_acc) {
+  const uint32_t a_base = smem_u32(c.smem + kSmemA);
+  const uint32_t rsw = static_cast<uint32_t>(c.row & 7);
+#pragma unroll
+  for (int cc = 0; cc < 4; cc += 2) {
+    uint32_t r[2][32];
+    tmem_ld32(c.tmem_row + c.half * 128 + cc * 32, r[0]);
+    tmem_ld32(c.tmem_row + c.half * 128 + cc * 32 + 32, r[1]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int n0 = c.half * 128 + (cc + u) * 32;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + 8 * j;
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
+        float v[8];
+        v[0] = __uint_as_float(r[u][8 * j + 0]) + b0.x;
+        v[1] = __uint_as_float(r[u][8 * j + 1]) + b0.y;
+        v[2] = __uint_as_float(r[u][8 * j + 2]) + b0.z;
+        v[3] = __uint_as_float(r[u][8 * j + 3]) + b0.w;
+        v[4] = __uint_as_float(r[u][8 * j + 4]) + b1.x;
+        v[5] = __uint_as_float(r[u][8 * j + 5]) + b1.y;
+        v[6] = __uint_as_float(r[u][8 * j + 6]) + b1.z;
+        v[7] = __uint_as_float(r[u][8 * j + 7]) + b1.w;
+        if (kRelu) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (kSigma) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(wsig + n));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(wsig + n + 4));
+          sig_acc = fmaf(v[0], w0.x, sig_acc);
+          sig_acc = fmaf(v[1], w0.y, sig_acc);
+          sig_acc = fmaf(v[2], w0.z, sig_acc);
+          sig_acc = fmaf(v[3], w0.w, sig_acc);
+          sig_acc = fmaf(v[4], w1.x, sig_acc);
+          sig_acc = fmaf(v[5], w1.y, sig_acc);
+          sig_acc = fmaf(v[6], w1.z, sig_acc);
+          sig_acc = fmaf(v[7], w1.w, sig_acc);
+        }
+        if (kStore) {
+          const uint32_t kb = static_cast<uint32_t>(n) >> 6;
+          const uint32_t chunk = (static_cast<uint32_t>(n) & 63u) >> 3;
+          const uint32_t addr = a_base + kb * 16384u + static_cast<uint32_t>(c.row) * 128u +
+                                ((chunk ^ rsw) << 4);
+          st_shared_v4(addr, pack_half2(v[0], v[1]), pack_half2(v[2], v[3]),
+                       pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+        }
+      }
+    }
+  }
+}
+
+// dir_encoding epilogue (N=128; this thread's 64 columns) fused with the rgb head
+// (models/nerf.py:119-120): d = relu(acc + dbias[n]); rgb_acc[c] += d * w_rgb[c][n].
+// dbias is either the per-ray vector (bias + direction part, shared memory) or b_dir (global).
+__device__ __forceinline__ void epi_dir(EpiCtx& c, const float* dbias, const float* __restrict__ wrgb,
+                                        float (&rgb_acc)[3]) {
+  uint32_t r[2][32];
+  tmem_ld32(c.tmem_row + c.half * 64, r[0]);
+  tmem_ld32(c.tmem_row + c.half * 64 + 32, r[1]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = c.half * 64 + u * 32 + 4 * j;
+      const float4 b = *reinterpret_cast<const float4*>(dbias + n);
+      const float4 wr = __ldg(reinterpret_cast<const float4*>(wrgb + n));
+      const float4 wg = __ldg(reinterpret_cast<const float4*>(wrgb + 128 + n));
+      const float4 wb = __ldg(reinterpret_cast<const float4*>(wrgb + 256 + n));
+      const float v0 = fmaxf(__uint_as_float(r[u][4 * j + 0]) + b.x, 0.f);
+      const float v1 = fmaxf(__uint_as_float(r[u][4 * j + 1]) + b.y, 0.f);
+      const float v2 = fmaxf(__uint_as_float(r[u][4 * j + 2]) + b.z, 0.f);
+      const float v3 = fmaxf(__uint_as_float(r[u][4 * j + 3]) + b.w, 0.f);
+      rgb_acc[0] = fmaf(v0, wr.x, rgb_acc[0]); rgb_acc[0] = fmaf(v1, wr.y, rgb_acc[0]);
+      rgb_acc[0] = fmaf(v2, wr.z, rgb_acc[0]); rgb_acc[0] = fmaf(v3, wr.w, rgb_acc[0]);
+      rgb_acc[1] = fmaf(v0, wg.x, rgb_acc[1]); rgb_acc[1] = fmaf(v1, wg.y, rgb_acc[1]);
+      rgb_acc[1] = fmaf(v2, wg.z, rgb_acc[1]); rgb_acc[1] = fmaf(v3, wg.w, rgb_acc[1]);
+      rgb_acc[2] = fmaf(v0, wb.x, rgb_acc[2]); rgb_acc[2] = fmaf(v1, wb.y, rgb_acc[2]);
+      rgb_acc[2] = fmaf(v2, wb.z, rgb_acc[2]); rgb_acc[2] = fmaf(v3, wb.w, rgb_acc[2]);
+    }
+  }
+}
+
+// Run the epilogue side of one tile.  Pre-condition: the caller has written the encoded
+// input into the ENC tile (all 256 threads) but has NOT signalled yet.
+//   dbias      : per-row direction bias vector for this thread's ray (smem, 128 floats), or
+//                nullptr to use b_dir from the image (dir_slice mode adds the direction
+//                part through the tensor core instead).
+//   dir_row    : dir_slice mode only - this row's 27 embedded direction values (global).
+// Outputs partial sums (this thread's column half): sigma and rgb pre-activation.
+__device__ __forceinline__ void epi_run_tile(EpiCtx& c, bool sigma_only, const float* dbias,
+                                             const float* __restrict__ dir_row, float& sig_part,
+                                             float (&rgb_part)[3]) {
+  const float* bias = c.f32 + kF32Bias;
+  const float* wsig = c.f32 + kF32WSigma;
+  sig_part = 0.f;
+  rgb_part[0] = rgb_part[1] = rgb_part[2] = 0.f;
+  float dummy = 0.f;
+  epi_signal_a(c);
+  for (int l = 0; l < 7; ++l) {
+    epi_wait_d(c);
+    epi_hidden<true, false, true>(c, bias + l * 256, nullptr, dummy);
+    epi_signal_a(c);
+  }
+  epi_wait_d(c);
+  if (sigma_only) {
+    epi_hidden<true, true, false>(c, bias + 7 * 256, wsig, sig_part);
+    return;   // next signal comes with the next tile's ENC write
+  }
+  epi_hidden<true, true, true>(c, bias + 7 * 256, wsig, sig_part);
+  epi_signal_a(c);
+  // xyz_encoding_final: bias only, no activation (models/nerf.py:116)
+  epi_wait_d(c);
+  epi_hidden<false, false, true>(c, bias + 8 * 256, nullptr, dummy);
+  if (dir_row != nullptr) {
+    // ENC tile is dead after layer 5: reuse it for the embedded direction (cols 27..63 zero)
+    uint8_t* enc = c.smem + kSmemEnc;
+    const int k0 = c.half * 32;
+    for (int k = k0; k < k0 + 32; ++k) {
+      const float v = (k < kEncDir) ? __ldg(dir_row + k) : 0.f;
+      *reinterpret_cast<__half*>(enc + sw128_off(c.row, k)) = __float2half_rn(v);
+    }
+  }
+  epi_signal_a(c);
+  epi_wait_d(c);
+  epi_dir(c, dbias != nullptr ? dbias : (bias + 9 * 256), c.f32 + kF32WRgb, rgb_part);
+}
+
+__device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf(-x)); }
+
+}  // namespace nerfb200

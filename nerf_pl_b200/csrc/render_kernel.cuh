@@ -1,0 +1,447 @@
+// Fused render_rays (models/rendering.py:58-244): stratified depths -> positional encoding
+// -> coarse MLP -> alpha compositing -> inverse-CDF resampling -> merge -> fine MLP ->
+// compositing, one persistent CTA per SM, two rays ("a group") at a time.  sigma / rgb never
+// leave the SM; HBM traffic is 32 B in and <= 40 B out per ray.
+#pragma once
+#include "mlp_engine.cuh"
+
+namespace nerfb200 {
+
+constexpr int kMaxSc = 128;     // max coarse samples / ray
+constexpr int kMaxImp = 128;    // max importance samples / ray
+constexpr int kMaxSf = 192;     // max fine samples / ray (N_samples + N_importance)
+constexpr int kMaxRows = 2 * kMaxSf;
+
+struct RenderParams {
+  const float* rays;            // (n_rays, ray_stride) : o(3) d(3) near far
+  long long ray_stride;         // in floats
+  int n_rays;
+  const uint8_t* net_coarse;    // packed images (layout.h)
+  const uint8_t* net_fine;      // may be null when n_importance == 0
+  int n_samples;                // S_c
+  int n_importance;
+  int use_disp;
+  float perturb;
+  float noise_std;
+  int white_back;
+  int test_time;
+  const float* perturb_rand;    // (n_rays, S_c)   U[0,1)   required iff perturb > 0
+  const float* noise_coarse;    // (n_rays, S_c)   N(0,1)   required iff noise_std > 0
+  const float* noise_fine;      // (n_rays, S_f)   N(0,1)   required iff noise_std > 0 && fine
+  const float* u_rand;          // (n_rays, N_imp) U[0,1)   required iff perturb > 0 && fine
+  float* rgb_coarse;            // (n_rays,3) nullable
+  float* depth_coarse;          // (n_rays)   nullable
+  float* opacity_coarse;        // (n_rays)
+  float* rgb_fine;              // (n_rays,3)
+  float* depth_fine;            // (n_rays)
+  float* opacity_fine;          // (n_rays)
+  float* z_fine;                // (n_rays, S_f) optional: merged sorted depths
+  float* weights_coarse;        // (n_rays, S_c) optional
+  float* weights_fine;          // (n_rays, S_f) optional
+  int* status;                  // device int: nonzero on device-detected error
+};
+
+struct alignas(16) Scratch {
+  Barriers bars;                       //   96
+  float dirbias[2][kDirW];             // 1024   per-ray b_dir + W_dir[:,256:283] . dir_enc
+  float sig_part[2][128];              // 1024   [half][row]
+  float rgb_part[2][3][128];           // 3072
+  float ray[2][8];                     //   64
+  float dnorm[2];
+  float pad0[2];
+  float direnc[2][28];                 //  224
+  float z[kMaxRows];                   // 1536   depths of the current pass, [ray][S]
+  float sigma[kMaxRows];               // 1536
+  float rgb[3][kMaxRows];              // 4608
+  float w[2][kMaxSf];                  // 1536   compositing weights of the current pass
+  float cdf[2][kMaxSc];                // 1024
+  float znew[2][kMaxImp];              // 1024   u (sorted) then the new depths
+  float zc[2][kMaxSc];                 // 1024   coarse depths kept for the merge
+};
+static_assert(sizeof(Scratch) <= kScratchBytes, "scratch does not fit");
+
+// torch.linspace(0, 1, n)[i] in fp32 (symmetric two-sided evaluation).
+__device__ __forceinline__ float linspace01(int i, int n) {
+  if (n <= 1) return 0.f;
+  const float step = __fdiv_rn(1.f, static_cast<float>(n - 1));
+  return (i < n / 2) ? __fmul_rn(step, static_cast<float>(i))
+                     : __fsub_rn(1.f, __fmul_rn(step, static_cast<float>(n - 1 - i)));
+}
+
+// models/rendering.py:189-193
+__device__ __forceinline__ float z_base(float near, float far, int i, int n, bool use_disp) {
+  const float t = linspace01(i, n);
+  const float omt = __fsub_rn(1.f, t);
+  if (!use_disp) return __fadd_rn(__fmul_rn(near, omt), __fmul_rn(far, t));
+  const float a = __fmul_rn(__fdiv_rn(1.f, near), omt);
+  const float b = __fmul_rn(__fdiv_rn(1.f, far), t);
+  return __fdiv_rn(1.f, __fadd_rn(a, b));
+}
+
+// Embedding.forward (models/nerf.py:33-38) of the 3 values x into out[3 + 6*n_freqs].
+__device__ __forceinline__ void embed3(const float x[3], int n_freqs, float* out) {
+  out[0] = x[0]; out[1] = x[1]; out[2] = x[2];
+  float f = 1.f;
+  for (int k = 0; k < n_freqs; ++k, f *= 2.f) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s, co;
+      sincosf(f * x[c], &s, &co);
+      out[3 + 6 * k + c] = s;
+      out[3 + 6 * k + 3 + c] = co;
+    }
+  }
+}
+
+// Encoded xyz of one sample row into the ENC tile; the two column-half threads of a row split
+// the ten frequencies.  Feature order models/nerf.py:33-38: [x, sin f0 x, cos f0 x, sin f1 x, ..].
+__device__ __forceinline__ void encode_row(uint8_t* enc, int row, int half, const float o[3],
+                                           const float d[3], float z) {
+  float x[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(o[c], __fmul_rn(d[c], z));   // rendering.py:206
+  if (half == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      *reinterpret_cast<__half*>(enc + sw128_off(row, c)) = __float2half_rn(x[c]);
+  } else {
+    *reinterpret_cast<__half*>(enc + sw128_off(row, 63)) = __float2half_rn(0.f);
+  }
+  const int k0 = half * 5;
+  float f = half ? 32.f : 1.f;
+#pragma unroll
+  for (int k = k0; k < k0 + 5; ++k, f *= 2.f) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s, co;
+      sincosf(f * x[c], &s, &co);
+      *reinterpret_cast<__half*>(enc + sw128_off(row, 3 + 6 * k + c)) = __float2half_rn(s);
+      *reinterpret_cast<__half*>(enc + sw128_off(row, 3 + 6 * k + 3 + c)) = __float2half_rn(co);
+    }
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Volume-rendering quadrature for one ray by one warp (models/rendering.py:143-170).
+// Each lane owns P = S/32 consecutive samples.  Writes weights to w[0..S).
+struct RayOut { float r, g, b, depth, opac; };
+__device__ __forceinline__ RayOut composite_ray(int lane, int S, const float* z, const float* sigma,
+                                                const float* r, const float* g, const float* b,
+                                                const float* __restrict__ noise, float noise_std,
+                                                float dnorm, bool want_rgb, float* w) {
+  const int P = S >> 5;          // 2..6
+  float alpha[6], tloc[6];
+  float prod = 1.f;
+  for (int p = 0; p < P; ++p) {
+    const int i = lane * P + p;
+    float delta = (i < S - 1) ? __fsub_rn(z[i + 1], z[i]) : 1e10f;
+    delta = __fmul_rn(delta, dnorm);
+    float s = sigma[i];
+    if (noise != nullptr) s = __fadd_rn(s, __fmul_rn(noise[i], noise_std));
+    const float a = __fsub_rn(1.f, expf(-__fmul_rn(delta, fmaxf(s, 0.f))));
+    alpha[p] = a;
+    tloc[p] = prod;
+    prod = __fmul_rn(prod, __fadd_rn(__fsub_rn(1.f, a), 1e-10f));
+  }
+  // exclusive multiplicative scan of the per-lane products
+  float incl = prod;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl *= v;
+  }
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) excl = 1.f;
+  RayOut out{0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int p = 0; p < P; ++p) {
+    const int i = lane * P + p;
+    const float wi = alpha[p] * (excl * tloc[p]);
+    w[i] = wi;
+    out.opac += wi;
+    if (want_rgb) {
+      out.r = fmaf(wi, r[i], out.r);
+      out.g = fmaf(wi, g[i], out.g);
+      out.b = fmaf(wi, b[i], out.b);
+      out.depth = fmaf(wi, z[i], out.depth);
+    }
+  }
+  out.opac = warp_sum(out.opac);
+  if (want_rgb) {
+    out.r = warp_sum(out.r); out.g = warp_sum(out.g); out.b = warp_sum(out.b);
+    out.depth = warp_sum(out.depth);
+  }
+  return out;
+}
+
+// sample_pdf (models/rendering.py:14-55) for one ray by one warp.
+//   zc[0..S)      coarse depths (sorted)        w[0..S) coarse weights
+//   bins = mid-points (S-1), weights = w[1..S-2] (S-2)
+//   u[0..K)       sorted sample positions in [0,1]; overwritten with the K new depths.
+//   cdf[0..S-1)   scratch
+__device__ __forceinline__ void sample_pdf_ray(int lane, int S, int K, const float* zc,
+                                               const float* w, float* cdf, float* u) {
+  const int nw = S - 2;            // N_samples_
+  // pdf normaliser
+  float part = 0.f;
+  for (int i = lane; i < nw; i += 32) part += __fadd_rn(w[1 + i], 1e-5f);
+  const float total = warp_sum(part);
+  // cdf[0] = 0, cdf[k] = sum_{i<k} pdf[i]: per-lane contiguous segments + warp scan
+  const int per = (nw + 31) >> 5;
+  float loc[4];
+  float run = 0.f;
+  for (int p = 0; p < per; ++p) {
+    const int i = lane * per + p;
+    const float pdf = (i < nw) ? __fdiv_rn(__fadd_rn(w[1 + i], 1e-5f), total) : 0.f;
+    run += pdf;
+    loc[p] = run;
+  }
+  float incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) { excl = 0.f; cdf[0] = 0.f; }
+  for (int p = 0; p < per; ++p) {
+    const int i = lane * per + p;
+    if (i < nw) cdf[i + 1] = excl + loc[p];
+  }
+  __syncwarp();
+  const int ncdf = nw + 1;         // == S-1 entries, last valid index nw
+  for (int j = lane; j < K; j += 32) {
+    const float uj = u[j];
+    // searchsorted(cdf, u, side='right'): number of entries <= u
+    int lo = 0, hi = ncdf;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= uj) lo = mid + 1; else hi = mid;
+    }
+    const int below = max(lo - 1, 0);
+    const int above = min(lo, nw);
+    const float c0 = cdf[below], c1 = cdf[above];
+    const float b0 = 0.5f * __fadd_rn(zc[below], zc[below + 1]);
+    const float b1 = 0.5f * __fadd_rn(zc[above], zc[above + 1]);
+    float denom = __fsub_rn(c1, c0);
+    if (denom < 1e-5f) denom = 1.f;
+    const float t = __fdiv_rn(__fsub_rn(uj, c0), denom);
+    u[j] = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+  }
+  __syncwarp();
+}
+
+template <bool kDummy>
+__global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Scratch* sc = reinterpret_cast<Scratch*>(smem + kSmemScratch);
+  Barriers* bars = &sc->bars;
+  if (!engine_setup(smem, bars)) {
+    if (threadIdx.x == 0) atomicExch(p.status, 101);
+    return;
+  }
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int Sc = p.n_samples;
+  const int K = p.n_importance;
+  const int Sf = Sc + K;
+  const bool fine = K > 0;
+  const bool coarse_sigma_only = p.test_time != 0;
+  const int tiles_c = (2 * Sc) >> 7;
+  const int tiles_f = fine ? ((2 * Sf) >> 7) : 0;
+  const int n_groups = (p.n_rays + 1) >> 1;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      RingState rs;
+      for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        for (int t = 0; t < tiles_c; ++t)
+          produce_tile(rs, smem, bars, p.net_coarse, coarse_sigma_only, false);
+        for (int t = 0; t < tiles_f; ++t) produce_tile(rs, smem, bars, p.net_fine, false, false);
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      RingState rs;
+      uint32_t a_phase = 0;
+      for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        for (int t = 0; t < tiles_c; ++t) mma_tile(rs, a_phase, smem, bars, coarse_sigma_only, false);
+        for (int t = 0; t < tiles_f; ++t) mma_tile(rs, a_phase, smem, bars, false, false);
+      }
+    }
+  } else {
+    EpiCtx c;
+    c.smem = smem;
+    c.bars = bars;
+    c.lane = lane;
+    c.row = (warp & 3) * 32 + lane;
+    c.half = warp >> 2;
+    c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    c.d_phase = 0;
+    const int t = threadIdx.x;   // 0..255
+    uint8_t* enc = smem + kSmemEnc;
+
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+      const int ray0 = 2 * g;
+      const bool valid1 = (ray0 + 1) < p.n_rays;
+      const int rid[2] = {ray0, valid1 ? ray0 + 1 : ray0};
+      // ---- rays, direction embedding (models/rendering.py:179-186)
+      if (t < 16) sc->ray[t >> 3][t & 7] = __ldg(p.rays + static_cast<long long>(rid[t >> 3]) * p.ray_stride + (t & 7));
+      epi_bar();
+      if (t < 2) {
+        const float* d = &sc->ray[t][3];
+        sc->dnorm[t] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+        embed3(d, 4, sc->direnc[t]);
+        sc->direnc[t][27] = 0.f;
+      }
+      // ---- coarse depths (models/rendering.py:189-204)
+      for (int e = t; e < 2 * Sc; e += kEpiThreads) {
+        const int r = e / Sc, i = e - r * Sc;
+        const float nr = sc->ray[r][6], fr = sc->ray[r][7];
+        float z = z_base(nr, fr, i, Sc, p.use_disp != 0);
+        if (p.perturb > 0.f) {
+          const float zl = (i > 0) ? z_base(nr, fr, i - 1, Sc, p.use_disp != 0) : z;
+          const float zu = (i < Sc - 1) ? z_base(nr, fr, i + 1, Sc, p.use_disp != 0) : z;
+          const float lower = (i > 0) ? __fmul_rn(0.5f, __fadd_rn(zl, z)) : z;
+          const float upper = (i < Sc - 1) ? __fmul_rn(0.5f, __fadd_rn(z, zu)) : z;
+          const float pr = __fmul_rn(p.perturb, __ldg(p.perturb_rand + static_cast<long long>(rid[r]) * Sc + i));
+          z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), pr));
+        }
+        sc->z[e] = z;
+        sc->zc[r][i] = z;
+      }
+      epi_bar();
+
+      // ================= two passes: coarse, fine =================
+      for (int pass = 0; pass < (fine ? 2 : 1); ++pass) {
+        const int S = pass ? Sf : Sc;
+        const int tiles = pass ? tiles_f : tiles_c;
+        const bool sigma_only = (pass == 0) && coarse_sigma_only;
+        const uint8_t* blob = pass ? p.net_fine : p.net_coarse;
+        c.f32 = reinterpret_cast<const float*>(blob + kHalfRegionBytes);
+        if (!sigma_only) {
+          // per-ray direction bias: b_dir + W_dir[:, 256:283] . dir_embedded   (fp32)
+          const int r = t >> 7, n = t & 127;
+          const float* wd = c.f32 + kF32WDirPart + n * 28;
+          float acc = __ldg(c.f32 + kF32Bias + 9 * 256 + n);
+#pragma unroll
+          for (int j = 0; j < 27; ++j) acc = fmaf(__ldg(wd + j), sc->direnc[r][j], acc);
+          sc->dirbias[r][n] = acc;
+          epi_bar();
+        }
+        for (int tile = 0; tile < tiles; ++tile) {
+          const int gr = tile * 128 + c.row;
+          const int r = gr / S;
+          encode_row(enc, c.row, c.half, &sc->ray[r][0], &sc->ray[r][3], sc->z[gr]);
+          float sig_part, rgb_part[3];
+          epi_run_tile(c, sigma_only, sc->dirbias[r], nullptr, sig_part, rgb_part);
+          sc->sig_part[c.half][c.row] = sig_part;
+          if (!sigma_only) {
+            sc->rgb_part[c.half][0][c.row] = rgb_part[0];
+            sc->rgb_part[c.half][1][c.row] = rgb_part[1];
+            sc->rgb_part[c.half][2][c.row] = rgb_part[2];
+          }
+          epi_bar();
+          if (c.half == 0) {
+            sc->sigma[gr] = sc->sig_part[0][c.row] + sc->sig_part[1][c.row] + __ldg(c.f32 + kF32BSigma);
+            if (!sigma_only) {
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch)
+                sc->rgb[ch][gr] = sigmoid_ref(sc->rgb_part[0][ch][c.row] + sc->rgb_part[1][ch][c.row] +
+                                              __ldg(c.f32 + kF32BRgb + ch));
+            }
+          }
+          epi_bar();
+        }
+        // ---- compositing: warp r renders ray r
+        if (warp < 2) {
+          const int r = warp;
+          const float* nz = nullptr;
+          if (p.noise_std > 0.f)
+            nz = (pass ? p.noise_fine : p.noise_coarse) + static_cast<long long>(rid[r]) * S;
+          const RayOut o = composite_ray(lane, S, sc->z + r * S, sc->sigma + r * S, sc->rgb[0] + r * S,
+                                         sc->rgb[1] + r * S, sc->rgb[2] + r * S, nz, p.noise_std,
+                                         sc->dnorm[r], !sigma_only, sc->w[r]);
+          __syncwarp();
+          const bool wr = (r == 0) || valid1;
+          if (wr) {
+            const long long ri = rid[r];
+            float* wout = pass ? p.weights_fine : p.weights_coarse;
+            if (wout != nullptr)
+              for (int i = lane; i < S; i += 32) wout[ri * S + i] = sc->w[r][i];
+            if (lane == 0) {
+              float add = (p.white_back != 0) ? __fsub_rn(1.f, o.opac) : 0.f;
+              if (pass == 0) {
+                p.opacity_coarse[ri] = o.opac;
+                if (!sigma_only) {
+                  p.rgb_coarse[3 * ri + 0] = o.r + add;
+                  p.rgb_coarse[3 * ri + 1] = o.g + add;
+                  p.rgb_coarse[3 * ri + 2] = o.b + add;
+                  p.depth_coarse[ri] = o.depth;
+                }
+              } else {
+                p.opacity_fine[ri] = o.opac;
+                p.rgb_fine[3 * ri + 0] = o.r + add;
+                p.rgb_fine[3 * ri + 1] = o.g + add;
+                p.rgb_fine[3 * ri + 2] = o.b + add;
+                p.depth_fine[ri] = o.depth;
+              }
+            }
+          }
+          // ---- hierarchical resampling (models/rendering.py:223-229)
+          if (pass == 0 && fine) {
+            if (p.perturb > 0.f) {
+              // u ~ U[0,1): rank-sort so the new depths come out ascending
+              const float* ur = p.u_rand + static_cast<long long>(rid[r]) * K;
+              for (int j = lane; j < K; j += 32) {
+                const float uj = __ldg(ur + j);
+                int rank = 0;
+                for (int q = 0; q < K; ++q) {
+                  const float uq = __ldg(ur + q);
+                  rank += (uq < uj) || (uq == uj && q < j);
+                }
+                sc->znew[r][rank] = uj;
+              }
+            } else {
+              for (int j = lane; j < K; j += 32) sc->znew[r][j] = linspace01(j, K);
+            }
+            __syncwarp();
+            sample_pdf_ray(lane, Sc, K, sc->zc[r], sc->w[r], sc->cdf[r], sc->znew[r]);
+          }
+        }
+        epi_bar();
+        // ---- merge: z_fine = sort(cat(z_coarse, z_new))  (models/rendering.py:229), rank sort
+        if (pass == 0 && fine) {
+          for (int e = t; e < 2 * Sf; e += kEpiThreads) {
+            const int r = e / Sf, i = e - r * Sf;
+            const float v = (i < Sc) ? sc->zc[r][i] : sc->znew[r][i - Sc];
+            int rank = 0;
+            for (int q = 0; q < Sc; ++q) {
+              const float x = sc->zc[r][q];
+              rank += (x < v) || (x == v && q < i);
+            }
+            for (int q = 0; q < K; ++q) {
+              const float x = sc->znew[r][q];
+              rank += (x < v) || (x == v && (q + Sc) < i);
+            }
+            sc->z[r * Sf + rank] = v;
+          }
+          epi_bar();
+          if (p.z_fine != nullptr) {
+            for (int e = t; e < 2 * Sf; e += kEpiThreads) {
+              const int r = e / Sf, i = e - r * Sf;
+              if (r == 0 || valid1) p.z_fine[static_cast<long long>(rid[r]) * Sf + i] = sc->z[e];
+            }
+          }
+        }
+      }
+    }
+  }
+  engine_teardown(bars);
+}
+
+}  // namespace nerfb200

@@ -1,0 +1,304 @@
+"""``render_rays`` with the reference's exact signature and result keys
+(reference: models/rendering.py:58-244), executed by one fused sm_100a kernel launch.
+
+Also exposes the pieces the reference exposes or depends on, each through the C ABI:
+``sample_pdf`` (models/rendering.py:14-55), ``searchsorted`` (torchsearchsorted
+searchsorted.py:20-53), ``volume_render`` (models/rendering.py:143-170).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .nerf import _stream_ptr, nerf_forward_torch, packed_weights
+
+__all__ = ["render_rays", "sample_pdf", "searchsorted", "volume_render"]
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _check_embeddings(embeddings: Sequence) -> None:
+    ex, ed = embeddings[0], embeddings[1]
+    ok = (getattr(ex, "N_freqs", None) == 10 and getattr(ed, "N_freqs", None) == 4
+          and getattr(ex, "in_channels", 3) == 3 and getattr(ed, "in_channels", 3) == 3)
+    fb = getattr(ex, "freq_bands", None)
+    if ok and fb is not None and len(fb) == 10:
+        ok = abs(float(fb[-1]) - 512.0) < 1e-3
+    if not ok:
+        raise ValueError("nerf_pl_b200.render_rays supports the reference's embeddings "
+                         "Embedding(3, 10) / Embedding(3, 4) with logscale=True")
+
+
+def searchsorted(a: torch.Tensor, v: torch.Tensor, out: Optional[torch.Tensor] = None,
+                 side: str = "left") -> torch.Tensor:
+    """Row-wise batched binary search; same contract as torchsearchsorted.searchsorted
+    (searchsorted.py:20-53): 2-D inputs, equal row counts or one of them with a single row,
+    int64 result of shape (max rows, v columns)."""
+    assert len(a.shape) == 2, "input `a` must be 2-D."
+    assert len(v.shape) == 2, "input `v` mus(t) be 2-D."
+    assert (a.shape[0] == v.shape[0]) or (a.shape[0] == 1) or (v.shape[0] == 1), \
+        "`a` and `v` must have the same number of rows or one of them must have only 1 row"
+    assert a.device == v.device, "`a` and `v` must be on the same device"
+    if side not in ("left", "right"):
+        raise ValueError("side must be 'left' or 'right'")
+    if not a.is_cuda:
+        raise RuntimeError("nerf_pl_b200.searchsorted runs on CUDA tensors only (no CPU fallback)")
+    lib = _lib.load()
+    nrow = max(a.shape[0], v.shape[0])
+    if out is None:
+        out = torch.empty(nrow, v.shape[1], dtype=torch.long, device=v.device)
+    else:
+        assert out.shape == (nrow, v.shape[1]) and out.dtype == torch.long and out.is_contiguous()
+    ac = a.to(torch.float32).contiguous()
+    vc = v.to(torch.float32).contiguous()
+    with torch.cuda.device(a.device):
+        _lib.check(lib.nerfb200_searchsorted(ac.data_ptr(), vc.data_ptr(), out.data_ptr(), ac.shape[0],
+                                             vc.shape[0], ac.shape[1], vc.shape[1],
+                                             1 if side == "right" else 0, _stream_ptr()),
+                   "nerfb200_searchsorted")
+    return out
+
+
+def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, N_importance: int, det: bool = False,
+               eps: float = 1e-5, u: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Inverse-CDF sampling of ``N_importance`` depths per ray (reference models/rendering.py:14-55).
+    ``u`` may be given to reproduce a specific random draw."""
+    if abs(eps - 1e-5) > 1e-12:
+        raise ValueError("nerf_pl_b200.sample_pdf implements the reference default eps=1e-5")
+    if not bins.is_cuda:
+        raise RuntimeError("nerf_pl_b200.sample_pdf runs on CUDA tensors only (no CPU fallback)")
+    n_rays, n_w = weights.shape
+    if bins.shape != (n_rays, n_w + 1):
+        raise ValueError("bins must be (N_rays, N_samples_+1)")
+    if u is None:
+        if det:
+            u = torch.linspace(0, 1, N_importance, device=bins.device).expand(n_rays, N_importance)
+        else:
+            u = torch.rand(n_rays, N_importance, device=bins.device)
+    u = u.to(torch.float32).contiguous()
+    lib = _lib.load()
+    out = torch.empty(n_rays, N_importance, dtype=torch.float32, device=bins.device)
+    bc, wc = bins.to(torch.float32).contiguous(), weights.detach().to(torch.float32).contiguous()
+    with torch.cuda.device(bins.device):
+        _lib.check(lib.nerfb200_sample_pdf(bc.data_ptr(), wc.data_ptr(), u.data_ptr(), n_rays, n_w,
+                                           N_importance, out.data_ptr(), _stream_ptr()),
+                   "nerfb200_sample_pdf")
+    return out
+
+
+def volume_render(sigmas: torch.Tensor, rgbs: Optional[torch.Tensor], z_vals: torch.Tensor,
+                  dirs: torch.Tensor, noise: Optional[torch.Tensor] = None, noise_std: float = 0.0,
+                  white_back: bool = False):
+    """Alpha-compositing quadrature (reference models/rendering.py:143-170).
+    Returns (weights, rgb | None, depth | None, opacity)."""
+    if not sigmas.is_cuda:
+        raise RuntimeError("nerf_pl_b200.volume_render runs on CUDA tensors only (no CPU fallback)")
+    n, S = sigmas.shape
+    lib = _lib.load()
+    dev = sigmas.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    weights = torch.empty(n, S, **f32)
+    opac = torch.empty(n, **f32)
+    rgb = torch.empty(n, 3, **f32) if rgbs is not None else None
+    depth = torch.empty(n, **f32) if rgbs is not None else None
+    keep = [sigmas.float().contiguous(), None if rgbs is None else rgbs.float().contiguous(),
+            z_vals.float().contiguous(), dirs.float().contiguous(),
+            None if noise is None else noise.float().contiguous()]
+    with torch.cuda.device(dev):
+        _lib.check(lib.nerfb200_composite(_ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]),
+                                          _ptr(keep[4]), float(noise_std), int(bool(white_back)), n, S,
+                                          weights.data_ptr(), _ptr(rgb), _ptr(depth), opac.data_ptr(),
+                                          _stream_ptr()), "nerfb200_composite")
+    return weights, rgb, depth, opac
+
+
+def _draw_randoms(n: int, S_c: int, K: int, perturb: float, noise_std: float, device, match_rng: bool):
+    """Draw the random inputs in the order the reference consumes the global torch RNG
+    (models/rendering.py:203 rand, :152 randn, :39 rand, :152 randn) so a seeded run sees the
+    same numbers.  With ``match_rng`` the unused randn draws (noise_std == 0) are still made, as
+    the reference does."""
+    pr = nc = ur = nf = None
+    if perturb > 0:
+        pr = torch.rand(n, S_c, device=device)
+    if noise_std > 0 or match_rng:
+        nc = torch.randn(n, S_c, device=device)
+    if K > 0:
+        if perturb > 0:
+            ur = torch.rand(n, K, device=device)
+        if noise_std > 0 or match_rng:
+            nf = torch.randn(n, S_c + K, device=device)
+    if noise_std <= 0:
+        nc = nf = None
+    return pr, nc, ur, nf
+
+
+def render_rays(models: List[torch.nn.Module],
+                embeddings: List[torch.nn.Module],
+                rays: torch.Tensor,
+                N_samples: int = 64,
+                use_disp: bool = False,
+                perturb: float = 0,
+                noise_std: float = 1,
+                N_importance: int = 0,
+                chunk: int = 1024 * 32,
+                white_back: bool = False,
+                test_time: bool = False,
+                *,
+                randoms: Optional[Dict[str, torch.Tensor]] = None,
+                match_reference_rng: bool = True,
+                extras: bool = False) -> Dict[str, torch.Tensor]:
+    """Render rays with the coarse (and fine) NeRF.  Drop-in for reference
+    ``models.rendering.render_rays`` (models/rendering.py:58-244): same positional arguments,
+    defaults and result keys/shapes/dtypes:
+
+    * ``test_time=False``: ``rgb_coarse (N,3)``, ``depth_coarse (N)``, ``opacity_coarse (N)``
+    * ``test_time=True`` : ``opacity_coarse`` only for the coarse pass
+    * ``N_importance>0`` : additionally ``rgb_fine``, ``depth_fine``, ``opacity_fine``
+
+    ``chunk`` is accepted and ignored (nothing is materialised per point, so there is nothing to
+    chunk).  Keyword-only extensions: ``randoms`` supplies pre-drawn ``perturb_rand``,
+    ``noise_coarse``, ``u_rand``, ``noise_fine`` tensors; ``extras=True`` adds ``z_vals_fine``,
+    ``weights_coarse``, ``weights_fine`` to the result.
+    """
+    del chunk
+    if rays.dim() != 2 or rays.shape[1] != 8:
+        raise ValueError("rays must be (N_rays, 8)")
+    if not rays.is_cuda:
+        raise RuntimeError("nerf_pl_b200.render_rays runs on CUDA tensors only (no CPU fallback)")
+    _check_embeddings(embeddings)
+    if N_importance > 0 and len(models) < 2:
+        raise ValueError("N_importance > 0 needs a fine model (models[1])")
+    needs_graph = torch.is_grad_enabled() and any(
+        p.requires_grad for m in models[:2] for p in m.parameters())
+
+    dev = rays.device
+    n = rays.shape[0]
+    S_c, K = int(N_samples), int(N_importance)
+    S_f = S_c + K
+    rays_c = rays.detach().to(torch.float32).contiguous()
+    perturb = float(perturb)
+    noise_std = float(noise_std)
+
+    if randoms is None:
+        pr, nc, ur, nf = _draw_randoms(n, S_c, K, perturb, noise_std, dev, match_reference_rng)
+    else:
+        pr, nc = randoms.get("perturb_rand"), randoms.get("noise_coarse")
+        ur, nf = randoms.get("u_rand"), randoms.get("noise_fine")
+    keep = [t.to(torch.float32).contiguous() if t is not None else None for t in (pr, nc, ur, nf)]
+    pr, nc, ur, nf = keep
+
+    f32 = dict(dtype=torch.float32, device=dev)
+    coarse_rgb = not test_time
+    out = {
+        "rgb_coarse": torch.empty(n, 3, **f32) if coarse_rgb else None,
+        "depth_coarse": torch.empty(n, **f32) if coarse_rgb else None,
+        "opacity_coarse": torch.empty(n, **f32),
+        "rgb_fine": torch.empty(n, 3, **f32) if K > 0 else None,
+        "depth_fine": torch.empty(n, **f32) if K > 0 else None,
+        "opacity_fine": torch.empty(n, **f32) if K > 0 else None,
+    }
+    want_extras = extras or needs_graph
+    z_fine = torch.empty(n, S_f, **f32) if (want_extras and K > 0) else None
+    w_c = torch.empty(n, S_c, **f32) if extras else None
+    w_f = torch.empty(n, S_f, **f32) if (extras and K > 0) else None
+
+    lib = _lib.load()
+    blob_c = packed_weights(models[0])
+    blob_f = packed_weights(models[1]) if K > 0 else None
+    args = _lib.RenderArgs(
+        rays=rays_c.data_ptr(), n_rays=n, ray_stride=rays_c.stride(0),
+        packed_coarse=blob_c.data_ptr(), packed_fine=_ptr(blob_f),
+        n_samples=S_c, n_importance=K, use_disp=int(bool(use_disp)), perturb=perturb,
+        noise_std=noise_std, white_back=int(bool(white_back)), test_time=int(bool(test_time)),
+        perturb_rand=_ptr(pr), noise_coarse=_ptr(nc), u_rand=_ptr(ur), noise_fine=_ptr(nf),
+        rgb_coarse=_ptr(out["rgb_coarse"]), depth_coarse=_ptr(out["depth_coarse"]),
+        opacity_coarse=_ptr(out["opacity_coarse"]), rgb_fine=_ptr(out["rgb_fine"]),
+        depth_fine=_ptr(out["depth_fine"]), opacity_fine=_ptr(out["opacity_fine"]),
+        z_fine=_ptr(z_fine), weights_coarse=_ptr(w_c), weights_fine=_ptr(w_f),
+        status=None, max_ctas=0)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nerfb200_render_rays(ctypes.byref(args), _stream_ptr()), "nerfb200_render_rays")
+
+    if needs_graph:
+        return _render_with_graph(models, embeddings, rays_c, S_c, K, bool(use_disp), perturb, noise_std,
+                                  bool(white_back), bool(test_time), pr, nc, nf, z_fine)
+
+    result = {k: v for k, v in out.items() if v is not None}
+    if extras:
+        if z_fine is not None:
+            result["z_vals_fine"] = z_fine
+            result["weights_fine"] = w_f
+        result["weights_coarse"] = w_c
+    return result
+
+
+# ---------------------------------------------------------------------------------------------
+# Autograd path (training): the fused kernel has produced the detached fine depths
+# (models/rendering.py:225-229: no gradient flows through sampling); the differentiable part
+# - embedding, MLP, quadrature at those depths - is evaluated with torch ops so that
+# .backward() fills the parameters' .grad exactly as in the reference.
+# TODO(round 2): replace with the fused tcgen05 backward (dgrad/wgrad) behind the same Function.
+def _coarse_depths(rays: torch.Tensor, S: int, use_disp: bool, perturb: float, pr) -> torch.Tensor:
+    near, far = rays[:, 6:7], rays[:, 7:8]
+    t = torch.linspace(0, 1, S, device=rays.device)
+    z = 1 / (1 / near * (1 - t) + 1 / far * t) if use_disp else near * (1 - t) + far * t
+    z = z.expand(rays.shape[0], S)
+    if perturb > 0:
+        mid = 0.5 * (z[:, :-1] + z[:, 1:])
+        upper = torch.cat((mid, z[:, -1:]), -1)
+        lower = torch.cat((z[:, :1], mid), -1)
+        z = lower + (upper - lower) * (perturb * pr)
+    return z
+
+
+def _embed_torch(x: torch.Tensor, n_freqs: int) -> torch.Tensor:
+    parts = [x]
+    for k in range(n_freqs):
+        parts += [torch.sin((2.0 ** k) * x), torch.cos((2.0 ** k) * x)]
+    return torch.cat(parts, -1)
+
+
+def _pass_torch(model, rays, z, noise, noise_std, white_back, sigma_only):
+    n, S = z.shape
+    o, d = rays[:, 0:3], rays[:, 3:6]
+    xyz = (o[:, None, :] + d[:, None, :] * z[:, :, None]).reshape(-1, 3)
+    x = _embed_torch(xyz, 10)
+    if not sigma_only:
+        de = _embed_torch(d, 4)
+        x = torch.cat((x, de.repeat_interleave(S, dim=0)), -1)
+    raw = nerf_forward_torch(model, x, sigma_only)
+    sig = raw.view(n, S) if sigma_only else raw.view(n, S, 4)[..., 3]
+    delta = torch.cat((z[:, 1:] - z[:, :-1], torch.full_like(z[:, :1], 1e10)), -1) * d.norm(dim=-1, keepdim=True)
+    if noise is not None:
+        sig = sig + noise * noise_std
+    alpha = 1 - torch.exp(-delta * torch.relu(sig))
+    trans = torch.cumprod(torch.cat((torch.ones_like(alpha[:, :1]), 1 - alpha + 1e-10), -1), -1)[:, :-1]
+    w = alpha * trans
+    opac = w.sum(1)
+    if sigma_only:
+        return None, None, opac
+    rgb = (w[..., None] * raw.view(n, S, 4)[..., :3]).sum(-2)
+    depth = (w * z).sum(-1)
+    if white_back:
+        rgb = rgb + 1 - opac[:, None]
+    return rgb, depth, opac
+
+
+def _render_with_graph(models, embeddings, rays, S_c, K, use_disp, perturb, noise_std, white_back,
+                       test_time, pr, nc, nf, z_fine):
+    z_c = _coarse_depths(rays, S_c, use_disp, perturb, pr)
+    rgb, depth, opac = _pass_torch(models[0], rays, z_c, nc if noise_std > 0 else None, noise_std,
+                                   white_back, test_time)
+    result = {"opacity_coarse": opac}
+    if not test_time:
+        result = {"rgb_coarse": rgb, "depth_coarse": depth, "opacity_coarse": opac}
+    if K > 0:
+        rgb, depth, opac = _pass_torch(models[1], rays, z_fine, nf if noise_std > 0 else None, noise_std,
+                                       white_back, False)
+        result.update(rgb_fine=rgb, depth_fine=depth, opacity_fine=opac)
+    return result

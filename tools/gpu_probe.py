@@ -1,0 +1,138 @@
+"""Bring-up probe for the tcgen05 engine (run on a B200 via gpurun; each step in its own process
+so a device trap in one step does not hide the others).
+
+    python tools/gpu_probe.py gemm | mlp | render | speed
+"""
+import ctypes
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import nerf_pl_b200 as nb  # noqa: E402
+from nerf_pl_b200 import _lib  # noqa: E402
+from nerf_pl_b200.rendering import _render_with_graph  # noqa: E402
+
+
+def make_models(seed=0, scale_heads=True):
+    torch.manual_seed(seed)
+    ms = [nb.NeRF().cuda(), nb.NeRF().cuda()]
+    if scale_heads:
+        with torch.no_grad():
+            for m in ms:
+                m.sigma.weight.mul_(30.0)
+                m.sigma.bias.add_(0.5)
+                m.rgb[0].weight.mul_(8.0)
+    return ms
+
+
+def make_rays(n, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    o = torch.tensor([0.0, 0.0, 4.0]) + 0.1 * torch.randn(n, 3, generator=g)
+    d = torch.randn(n, 3, generator=g)
+    d[:, 2] = -d[:, 2].abs() - 1.0
+    d = d / d.norm(dim=-1, keepdim=True)
+    near = torch.full((n, 1), 2.0)
+    far = torch.full((n, 1), 6.0)
+    return torch.cat([o, d, near, far], -1).cuda()
+
+
+def step_gemm():
+    lib = _lib.load()
+    m = make_models()[0]
+    blob = nb.packed_weights(m)
+    torch.cuda.synchronize()
+    params = nb.nerf_parameters(m)
+    a = torch.randn(128, 64, device="cuda")
+    a16 = a.half().float()
+    cases = {
+        0: (params[0], 0, 63, 256),
+        5: (params[4], 0, 64, 256),       # xyz_encoding_3 k-block 0 (slice 1+4*1+0)
+        8: (params[4], 192, 64, 256),     # xyz_encoding_3 k-block 3
+        13: (params[8], 0, 63, 256),
+        15: (params[8], 63 + 64, 64, 256),
+        34: (params[18], 0, 64, 128),
+        38: (params[18], 256, 27, 128),
+    }
+    ok = True
+    for sl, (W, koff, kval, N) in cases.items():
+        d = torch.zeros(128, N, device="cuda")
+        rc = lib.nerfb200_debug_gemm(a.data_ptr(), blob.data_ptr(), sl, d.data_ptr(), None)
+        torch.cuda.synchronize()
+        Wk = torch.zeros(N, 64, device="cuda")
+        Wk[:, :kval] = W[:, koff:koff + kval].detach().half().float()
+        ref = a16 @ Wk.t()
+        err = (d - ref).abs().max().item()
+        print(f"gemm slice {sl:2d} N={N} rc={rc} max_abs_err={err:.3e} ref_absmax={ref.abs().max().item():.3f}")
+        ok &= err < 1e-3
+    print("GEMM_OK" if ok else "GEMM_FAIL")
+
+
+def step_mlp():
+    m = make_models()[0]
+    torch.manual_seed(1)
+    for n in (128, 1000, 40000):
+        x = torch.randn(n, 90, device="cuda")
+        x[:, :63].clamp_(-1, 1)
+        with torch.no_grad():
+            ref = nb.nerf_forward_torch(m, x, False)
+            out = nb.nerf_forward_fused(m, x, False)
+            refs = nb.nerf_forward_torch(m, x[:, :63].contiguous(), True)
+            outs = nb.nerf_forward_fused(m, x[:, :63].contiguous(), True)
+        torch.cuda.synchronize()
+        e_rgb = (out[:, :3] - ref[:, :3]).abs().max().item()
+        e_sig = ((out[:, 3] - ref[:, 3]).abs() / (1 + ref[:, 3].abs())).max().item()
+        e_so = ((outs - refs).abs() / (1 + refs.abs())).max().item()
+        print(f"mlp n={n}: rgb max_abs={e_rgb:.3e} sigma rel={e_sig:.3e} sigma_only rel={e_so:.3e}")
+    print("MLP_DONE")
+
+
+def step_render():
+    ms = make_models()
+    emb = [nb.Embedding(3, 10), nb.Embedding(3, 4)]
+    for (n, K, tt, wb) in ((2, 64, False, True), (256, 64, False, True), (1001, 64, True, False), (512, 0, False, True)):
+        rays = make_rays(n)
+        with torch.no_grad():
+            out = nb.render_rays(ms, emb, rays, 64, False, 0, 0, K, 32768, wb, test_time=tt, extras=True)
+            zf = out.get("z_vals_fine")
+            ref = _render_with_graph(ms, emb, rays, 64, K, False, 0.0, 0.0, wb, tt, None, None, None, zf)
+        torch.cuda.synchronize()
+        msg = []
+        for k, v in ref.items():
+            msg.append(f"{k}:{(out[k] - v).abs().max().item():.2e}")
+        print(f"render n={n} K={K} tt={tt}: " + " ".join(msg))
+        if zf is not None:
+            print("   z_fine sorted:", bool((zf[:, 1:] >= zf[:, :-1]).all().item()),
+                  "range", zf.min().item(), zf.max().item())
+    print("RENDER_DONE")
+
+
+def step_speed():
+    ms = make_models()
+    emb = [nb.Embedding(3, 10), nb.Embedding(3, 4)]
+    for n in (1024, 32768, 160000):
+        rays = make_rays(n)
+        with torch.no_grad():
+            for _ in range(3):
+                nb.render_rays(ms, emb, rays, 64, False, 0, 0, 64, 32768, True, test_time=True)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            e0.record()
+            for _ in range(reps):
+                nb.render_rays(ms, emb, rays, 64, False, 0, 0, 64, 32768, True, test_time=True)
+            e1.record()
+            torch.cuda.synchronize()
+        ms_per = e0.elapsed_time(e1) / reps
+        sps = n * 192 / (ms_per * 1e-3)
+        flops = n * 214794240 / (ms_per * 1e-3)
+        print(f"speed n={n}: {ms_per:.3f} ms  {sps:.3e} ray-samples/s  {flops / 1e12:.1f} TFLOP/s")
+    print("SPEED_DONE")
+
+
+if __name__ == "__main__":
+    t0 = time.time()
+    {"gemm": step_gemm, "mlp": step_mlp, "render": step_render, "speed": step_speed}[sys.argv[1]]()
+    print(f"[{sys.argv[1]}] {time.time() - t0:.1f}s")
