@@ -1,0 +1,301 @@
+"""bench.py — ray-samples/s of the render_rays hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1]): Blender-lego-shaped 400x400 pinhole rays, N_samples=64,
+N_importance=64, batch_size=1024 rays per GPU per step, training-mode forward
+(perturb=1, noise_std=0, white_back, coarse rgb computed) = 1024 x (64 + 128) = 196,608 MLP
+evaluations per GPU per step.  A "step" is one render_rays pass over one such batch.
+Synthetic rays / random-init (pseudo-trained) weights: no dataset or checkpoint on the box.
+
+One JSON line on stdout (rank 0):  value = device-timed whole-job ray-samples/s with the batch
+resident in HBM; e2e = same through the public Python API with pinned HOST buffers (H2D of the
+rays and D2H of rgb_fine inside the timed region); roofline = the fused kernel against the
+measured dense tensor peak; cpu_baseline = the numpy oracle timed on the host cores.
+`--impl reference` times the reference algorithm's CPU restatement (oracle/) on the host cores —
+the reference itself (PyTorch + torchsearchsorted) cannot travel to the GPU box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SAMPLES, N_IMPORTANCE = 64, 64
+BATCH = 1024
+SAMPLES_PER_RAY = N_SAMPLES + (N_SAMPLES + N_IMPORTANCE)          # 192
+FLOP_PER_RAY_TRAIN = 192 * 1186816                               # test_time=False  
+IMG_W = IMG_H = 400
+CAMERA_ANGLE_X = 0.6911112070083618                              # lego transforms_*.json
+
+
+def blender_rays(n, seed):
+    """n random rays of a 400x400 Blender-style pinhole camera on a radius-4 sphere looking at the
+    origin: unit directions, near=2, far=6 (reference datasets/ray_utils.py:5-43, blender.py:28-35)."""
+    rs = np.random.RandomState(seed)
+    focal = 0.5 * IMG_W / np.tan(0.5 * CAMERA_ANGLE_X)
+    th, ph = rs.uniform(0, 2 * np.pi), rs.uniform(np.pi / 6, np.pi / 3)
+    cam = 4.0 * np.array([np.cos(th) * np.sin(ph), np.sin(th) * np.sin(ph), np.cos(ph)])
+    fwd = -cam / np.linalg.norm(cam)
+    right = np.cross(fwd, np.array([0.0, 0.0, 1.0])); right /= np.linalg.norm(right)
+    up = np.cross(right, fwd)
+    px = rs.randint(0, IMG_W, n); py = rs.randint(0, IMG_H, n)
+    dc = np.stack([(px - IMG_W / 2) / focal, -(py - IMG_H / 2) / focal, -np.ones(n)], -1)
+    d = dc[:, :1] * right + dc[:, 1:2] * up - dc[:, 2:3] * fwd
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    o = np.broadcast_to(cam, (n, 3))
+    return np.concatenate([o, d, np.full((n, 1), 2.0), np.full((n, 1), 6.0)], -1).astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst cuBLAS 8192^3)"
+    return 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+
+
+def cpu_oracle_throughput(n_rays, reps, seed=0):
+    """ray-samples/s of the oracle on the host cores over `reps` batches of n_rays (same workload)."""
+    from oracle import nerf_oracle as orc
+    ws = [orc.make_weights(11), orc.make_weights(12)]
+    rays = blender_rays(n_rays, seed)
+    rs = np.random.RandomState(seed)
+    rnd = {"perturb_rand": rs.rand(n_rays, N_SAMPLES).astype(np.float32),
+           "u_rand": rs.rand(n_rays, N_IMPORTANCE).astype(np.float32)}
+    orc.render_rays(ws, rays[:32], N_SAMPLES, False, 1.0, 0.0, N_IMPORTANCE, True, False,
+                    {k: v[:32] for k, v in rnd.items()})       # warm BLAS threads
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.render_rays(ws, rays, N_SAMPLES, False, 1.0, 0.0, N_IMPORTANCE, True, False, rnd)
+        times.append(time.perf_counter() - t0)
+    return n_rays * SAMPLES_PER_RAY / float(np.median(times)), float(np.median(times))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_rays = 256                      # bounded sample of the 1024-ray batch (same per-ray work)
+    for _ in range(max(args.warmup, 1)):
+        cpu_oracle_throughput(n_rays, 1)
+    vals = [cpu_oracle_throughput(n_rays, 1, seed=i)[0] for i in range(args.steps)]
+    v = float(np.median(vals))
+    ms = n_rays * SAMPLES_PER_RAY / v * 1e3
+    sample = f"{n_rays} rays of the 1024-ray batch per step (64+128 samples/ray), numpy/BLAS on {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "ray-samples/sec (coarse+fine)", "value": v, "unit": "ray-samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": "ray-samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n_gpus):
+    return {"workload": "blender_lego_400x400 N_samples=64 N_importance=64 batch_size=1024/GPU, "
+                        "render_rays training-mode forward (perturb=1, noise_std=0, white_back, coarse rgb)",
+            "rays_per_step_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "samples_per_ray": SAMPLES_PER_RAY,
+            "parallelism": f"ray-sharded dp{n_gpus}, all_gather of rgb_fine" if n_gpus > 1 else "single GPU",
+            "l2": "flushed between timed steps (256 MiB write)"}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import nerf_pl_b200 as nb
+    from nerf_pl_b200 import _lib
+    from oracle import nerf_oracle as orc
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    ws = [orc.make_weights(11), orc.make_weights(12)]     # weight *generator* only (random init)
+    models = []
+    for w in ws:
+        m = nb.NeRF()
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+        models.append(m.to(dev).eval())
+    emb = [nb.Embedding(3, 10), nb.Embedding(3, 4)]
+    n_batches = 8
+    host_rays = [torch.from_numpy(blender_rays(BATCH, 100 * rank + i)).pin_memory() for i in range(n_batches)]
+    dev_rays = [r.to(dev) for r in host_rays]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    gather = [torch.empty(BATCH, 3, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step(rays):
+        out = nb.render_rays(models, emb, rays, N_SAMPLES, False, 1.0, 0.0, N_IMPORTANCE, 1024 * 32, True,
+                             test_time=False)
+        if world > 1:
+            dist.all_gather(gather, out["rgb_fine"])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            step(dev_rays[i % n_batches])
+        barrier()
+        # ---- device-timed steps (inputs resident in HBM); L2 flushed between steps, not timed
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        l0 = lib.nerfb200_launch_count()
+        barrier()
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            ev[i][0].record()
+            step(dev_rays[i % n_batches])
+            ev[i][1].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        launches = lib.nerfb200_launch_count() - l0
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        total_ms = float(sum(step_ms))
+
+        # ---- kernel-only timing for the roofline (pre-drawn randoms: the only kernel between the
+        # events is the fused render kernel, on torch's current stream, which is the launch stream)
+        rnd = {"perturb_rand": torch.rand(BATCH, N_SAMPLES, device=dev),
+               "u_rand": torch.rand(BATCH, N_IMPORTANCE, device=dev)}
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            kev[i][0].record()
+            nb.render_rays(models, emb, dev_rays[i % n_batches], N_SAMPLES, False, 1.0, 0.0, N_IMPORTANCE,
+                           1024 * 32, True, test_time=False, randoms=rnd)
+            kev[i][1].record()
+        torch.cuda.synchronize()
+        kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+
+        # ---- end to end through the public API with HOST buffers
+        barrier()
+        eev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        host_out = torch.empty(BATCH, 3).pin_memory()
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            eev[i][0].record()
+            r = host_rays[i % n_batches].to(dev, non_blocking=True)
+            out = step(r)
+            host_out.copy_(out["rgb_fine"], non_blocking=True)
+            eev[i][1].record()
+            eev[i][1].synchronize()          # the result is read on the host every step
+        barrier()
+        e2e_ms = float(sum(a.elapsed_time(b) for a, b in eev))
+        clocks = sampler.stop() if rank == 0 else None
+
+    # max over ranks
+    t = torch.tensor([total_ms, e2e_ms, kern_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, kern_ms = [float(x) for x in t.tolist()]
+    if rank == 0:
+        samples = BATCH * SAMPLES_PER_RAY * world * args.steps
+        value = samples / (total_ms * 1e-3)
+        peak, peak_src = measured_peaks()
+        ach = BATCH * FLOP_PER_RAY_TRAIN / (kern_ms * 1e-3) / 1e12
+        cpu_v, cpu_t = cpu_oracle_throughput(256, 3)
+        cores = os.cpu_count() or 1
+        line = {
+            "metric": "ray-samples/sec (coarse+fine)", "value": value, "unit": "ray-samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate, "
+            "fp32 encoding/compositing)", "data": "synthetic", "config": workload_config(world),
+            "clocks": clocks,
+            "e2e": {"value": samples / (e2e_ms * 1e-3), "unit": "ray-samples/s",
+                    "h2d_bytes_per_step": BATCH * 8 * 4, "d2h_bytes_per_step": BATCH * 3 * 4},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "render_rays_kernel", "kernel_ms": kern_ms,
+                         "flop_per_launch": BATCH * FLOP_PER_RAY_TRAIN},
+            "cpu_baseline": {"value": cpu_v, "unit": "ray-samples/s", "cores": cores, "kind": "port",
+                             "sample": f"256 rays of the same batch, 3 reps, median {cpu_t:.2f} s, numpy/BLAS"},
+            "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -45,8 +45,9 @@ struct Barriers {
   uint64_t a_ready;
   uint64_t d_ready;
   uint32_t tmem_base;
-  uint32_t pad;
+  uint32_t pad[3];
 };
+static_assert(sizeof(Barriers) % 16 == 0, "Barriers must keep 16-byte alignment of what follows");
 
 struct RingState {
   uint32_t stage = 0, phase = 0;

@@ -43,7 +43,7 @@ struct RenderParams {
 
 struct alignas(16) Scratch {
   Barriers bars;                       //   96
-  float dirbias[2][kDirW];             // 1024   per-ray b_dir + W_dir[:,256:283] . dir_enc
+  alignas(16) float dirbias[2][kDirW]; // 1024   per-ray b_dir + W_dir[:,256:283] . dir_enc
   float sig_part[2][128];              // 1024   [half][row]
   float rgb_part[2][3][128];           // 3072
   float ray[2][8];                     //   64

@@ -1,0 +1,39 @@
+"""The golden render cases (mirrors tests/golden/make_golden.py CASES) and loaders."""
+import os
+
+import numpy as np
+
+from oracle import nerf_oracle as orc
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# name: (n_rays, kind, ray seed, N_samples, N_importance, use_disp, perturb, noise_std, white_back, test_time)
+CASES = {
+    "c1_coarse_only": (256, "blender", 1, 64, 0, False, 0.0, 0.0, True, False),
+    "blender_64_64": (128, "blender", 2, 64, 64, False, 0.0, 0.0, True, False),
+    "blender_64_64_test": (128, "blender", 3, 64, 64, False, 0.0, 0.0, True, True),
+    "ndc_64_64_test": (96, "ndc", 4, 64, 64, False, 0.0, 0.0, False, True),
+    "blender_train_rng": (64, "blender", 5, 64, 64, False, 1.0, 1.0, True, False),
+    "blender_disp": (64, "blender", 6, 64, 64, True, 0.0, 0.0, True, False),
+    "blender_64_128": (64, "blender", 7, 64, 128, False, 0.0, 0.0, True, True),
+    "odd_rays": (33, "blender", 8, 64, 64, False, 0.0, 0.0, False, False),
+}
+W_SEEDS = (11, 12)
+RANDOM_KEYS = ("perturb_rand", "noise_coarse", "u_rand", "noise_fine")
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN, f"render_{name}.npz"))
+    rays = z["rays"]
+    randoms = {k: z[k] for k in RANDOM_KEYS if k in z.files}
+    ref = {k[4:]: z[k] for k in z.files if k.startswith("out_")}
+    return rays, randoms, ref
+
+
+def weights():
+    return [orc.make_weights(s) for s in W_SEEDS]
+
+
+def error_stats(a, b):
+    d = np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)).ravel()
+    return float(d.max()), float(np.percentile(d, 99.9)), float(d.mean())

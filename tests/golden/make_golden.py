@@ -1,0 +1,115 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference
+(kwea123/nerf_pl, /root/reference, read-only) on CPU in the build container.
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+The reference's renderer imports `torchsearchsorted`, whose native extension does not build
+against torch 2.11; it is shimmed with torch.searchsorted, which the survey
+verified to be bit-identical on the reference's own test grid.  Inputs come from the oracle's
+deterministic generators (oracle/nerf_oracle.py make_weights / make_rays), so tests can rebuild
+them from seeds and only rays + reference outputs are stored.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import nerf_oracle as orc  # noqa: E402
+
+REF = os.environ.get("NERF_PL_REFERENCE", "/root/reference")
+
+
+def import_reference():
+    shim = types.ModuleType("torchsearchsorted")
+    shim.searchsorted = lambda a, v, out=None, side="left": torch.searchsorted(
+        a.contiguous(), v.contiguous(), right=(side == "right"))
+    sys.modules["torchsearchsorted"] = shim
+    sys.path.insert(0, REF)
+    from models.nerf import Embedding, NeRF
+    from models.rendering import render_rays, sample_pdf
+    return Embedding, NeRF, render_rays, sample_pdf
+
+
+def ref_model(NeRF, weights):
+    m = NeRF()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+    return m.eval()
+
+
+# name: (n_rays, ray kind, ray seed, N_samples, N_importance, use_disp, perturb, noise_std,
+#        white_back, test_time)
+CASES = {
+    "c1_coarse_only": (256, "blender", 1, 64, 0, False, 0.0, 0.0, True, False),
+    "blender_64_64": (128, "blender", 2, 64, 64, False, 0.0, 0.0, True, False),
+    "blender_64_64_test": (128, "blender", 3, 64, 64, False, 0.0, 0.0, True, True),
+    "ndc_64_64_test": (96, "ndc", 4, 64, 64, False, 0.0, 0.0, False, True),
+    "blender_train_rng": (64, "blender", 5, 64, 64, False, 1.0, 1.0, True, False),
+    "blender_disp": (64, "blender", 6, 64, 64, True, 0.0, 0.0, True, False),
+    "blender_64_128": (64, "blender", 7, 64, 128, False, 0.0, 0.0, True, True),
+    "odd_rays": (33, "blender", 8, 64, 64, False, 0.0, 0.0, False, False),
+}
+W_SEEDS = (11, 12)   # coarse, fine
+
+
+def main():
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    Embedding, NeRF, render_rays, sample_pdf = import_reference()
+    ws = [orc.make_weights(s) for s in W_SEEDS]
+    models = [ref_model(NeRF, w) for w in ws]
+    emb = [Embedding(3, 10), Embedding(3, 4)]
+    for name, (n, kind, rseed, S, K, disp, perturb, noise, wb, tt) in CASES.items():
+        rays = orc.make_rays(n, rseed, kind)
+        store = {"rays": rays}
+        torch.manual_seed(1000 + rseed)
+        if perturb > 0 or noise > 0:
+            # replay the reference's draws (models/rendering.py:203, :152, :39, :152) to record them
+            g = torch.get_rng_state()
+            if perturb > 0:
+                store["perturb_rand"] = torch.rand(n, S).numpy()
+            store["noise_coarse"] = torch.randn(n, S).numpy()
+            if K > 0:
+                if perturb > 0:
+                    store["u_rand"] = torch.rand(n, K).numpy()
+                store["noise_fine"] = torch.randn(n, S + K).numpy()
+            torch.set_rng_state(g)
+        with torch.no_grad():
+            out = render_rays(models, emb, torch.from_numpy(rays), S, disp, perturb, noise, K, 1024 * 32,
+                              wb, test_time=tt)
+        for k, v in out.items():
+            store["out_" + k] = v.numpy()
+        np.savez_compressed(os.path.join(HERE, f"render_{name}.npz"), **store)
+        print(name, {k: tuple(v.shape) for k, v in out.items()})
+
+    # unit vectors: Embedding, NeRF.forward, sample_pdf
+    rs = np.random.RandomState(21)
+    x3 = rs.uniform(-6, 6, (64, 3)).astype(np.float32)
+    with torch.no_grad():
+        e10 = emb[0](torch.from_numpy(x3)).numpy()
+        e4 = emb[1](torch.from_numpy(x3 / 6)).numpy()
+        xin = np.concatenate([e10, e4], -1)
+        full = models[0](torch.from_numpy(xin)).numpy()
+        sig = models[1](torch.from_numpy(e10), sigma_only=True).numpy()
+        bins = np.sort(rs.uniform(2, 6, (32, 63)).astype(np.float32), -1)
+        wts = (rs.uniform(0, 1, (32, 62)) ** 4).astype(np.float32)
+        wts[:4] = 0
+        u = rs.uniform(0, 1, (32, 64)).astype(np.float32)
+        sp_det = sample_pdf(torch.from_numpy(bins), torch.from_numpy(wts), 64, det=True).numpy()
+        # non-det: replay the rand draw
+        torch.manual_seed(77)
+        u_ref = torch.rand(32, 48).numpy()
+        torch.manual_seed(77)
+        sp_rand = sample_pdf(torch.from_numpy(bins), torch.from_numpy(wts), 48, det=False).numpy()
+    np.savez_compressed(os.path.join(HERE, "units.npz"), x3=x3, embed10=e10, embed4=e4, nerf_in=xin,
+                        nerf_full=full, nerf_sigma=sig, pdf_bins=bins, pdf_weights=wts, pdf_det=sp_det,
+                        pdf_u=u_ref, pdf_rand=sp_rand, linspace64=torch.linspace(0, 1, 64).numpy(),
+                        linspace128=torch.linspace(0, 1, 128).numpy())
+    print("units ok")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,90 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, exports
+every symbol include/nerf_pl_b200.h declares, validates arguments without touching a GPU, and the
+Python mirror keeps the reference's names / signatures / state_dict keys."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+import nerf_pl_b200 as nb
+from nerf_pl_b200 import _lib
+from oracle import nerf_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    _lib.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "nerf_pl_b200.h")).read()
+    declared = set(re.findall(r"\b(nerfb200_[a-z_0-9]+)\s*\(", hdr))
+    declared.discard("nerfb200_render_args")
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_abi_basics(lib):
+    assert lib.nerfb200_abi_version() == 1
+    # layout.h: 34 x 32 KiB + 5 x 16 KiB fp16 slices + fp32 tail
+    assert lib.nerfb200_packed_bytes() == 34 * 32768 + 5 * 16384 + 4 * (10 * 256 + 256 + 4 + 384 + 4 + 128 * 28)
+    assert lib.nerfb200_launch_count() >= 0
+
+
+def test_argument_validation_without_gpu(lib):
+    a = _lib.RenderArgs(n_rays=4, n_samples=48, n_importance=0)
+    assert lib.nerfb200_render_rays(ctypes.byref(a), None) == -2          # unsupported N_samples
+    assert b"N_samples" in lib.nerfb200_last_error()
+    a = _lib.RenderArgs(n_rays=4, n_samples=64, n_importance=64)
+    assert lib.nerfb200_render_rays(ctypes.byref(a), None) == -1          # NULL rays
+    a = _lib.RenderArgs(n_rays=0, n_samples=64, n_importance=0)
+    assert lib.nerfb200_render_rays(ctypes.byref(a), None) == 0           # empty input is a no-op
+    assert lib.nerfb200_searchsorted(None, None, None, 3, 2, 4, 4, 1, None) == -1   # row mismatch
+    assert lib.nerfb200_searchsorted(None, None, None, 0, 0, 4, 4, 1, None) == 0    # empty
+    assert lib.nerfb200_composite(None, None, None, None, None, 0.0, 0, 4, 48, None, None, None, None, None) == -2
+    assert lib.nerfb200_nerf_forward(None, 0, 90, None, 0, None, None) == 0
+    assert lib.nerfb200_embed(None, 5, 10, None, None) == -1
+
+
+def test_python_mirror_matches_reference_interface():
+    sig = inspect.signature(nb.render_rays)
+    names = list(sig.parameters)[:11]
+    assert names == ["models", "embeddings", "rays", "N_samples", "use_disp", "perturb", "noise_std",
+                     "N_importance", "chunk", "white_back", "test_time"]      # models/rendering.py:58-69
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert (d["N_samples"], d["use_disp"], d["perturb"], d["noise_std"], d["N_importance"], d["chunk"],
+            d["white_back"], d["test_time"]) == (64, False, 0, 1, 0, 1024 * 32, False, False)
+    m = nb.NeRF()
+    assert list(m.state_dict().keys()) == orc.PARAM_KEYS                    # models/nerf.py:69-81
+    assert sum(p.numel() for p in m.parameters()) == 595844
+    e = nb.Embedding(3, 10)
+    assert e.out_channels == 63 and nb.Embedding(3, 4).out_channels == 27
+    assert torch.equal(e.freq_bands, 2 ** torch.arange(10.0))
+
+
+def test_no_cpu_fallback():
+    m = nb.NeRF()
+    emb = [nb.Embedding(3, 10), nb.Embedding(3, 4)]
+    with pytest.raises(RuntimeError):
+        nb.render_rays([m, m], emb, torch.zeros(4, 8), 64, False, 0, 0, 64)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 90))
+    with pytest.raises(RuntimeError):
+        emb[0](torch.zeros(2, 3))
+    with pytest.raises(RuntimeError):
+        nb.searchsorted(torch.zeros(1, 3), torch.zeros(1, 3))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "nerf_pl_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src, fn

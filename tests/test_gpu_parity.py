@@ -1,0 +1,249 @@
+"""GPU parity tests (pytest -m gpu): the sm_100a kernels, called through the C ABI, against
+(a) the committed outputs of the reference's own Python path (tests/golden) and (b) the numpy
+oracle on the same seeded inputs.
+
+Tolerances (floating-point path, BASELINE.json north_star: "rgb_fine within 1e-3 abs"):
+  rgb_*      1e-3 absolute      (MLP in fp16 operands / fp32 accumulate, rest fp32)
+  opacity_*  1e-3 absolute
+  depth_*    4e-3 absolute      (depths are 2..6: 1e-3 relative)
+Integer/index work (searchsorted) is bit-exact.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import nerf_pl_b200 as nb
+from nerf_pl_b200 import _lib
+from oracle import nerf_oracle as orc
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"rgb": 1e-3, "opacity": 1e-3, "depth": 4e-3}
+
+
+def tol_for(key):
+    return TOL[key.split("_")[0]]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ws():
+    return cases.weights()
+
+
+@pytest.fixture(scope="module")
+def models(ws, dev):
+    out = []
+    for w in ws:
+        m = nb.NeRF()
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+        out.append(m.to(dev).eval())
+    return out
+
+
+@pytest.fixture(scope="module")
+def emb():
+    return [nb.Embedding(3, 10), nb.Embedding(3, 4)]
+
+
+def to_dev(d, dev):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in d.items()}
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_render_rays_vs_reference_golden(name, models, emb, ws, dev):
+    n, kind, rseed, S, K, disp, perturb, noise, wb, tt = cases.CASES[name]
+    rays, randoms, ref = cases.load_case(name)
+    with torch.no_grad():
+        out = nb.render_rays(models, emb, torch.from_numpy(rays).to(dev), S, disp, perturb, noise, K, 1024 * 32,
+                             wb, test_time=tt, randoms=to_dev(randoms, dev))
+    torch.cuda.synchronize()
+    assert set(out) == set(ref)                                   # result keys (models/rendering.py:209-242)
+    oracle = orc.render_rays(ws, rays, S, disp, perturb, noise, K, wb, tt, randoms)
+    for k, v in ref.items():
+        got = out[k].cpu().numpy()
+        assert got.shape == v.shape and got.dtype == np.float32
+        mx, p999, mean = cases.error_stats(got, v)
+        mxo, _, _ = cases.error_stats(got, oracle[k])
+        print(f"{name}/{k}: vs reference max {mx:.2e} p99.9 {p999:.2e} mean {mean:.2e}; vs oracle max {mxo:.2e}")
+        assert mx < tol_for(k), f"{name}/{k} vs reference: max {mx:.3e}"
+        assert mxo < tol_for(k), f"{name}/{k} vs oracle: max {mxo:.3e}"
+    if "rgb_fine" in ref:
+        assert orc.psnr(out["rgb_fine"].cpu().numpy(), ref["rgb_fine"]) > 60.0
+
+
+def test_units_vs_reference_golden(models, emb, dev):
+    u = np.load(os.path.join(cases.GOLDEN, "units.npz"))
+    x3 = torch.from_numpy(u["x3"]).to(dev)
+    np.testing.assert_allclose(emb[0](x3).cpu().numpy(), u["embed10"], atol=2e-6, rtol=0)   # a2
+    np.testing.assert_allclose(emb[1](x3 / 6).cpu().numpy(), u["embed4"], atol=2e-6, rtol=0)
+    with torch.no_grad():
+        full = models[0](torch.from_numpy(u["nerf_in"]).to(dev)).cpu().numpy()              # a4
+        sig = models[1](torch.from_numpy(u["embed10"]).to(dev), sigma_only=True).cpu().numpy()
+    assert full.shape == (64, 4) and sig.shape == (64, 1)
+    assert np.abs(full[:, :3] - u["nerf_full"][:, :3]).max() < 1e-3
+    assert (np.abs(full[:, 3] - u["nerf_full"][:, 3]) / (1 + np.abs(u["nerf_full"][:, 3]))).max() < 2e-3
+    assert (np.abs(sig - u["nerf_sigma"]) / (1 + np.abs(u["nerf_sigma"]))).max() < 2e-3
+    bins, wts = torch.from_numpy(u["pdf_bins"]).to(dev), torch.from_numpy(u["pdf_weights"]).to(dev)
+    det = nb.sample_pdf(bins, wts, 64, det=True).cpu().numpy()                               # a8
+    np.testing.assert_allclose(det[:, :-1], u["pdf_det"][:, :-1], atol=1e-4, rtol=0)
+    last_bin = u["pdf_bins"][:, -1] - u["pdf_bins"][:, -2]
+    assert np.all(np.abs(det[:, -1] - u["pdf_det"][:, -1]) <= last_bin + 1e-5)
+    rnd = nb.sample_pdf(bins, wts, 48, det=False, u=torch.from_numpy(u["pdf_u"]).to(dev)).cpu().numpy()
+    np.testing.assert_allclose(rnd, u["pdf_rand"], atol=1e-4, rtol=0)
+
+
+@pytest.mark.parametrize("side", ["left", "right"])
+def test_searchsorted_reference_grid(side, dev):
+    """torchsearchsorted/test/test_searchsorted.py:27-44 grid, exact integer equality (a9)."""
+    rs = np.random.RandomState(0)
+    for Ba, Bv in ((1, 1), (100, 100), (200, 200), (1, 100), (100, 1)):
+        for A in (1, 50, 500):
+            for V in (1, 12, 120):
+                a = np.sort(rs.rand(Ba, A).astype(np.float32), -1)
+                v = rs.rand(Bv, V).astype(np.float32)
+                if A > 4:
+                    v[:, 0] = a[0, 3] if Ba == 1 else a[:Bv, 3] if Bv <= Ba else a[0, 3]   # exact ties
+                got = nb.searchsorted(torch.from_numpy(a).to(dev), torch.from_numpy(v).to(dev), side=side)
+                assert got.dtype == torch.long and got.is_cuda
+                np.testing.assert_array_equal(got.cpu().numpy(), orc.searchsorted(a, v, side))
+    # hot-path shape: cdf (R,63), deterministic u with ties at 0 and 1
+    cdf = np.sort(rs.rand(4096, 63).astype(np.float32), -1)
+    cdf[:, 0], cdf[:, -1] = 0.0, 1.0
+    uu = np.broadcast_to(orc.linspace01(64), (4096, 64)).copy()
+    got = nb.searchsorted(torch.from_numpy(cdf).to(dev), torch.from_numpy(uu).to(dev), side=side)
+    np.testing.assert_array_equal(got.cpu().numpy(), orc.searchsorted(cdf, uu, side))
+
+
+def test_searchsorted_errors(dev):
+    with pytest.raises(AssertionError):
+        nb.searchsorted(torch.zeros(3, 4, device=dev), torch.zeros(2, 4, device=dev))
+    with pytest.raises(AssertionError):
+        nb.searchsorted(torch.zeros(4, device=dev), torch.zeros(2, 4, device=dev))
+    assert nb.searchsorted(torch.zeros(2, 0, device=dev), torch.zeros(2, 3, device=dev)).sum().item() == 0
+
+
+@pytest.mark.parametrize("S,with_rgb,wb", [(64, True, True), (128, True, False), (192, False, False), (64, False, True)])
+def test_volume_render_vs_oracle(S, with_rgb, wb, dev):
+    rs = np.random.RandomState(S)
+    n = 257
+    sig = (rs.randn(n, S) * 3).astype(np.float32)
+    rgb = rs.rand(n, S, 3).astype(np.float32) if with_rgb else None
+    z = np.sort(rs.uniform(2, 6, (n, S)).astype(np.float32), -1)
+    d = rs.randn(n, 3).astype(np.float32)
+    noise = rs.randn(n, S).astype(np.float32)
+    w, c, dp, op = nb.volume_render(torch.from_numpy(sig).to(dev), None if rgb is None else torch.from_numpy(rgb).to(dev),
+                                    torch.from_numpy(z).to(dev), torch.from_numpy(d).to(dev),
+                                    torch.from_numpy(noise).to(dev), 0.7, wb)
+    ow, oc, od, oo = orc.volume_render(sig, rgb, z, d, noise, 0.7, wb)
+    np.testing.assert_allclose(w.cpu().numpy(), ow, atol=2e-6, rtol=1e-5)
+    np.testing.assert_allclose(op.cpu().numpy(), oo, atol=5e-6, rtol=1e-5)
+    if with_rgb:
+        np.testing.assert_allclose(c.cpu().numpy(), oc, atol=5e-6, rtol=1e-5)
+        np.testing.assert_allclose(dp.cpu().numpy(), od, atol=2e-5, rtol=1e-5)
+
+
+def test_full_image_properties(models, emb, ws, dev):
+    """BASELINE.json configs[2]: one 400x400 view (160,000 rays) in eval.py's 32768-ray chunks,
+    test_time=True.  Size-independent properties + a random 384-ray subset against the oracle."""
+    import bench
+    n = 160000
+    rays_np = bench.blender_rays(n, 5)
+    rays = torch.from_numpy(rays_np).to(dev)
+    with torch.no_grad():
+        chunks = [nb.render_rays(models, emb, rays[i:i + 32768], 64, False, 0, 0, 64, 32768, True,
+                                 test_time=True, extras=True) for i in range(0, n, 32768)]
+        whole = nb.render_rays(models, emb, rays, 64, False, 0, 0, 64, 32768, True, test_time=True, extras=True)
+        again = nb.render_rays(models, emb, rays, 64, False, 0, 0, 64, 32768, True, test_time=True, extras=True)
+    torch.cuda.synchronize()
+    assert set(whole) - {"z_vals_fine", "weights_fine", "weights_coarse"} == {
+        "opacity_coarse", "rgb_fine", "depth_fine", "opacity_fine"}
+    for k in whole:
+        cat = torch.cat([c[k] for c in chunks], 0)
+        assert torch.equal(cat, whole[k]), f"chunking changed {k}"          # rays are independent units
+        assert torch.equal(again[k], whole[k]), f"non-deterministic {k}"
+        assert torch.isfinite(whole[k]).all()
+    z = whole["z_vals_fine"]
+    assert z.shape == (n, 128) and bool((z[:, 1:] >= z[:, :-1]).all())       # sorted merge (:229)
+    t = torch.from_numpy(orc.linspace01(64)).to(dev)
+    zc = rays[:, 6:7] * (1 - t) + rays[:, 7:8] * t
+    pos = torch.searchsorted(z.contiguous(), zc.contiguous())
+    assert torch.allclose(torch.gather(z, 1, pos.clamp(max=127)), zc, atol=1e-6)   # coarse depths are kept
+    assert bool((z >= rays[:, 6:7] - 1e-6).all()) and bool((z <= rays[:, 7:8] + 1e-6).all())
+    for k in ("opacity_coarse", "opacity_fine"):
+        assert float(whole[k].min()) >= 0.0 and float(whole[k].max()) <= 1.0 + 1e-5
+    assert torch.allclose(whole["weights_fine"].sum(1), whole["opacity_fine"], atol=1e-5)
+    assert float(whole["rgb_fine"].min()) >= -1e-5 and float(whole["rgb_fine"].max()) <= 1.0 + 1e-4
+    idx = np.random.RandomState(0).choice(n, 384, replace=False)
+    ref = orc.render_rays(ws, rays_np[idx], 64, False, 0.0, 0.0, 64, True, True)
+    for k, v in ref.items():
+        mx, p999, mean = cases.error_stats(whole[k][torch.from_numpy(idx).to(dev)].cpu().numpy(), v)
+        print(f"full-image subset {k}: max {mx:.2e} p99.9 {p999:.2e} mean {mean:.2e}")
+        assert mx < tol_for(k)
+
+
+def test_host_buffer_entry_matches_device_path(models, emb, dev):
+    """nerfb200_render_rays_host (host pointers, copies inside) == device-pointer path, bitwise."""
+    lib = _lib.load()
+    n = 777
+    rays = orc.make_rays(n, 9)
+    with torch.no_grad():
+        ref = nb.render_rays(models, emb, torch.from_numpy(rays).to(dev), 64, False, 0, 0, 64, 32768, True)
+    torch.cuda.synchronize()
+    bufs = {k: np.zeros(tuple(v.shape), np.float32) for k, v in ref.items()}
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    args = _lib.RenderArgs(rays=p(rays), n_rays=n, ray_stride=8,
+                           packed_coarse=nb.packed_weights(models[0]).data_ptr(),
+                           packed_fine=nb.packed_weights(models[1]).data_ptr(),
+                           n_samples=64, n_importance=64, use_disp=0, perturb=0.0, noise_std=0.0, white_back=1,
+                           test_time=0, rgb_coarse=p(bufs["rgb_coarse"]), depth_coarse=p(bufs["depth_coarse"]),
+                           opacity_coarse=p(bufs["opacity_coarse"]), rgb_fine=p(bufs["rgb_fine"]),
+                           depth_fine=p(bufs["depth_fine"]), opacity_fine=p(bufs["opacity_fine"]))
+    assert lib.nerfb200_render_rays_host(ctypes.byref(args), None) == 0, lib.nerfb200_last_error()
+    for k, v in ref.items():
+        np.testing.assert_array_equal(bufs[k], v.cpu().numpy())
+
+
+def test_weight_cache_tracks_parameter_updates(ws, emb, dev):
+    m = [nb.NeRF().to(dev), nb.NeRF().to(dev)]
+    rays = torch.from_numpy(orc.make_rays(64, 1)).to(dev)
+    with torch.no_grad():
+        a = nb.render_rays(m, emb, rays, 64, False, 0, 0, 64)["rgb_fine"].clone()
+        m[1].rgb[0].bias.add_(1.0)            # in-place update bumps _version, like an optimizer step
+        b = nb.render_rays(m, emb, rays, 64, False, 0, 0, 64)["rgb_fine"]
+    assert not torch.equal(a, b)
+
+
+def test_training_path_produces_gradients(ws, emb, dev):
+    """Autograd drop-in (train.py:103-117): loss.backward() fills .grad of both NeRFs."""
+    m = [nb.NeRF().to(dev), nb.NeRF().to(dev)]
+    rays = torch.from_numpy(orc.make_rays(128, 2)).to(dev)
+    torch.manual_seed(0)
+    out = nb.render_rays(m, emb, rays, 64, False, 1.0, 1.0, 64, 32768, True)
+    loss = ((out["rgb_coarse"] - 0.5) ** 2).mean() + ((out["rgb_fine"] - 0.5) ** 2).mean()   # losses.py:9-14
+    loss.backward()
+    for net in m:
+        for name, p in net.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), name
+    assert float(m[0].xyz_encoding_1[0].weight.grad.abs().sum()) > 0
+    assert float(m[1].rgb[0].weight.grad.abs().sum()) > 0
+
+
+def test_unsupported_shapes_fail_loudly(models, emb, dev):
+    rays = torch.from_numpy(orc.make_rays(8, 1)).to(dev)
+    with pytest.raises(ValueError):
+        nb.render_rays(models, emb, rays, 48, False, 0, 0, 0)
+    with pytest.raises(ValueError):
+        nb.render_rays(models, [nb.Embedding(3, 6), nb.Embedding(3, 4)], rays, 64, False, 0, 0, 0)
+    with pytest.raises(ValueError):
+        nb.render_rays(models[:1], emb, rays, 64, False, 0, 0, 64)
+    out = nb.render_rays(models[:1], emb, rays[:0], 64, False, 0, 0, 0)          # empty input
+    assert out["rgb_coarse"].shape == (0, 3)

@@ -1,0 +1,72 @@
+"""Pin the CPU oracle (oracle/nerf_oracle.py) against outputs of the reference's own Python path
+(tests/golden/*.npz, produced by tests/golden/make_golden.py from /root/reference).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import nerf_oracle as orc
+from tests import cases
+
+# fp32 numpy (OpenBLAS) vs fp32 torch (MKL): GEMM blocking differs in the last bits; through 10
+# layers and the 1e10 far-plane delta that shows up at the 1e-5 level.
+TOL = 2e-4
+
+
+@pytest.fixture(scope="module")
+def ws():
+    return cases.weights()
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_render_rays_matches_reference(name, ws):
+    n, kind, rseed, S, K, disp, perturb, noise, wb, tt = cases.CASES[name]
+    rays, randoms, ref = cases.load_case(name)
+    np.testing.assert_array_equal(rays, orc.make_rays(n, rseed, kind))
+    out = orc.render_rays(ws, rays, S, disp, perturb, noise, K, wb, tt, randoms)
+    assert set(out) == set(ref), (sorted(out), sorted(ref))
+    for k in ref:
+        assert out[k].shape == ref[k].shape and out[k].dtype == np.float32
+        mx, p999, mean = cases.error_stats(out[k], ref[k])
+        assert mx < TOL, f"{name}/{k}: max {mx:.3e} p99.9 {p999:.3e} mean {mean:.3e}"
+
+
+def test_units_match_reference(ws):
+    u = np.load(os.path.join(cases.GOLDEN, "units.npz"))
+    np.testing.assert_allclose(orc.embed(u["x3"], 10), u["embed10"], atol=2e-6, rtol=0)
+    np.testing.assert_allclose(orc.embed(u["x3"] / 6, 4), u["embed4"], atol=2e-6, rtol=0)
+    assert orc.embed(u["x3"], 10).shape == (64, 63)
+    np.testing.assert_allclose(orc.nerf_forward(ws[0], u["nerf_in"]), u["nerf_full"], atol=5e-5, rtol=1e-5)
+    np.testing.assert_allclose(orc.nerf_forward(ws[1], u["embed10"], sigma_only=True), u["nerf_sigma"],
+                               atol=5e-5, rtol=1e-5)
+    # sample_pdf: u == 1.0 (last deterministic sample) sits exactly on cdf[-1] ~ 1 +- 1 ulp, where the
+    # reference's searchsorted(right) flips between the last two bins depending on the summation order
+    # of cumsum (models/rendering.py:31,42-48) - an ill-conditioned point of the reference itself.
+    # Compare it to within the last bin's width, everything else tightly.
+    det = orc.sample_pdf(u["pdf_bins"], u["pdf_weights"], 64, det=True)
+    # conditioning: a 1-ulp cdf difference (6e-8) is amplified by bin_width / denom, denom >= 1e-5
+    np.testing.assert_allclose(det[:, :-1], u["pdf_det"][:, :-1], atol=1e-4, rtol=0)
+    last_bin = u["pdf_bins"][:, -1] - u["pdf_bins"][:, -2]
+    assert np.all(np.abs(det[:, -1] - u["pdf_det"][:, -1]) <= last_bin + 1e-5)
+    np.testing.assert_allclose(orc.sample_pdf(u["pdf_bins"], u["pdf_weights"], 48, det=False, u=u["pdf_u"]),
+                               u["pdf_rand"], atol=1e-4, rtol=0)
+    # torch.linspace: ATen's CPU kernel evaluates base + lane*step per SIMD vector (so its last bit
+    # depends on the host's vector width); the scalar two-sided formula agrees to 1 ulp.
+    np.testing.assert_allclose(orc.linspace01(64), u["linspace64"], atol=6e-8, rtol=0)
+    np.testing.assert_allclose(orc.linspace01(128), u["linspace128"], atol=6e-8, rtol=0)
+
+
+@pytest.mark.parametrize("side", ["left", "right"])
+def test_searchsorted_grid(side):
+    """The reference's own searchsorted test grid (torchsearchsorted/test/test_searchsorted.py:27-44)
+    against numpy semantics incl. single-row broadcast."""
+    rs = np.random.RandomState(0)
+    for Ba, Bv in ((1, 1), (100, 100), (1, 100), (100, 1)):
+        for A in (1, 50, 500):
+            for V in (1, 12, 120):
+                a = np.sort(rs.rand(Ba, A).astype(np.float32), -1)
+                v = rs.rand(Bv, V).astype(np.float32)
+                out = orc.searchsorted(a, v, side)
+                assert out.dtype == np.int64 and out.shape == (max(Ba, Bv), V)
+                r = max(Ba, Bv) - 1
+                np.testing.assert_array_equal(out[r], np.searchsorted(a[min(r, Ba - 1)], v[min(r, Bv - 1)], side))
