@@ -140,6 +140,9 @@ int64_t nerfb200_launch_count(void);
  * engine: d (128, N) with N = 256 for slices 0..33 and 128 for slices 34..38 (csrc/layout.h).
  * Unit-test hook for the shared-memory / descriptor layout; not part of the reference API. */
 int nerfb200_debug_gemm(const float* a, const void* packed, int32_t slice, float* d, void* stream);
+/* Experiment hook: with NERFB200_FLAGS bit 1 set, CTA 0 of the last render launch records
+ * (tag, SM clock) pairs for its epilogue / MMA roles; this copies 3*512*2 int64 to host. */
+int nerfb200_debug_timeline(int64_t* host_out, int64_t n_values);
 /* Device properties the launcher uses: SM count of the current device (0 if none). */
 int nerfb200_sm_count(void);
 

@@ -40,6 +40,7 @@ EXPORTS = [
     "nerfb200_composite",
     "nerfb200_launch_count",
     "nerfb200_debug_gemm",
+    "nerfb200_debug_timeline",
     "nerfb200_sm_count",
 ]
 
@@ -132,6 +133,8 @@ def _declare(lib: ctypes.CDLL) -> None:
                                        c_void_p, c_void_p]
     lib.nerfb200_debug_gemm.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]
     lib.nerfb200_debug_gemm.restype = c_int32
+    lib.nerfb200_debug_timeline.argtypes = [c_void_p, c_int64]
+    lib.nerfb200_debug_timeline.restype = c_int32
     lib.nerfb200_launch_count.restype = c_int64
     lib.nerfb200_sm_count.restype = c_int32
     for name in ("nerfb200_pack_weights", "nerfb200_render_rays", "nerfb200_render_rays_host",

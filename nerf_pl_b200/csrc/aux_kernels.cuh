@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const MlpParam
     c.half = warp >> 2;
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     c.d_phase = 0;
+    c.tl = nullptr;
     c.f32 = reinterpret_cast<const float*>(p.net + kHalfRegionBytes);
     uint8_t* enc = smem + kSmemEnc;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -334,6 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_probe_kernel(const float* __
     c.half = warp >> 2;
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     c.d_phase = 0;
+    c.tl = nullptr;
     uint8_t* enc = smem + kSmemEnc;
     for (int k = c.half * 32; k < c.half * 32 + 32; ++k)
       *reinterpret_cast<__half*>(enc + sw128_off(c.row, k)) = __float2half_rn(a[c.row * 64 + k]);

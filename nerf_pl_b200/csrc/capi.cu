@@ -1,6 +1,7 @@
 // C ABI of libnerf_pl_b200.so (declarations + reference citations: include/nerf_pl_b200.h).
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -33,6 +34,7 @@ struct DeviceInfo {
   int cc_major = 0;
   bool attrs_set = false;
   int* status = nullptr;
+  long long* timeline = nullptr;
 };
 std::mutex g_mu;
 DeviceInfo g_dev[64];
@@ -188,6 +190,18 @@ int nerfb200_render_rays(const nerfb200_render_args* a, void* stream) {
   p.weights_coarse = a->weights_coarse;
   p.weights_fine = a->weights_fine;
   p.status = a->status ? a->status : d->status;
+  {
+    const char* f = std::getenv("NERFB200_FLAGS");   // experiment switches; unset in production
+    p.flags = f ? static_cast<unsigned>(std::strtoul(f, nullptr, 0)) : 0u;
+    p.timeline = nullptr;
+    if (p.flags & 2u) {
+      if (!d->timeline) {
+        CUDA_TRY(cudaMalloc(&d->timeline, 3 * kTlMax * 2 * sizeof(long long)), "timeline alloc");
+      }
+      CUDA_TRY(cudaMemsetAsync(d->timeline, 0, 3 * kTlMax * 2 * sizeof(long long), static_cast<cudaStream_t>(stream)), "timeline memset");
+      p.timeline = d->timeline;
+    }
+  }
   const int n_groups = (p.n_rays + 1) / 2;
   int ctas = d->sm_count;
   if (a->max_ctas > 0 && a->max_ctas < ctas) ctas = a->max_ctas;
@@ -370,6 +384,18 @@ int nerfb200_composite(const float* sigmas, const float* rgbs, const float* z_va
       sigmas, rgbs, z_vals, dirs, noise, noise_std, white_back, n_rays, S, weights, rgb, depth, opacity);
   g_launches++;
   CUDA_TRY(cudaGetLastError(), "composite launch");
+  return 0;
+}
+
+int nerfb200_debug_timeline(int64_t* host_out, int64_t n_values) {
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (!di->timeline || !host_out) return fail(NERFB200_EINVAL, "debug_timeline: no timeline recorded%s");
+  const int64_t cap = 3 * kTlMax * 2;
+  CUDA_TRY(cudaDeviceSynchronize(), "timeline sync");
+  CUDA_TRY(cudaMemcpy(host_out, di->timeline, sizeof(long long) * (n_values < cap ? n_values : cap),
+                      cudaMemcpyDeviceToHost), "timeline copy");
   return 0;
 }
 

@@ -49,6 +49,21 @@ struct Barriers {
 };
 static_assert(sizeof(Barriers) % 16 == 0, "Barriers must keep 16-byte alignment of what follows");
 
+// Optional device timeline (experiments only): CTA 0 appends (tag, clock) pairs per role.
+struct Timeline {
+  long long* buf;      // [3 roles][kTlMax][2]
+  int n[3];
+};
+constexpr int kTlMax = 512;
+__device__ __forceinline__ void tl_mark(Timeline* tl, int role, int tag) {
+  if (tl == nullptr || tl->buf == nullptr) return;
+  int i = tl->n[role];
+  if (i >= kTlMax) return;
+  tl->buf[(role * kTlMax + i) * 2 + 0] = tag;
+  tl->buf[(role * kTlMax + i) * 2 + 1] = clock64();
+  tl->n[role] = i + 1;
+}
+
 struct RingState {
   uint32_t stage = 0, phase = 0;
   __device__ __forceinline__ void advance() {
@@ -122,7 +137,8 @@ __device__ __forceinline__ void produce_tile(RingState& rs, uint8_t* smem, Barri
 // -------------------------------------------------------------------- MMA
 // One thread.  Issues all MMAs of one tile.
 __device__ __forceinline__ void mma_tile(RingState& rs, uint32_t& a_phase, uint8_t* smem,
-                                         Barriers* bars, bool sigma_only, bool dir_slice) {
+                                         Barriers* bars, bool sigma_only, bool dir_slice,
+                                         uint32_t flags = 0, Timeline* tl = nullptr) {
   const uint32_t tmem_d = bars->tmem_base;
   const uint32_t a_base = smem_u32(smem + kSmemA);
   const uint32_t enc_base = smem_u32(smem + kSmemEnc);
@@ -131,6 +147,7 @@ __device__ __forceinline__ void mma_tile(RingState& rs, uint32_t& a_phase, uint8
     mbar_wait(smem_u32(&bars->a_ready), a_phase, 3);
     a_phase ^= 1;
     tc_fence_after();
+    tl_mark(tl, 1, 100 + l);
     const int n_slices = (l == 0) ? 1 : (l == 4) ? 5 : (l == 9 && dir_slice) ? 5 : 4;
     const uint32_t idesc = (l == 9) ? make_idesc_f16(128) : make_idesc_f16(256);
     for (int s = 0; s < n_slices; ++s) {
@@ -142,15 +159,26 @@ __device__ __forceinline__ void mma_tile(RingState& rs, uint32_t& a_phase, uint8
       tc_fence_after();
       const uint64_t adesc = make_desc_sw128(a_addr);
       const uint64_t bdesc = make_desc_sw128(b_addr);
+      if ((flags & 1u) && l != 9) {
+        // experiment: two N=128 MMAs per K step (B rows 128..255 start 16 KiB into the slice)
+        const uint32_t id128 = make_idesc_f16(128);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in the addr field
-        umma_f16(tmem_d, adesc + 2 * j, bdesc + 2 * j, idesc, (s | j) != 0 ? 1u : 0u);
+        for (int j = 0; j < 4; ++j) {
+          umma_f16(tmem_d, adesc + 2 * j, bdesc + 2 * j, id128, (s | j) != 0 ? 1u : 0u);
+          umma_f16(tmem_d + 128, adesc + 2 * j, bdesc + 1024 + 2 * j, id128, (s | j) != 0 ? 1u : 0u);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in the addr field
+          umma_f16(tmem_d, adesc + 2 * j, bdesc + 2 * j, idesc, (s | j) != 0 ? 1u : 0u);
+        }
       }
       umma_commit(smem_u32(&bars->empty[rs.stage]));
       rs.advance();
     }
     umma_commit(smem_u32(&bars->d_ready));
+    tl_mark(tl, 1, 200 + l);
   }
 }
 
@@ -164,6 +192,7 @@ struct EpiCtx {
   int row;                         // 0..127 : tile row == TMEM lane
   int half;                        // 0/1    : column half
   int lane;
+  Timeline* tl;                    // non-null only for the one traced thread
 };
 
 __device__ __forceinline__ void epi_bar() {   // all 256 epilogue threads
@@ -174,6 +203,7 @@ __device__ __forceinline__ void epi_signal_a(EpiCtx& c) {
   tc_fence_before();
   __syncwarp();
   if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_ready));
+  tl_mark(c.tl, 0, 6);
 }
 __device__ __forceinline__ void epi_wait_d(EpiCtx& c) {
   mbar_wait(smem_u32(&c.bars->d_ready), c.d_phase, 5);
@@ -191,63 +221,99 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t
                : "memory");
 }
 
-// Hidden layer epilogue over this thread's 128 columns: v = act(acc + bias), stored as the
-// next layer's fp16 A operand.  Optionally accumulates the sigma head (models/nerf.py:112).
+// Packed fp32x2 add (FADD2) and fp32x2 -> fp16x2 conversion with / without fused ReLU (F2FP.RELU).
+__device__ __forceinline__ void add_f32x2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{ .reg .b64 a, b, d; mov.b64 a, {%2,%3}; mov.b64 b, {%4,%5}; add.rn.f32x2 d, a, b; mov.b64 {%0,%1}, d; }"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ uint32_t cvt_f16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// One 32-column chunk of a hidden-layer epilogue: v = act(acc + bias) -> fp16 A operand of the
+// next layer (4 x 16-byte stores into the SWIZZLE_128B tile); optionally the sigma-head dot.
+template <bool kRelu, bool kSigma, bool kStore>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float4 (&b)[8], int n0,
+                                          uint32_t a_row_base, uint32_t rsw,
+                                          const float* __restrict__ wsig, float& sig_acc) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v[8];
+    add_f32x2(v[0], v[1], __uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]), b[2 * j].x, b[2 * j].y);
+    add_f32x2(v[2], v[3], __uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]), b[2 * j].z, b[2 * j].w);
+    add_f32x2(v[4], v[5], __uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]), b[2 * j + 1].x, b[2 * j + 1].y);
+    add_f32x2(v[6], v[7], __uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]), b[2 * j + 1].z, b[2 * j + 1].w);
+    const int n = n0 + 8 * j;
+    if (kSigma) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wsig + n));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wsig + n + 4));
+      sig_acc = fmaf(fmaxf(v[0], 0.f), w0.x, sig_acc);
+      sig_acc = fmaf(fmaxf(v[1], 0.f), w0.y, sig_acc);
+      sig_acc = fmaf(fmaxf(v[2], 0.f), w0.z, sig_acc);
+      sig_acc = fmaf(fmaxf(v[3], 0.f), w0.w, sig_acc);
+      sig_acc = fmaf(fmaxf(v[4], 0.f), w1.x, sig_acc);
+      sig_acc = fmaf(fmaxf(v[5], 0.f), w1.y, sig_acc);
+      sig_acc = fmaf(fmaxf(v[6], 0.f), w1.z, sig_acc);
+      sig_acc = fmaf(fmaxf(v[7], 0.f), w1.w, sig_acc);
+    }
+    if (kStore) {
+      uint32_t h0, h1, h2, h3;
+      if (kRelu) {
+        h0 = cvt_f16x2_relu(v[0], v[1]); h1 = cvt_f16x2_relu(v[2], v[3]);
+        h2 = cvt_f16x2_relu(v[4], v[5]); h3 = cvt_f16x2_relu(v[6], v[7]);
+      } else {
+        h0 = cvt_f16x2(v[0], v[1]); h1 = cvt_f16x2(v[2], v[3]);
+        h2 = cvt_f16x2(v[4], v[5]); h3 = cvt_f16x2(v[6], v[7]);
+      }
+      const uint32_t kb = static_cast<uint32_t>(n) >> 6;
+      const uint32_t chunk = (static_cast<uint32_t>(n) & 63u) >> 3;
+      st_shared_v4(a_row_base + kb * 16384u + ((chunk ^ rsw) << 4), h0, h1, h2, h3);
+    }
+  }
+}
+
+__device__ __forceinline__ void ld_bias32(const float* __restrict__ bias, int n0, float4 (&b)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias + n0) + i);
+}
+
+// Hidden-layer epilogue over this thread's 128 columns.  The bias of the first two chunks is
+// fetched BEFORE waiting for the accumulator, so its latency hides behind the MMA.
 template <bool kRelu, bool kSigma, bool kStore>
 __device__ __forceinline__ void epi_hidden(EpiCtx& c, const float* __restrict__ bias,
                                            const float* __restrict__ wsig, float& sig_acc) {
-  const uint32_t a_base = smem_u32(c.smem + kSmemA);
+  const uint32_t a_row_base = smem_u32(c.smem + kSmemA) + static_cast<uint32_t>(c.row) * 128u;
   const uint32_t rsw = static_cast<uint32_t>(c.row & 7);
-#pragma unroll
-  for (int cc = 0; cc < 4; cc += 2) {
-    uint32_t r[2][32];
-    tmem_ld32(c.tmem_row + c.half * 128 + cc * 32, r[0]);
-    tmem_ld32(c.tmem_row + c.half * 128 + cc * 32 + 32, r[1]);
-    tmem_ld_wait();
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int n0 = c.half * 128 + (cc + u) * 32;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = n0 + 8 * j;
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
-        float v[8];
-        v[0] = __uint_as_float(r[u][8 * j + 0]) + b0.x;
-        v[1] = __uint_as_float(r[u][8 * j + 1]) + b0.y;
-        v[2] = __uint_as_float(r[u][8 * j + 2]) + b0.z;
-        v[3] = __uint_as_float(r[u][8 * j + 3]) + b0.w;
-        v[4] = __uint_as_float(r[u][8 * j + 4]) + b1.x;
-        v[5] = __uint_as_float(r[u][8 * j + 5]) + b1.y;
-        v[6] = __uint_as_float(r[u][8 * j + 6]) + b1.z;
-        v[7] = __uint_as_float(r[u][8 * j + 7]) + b1.w;
-        if (kRelu) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        if (kSigma) {
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(wsig + n));
-          const float4 w1 = __ldg(reinterpret_cast<const float4*>(wsig + n + 4));
-          sig_acc = fmaf(v[0], w0.x, sig_acc);
-          sig_acc = fmaf(v[1], w0.y, sig_acc);
-          sig_acc = fmaf(v[2], w0.z, sig_acc);
-          sig_acc = fmaf(v[3], w0.w, sig_acc);
-          sig_acc = fmaf(v[4], w1.x, sig_acc);
-          sig_acc = fmaf(v[5], w1.y, sig_acc);
-          sig_acc = fmaf(v[6], w1.z, sig_acc);
-          sig_acc = fmaf(v[7], w1.w, sig_acc);
-        }
-        if (kStore) {
-          const uint32_t kb = static_cast<uint32_t>(n) >> 6;
-          const uint32_t chunk = (static_cast<uint32_t>(n) & 63u) >> 3;
-          const uint32_t addr = a_base + kb * 16384u + static_cast<uint32_t>(c.row) * 128u +
-                                ((chunk ^ rsw) << 4);
-          st_shared_v4(addr, pack_half2(v[0], v[1]), pack_half2(v[2], v[3]),
-                       pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
-        }
-      }
-    }
-  }
+  const int nb = c.half * 128;
+  float4 b0[8], b1[8];
+  ld_bias32(bias, nb, b0);
+  ld_bias32(bias, nb + 32, b1);
+  tl_mark(c.tl, 0, 1);
+  epi_wait_d(c);
+  tl_mark(c.tl, 0, 2);
+  uint32_t r0[32], r1[32];
+  tmem_ld32(c.tmem_row + nb, r0);
+  tmem_ld32(c.tmem_row + nb + 32, r1);
+  tmem_ld_wait();
+  tl_mark(c.tl, 0, 3);
+  epi_chunk<kRelu, kSigma, kStore>(r0, b0, nb, a_row_base, rsw, wsig, sig_acc);
+  ld_bias32(bias, nb + 64, b0);
+  tmem_ld32(c.tmem_row + nb + 64, r0);
+  epi_chunk<kRelu, kSigma, kStore>(r1, b1, nb + 32, a_row_base, rsw, wsig, sig_acc);
+  ld_bias32(bias, nb + 96, b1);
+  tmem_ld32(c.tmem_row + nb + 96, r1);
+  tmem_ld_wait();
+  tl_mark(c.tl, 0, 4);
+  epi_chunk<kRelu, kSigma, kStore>(r0, b0, nb + 64, a_row_base, rsw, wsig, sig_acc);
+  epi_chunk<kRelu, kSigma, kStore>(r1, b1, nb + 96, a_row_base, rsw, wsig, sig_acc);
+  tl_mark(c.tl, 0, 5);
 }
 
 // dir_encoding epilogue (N=128; this thread's 64 columns) fused with the rgb head
@@ -299,11 +365,9 @@ __device__ __forceinline__ void epi_run_tile(EpiCtx& c, bool sigma_only, const f
   float dummy = 0.f;
   epi_signal_a(c);
   for (int l = 0; l < 7; ++l) {
-    epi_wait_d(c);
     epi_hidden<true, false, true>(c, bias + l * 256, nullptr, dummy);
     epi_signal_a(c);
   }
-  epi_wait_d(c);
   if (sigma_only) {
     epi_hidden<true, true, false>(c, bias + 7 * 256, wsig, sig_part);
     return;   // next signal comes with the next tile's ENC write
@@ -311,7 +375,6 @@ __device__ __forceinline__ void epi_run_tile(EpiCtx& c, bool sigma_only, const f
   epi_hidden<true, true, true>(c, bias + 7 * 256, wsig, sig_part);
   epi_signal_a(c);
   // xyz_encoding_final: bias only, no activation (models/nerf.py:116)
-  epi_wait_d(c);
   epi_hidden<false, false, true>(c, bias + 8 * 256, nullptr, dummy);
   if (dir_row != nullptr) {
     // ENC tile is dead after layer 5: reuse it for the embedded direction (cols 27..63 zero)

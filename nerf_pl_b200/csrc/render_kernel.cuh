@@ -39,6 +39,8 @@ struct RenderParams {
   float* weights_coarse;        // (n_rays, S_c) optional
   float* weights_fine;          // (n_rays, S_f) optional
   int* status;                  // device int: nonzero on device-detected error
+  unsigned flags;               // experiment switches (NERFB200_FLAGS), 0 in production
+  long long* timeline;          // experiment: device timeline buffer (flags & 2), else null
 };
 
 struct alignas(16) Scratch {
@@ -109,7 +111,7 @@ __device__ __forceinline__ void encode_row(uint8_t* enc, int row, int half, cons
   }
   const int k0 = half * 5;
   float f = half ? 32.f : 1.f;
-#pragma unroll
+#pragma unroll 1
   for (int k = k0; k < k0 + 5; ++k, f *= 2.f) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -268,9 +270,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
     if (lane == 0) {
       RingState rs;
       uint32_t a_phase = 0;
+      Timeline tlm{(blockIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
       for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        for (int t = 0; t < tiles_c; ++t) mma_tile(rs, a_phase, smem, bars, coarse_sigma_only, false);
-        for (int t = 0; t < tiles_f; ++t) mma_tile(rs, a_phase, smem, bars, false, false);
+        for (int t = 0; t < tiles_c; ++t) mma_tile(rs, a_phase, smem, bars, coarse_sigma_only, false, p.flags, &tlm);
+        for (int t = 0; t < tiles_f; ++t) mma_tile(rs, a_phase, smem, bars, false, false, p.flags, &tlm);
       }
     }
   } else {
@@ -282,6 +285,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
     c.half = warp >> 2;
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     c.d_phase = 0;
+    Timeline tle{(blockIdx.x == 0 && threadIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
+    c.tl = &tle;
     const int t = threadIdx.x;   // 0..255
     uint8_t* enc = smem + kSmemEnc;
 
@@ -336,6 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
         for (int tile = 0; tile < tiles; ++tile) {
           const int gr = tile * 128 + c.row;
           const int r = gr / S;
+          tl_mark(c.tl, 0, 10);
           encode_row(enc, c.row, c.half, &sc->ray[r][0], &sc->ray[r][3], sc->z[gr]);
           float sig_part, rgb_part[3];
           epi_run_tile(c, sigma_only, sc->dirbias[r], nullptr, sig_part, rgb_part);
@@ -358,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
           epi_bar();
         }
         // ---- compositing: warp r renders ray r
+        tl_mark(c.tl, 0, 20);
         if (warp < 2) {
           const int r = warp;
           const float* nz = nullptr;
@@ -414,6 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
           }
         }
         epi_bar();
+        tl_mark(c.tl, 0, 21);
         // ---- merge: z_fine = sort(cat(z_coarse, z_new))  (models/rendering.py:229), rank sort
         if (pass == 0 && fine) {
           for (int e = t; e < 2 * Sf; e += kEpiThreads) {

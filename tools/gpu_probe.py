@@ -132,7 +132,35 @@ def step_speed():
     print("SPEED_DONE")
 
 
+def step_timeline():
+    import numpy as np
+    os.environ["NERFB200_FLAGS"] = str(int(os.environ.get("NERFB200_FLAGS", "0")) | 2)
+    lib = _lib.load()
+    ms = make_models()
+    emb = [nb.Embedding(3, 10), nb.Embedding(3, 4)]
+    rays = make_rays(32768)
+    tt = bool(int(os.environ.get("TT", "1")))
+    with torch.no_grad():
+        for _ in range(2):
+            nb.render_rays(ms, emb, rays, 64, False, 0, 0, 64, 32768, True, test_time=tt)
+    torch.cuda.synchronize()
+    buf = np.zeros((3, 512, 2), dtype=np.int64)
+    rc = lib.nerfb200_debug_timeline(buf.ctypes.data, buf.size)
+    print("timeline rc", rc)
+    for role, name in ((0, "EPI"), (1, "MMA")):
+        ev = buf[role]
+        n = int((ev[:, 1] != 0).sum())
+        t0 = ev[0, 1]
+        print(f"--- {name}: {n} events")
+        prev = t0
+        for i in range(min(n, 260)):
+            tag, t = int(ev[i, 0]), int(ev[i, 1])
+            print(f"{name} {i:4d} tag={tag:4d} t={t - t0:9d} dt={t - prev:7d}")
+            prev = t
+    print("TIMELINE_DONE")
+
+
 if __name__ == "__main__":
     t0 = time.time()
-    {"gemm": step_gemm, "mlp": step_mlp, "render": step_render, "speed": step_speed}[sys.argv[1]]()
+    {"gemm": step_gemm, "mlp": step_mlp, "render": step_render, "speed": step_speed, "timeline": step_timeline}[sys.argv[1]]()
     print(f"[{sys.argv[1]}] {time.time() - t0:.1f}s")
