@@ -136,10 +136,15 @@ int nerfb200_composite(const float* sigmas, const float* rgbs, const float* z_va
  * Number of kernels this library has launched on the calling process so far (all entry
  * points).  bench.py reports the delta as `gpu_launches`. */
 int64_t nerfb200_launch_count(void);
-/* One K=64 weight slice of a packed image against a (128,64) fp32 A tile through the tcgen05
- * engine: d (128, N) with N = 256 for slices 0..33 and 128 for slices 34..38 (csrc/layout.h).
- * Unit-test hook for the shared-memory / descriptor layout; not part of the reference API. */
-int nerfb200_debug_gemm(const float* a, const void* packed, int32_t slice, float* d, void* stream);
+/* One [128 x 64] weight half-slice of a packed image (csrc/layout.h, index 0..72) against a
+ * (128,64) fp32 A tile through the tcgen05 engine: d (128,128).  mode 0 stages A in shared
+ * memory (SS MMA), mode 1 in tensor memory (TS MMA).  Unit-test hook for the operand layouts;
+ * not part of the reference API. */
+int nerfb200_debug_gemm(const float* a, const void* packed, int32_t half_slice, int32_t mode, float* d,
+                        void* stream);
+/* Raw tcgen05.mma issue-rate microbenchmark (timing only): out_dev (n_ctas, 8) int64 device
+ * buffer; column v = SM cycles for reps x 16 MMAs of variant v (csrc/aux_kernels.cuh). */
+int nerfb200_debug_mma_bench(int64_t* out_dev, int32_t n_ctas, int32_t reps, void* stream);
 /* Experiment hook: with NERFB200_FLAGS bit 1 set, CTA 0 of the last render launch records
  * (tag, SM clock) pairs for its epilogue / MMA roles; this copies 3*512*2 int64 to host. */
 int nerfb200_debug_timeline(int64_t* host_out, int64_t n_values);

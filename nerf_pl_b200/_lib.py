@@ -41,6 +41,7 @@ EXPORTS = [
     "nerfb200_launch_count",
     "nerfb200_debug_gemm",
     "nerfb200_debug_timeline",
+    "nerfb200_debug_mma_bench",
     "nerfb200_sm_count",
 ]
 
@@ -131,8 +132,10 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.nerfb200_composite.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                        c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p]
-    lib.nerfb200_debug_gemm.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]
+    lib.nerfb200_debug_gemm.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
     lib.nerfb200_debug_gemm.restype = c_int32
+    lib.nerfb200_debug_mma_bench.argtypes = [c_void_p, c_int32, c_int32, c_void_p]
+    lib.nerfb200_debug_mma_bench.restype = c_int32
     lib.nerfb200_debug_timeline.argtypes = [c_void_p, c_int64]
     lib.nerfb200_debug_timeline.restype = c_int32
     lib.nerfb200_launch_count.restype = c_int64

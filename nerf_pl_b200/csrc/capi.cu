@@ -57,6 +57,8 @@ int device_info(DeviceInfo** out) {
                                   static_cast<int>(kSmemTotal)), "smem attr mlp");
     CUDA_TRY(cudaFuncSetAttribute(gemm_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kSmemTotal)), "smem attr probe");
+    CUDA_TRY(cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kSmemTotal)), "smem attr bench");
     CUDA_TRY(cudaMalloc(&d.status, sizeof(int)), "status alloc");
     CUDA_TRY(cudaMemset(d.status, 0, sizeof(int)), "status memset");
     d.attrs_set = true;
@@ -399,14 +401,27 @@ int nerfb200_debug_timeline(int64_t* host_out, int64_t n_values) {
   return 0;
 }
 
-int nerfb200_debug_gemm(const float* a, const void* packed, int32_t slice, float* d, void* stream) {
+int nerfb200_debug_mma_bench(int64_t* out_dev, int32_t n_ctas, int32_t reps, void* stream) {
+  if (!out_dev || n_ctas < 1 || reps < 1) return fail(NERFB200_EINVAL, "debug_mma_bench: bad argument%s");
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  mma_bench_kernel<<<n_ctas, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<long long*>(out_dev), reps, di->status);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "debug_mma_bench launch");
+  return 0;
+}
+
+int nerfb200_debug_gemm(const float* a, const void* packed, int32_t half_slice, int32_t mode, float* d,
+                        void* stream) {
   if (!a || !packed || !d) return fail(NERFB200_EINVAL, "debug_gemm: NULL argument%s");
-  if (slice < 0 || slice >= kNumSlices256 + kNumSlices128) return fail(NERFB200_EINVAL, "debug_gemm: bad slice%s");
+  if (half_slice < 0 || half_slice >= kNumHs) return fail(NERFB200_EINVAL, "debug_gemm: bad half-slice%s");
   DeviceInfo* di = nullptr;
   int rc = device_info(&di);
   if (rc) return rc;
   gemm_probe_kernel<<<1, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(
-      a, static_cast<const uint8_t*>(packed), slice, d, di->status);
+      a, static_cast<const uint8_t*>(packed), half_slice, mode, d, di->status);
   g_launches++;
   CUDA_TRY(cudaGetLastError(), "debug_gemm launch");
   return 0;

@@ -1,18 +1,28 @@
 // The NeRF MLP (models/nerf.py:83-124) as a warp-specialised tcgen05 tile engine.
 //
-// One CTA owns one 128-row tile of samples at a time:
-//   * warps 0..7  "epilogue" warps.  Warp w reads TMEM lane quadrant (w & 3) and column
-//                 half (w >> 2).  They write the fp16 A operand (encoded input, then
-//                 each layer's activations) into shared memory in the UMMA K-major
-//                 SWIZZLE_128B layout, and do bias/ReLU/heads on the fp32 accumulator.
-//   * warp 8      weight producer: streams the packed K-slices (layout.h) of the
-//                 network through a 4-stage 32 KiB ring with cp.async.bulk + mbarriers.
-//                 It runs ahead of the MMA by up to one full layer.
-//   * warp 9      MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16)
-//                 with the accumulator in TMEM, tcgen05.commit frees ring stages and
-//                 signals "accumulator ready".
-// Layer l+1's MMA reads the A tile that layer l's epilogue wrote, so MMA and epilogue of
-// one tile alternate; the producer keeps the next layer's weights resident meanwhile.
+// One CTA owns one 128-row tile of samples at a time.  The hidden activations never touch
+// shared memory: each layer's fp32 accumulator lives in TMEM, the epilogue warps read it
+// (tcgen05.ld), apply bias / ReLU, convert to fp16 and write it back to TMEM (tcgen05.st) as
+// the A operand of the next layer's tcgen05.mma (A-from-TMEM form).  Shared memory only holds
+// the encoded-input tile and the weight ring, so its bandwidth is spent on weights alone.
+//
+//   TMEM (512 columns x 128 lanes, lane = tile row):
+//     [  0,128) D0   accumulator, output features   0..127  ("n0")
+//     [128,256) D1   accumulator, output features 128..255  ("n1")
+//     [256,384) A0   fp16 activations (2 per column) read by odd layers
+//     [384,512) A1   fp16 activations                read by even layers
+//   warps 0..3  epilogue of D0 (warp w owns TMEM lanes 32w..32w+31): writes A' columns 0..127
+//   warps 4..7  epilogue of D1:                                      writes A' columns 128..255
+//   warp 8      weight producer: streams 16 KiB half-slices (layout.h) through a 12-stage ring
+//               with cp.async.bulk + mbarriers, running up to 1.5 layers ahead
+//   warp 9      MMA issuer (one thread): tcgen05.mma M=128, N=128, K=16
+//
+// Pipelining inside a tile: layer l is issued as  n0:[k0 k1 | k2 k3]  n1:[k0 k1 k2 k3].
+// The n0 half of layer l+1 needs only A' columns 0..127 for its k0,k1 blocks, i.e. the D0
+// epilogue of layer l, which ran while the tensor core was busy with n1 of layer l.  So the
+// tensor core only waits for the D1 epilogue (before k2 of n0), and the D0 epilogue is free.
+// Double-buffering A (A0/A1) lets an epilogue write layer l+1's input while layer l's n1 MMAs
+// still read layer l's input.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -26,15 +36,15 @@ constexpr int kEpiThreads = kEpiWarps * 32;   // 256
 constexpr int kProducerWarp = 8;
 constexpr int kMmaWarp = 9;
 constexpr int kThreads = 320;
-constexpr int kStages = 4;
-constexpr int kTmemCols = 256;
+constexpr int kStages = 12;
+constexpr int kTmemCols = 512;
+constexpr uint32_t kTmemD0 = 0, kTmemD1 = 128, kTmemA0 = 256, kTmemA1 = 384;
 
-constexpr uint32_t kSmemA = 0;                       // [4][128 x 64] fp16  64 KiB
-constexpr uint32_t kSmemEnc = 65536;                 // [128 x 64] fp16     16 KiB
-constexpr uint32_t kSmemRing = 81920;                // 4 x 32 KiB
-constexpr uint32_t kSmemScratch = 212992;            // barriers + per-group scratch
+constexpr uint32_t kSmemEnc = 0;                     // [128 x 64] fp16     16 KiB
+constexpr uint32_t kSmemRing = 16384;                // 12 x 16 KiB
+constexpr uint32_t kSmemScratch = kSmemRing + kStages * kHsBytes;   // 212992
 constexpr uint32_t kSmemTotal = 232448;              // 227 KiB (max opt-in)
-constexpr uint32_t kScratchBytes = kSmemTotal - kSmemScratch;   // 19456
+constexpr uint32_t kScratchBytes = kSmemTotal - kSmemScratch;       // 19456
 
 constexpr int kLayersFull = 10;       // L1..L8, final, dir
 constexpr int kLayersSigma = 8;       // L1..L8
@@ -42,8 +52,8 @@ constexpr int kLayersSigma = 8;       // L1..L8
 struct Barriers {
   uint64_t full[kStages];
   uint64_t empty[kStages];
-  uint64_t a_ready;
-  uint64_t d_ready;
+  uint64_t a_ready[2];     // epilogue half h -> MMA : "A' columns of half h written, D_h drained"
+  uint64_t d_ready[2];     // MMA -> epilogue        : "accumulator D_h complete"
   uint32_t tmem_base;
   uint32_t pad[3];
 };
@@ -81,8 +91,10 @@ __device__ __forceinline__ bool engine_setup(uint8_t* smem, Barriers* bars) {
       mbar_init(smem_u32(&bars->full[i]), 1);
       mbar_init(smem_u32(&bars->empty[i]), 1);
     }
-    mbar_init(smem_u32(&bars->a_ready), kEpiWarps);
-    mbar_init(smem_u32(&bars->d_ready), 1);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(smem_u32(&bars->a_ready[h]), kEpiWarps / 2);
+      mbar_init(smem_u32(&bars->d_ready[h]), 1);
+    }
     fence_mbar_init();
   }
   if (warp == kMmaWarp) {
@@ -104,81 +116,85 @@ __device__ __forceinline__ void engine_teardown(Barriers* bars) {
 }
 
 // --------------------------------------------------------------- producer
-// One thread.  Streams the slices of one network for one tile.
+// One thread.  Streams the half-slices of one network for one tile, in consumption order.
 __device__ __forceinline__ void produce_tile(RingState& rs, uint8_t* smem, Barriers* bars,
                                              const uint8_t* __restrict__ blob, bool sigma_only,
                                              bool dir_slice) {
-  const int n256 = sigma_only ? kNumSlicesSigmaOnly : kNumSlices256;
-  for (int i = 0; i < n256; ++i) {
+  const int n = sigma_only ? kNumHsSigmaOnly : (dir_slice ? kNumHs : kNumHs - 1);
+  for (int i = 0; i < n; ++i) {
     mbar_wait(smem_u32(&bars->empty[rs.stage]), rs.phase ^ 1, 1);
     const uint32_t full = smem_u32(&bars->full[rs.stage]);
-    const uint32_t dst = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
-    mbar_arrive_expect_tx(full, kSliceBytes256);
-    const uint8_t* src = blob + static_cast<size_t>(i) * kSliceBytes256;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) bulk_g2s(dst + c * 8192, src + c * 8192, 8192, full);
+    const uint32_t dst = smem_u32(smem + kSmemRing + rs.stage * kHsBytes);
+    mbar_arrive_expect_tx(full, kHsBytes);
+    const uint8_t* src = blob + static_cast<size_t>(i) * kHsBytes;
+    bulk_g2s(dst, src, 8192, full);
+    bulk_g2s(dst + 8192, src + 8192, 8192, full);
     rs.advance();
-  }
-  if (!sigma_only) {
-    const int n128 = dir_slice ? 5 : 4;
-    for (int i = 0; i < n128; ++i) {
-      mbar_wait(smem_u32(&bars->empty[rs.stage]), rs.phase ^ 1, 2);
-      const uint32_t full = smem_u32(&bars->full[rs.stage]);
-      const uint32_t dst = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
-      mbar_arrive_expect_tx(full, kSliceBytes128);
-      const uint8_t* src = blob + kOffDir + static_cast<size_t>(i) * kSliceBytes128;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) bulk_g2s(dst + c * 8192, src + c * 8192, 8192, full);
-      rs.advance();
-    }
   }
 }
 
 // -------------------------------------------------------------------- MMA
-// One thread.  Issues all MMAs of one tile.
-__device__ __forceinline__ void mma_tile(RingState& rs, uint32_t& a_phase, uint8_t* smem,
+// One thread.  Issues all MMAs of one tile (schedule in the header comment).
+__device__ __forceinline__ void mma_tile(RingState& rs, uint32_t (&a_phase)[2], uint8_t* smem,
                                          Barriers* bars, bool sigma_only, bool dir_slice,
-                                         uint32_t flags = 0, Timeline* tl = nullptr) {
-  const uint32_t tmem_d = bars->tmem_base;
-  const uint32_t a_base = smem_u32(smem + kSmemA);
+                                         Timeline* tl = nullptr) {
+  const uint32_t tmem = bars->tmem_base;
   const uint32_t enc_base = smem_u32(smem + kSmemEnc);
+  const uint32_t idesc = make_idesc_f16(128);
   const int n_layers = sigma_only ? kLayersSigma : kLayersFull;
   for (int l = 0; l < n_layers; ++l) {
-    mbar_wait(smem_u32(&bars->a_ready), a_phase, 3);
-    a_phase ^= 1;
-    tc_fence_after();
-    tl_mark(tl, 1, 100 + l);
-    const int n_slices = (l == 0) ? 1 : (l == 4) ? 5 : (l == 9 && dir_slice) ? 5 : 4;
-    const uint32_t idesc = (l == 9) ? make_idesc_f16(128) : make_idesc_f16(256);
-    for (int s = 0; s < n_slices; ++s) {
-      const bool from_enc = (l == 0) || (l == 4 && s == 0) || (l == 9 && s == 4);
-      const int kb = (l == 4) ? s - 1 : s;
-      const uint32_t a_addr = from_enc ? enc_base : a_base + kb * 16384;
-      const uint32_t b_addr = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
-      mbar_wait(smem_u32(&bars->full[rs.stage]), rs.phase, 4);
-      tc_fence_after();
-      const uint64_t adesc = make_desc_sw128(a_addr);
-      const uint64_t bdesc = make_desc_sw128(b_addr);
-      if ((flags & 1u) && l != 9) {
-        // experiment: two N=128 MMAs per K step (B rows 128..255 start 16 KiB into the slice)
-        const uint32_t id128 = make_idesc_f16(128);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          umma_f16(tmem_d, adesc + 2 * j, bdesc + 2 * j, id128, (s | j) != 0 ? 1u : 0u);
-          umma_f16(tmem_d + 128, adesc + 2 * j, bdesc + 1024 + 2 * j, id128, (s | j) != 0 ? 1u : 0u);
+    const bool has_enc = (l == 0) || (l == 4);
+    const int n_k = (l == 0) ? 0 : 4;                       // hidden K blocks
+    const bool has_dir = (l == 9) && dir_slice;
+    const uint32_t a_tmem = tmem + ((l & 1) ? kTmemA0 : kTmemA1);   // layer l reads A0 if l odd
+    const int n_halves = (l == 9) ? 1 : 2;
+    for (int nh = 0; nh < n_halves; ++nh) {
+      const uint32_t d_tmem = tmem + (nh ? kTmemD1 : kTmemD0);
+      const int n_items = (has_enc ? 1 : 0) + n_k + (has_dir ? 1 : 0);
+      for (int it = 0; it < n_items; ++it) {
+        const bool from_enc = (has_enc && it == 0) || (has_dir && it == n_items - 1);
+        const int kb = it - (has_enc ? 1 : 0);              // hidden K block index when !from_enc
+        if (nh == 0) {
+          // operand / accumulator readiness (see header): half 0 before the first MMA of the
+          // layer, half 1 before the first MMA that reads A' columns 128..255 (or, layer 0, the
+          // ENC tile both halves wrote at tile start).
+          if (it == 0) {
+            mbar_wait(smem_u32(&bars->a_ready[0]), a_phase[0], 3);
+            a_phase[0] ^= 1;
+            if (l == 0) {
+              mbar_wait(smem_u32(&bars->a_ready[1]), a_phase[1], 3);
+              a_phase[1] ^= 1;
+            }
+            tc_fence_after();
+            tl_mark(tl, 1, 100 + l);
+          }
+          if (l != 0 && !from_enc && kb == 2) {
+            mbar_wait(smem_u32(&bars->a_ready[1]), a_phase[1], 3);
+            a_phase[1] ^= 1;
+            tc_fence_after();
+            tl_mark(tl, 1, 300 + l);
+          }
         }
-      } else {
+        const uint32_t b_addr = smem_u32(smem + kSmemRing + rs.stage * kHsBytes);
+        mbar_wait(smem_u32(&bars->full[rs.stage]), rs.phase, 4);
+        tc_fence_after();
+        const uint64_t bdesc = make_desc_sw128(b_addr);
+        if (from_enc) {
+          const uint64_t adesc = make_desc_sw128(enc_base);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in the addr field
-          umma_f16(tmem_d, adesc + 2 * j, bdesc + 2 * j, idesc, (s | j) != 0 ? 1u : 0u);
+          for (int j = 0; j < 4; ++j)   // +32 B per K=16 step inside the 128-byte swizzle row
+            umma_f16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (it | j) != 0 ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)   // A: 64 K-values per block = 32 columns, 8 per K=16 step
+            umma_f16_ts(d_tmem, a_tmem + kb * 32 + j * 8, bdesc + 2 * j, idesc, (it | j) != 0 ? 1u : 0u);
         }
+        umma_commit(smem_u32(&bars->empty[rs.stage]));
+        rs.advance();
       }
-      umma_commit(smem_u32(&bars->empty[rs.stage]));
-      rs.advance();
+      umma_commit(smem_u32(&bars->d_ready[nh]));
+      tl_mark(tl, 1, 200 + 10 * nh + l);
     }
-    umma_commit(smem_u32(&bars->d_ready));
-    tl_mark(tl, 1, 200 + l);
   }
 }
 
@@ -188,9 +204,9 @@ struct EpiCtx {
   Barriers* bars;
   const float* __restrict__ f32;   // fp32 region of the current network image
   uint32_t tmem_row;               // tmem base + (lane quadrant << 16)
-  uint32_t d_phase;
+  uint32_t d_count[2];             // completed phases of d_ready[0|1] so far (static schedule)
   int row;                         // 0..127 : tile row == TMEM lane
-  int half;                        // 0/1    : column half
+  int half;                        // 0/1    : which accumulator half this warp drains
   int lane;
   Timeline* tl;                    // non-null only for the one traced thread
 };
@@ -198,30 +214,24 @@ struct EpiCtx {
 __device__ __forceinline__ void epi_bar() {   // all 256 epilogue threads
   asm volatile("bar.sync 1, 256;" ::: "memory");
 }
-__device__ __forceinline__ void epi_signal_a(EpiCtx& c) {
-  fence_proxy_async();
+// `smem_written`: the ENC tile was written with generic stores (needs the async-proxy fence).
+__device__ __forceinline__ void epi_signal_a(EpiCtx& c, bool smem_written) {
+  if (smem_written) fence_proxy_async();
+  tmem_st_wait();
   tc_fence_before();
   __syncwarp();
-  if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_ready));
+  if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_ready[c.half]));
   tl_mark(c.tl, 0, 6);
 }
-__device__ __forceinline__ void epi_wait_d(EpiCtx& c) {
-  mbar_wait(smem_u32(&c.bars->d_ready), c.d_phase, 5);
-  c.d_phase ^= 1;
+// Wait for accumulator `which` of the current layer; every epilogue thread advances both
+// counters with the static schedule (`also_other`: the other accumulator completes this layer too).
+__device__ __forceinline__ void epi_wait_d(EpiCtx& c, int which, bool also_other) {
+  mbar_wait(smem_u32(&c.bars->d_ready[which]), c.d_count[which] & 1u, 5);
+  c.d_count[which]++;
+  if (also_other) c.d_count[which ^ 1]++;
   tc_fence_after();
 }
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z,
-                                             uint32_t w) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w)
-               : "memory");
-}
-
-// Packed fp32x2 add (FADD2) and fp32x2 -> fp16x2 conversion with / without fused ReLU (F2FP.RELU).
 __device__ __forceinline__ void add_f32x2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
   asm("{ .reg .b64 a, b, d; mov.b64 a, {%2,%3}; mov.b64 b, {%4,%5}; add.rn.f32x2 d, a, b; mov.b64 {%0,%1}, d; }"
       : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
@@ -237,12 +247,13 @@ __device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
   return d;
 }
 
-// One 32-column chunk of a hidden-layer epilogue: v = act(acc + bias) -> fp16 A operand of the
-// next layer (4 x 16-byte stores into the SWIZZLE_128B tile); optionally the sigma-head dot.
+// One 32-column chunk of a hidden-layer epilogue: v = act(acc + bias) -> 16 packed fp16x2
+// columns of the next layer's A operand in TMEM; optionally the sigma-head dot product.
 template <bool kRelu, bool kSigma, bool kStore>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float4 (&b)[8], int n0,
-                                          uint32_t a_row_base, uint32_t rsw,
-                                          const float* __restrict__ wsig, float& sig_acc) {
+                                          uint32_t a_dst, const float* __restrict__ wsig,
+                                          float& sig_acc) {
+  uint32_t h[16];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float v[8];
@@ -250,8 +261,8 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float4 
     add_f32x2(v[2], v[3], __uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]), b[2 * j].z, b[2 * j].w);
     add_f32x2(v[4], v[5], __uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]), b[2 * j + 1].x, b[2 * j + 1].y);
     add_f32x2(v[6], v[7], __uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]), b[2 * j + 1].z, b[2 * j + 1].w);
-    const int n = n0 + 8 * j;
     if (kSigma) {
+      const int n = n0 + 8 * j;
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(wsig + n));
       const float4 w1 = __ldg(reinterpret_cast<const float4*>(wsig + n + 4));
       sig_acc = fmaf(fmaxf(v[0], 0.f), w0.x, sig_acc);
@@ -264,19 +275,16 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float4 
       sig_acc = fmaf(fmaxf(v[7], 0.f), w1.w, sig_acc);
     }
     if (kStore) {
-      uint32_t h0, h1, h2, h3;
       if (kRelu) {
-        h0 = cvt_f16x2_relu(v[0], v[1]); h1 = cvt_f16x2_relu(v[2], v[3]);
-        h2 = cvt_f16x2_relu(v[4], v[5]); h3 = cvt_f16x2_relu(v[6], v[7]);
+        h[4 * j + 0] = cvt_f16x2_relu(v[0], v[1]); h[4 * j + 1] = cvt_f16x2_relu(v[2], v[3]);
+        h[4 * j + 2] = cvt_f16x2_relu(v[4], v[5]); h[4 * j + 3] = cvt_f16x2_relu(v[6], v[7]);
       } else {
-        h0 = cvt_f16x2(v[0], v[1]); h1 = cvt_f16x2(v[2], v[3]);
-        h2 = cvt_f16x2(v[4], v[5]); h3 = cvt_f16x2(v[6], v[7]);
+        h[4 * j + 0] = cvt_f16x2(v[0], v[1]); h[4 * j + 1] = cvt_f16x2(v[2], v[3]);
+        h[4 * j + 2] = cvt_f16x2(v[4], v[5]); h[4 * j + 3] = cvt_f16x2(v[6], v[7]);
       }
-      const uint32_t kb = static_cast<uint32_t>(n) >> 6;
-      const uint32_t chunk = (static_cast<uint32_t>(n) & 63u) >> 3;
-      st_shared_v4(a_row_base + kb * 16384u + ((chunk ^ rsw) << 4), h0, h1, h2, h3);
     }
   }
+  if (kStore) tmem_st16(a_dst, h);
 }
 
 __device__ __forceinline__ void ld_bias32(const float* __restrict__ bias, int n0, float4 (&b)[8]) {
@@ -284,46 +292,47 @@ __device__ __forceinline__ void ld_bias32(const float* __restrict__ bias, int n0
   for (int i = 0; i < 8; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias + n0) + i);
 }
 
-// Hidden-layer epilogue over this thread's 128 columns.  The bias of the first two chunks is
-// fetched BEFORE waiting for the accumulator, so its latency hides behind the MMA.
+// Hidden-layer epilogue of accumulator half c.half (128 columns) for layer `l`.  The bias of the
+// first two chunks is fetched BEFORE waiting for the accumulator, so its latency hides behind the MMA.
 template <bool kRelu, bool kSigma, bool kStore>
-__device__ __forceinline__ void epi_hidden(EpiCtx& c, const float* __restrict__ bias,
+__device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* __restrict__ bias,
                                            const float* __restrict__ wsig, float& sig_acc) {
-  const uint32_t a_row_base = smem_u32(c.smem + kSmemA) + static_cast<uint32_t>(c.row) * 128u;
-  const uint32_t rsw = static_cast<uint32_t>(c.row & 7);
   const int nb = c.half * 128;
+  // layer l writes the operand of layer l+1, which reads A0 if (l+1) is odd, else A1
+  const uint32_t a_dst = c.tmem_row + (((l + 1) & 1) ? kTmemA0 : kTmemA1) + c.half * 64;
+  const uint32_t d_src = c.tmem_row + nb;            // D0 at column 0, D1 at column 128
   float4 b0[8], b1[8];
   ld_bias32(bias, nb, b0);
   ld_bias32(bias, nb + 32, b1);
   tl_mark(c.tl, 0, 1);
-  epi_wait_d(c);
+  epi_wait_d(c, c.half, true);
   tl_mark(c.tl, 0, 2);
   uint32_t r0[32], r1[32];
-  tmem_ld32(c.tmem_row + nb, r0);
-  tmem_ld32(c.tmem_row + nb + 32, r1);
+  tmem_ld32(d_src, r0);
+  tmem_ld32(d_src + 32, r1);
   tmem_ld_wait();
   tl_mark(c.tl, 0, 3);
-  epi_chunk<kRelu, kSigma, kStore>(r0, b0, nb, a_row_base, rsw, wsig, sig_acc);
+  epi_chunk<kRelu, kSigma, kStore>(r0, b0, nb, a_dst, wsig, sig_acc);
   ld_bias32(bias, nb + 64, b0);
-  tmem_ld32(c.tmem_row + nb + 64, r0);
-  epi_chunk<kRelu, kSigma, kStore>(r1, b1, nb + 32, a_row_base, rsw, wsig, sig_acc);
+  tmem_ld32(d_src + 64, r0);
+  epi_chunk<kRelu, kSigma, kStore>(r1, b1, nb + 32, a_dst + 16, wsig, sig_acc);
   ld_bias32(bias, nb + 96, b1);
-  tmem_ld32(c.tmem_row + nb + 96, r1);
+  tmem_ld32(d_src + 96, r1);
   tmem_ld_wait();
   tl_mark(c.tl, 0, 4);
-  epi_chunk<kRelu, kSigma, kStore>(r0, b0, nb + 64, a_row_base, rsw, wsig, sig_acc);
-  epi_chunk<kRelu, kSigma, kStore>(r1, b1, nb + 96, a_row_base, rsw, wsig, sig_acc);
+  epi_chunk<kRelu, kSigma, kStore>(r0, b0, nb + 64, a_dst + 32, wsig, sig_acc);
+  epi_chunk<kRelu, kSigma, kStore>(r1, b1, nb + 96, a_dst + 48, wsig, sig_acc);
   tl_mark(c.tl, 0, 5);
 }
 
-// dir_encoding epilogue (N=128; this thread's 64 columns) fused with the rgb head
+// dir_encoding epilogue (N=128 accumulator D0; this thread's 64 columns) fused with the rgb head
 // (models/nerf.py:119-120): d = relu(acc + dbias[n]); rgb_acc[c] += d * w_rgb[c][n].
 // dbias is either the per-ray vector (bias + direction part, shared memory) or b_dir (global).
 __device__ __forceinline__ void epi_dir(EpiCtx& c, const float* dbias, const float* __restrict__ wrgb,
                                         float (&rgb_acc)[3]) {
   uint32_t r[2][32];
-  tmem_ld32(c.tmem_row + c.half * 64, r[0]);
-  tmem_ld32(c.tmem_row + c.half * 64 + 32, r[1]);
+  tmem_ld32(c.tmem_row + kTmemD0 + c.half * 64, r[0]);
+  tmem_ld32(c.tmem_row + kTmemD0 + c.half * 64 + 32, r[1]);
   tmem_ld_wait();
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
@@ -363,19 +372,19 @@ __device__ __forceinline__ void epi_run_tile(EpiCtx& c, bool sigma_only, const f
   sig_part = 0.f;
   rgb_part[0] = rgb_part[1] = rgb_part[2] = 0.f;
   float dummy = 0.f;
-  epi_signal_a(c);
+  epi_signal_a(c, true);
   for (int l = 0; l < 7; ++l) {
-    epi_hidden<true, false, true>(c, bias + l * 256, nullptr, dummy);
-    epi_signal_a(c);
+    epi_hidden<true, false, true>(c, l, bias + l * 256, nullptr, dummy);
+    epi_signal_a(c, false);
   }
   if (sigma_only) {
-    epi_hidden<true, true, false>(c, bias + 7 * 256, wsig, sig_part);
+    epi_hidden<true, true, false>(c, 7, bias + 7 * 256, wsig, sig_part);
     return;   // next signal comes with the next tile's ENC write
   }
-  epi_hidden<true, true, true>(c, bias + 7 * 256, wsig, sig_part);
-  epi_signal_a(c);
+  epi_hidden<true, true, true>(c, 7, bias + 7 * 256, wsig, sig_part);
+  epi_signal_a(c, false);
   // xyz_encoding_final: bias only, no activation (models/nerf.py:116)
-  epi_hidden<false, false, true>(c, bias + 8 * 256, nullptr, dummy);
+  epi_hidden<false, false, true>(c, 8, bias + 8 * 256, nullptr, dummy);
   if (dir_row != nullptr) {
     // ENC tile is dead after layer 5: reuse it for the embedded direction (cols 27..63 zero)
     uint8_t* enc = c.smem + kSmemEnc;
@@ -385,8 +394,8 @@ __device__ __forceinline__ void epi_run_tile(EpiCtx& c, bool sigma_only, const f
       *reinterpret_cast<__half*>(enc + sw128_off(c.row, k)) = __float2half_rn(v);
     }
   }
-  epi_signal_a(c);
-  epi_wait_d(c);
+  epi_signal_a(c, dir_row != nullptr);
+  epi_wait_d(c, 0, false);           // dir layer: only D0
   epi_dir(c, dbias != nullptr ? dbias : (bias + 9 * 256), c.f32 + kF32WRgb, rgb_part);
 }
 

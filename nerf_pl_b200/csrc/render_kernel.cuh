@@ -269,11 +269,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
   } else if (warp == kMmaWarp) {
     if (lane == 0) {
       RingState rs;
-      uint32_t a_phase = 0;
+      uint32_t a_phase[2] = {0, 0};
       Timeline tlm{(blockIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
       for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        for (int t = 0; t < tiles_c; ++t) mma_tile(rs, a_phase, smem, bars, coarse_sigma_only, false, p.flags, &tlm);
-        for (int t = 0; t < tiles_f; ++t) mma_tile(rs, a_phase, smem, bars, false, false, p.flags, &tlm);
+        for (int t = 0; t < tiles_c; ++t) mma_tile(rs, a_phase, smem, bars, coarse_sigma_only, false, &tlm);
+        for (int t = 0; t < tiles_f; ++t) mma_tile(rs, a_phase, smem, bars, false, false, &tlm);
       }
     }
   } else {
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
     c.row = (warp & 3) * 32 + lane;
     c.half = warp >> 2;
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    c.d_phase = 0;
+    c.d_count[0] = c.d_count[1] = 0;
     Timeline tle{(blockIdx.x == 0 && threadIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
     c.tl = &tle;
     const int t = threadIdx.x;   // 0..255

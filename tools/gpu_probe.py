@@ -47,26 +47,25 @@ def step_gemm():
     params = nb.nerf_parameters(m)
     a = torch.randn(128, 64, device="cuda")
     a16 = a.half().float()
+    # half-slice -> (weight, row offset, k offset, valid k)   (csrc/layout.h)
     cases = {
-        0: (params[0], 0, 63, 256),
-        5: (params[4], 0, 64, 256),       # xyz_encoding_3 k-block 0 (slice 1+4*1+0)
-        8: (params[4], 192, 64, 256),     # xyz_encoding_3 k-block 3
-        13: (params[8], 0, 63, 256),
-        15: (params[8], 63 + 64, 64, 256),
-        34: (params[18], 0, 64, 128),
-        38: (params[18], 256, 27, 128),
+        0: (params[0], 0, 0, 63), 1: (params[0], 128, 0, 63),
+        2: (params[2], 0, 0, 64), 9: (params[2], 128, 192, 64),
+        26: (params[8], 0, 0, 63), 28: (params[8], 0, 63 + 64, 64), 35: (params[8], 128, 63 + 192, 64),
+        60: (params[16], 0, 0, 64), 68: (params[18], 0, 0, 64), 72: (params[18], 0, 256, 27),
     }
     ok = True
-    for sl, (W, koff, kval, N) in cases.items():
-        d = torch.zeros(128, N, device="cuda")
-        rc = lib.nerfb200_debug_gemm(a.data_ptr(), blob.data_ptr(), sl, d.data_ptr(), None)
-        torch.cuda.synchronize()
-        Wk = torch.zeros(N, 64, device="cuda")
-        Wk[:, :kval] = W[:, koff:koff + kval].detach().half().float()
-        ref = a16 @ Wk.t()
-        err = (d - ref).abs().max().item()
-        print(f"gemm slice {sl:2d} N={N} rc={rc} max_abs_err={err:.3e} ref_absmax={ref.abs().max().item():.3f}")
-        ok &= err < 1e-3
+    for mode in (0, 1):
+        for hs, (W, roff, koff, kval) in cases.items():
+            d = torch.zeros(128, 128, device="cuda")
+            rc = lib.nerfb200_debug_gemm(a.data_ptr(), blob.data_ptr(), hs, mode, d.data_ptr(), None)
+            torch.cuda.synchronize()
+            Wk = torch.zeros(128, 64, device="cuda")
+            Wk[:, :kval] = W[roff:roff + 128, koff:koff + kval].detach().half().float()
+            ref = a16 @ Wk.t()
+            err = (d - ref).abs().max().item()
+            print(f"gemm mode {mode} hs {hs:2d} rc={rc} max_abs_err={err:.3e} ref_absmax={ref.abs().max().item():.3f}")
+            ok &= err < 1e-3
     print("GEMM_OK" if ok else "GEMM_FAIL")
 
 
@@ -132,6 +131,23 @@ def step_speed():
     print("SPEED_DONE")
 
 
+def step_mmabench():
+    lib = _lib.load()
+    names = ["SS N=256", "SS N=128", "TS N=128", "TS N=256", "TS N=128 alt D"]
+    for n_ctas in (1, 148):
+        out = torch.zeros(n_ctas, 8, dtype=torch.long, device="cuda")
+        reps = 16
+        for _ in range(2):
+            rc = lib.nerfb200_debug_mma_bench(out.data_ptr(), n_ctas, reps, None)
+        torch.cuda.synchronize()
+        o = out.cpu().numpy()
+        for v, nm in enumerate(names):
+            cyc = o[:, v].astype(float)
+            per = cyc / (reps * 16)
+            print(f"mmabench ctas={n_ctas:3d} {nm:16s} rc={rc} cycles/MMA median {sorted(per)[len(per) // 2]:.1f} min {per.min():.1f} max {per.max():.1f}")
+    print("MMABENCH_DONE")
+
+
 def step_timeline():
     import numpy as np
     os.environ["NERFB200_FLAGS"] = str(int(os.environ.get("NERFB200_FLAGS", "0")) | 2)
@@ -162,5 +178,5 @@ def step_timeline():
 
 if __name__ == "__main__":
     t0 = time.time()
-    {"gemm": step_gemm, "mlp": step_mlp, "render": step_render, "speed": step_speed, "timeline": step_timeline}[sys.argv[1]]()
+    {"gemm": step_gemm, "mlp": step_mlp, "render": step_render, "speed": step_speed, "timeline": step_timeline, "mmabench": step_mmabench}[sys.argv[1]]()
     print(f"[{sys.argv[1]}] {time.time() - t0:.1f}s")
