@@ -136,11 +136,11 @@ int nerfb200_composite(const float* sigmas, const float* rgbs, const float* z_va
  * Number of kernels this library has launched on the calling process so far (all entry
  * points).  bench.py reports the delta as `gpu_launches`. */
 int64_t nerfb200_launch_count(void);
-/* One [128 x 64] weight half-slice of a packed image (csrc/layout.h, index 0..72) against a
- * (128,64) fp32 A tile through the tcgen05 engine: d (128,128).  mode 0 stages A in shared
- * memory (SS MMA), mode 1 in tensor memory (TS MMA).  Unit-test hook for the operand layouts;
- * not part of the reference API. */
-int nerfb200_debug_gemm(const float* a, const void* packed, int32_t half_slice, int32_t mode, float* d,
+/* One K=64 weight slice of a packed image (csrc/layout.h) against a (128,64) fp32 A tile
+ * through the tcgen05 engine: d (128, N), N = 256 for slices 0..33 and 128 for 34..38.
+ * mode 0 stages A in shared memory (SS MMA), mode 1 in tensor memory (TS MMA).  Unit-test hook
+ * for the operand layouts; not part of the reference API. */
+int nerfb200_debug_gemm(const float* a, const void* packed, int32_t slice, int32_t mode, float* d,
                         void* stream);
 /* Raw tcgen05.mma issue-rate microbenchmark (timing only): out_dev (n_ctas, 8) int64 device
  * buffer; column v = SM cycles for reps x 16 MMAs of variant v (csrc/aux_kernels.cuh). */

@@ -13,35 +13,38 @@ struct PackParams {
   uint8_t* out;
 };
 
-// One thread per fp16 element of the half-slice region, then the fp32 tail.
+// One thread per fp16 element of the slice region, then the fp32 tail.
 __global__ void pack_weights_kernel(const PackParams pp) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long n_half = kHalfRegionBytes / 2;
   if (idx < n_half) {
-    const int hs = static_cast<int>(idx / (128 * 64));
-    const int rem = static_cast<int>(idx % (128 * 64));
-    const int n = rem / 64, k = rem % 64;
-    // half-slice -> layer l, N-half nh, item (layout.h)
-    int l = 9;
-    while (hs < hs_layer_start(l)) --l;
-    const int per_half = hs_items_per_half(l);
-    const int within = hs - hs_layer_start(l);
-    const int nh = within / per_half, it = within % per_half;
-    // (weight tensor, in_features, input-feature offset, valid k) of this item
-    const float* W; int ld, koff, kvalid;
-    if (l == 0) { W = pp.p[0]; ld = 63; koff = 0; kvalid = 63; }
-    else if (l == 4) {
-      W = pp.p[8]; ld = 319;
-      if (it == 0) { koff = 0; kvalid = 63; } else { koff = 63 + (it - 1) * 64; kvalid = 64; }
-    } else if (l <= 7) { W = pp.p[2 * l]; ld = 256; koff = it * 64; kvalid = 64; }
-    else if (l == 8) { W = pp.p[16]; ld = 256; koff = it * 64; kvalid = 64; }
-    else {
-      W = pp.p[18]; ld = 283;
-      if (it < 4) { koff = it * 64; kvalid = 64; } else { koff = 256; kvalid = 27; }
+    int slice, n, k, N;
+    const long long n256 = static_cast<long long>(kNumSlices256) * 256 * 64;
+    if (idx < n256) {
+      slice = static_cast<int>(idx / (256 * 64));
+      const int rem = static_cast<int>(idx % (256 * 64));
+      n = rem / 64; k = rem % 64; N = 256;
+    } else {
+      const long long j = idx - n256;
+      slice = kNumSlices256 + static_cast<int>(j / (128 * 64));
+      const int rem = static_cast<int>(j % (128 * 64));
+      n = rem / 64; k = rem % 64; N = 128;
     }
-    const int row = nh * 128 + n;
-    const float v = (k < kvalid) ? W[static_cast<long long>(row) * ld + koff + k] : 0.f;
-    *reinterpret_cast<__half*>(pp.out + static_cast<size_t>(hs) * kHsBytes + sw128_off(n, k)) = __float2half_rn(v);
+    // slice -> (weight tensor, input-feature offset, in_features, valid k)
+    const float* W; int ld, koff, kvalid;
+    if (slice == 0) { W = pp.p[0]; ld = 63; koff = 0; kvalid = 63; }
+    else if (slice <= 12) { const int l = 1 + (slice - 1) / 4; W = pp.p[2 * l]; ld = 256; koff = ((slice - 1) % 4) * 64; kvalid = 64; }
+    else if (slice == 13) { W = pp.p[8]; ld = 319; koff = 0; kvalid = 63; }
+    else if (slice <= 17) { W = pp.p[8]; ld = 319; koff = 63 + (slice - 14) * 64; kvalid = 64; }
+    else if (slice <= 29) { const int l = 5 + (slice - 18) / 4; W = pp.p[2 * l]; ld = 256; koff = ((slice - 18) % 4) * 64; kvalid = 64; }
+    else if (slice <= 33) { W = pp.p[16]; ld = 256; koff = (slice - 30) * 64; kvalid = 64; }
+    else if (slice <= 37) { W = pp.p[18]; ld = 283; koff = (slice - 34) * 64; kvalid = 64; }
+    else { W = pp.p[18]; ld = 283; koff = 256; kvalid = 27; }
+    const float v = (k < kvalid) ? W[static_cast<long long>(n) * ld + koff + k] : 0.f;
+    const uint32_t base = (slice < kNumSlices256) ? slice * kSliceBytes256
+                                                   : kOffDir + (slice - kNumSlices256) * kSliceBytes128;
+    (void)N;
+    *reinterpret_cast<__half*>(pp.out + base + sw128_off(n, k)) = __float2half_rn(v);
     return;
   }
   const long long f = idx - n_half;
@@ -85,6 +88,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const MlpParam
     if (threadIdx.x == 0) atomicExch(p.status, 101);
     return;
   }
+  load_consts(smem, 0, p.net);
+  __syncthreads();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const long long n_tiles = (p.n + 127) / 128;
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const MlpParam
   } else if (warp == kMmaWarp) {
     if (lane == 0) {
       RingState rs;
-      uint32_t a_phase[2] = {0, 0};
+      uint32_t a_phase = 0;
       for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) mma_tile(rs, a_phase, smem, bars, so, !so);
     }
   } else {
@@ -106,9 +111,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const MlpParam
     c.row = (warp & 3) * 32 + lane;
     c.half = warp >> 2;
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    c.d_count[0] = c.d_count[1] = 0;
+    c.d_phase = 0;
     c.tl = nullptr;
     c.f32 = reinterpret_cast<const float*>(p.net + kHalfRegionBytes);
+    c.cst = consts_ptr(smem, 0);
     uint8_t* enc = smem + kSmemEnc;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long gi = tile * 128 + c.row;
@@ -129,14 +135,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const MlpParam
       }
       epi_bar();
       if (c.half == 0 && valid) {
-        const float sg = sc->sig_part[0][c.row] + sc->sig_part[1][c.row] + __ldg(c.f32 + kF32BSigma);
+        const float sg = sc->sig_part[0][c.row] + sc->sig_part[1][c.row] + c.cst[kF32BSigma];
         if (so) {
           p.out[gi] = sg;
         } else {
           float4 o;
-          o.x = sigmoid_ref(sc->rgb_part[0][0][c.row] + sc->rgb_part[1][0][c.row] + __ldg(c.f32 + kF32BRgb + 0));
-          o.y = sigmoid_ref(sc->rgb_part[0][1][c.row] + sc->rgb_part[1][1][c.row] + __ldg(c.f32 + kF32BRgb + 1));
-          o.z = sigmoid_ref(sc->rgb_part[0][2][c.row] + sc->rgb_part[1][2][c.row] + __ldg(c.f32 + kF32BRgb + 2));
+          o.x = sigmoid_ref(sc->rgb_part[0][0][c.row] + sc->rgb_part[1][0][c.row] + c.cst[kF32BRgb + 0]);
+          o.y = sigmoid_ref(sc->rgb_part[0][1][c.row] + sc->rgb_part[1][1][c.row] + c.cst[kF32BRgb + 1]);
+          o.z = sigmoid_ref(sc->rgb_part[0][2][c.row] + sc->rgb_part[1][2][c.row] + c.cst[kF32BRgb + 2]);
           o.w = sg;
           *reinterpret_cast<float4*>(p.out + gi * 4) = o;
         }
@@ -286,14 +292,14 @@ __global__ void composite_kernel(const float* __restrict__ sigmas, const float* 
   }
 }
 
-// ------------------------------------------------ diagnostics: one half-slice through the engine
-// d[128 x 128] = fp16(a[128 x 64]) . halfslice^T read back from TMEM unmodified.
-//   mode 0: A staged in the ENC shared-memory tile (SS MMA, as layer 0 / the skip part of layer 4)
-//   mode 1: A written to TMEM with tcgen05.st (TS MMA, as every hidden layer)
+// ------------------------------------------------ diagnostics: one K=64 slice through the engine
+// d[128 x N] = fp16(a[128 x 64]) . slice^T, N = 256 (slices 0..33) or 128 (34..38), read back from
+// TMEM unmodified.  mode 0: A staged in the ENC shared-memory tile (SS MMA, as layer 1 / the skip
+// part of layer 5); mode 1: A written to TMEM with tcgen05.st (TS MMA, as every hidden layer).
 // Isolates descriptor / swizzle / TMEM layouts from the layer protocol.
 __global__ void __launch_bounds__(kThreads, 1) gemm_probe_kernel(const float* __restrict__ a,
                                                                  const uint8_t* __restrict__ blob,
-                                                                 int hs, int mode, float* __restrict__ d,
+                                                                 int slice, int mode, float* __restrict__ d,
                                                                  int* status) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Scratch* sc = reinterpret_cast<Scratch*>(smem + kSmemScratch);
@@ -303,32 +309,34 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_probe_kernel(const float* __
     return;
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool wide = slice < kNumSlices256;
+  const int N = wide ? 256 : 128;
   if (warp == kProducerWarp) {
     if (lane == 0) {
       const uint32_t full = smem_u32(&bars->full[0]);
-      const uint8_t* src = blob + static_cast<size_t>(hs) * kHsBytes;
+      const uint32_t bytes = wide ? kSliceBytes256 : kSliceBytes128;
+      const uint8_t* src = wide ? blob + static_cast<size_t>(slice) * kSliceBytes256
+                                : blob + kOffDir + static_cast<size_t>(slice - kNumSlices256) * kSliceBytes128;
       mbar_wait(smem_u32(&bars->empty[0]), 1, 11);
-      mbar_arrive_expect_tx(full, kHsBytes);
-      bulk_g2s(smem_u32(smem + kSmemRing), src, 8192, full);
-      bulk_g2s(smem_u32(smem + kSmemRing) + 8192, src + 8192, 8192, full);
+      mbar_arrive_expect_tx(full, bytes);
+      for (uint32_t c = 0; c < bytes; c += 8192) bulk_g2s(smem_u32(smem + kSmemRing) + c, src + c, 8192, full);
     }
   } else if (warp == kMmaWarp) {
     if (lane == 0) {
-      mbar_wait(smem_u32(&bars->a_ready[0]), 0, 12);
-      mbar_wait(smem_u32(&bars->a_ready[1]), 0, 12);
+      mbar_wait(smem_u32(&bars->a_ready), 0, 12);
       tc_fence_after();
       mbar_wait(smem_u32(&bars->full[0]), 0, 13);
       tc_fence_after();
       const uint64_t bdesc = make_desc_sw128(smem_u32(smem + kSmemRing));
-      const uint32_t idesc = make_idesc_f16(128);
+      const uint32_t idesc = make_idesc_f16(N);
       if (mode == 0) {
         const uint64_t adesc = make_desc_sw128(smem_u32(smem + kSmemEnc));
-        for (int j = 0; j < 4; ++j) umma_f16(bars->tmem_base + kTmemD0, adesc + 2 * j, bdesc + 2 * j, idesc, j != 0);
+        for (int j = 0; j < 4; ++j) umma_f16(bars->tmem_base + kTmemD, adesc + 2 * j, bdesc + 2 * j, idesc, j != 0);
       } else {
         for (int j = 0; j < 4; ++j)
-          umma_f16_ts(bars->tmem_base + kTmemD0, bars->tmem_base + kTmemA0 + 8 * j, bdesc + 2 * j, idesc, j != 0);
+          umma_f16_ts(bars->tmem_base + kTmemD, bars->tmem_base + kTmemA + 8 * j, bdesc + 2 * j, idesc, j != 0);
       }
-      umma_commit(smem_u32(&bars->d_ready[0]));
+      umma_commit(smem_u32(&bars->d_ready));
     }
   } else {
     EpiCtx c;
@@ -336,26 +344,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_probe_kernel(const float* __
     c.row = (warp & 3) * 32 + lane;
     c.half = warp >> 2;
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    c.d_count[0] = c.d_count[1] = 0;
+    c.d_phase = 0;
     c.tl = nullptr;
     if (mode == 0) {
       uint8_t* enc = smem + kSmemEnc;
       for (int k = c.half * 32; k < c.half * 32 + 32; ++k)
         *reinterpret_cast<__half*>(enc + sw128_off(c.row, k)) = __float2half_rn(a[c.row * 64 + k]);
     } else {
-      // this thread's 32 K-values -> 16 packed columns at A0 + 16*half
-      uint32_t h[16];
+      uint32_t h[16];   // this thread's 32 K-values -> 16 packed columns at A + 16*half
       for (int i = 0; i < 16; ++i)
         h[i] = cvt_f16x2(a[c.row * 64 + c.half * 32 + 2 * i], a[c.row * 64 + c.half * 32 + 2 * i + 1]);
-      tmem_st16(c.tmem_row + kTmemA0 + 16 * c.half, h);
+      tmem_st16(c.tmem_row + kTmemA + 16 * c.half, h);
     }
     epi_signal_a(c, mode == 0);
-    epi_wait_d(c, 0, false);
-    for (int cc = 0; cc < 64; cc += 32) {
+    epi_wait_d(c);
+    const int ncol = N / 2;
+    for (int cc = 0; cc < ncol; cc += 32) {
       uint32_t r[32];
-      tmem_ld32(c.tmem_row + kTmemD0 + c.half * 64 + cc, r);
+      tmem_ld32(c.tmem_row + kTmemD + c.half * ncol + cc, r);
       tmem_ld_wait();
-      for (int i = 0; i < 32; ++i) d[c.row * 128 + c.half * 64 + cc + i] = __uint_as_float(r[i]);
+      for (int i = 0; i < 32; ++i) d[c.row * N + c.half * ncol + cc + i] = __uint_as_float(r[i]);
     }
   }
   engine_teardown(bars);
@@ -391,14 +399,14 @@ __global__ void __launch_bounds__(kThreads, 1) mma_bench_kernel(long long* __res
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const uint32_t j = i & 3;
-          const uint64_t b = bdesc + 2 * j + ((i >> 2) * 1024);      // next 16 KiB stage per K block
-          if (v <= 1) umma_f16(tmem + kTmemD0, adesc + 2 * j, b, idesc, 1u);
-          else if (v == 4) umma_f16_ts(tmem + ((i & 4) ? kTmemD1 : kTmemD0), tmem + kTmemA0 + (i >> 2) * 32 + j * 8, b, idesc, 1u);
-          else umma_f16_ts(tmem + kTmemD0, tmem + kTmemA0 + (i >> 2) * 32 + j * 8, b, idesc, 1u);
+          const uint64_t b = bdesc + 2 * j + ((i >> 2) * 2048);      // next 32 KiB stage per K block
+          if (v <= 1) umma_f16(tmem + kTmemD, adesc + 2 * j, b, idesc, 1u);
+          else if (v == 4) umma_f16_ts(tmem + kTmemD + ((i & 4) ? 128 : 0), tmem + kTmemA + (i >> 2) * 32 + j * 8, b, idesc, 1u);
+          else umma_f16_ts(tmem + kTmemD, tmem + kTmemA + (i >> 2) * 32 + j * 8, b, idesc, 1u);
         }
       }
-      umma_commit(smem_u32(&bars->d_ready[0]));
-      mbar_wait(smem_u32(&bars->d_ready[0]), phase, 21);
+      umma_commit(smem_u32(&bars->d_ready));
+      mbar_wait(smem_u32(&bars->d_ready), phase, 21);
       phase ^= 1;
       out[blockIdx.x * 8 + v] = clock64() - t0;
     }

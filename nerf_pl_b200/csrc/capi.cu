@@ -413,15 +413,15 @@ int nerfb200_debug_mma_bench(int64_t* out_dev, int32_t n_ctas, int32_t reps, voi
   return 0;
 }
 
-int nerfb200_debug_gemm(const float* a, const void* packed, int32_t half_slice, int32_t mode, float* d,
+int nerfb200_debug_gemm(const float* a, const void* packed, int32_t slice, int32_t mode, float* d,
                         void* stream) {
   if (!a || !packed || !d) return fail(NERFB200_EINVAL, "debug_gemm: NULL argument%s");
-  if (half_slice < 0 || half_slice >= kNumHs) return fail(NERFB200_EINVAL, "debug_gemm: bad half-slice%s");
+  if (slice < 0 || slice >= kNumSlices256 + kNumSlices128) return fail(NERFB200_EINVAL, "debug_gemm: bad slice%s");
   DeviceInfo* di = nullptr;
   int rc = device_info(&di);
   if (rc) return rc;
   gemm_probe_kernel<<<1, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(
-      a, static_cast<const uint8_t*>(packed), half_slice, mode, d, di->status);
+      a, static_cast<const uint8_t*>(packed), slice, mode, d, di->status);
   g_launches++;
   CUDA_TRY(cudaGetLastError(), "debug_gemm launch");
   return 0;

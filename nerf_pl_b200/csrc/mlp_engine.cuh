@@ -6,23 +6,22 @@
 // the A operand of the next layer's tcgen05.mma (A-from-TMEM form).  Shared memory only holds
 // the encoded-input tile and the weight ring, so its bandwidth is spent on weights alone.
 //
-//   TMEM (512 columns x 128 lanes, lane = tile row):
-//     [  0,128) D0   accumulator, output features   0..127  ("n0")
-//     [128,256) D1   accumulator, output features 128..255  ("n1")
-//     [256,384) A0   fp16 activations (2 per column) read by odd layers
-//     [384,512) A1   fp16 activations                read by even layers
-//   warps 0..3  epilogue of D0 (warp w owns TMEM lanes 32w..32w+31): writes A' columns 0..127
-//   warps 4..7  epilogue of D1:                                      writes A' columns 128..255
-//   warp 8      weight producer: streams 16 KiB half-slices (layout.h) through a 12-stage ring
-//               with cp.async.bulk + mbarriers, running up to 1.5 layers ahead
-//   warp 9      MMA issuer (one thread): tcgen05.mma M=128, N=128, K=16
-//
-// Pipelining inside a tile: layer l is issued as  n0:[k0 k1 | k2 k3]  n1:[k0 k1 k2 k3].
-// The n0 half of layer l+1 needs only A' columns 0..127 for its k0,k1 blocks, i.e. the D0
-// epilogue of layer l, which ran while the tensor core was busy with n1 of layer l.  So the
-// tensor core only waits for the D1 epilogue (before k2 of n0), and the D0 epilogue is free.
-// Double-buffering A (A0/A1) lets an epilogue write layer l+1's input while layer l's n1 MMAs
-// still read layer l's input.
+//   TMEM (512 columns allocated, lane = tile row):
+//     [  0,256) D   fp32 accumulator, 256 output features
+//     [256,384) A   fp16 activations (2 per 32-bit column), the next layer's A operand;
+//                   rewritten in place by the epilogue once the layer's MMAs have retired
+//   warps 0..7  epilogue: warp w owns TMEM lanes 32(w&3).. and accumulator columns 128(w>>2)..
+//   warp 8      weight producer: streams the packed 32 KiB K-slices (layout.h) through a
+//               5-stage ring with cp.async.bulk + mbarriers, up to 1.25 layers ahead
+//   smem also keeps the fp32 biases and head weights of both networks resident (25 KiB), so the
+//   epilogue reads them with broadcast LDS instead of L1/L2 loads
+//   warp 9      MMA issuer (one thread): tcgen05.mma M=128, N=256|128, K=16; A from TMEM for
+//               hidden K blocks (139 cycles per K step measured, vs 129 from smem), from the
+//               ENC shared-memory tile for the encoded-input slices
+// MMA and epilogue of a tile alternate (the epilogue needs the whole accumulator, the next
+// layer needs the whole A); the producer keeps the following layer's weights resident.
+// Measured alternatives: A in shared memory costs 64 KiB of smem writes + reads per
+// layer; N=128 split accumulators with A in TMEM run the tensor core at half rate.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -36,13 +35,16 @@ constexpr int kEpiThreads = kEpiWarps * 32;   // 256
 constexpr int kProducerWarp = 8;
 constexpr int kMmaWarp = 9;
 constexpr int kThreads = 320;
-constexpr int kStages = 12;
+constexpr int kStages = 5;
 constexpr int kTmemCols = 512;
-constexpr uint32_t kTmemD0 = 0, kTmemD1 = 128, kTmemA0 = 256, kTmemA1 = 384;
+constexpr uint32_t kTmemD = 0, kTmemA = 256;
 
 constexpr uint32_t kSmemEnc = 0;                     // [128 x 64] fp16     16 KiB
-constexpr uint32_t kSmemRing = 16384;                // 12 x 16 KiB
-constexpr uint32_t kSmemScratch = kSmemRing + kStages * kHsBytes;   // 212992
+constexpr uint32_t kSmemRing = 16384;                // 5 x 32 KiB
+constexpr uint32_t kSmemConsts = kSmemRing + kStages * kSliceBytes256;    // 180224: fp32 biases + heads
+constexpr uint32_t kConstFloats = kF32WDirPart;      // biases, sigma head, rgb head of one network
+constexpr uint32_t kSmemScratch = kSmemConsts + 32768;                    // 212992
+static_assert(2 * kConstFloats * 4 <= 32768, "constants of two networks must fit");
 constexpr uint32_t kSmemTotal = 232448;              // 227 KiB (max opt-in)
 constexpr uint32_t kScratchBytes = kSmemTotal - kSmemScratch;       // 19456
 
@@ -52,8 +54,8 @@ constexpr int kLayersSigma = 8;       // L1..L8
 struct Barriers {
   uint64_t full[kStages];
   uint64_t empty[kStages];
-  uint64_t a_ready[2];     // epilogue half h -> MMA : "A' columns of half h written, D_h drained"
-  uint64_t d_ready[2];     // MMA -> epilogue        : "accumulator D_h complete"
+  uint64_t a_ready;        // epilogue -> MMA : "A operand written, accumulator drained"
+  uint64_t d_ready;        // MMA -> epilogue : "accumulator complete"
   uint32_t tmem_base;
   uint32_t pad[3];
 };
@@ -91,10 +93,8 @@ __device__ __forceinline__ bool engine_setup(uint8_t* smem, Barriers* bars) {
       mbar_init(smem_u32(&bars->full[i]), 1);
       mbar_init(smem_u32(&bars->empty[i]), 1);
     }
-    for (int h = 0; h < 2; ++h) {
-      mbar_init(smem_u32(&bars->a_ready[h]), kEpiWarps / 2);
-      mbar_init(smem_u32(&bars->d_ready[h]), 1);
-    }
+    mbar_init(smem_u32(&bars->a_ready), kEpiWarps);
+    mbar_init(smem_u32(&bars->d_ready), 1);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) {
@@ -115,86 +115,87 @@ __device__ __forceinline__ void engine_teardown(Barriers* bars) {
   }
 }
 
+// Copy the fp32 constants (biases + heads) of a network image into shared-memory slot `slot`.
+// Called by all threads before the first tile; followed by a __syncthreads().
+__device__ __forceinline__ void load_consts(uint8_t* smem, int slot, const uint8_t* __restrict__ blob) {
+  if (blob == nullptr) return;
+  const float4* src = reinterpret_cast<const float4*>(blob + kHalfRegionBytes);
+  float4* dst = reinterpret_cast<float4*>(smem + kSmemConsts) + slot * (kConstFloats / 4);
+  for (uint32_t i = threadIdx.x; i < kConstFloats / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+__device__ __forceinline__ const float* consts_ptr(uint8_t* smem, int slot) {
+  return reinterpret_cast<const float*>(smem + kSmemConsts) + slot * kConstFloats;
+}
+
 // --------------------------------------------------------------- producer
-// One thread.  Streams the half-slices of one network for one tile, in consumption order.
+// One thread.  Streams the slices of one network for one tile, in consumption order.
 __device__ __forceinline__ void produce_tile(RingState& rs, uint8_t* smem, Barriers* bars,
                                              const uint8_t* __restrict__ blob, bool sigma_only,
                                              bool dir_slice) {
-  const int n = sigma_only ? kNumHsSigmaOnly : (dir_slice ? kNumHs : kNumHs - 1);
-  for (int i = 0; i < n; ++i) {
+  const int n256 = sigma_only ? kNumSlicesSigmaOnly : kNumSlices256;
+  for (int i = 0; i < n256; ++i) {
     mbar_wait(smem_u32(&bars->empty[rs.stage]), rs.phase ^ 1, 1);
     const uint32_t full = smem_u32(&bars->full[rs.stage]);
-    const uint32_t dst = smem_u32(smem + kSmemRing + rs.stage * kHsBytes);
-    mbar_arrive_expect_tx(full, kHsBytes);
-    const uint8_t* src = blob + static_cast<size_t>(i) * kHsBytes;
-    bulk_g2s(dst, src, 8192, full);
-    bulk_g2s(dst + 8192, src + 8192, 8192, full);
+    const uint32_t dst = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
+    mbar_arrive_expect_tx(full, kSliceBytes256);
+    const uint8_t* src = blob + static_cast<size_t>(i) * kSliceBytes256;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bulk_g2s(dst + c * 8192, src + c * 8192, 8192, full);
     rs.advance();
+  }
+  if (!sigma_only) {
+    const int n128 = dir_slice ? 5 : 4;
+    for (int i = 0; i < n128; ++i) {
+      mbar_wait(smem_u32(&bars->empty[rs.stage]), rs.phase ^ 1, 2);
+      const uint32_t full = smem_u32(&bars->full[rs.stage]);
+      const uint32_t dst = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
+      mbar_arrive_expect_tx(full, kSliceBytes128);
+      const uint8_t* src = blob + kOffDir + static_cast<size_t>(i) * kSliceBytes128;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) bulk_g2s(dst + c * 8192, src + c * 8192, 8192, full);
+      rs.advance();
+    }
   }
 }
 
 // -------------------------------------------------------------------- MMA
-// One thread.  Issues all MMAs of one tile (schedule in the header comment).
-__device__ __forceinline__ void mma_tile(RingState& rs, uint32_t (&a_phase)[2], uint8_t* smem,
+// One thread.  Issues all MMAs of one tile.
+__device__ __forceinline__ void mma_tile(RingState& rs, uint32_t& a_phase, uint8_t* smem,
                                          Barriers* bars, bool sigma_only, bool dir_slice,
                                          Timeline* tl = nullptr) {
   const uint32_t tmem = bars->tmem_base;
   const uint32_t enc_base = smem_u32(smem + kSmemEnc);
-  const uint32_t idesc = make_idesc_f16(128);
   const int n_layers = sigma_only ? kLayersSigma : kLayersFull;
   for (int l = 0; l < n_layers; ++l) {
-    const bool has_enc = (l == 0) || (l == 4);
-    const int n_k = (l == 0) ? 0 : 4;                       // hidden K blocks
-    const bool has_dir = (l == 9) && dir_slice;
-    const uint32_t a_tmem = tmem + ((l & 1) ? kTmemA0 : kTmemA1);   // layer l reads A0 if l odd
-    const int n_halves = (l == 9) ? 1 : 2;
-    for (int nh = 0; nh < n_halves; ++nh) {
-      const uint32_t d_tmem = tmem + (nh ? kTmemD1 : kTmemD0);
-      const int n_items = (has_enc ? 1 : 0) + n_k + (has_dir ? 1 : 0);
-      for (int it = 0; it < n_items; ++it) {
-        const bool from_enc = (has_enc && it == 0) || (has_dir && it == n_items - 1);
-        const int kb = it - (has_enc ? 1 : 0);              // hidden K block index when !from_enc
-        if (nh == 0) {
-          // operand / accumulator readiness (see header): half 0 before the first MMA of the
-          // layer, half 1 before the first MMA that reads A' columns 128..255 (or, layer 0, the
-          // ENC tile both halves wrote at tile start).
-          if (it == 0) {
-            mbar_wait(smem_u32(&bars->a_ready[0]), a_phase[0], 3);
-            a_phase[0] ^= 1;
-            if (l == 0) {
-              mbar_wait(smem_u32(&bars->a_ready[1]), a_phase[1], 3);
-              a_phase[1] ^= 1;
-            }
-            tc_fence_after();
-            tl_mark(tl, 1, 100 + l);
-          }
-          if (l != 0 && !from_enc && kb == 2) {
-            mbar_wait(smem_u32(&bars->a_ready[1]), a_phase[1], 3);
-            a_phase[1] ^= 1;
-            tc_fence_after();
-            tl_mark(tl, 1, 300 + l);
-          }
-        }
-        const uint32_t b_addr = smem_u32(smem + kSmemRing + rs.stage * kHsBytes);
-        mbar_wait(smem_u32(&bars->full[rs.stage]), rs.phase, 4);
-        tc_fence_after();
-        const uint64_t bdesc = make_desc_sw128(b_addr);
-        if (from_enc) {
-          const uint64_t adesc = make_desc_sw128(enc_base);
+    mbar_wait(smem_u32(&bars->a_ready), a_phase, 3);
+    a_phase ^= 1;
+    tc_fence_after();
+    tl_mark(tl, 1, 100 + l);
+    const int n_slices = (l == 0) ? 1 : (l == 4) ? 5 : (l == 9 && dir_slice) ? 5 : 4;
+    const uint32_t idesc = (l == 9) ? make_idesc_f16(128) : make_idesc_f16(256);
+    for (int s = 0; s < n_slices; ++s) {
+      const bool from_enc = (l == 0) || (l == 4 && s == 0) || (l == 9 && s == 4);
+      const int kb = (l == 4) ? s - 1 : s;
+      const uint32_t b_addr = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
+      mbar_wait(smem_u32(&bars->full[rs.stage]), rs.phase, 4);
+      tc_fence_after();
+      const uint64_t bdesc = make_desc_sw128(b_addr);
+      if (from_enc) {
+        const uint64_t adesc = make_desc_sw128(enc_base);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)   // +32 B per K=16 step inside the 128-byte swizzle row
-            umma_f16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (it | j) != 0 ? 1u : 0u);
-        } else {
+        for (int j = 0; j < 4; ++j)   // +32 B per K=16 step inside the 128-byte swizzle row
+          umma_f16(tmem + kTmemD, adesc + 2 * j, bdesc + 2 * j, idesc, (s | j) != 0 ? 1u : 0u);
+      } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)   // A: 64 K-values per block = 32 columns, 8 per K=16 step
-            umma_f16_ts(d_tmem, a_tmem + kb * 32 + j * 8, bdesc + 2 * j, idesc, (it | j) != 0 ? 1u : 0u);
-        }
-        umma_commit(smem_u32(&bars->empty[rs.stage]));
-        rs.advance();
+        for (int j = 0; j < 4; ++j)   // A: 64 K-values per block = 32 columns, 8 per K=16 step
+          umma_f16_ts(tmem + kTmemD, tmem + kTmemA + kb * 32 + j * 8, bdesc + 2 * j, idesc,
+                      (s | j) != 0 ? 1u : 0u);
       }
-      umma_commit(smem_u32(&bars->d_ready[nh]));
-      tl_mark(tl, 1, 200 + 10 * nh + l);
+      umma_commit(smem_u32(&bars->empty[rs.stage]));
+      rs.advance();
     }
+    umma_commit(smem_u32(&bars->d_ready));
+    tl_mark(tl, 1, 200 + l);
   }
 }
 
@@ -202,11 +203,12 @@ __device__ __forceinline__ void mma_tile(RingState& rs, uint32_t (&a_phase)[2], 
 struct EpiCtx {
   uint8_t* smem;
   Barriers* bars;
-  const float* __restrict__ f32;   // fp32 region of the current network image
+  const float* __restrict__ f32;   // fp32 region of the current network image (global)
+  const float* cst;                // its first kConstFloats floats, resident in shared memory
   uint32_t tmem_row;               // tmem base + (lane quadrant << 16)
-  uint32_t d_count[2];             // completed phases of d_ready[0|1] so far (static schedule)
+  uint32_t d_phase;
   int row;                         // 0..127 : tile row == TMEM lane
-  int half;                        // 0/1    : which accumulator half this warp drains
+  int half;                        // 0/1    : which accumulator column half this warp drains
   int lane;
   Timeline* tl;                    // non-null only for the one traced thread
 };
@@ -220,15 +222,12 @@ __device__ __forceinline__ void epi_signal_a(EpiCtx& c, bool smem_written) {
   tmem_st_wait();
   tc_fence_before();
   __syncwarp();
-  if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_ready[c.half]));
+  if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_ready));
   tl_mark(c.tl, 0, 6);
 }
-// Wait for accumulator `which` of the current layer; every epilogue thread advances both
-// counters with the static schedule (`also_other`: the other accumulator completes this layer too).
-__device__ __forceinline__ void epi_wait_d(EpiCtx& c, int which, bool also_other) {
-  mbar_wait(smem_u32(&c.bars->d_ready[which]), c.d_count[which] & 1u, 5);
-  c.d_count[which]++;
-  if (also_other) c.d_count[which ^ 1]++;
+__device__ __forceinline__ void epi_wait_d(EpiCtx& c) {
+  mbar_wait(smem_u32(&c.bars->d_ready), c.d_phase, 5);
+  c.d_phase ^= 1;
   tc_fence_after();
 }
 
@@ -249,22 +248,24 @@ __device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
 
 // One 32-column chunk of a hidden-layer epilogue: v = act(acc + bias) -> 16 packed fp16x2
 // columns of the next layer's A operand in TMEM; optionally the sigma-head dot product.
+// bias / wsig point into shared memory (all lanes read the same address: broadcast LDS).
 template <bool kRelu, bool kSigma, bool kStore>
-__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float4 (&b)[8], int n0,
-                                          uint32_t a_dst, const float* __restrict__ wsig,
-                                          float& sig_acc) {
+__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* bias, int n0,
+                                          uint32_t a_dst, const float* wsig, float& sig_acc) {
   uint32_t h[16];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
+    const int n = n0 + 8 * j;
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + n);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias + n + 4);
     float v[8];
-    add_f32x2(v[0], v[1], __uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]), b[2 * j].x, b[2 * j].y);
-    add_f32x2(v[2], v[3], __uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]), b[2 * j].z, b[2 * j].w);
-    add_f32x2(v[4], v[5], __uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]), b[2 * j + 1].x, b[2 * j + 1].y);
-    add_f32x2(v[6], v[7], __uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]), b[2 * j + 1].z, b[2 * j + 1].w);
+    add_f32x2(v[0], v[1], __uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]), b0.x, b0.y);
+    add_f32x2(v[2], v[3], __uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]), b0.z, b0.w);
+    add_f32x2(v[4], v[5], __uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]), b1.x, b1.y);
+    add_f32x2(v[6], v[7], __uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]), b1.z, b1.w);
     if (kSigma) {
-      const int n = n0 + 8 * j;
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wsig + n));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wsig + n + 4));
+      const float4 w0 = *reinterpret_cast<const float4*>(wsig + n);
+      const float4 w1 = *reinterpret_cast<const float4*>(wsig + n + 4);
       sig_acc = fmaf(fmaxf(v[0], 0.f), w0.x, sig_acc);
       sig_acc = fmaf(fmaxf(v[1], 0.f), w0.y, sig_acc);
       sig_acc = fmaf(fmaxf(v[2], 0.f), w0.z, sig_acc);
@@ -287,52 +288,40 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float4 
   if (kStore) tmem_st16(a_dst, h);
 }
 
-__device__ __forceinline__ void ld_bias32(const float* __restrict__ bias, int n0, float4 (&b)[8]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias + n0) + i);
-}
-
-// Hidden-layer epilogue of accumulator half c.half (128 columns) for layer `l`.  The bias of the
-// first two chunks is fetched BEFORE waiting for the accumulator, so its latency hides behind the MMA.
+// Hidden-layer epilogue of this thread's 128 accumulator columns.
 template <bool kRelu, bool kSigma, bool kStore>
-__device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* __restrict__ bias,
-                                           const float* __restrict__ wsig, float& sig_acc) {
+__device__ __forceinline__ void epi_hidden(EpiCtx& c, const float* bias, const float* wsig,
+                                           float& sig_acc) {
   const int nb = c.half * 128;
-  // layer l writes the operand of layer l+1, which reads A0 if (l+1) is odd, else A1
-  const uint32_t a_dst = c.tmem_row + (((l + 1) & 1) ? kTmemA0 : kTmemA1) + c.half * 64;
-  const uint32_t d_src = c.tmem_row + nb;            // D0 at column 0, D1 at column 128
-  float4 b0[8], b1[8];
-  ld_bias32(bias, nb, b0);
-  ld_bias32(bias, nb + 32, b1);
+  const uint32_t a_dst = c.tmem_row + kTmemA + c.half * 64;   // 2 fp16 per column
+  const uint32_t d_src = c.tmem_row + kTmemD + nb;
   tl_mark(c.tl, 0, 1);
-  epi_wait_d(c, c.half, true);
+  epi_wait_d(c);
   tl_mark(c.tl, 0, 2);
   uint32_t r0[32], r1[32];
   tmem_ld32(d_src, r0);
   tmem_ld32(d_src + 32, r1);
   tmem_ld_wait();
   tl_mark(c.tl, 0, 3);
-  epi_chunk<kRelu, kSigma, kStore>(r0, b0, nb, a_dst, wsig, sig_acc);
-  ld_bias32(bias, nb + 64, b0);
+  epi_chunk<kRelu, kSigma, kStore>(r0, bias, nb, a_dst, wsig, sig_acc);
   tmem_ld32(d_src + 64, r0);
-  epi_chunk<kRelu, kSigma, kStore>(r1, b1, nb + 32, a_dst + 16, wsig, sig_acc);
-  ld_bias32(bias, nb + 96, b1);
+  epi_chunk<kRelu, kSigma, kStore>(r1, bias, nb + 32, a_dst + 16, wsig, sig_acc);
   tmem_ld32(d_src + 96, r1);
   tmem_ld_wait();
   tl_mark(c.tl, 0, 4);
-  epi_chunk<kRelu, kSigma, kStore>(r0, b0, nb + 64, a_dst + 32, wsig, sig_acc);
-  epi_chunk<kRelu, kSigma, kStore>(r1, b1, nb + 96, a_dst + 48, wsig, sig_acc);
+  epi_chunk<kRelu, kSigma, kStore>(r0, bias, nb + 64, a_dst + 32, wsig, sig_acc);
+  epi_chunk<kRelu, kSigma, kStore>(r1, bias, nb + 96, a_dst + 48, wsig, sig_acc);
   tl_mark(c.tl, 0, 5);
 }
 
-// dir_encoding epilogue (N=128 accumulator D0; this thread's 64 columns) fused with the rgb head
+// dir_encoding epilogue (N=128; this thread's 64 columns) fused with the rgb head
 // (models/nerf.py:119-120): d = relu(acc + dbias[n]); rgb_acc[c] += d * w_rgb[c][n].
 // dbias is either the per-ray vector (bias + direction part, shared memory) or b_dir (global).
-__device__ __forceinline__ void epi_dir(EpiCtx& c, const float* dbias, const float* __restrict__ wrgb,
+__device__ __forceinline__ void epi_dir(EpiCtx& c, const float* dbias, const float* wrgb,
                                         float (&rgb_acc)[3]) {
   uint32_t r[2][32];
-  tmem_ld32(c.tmem_row + kTmemD0 + c.half * 64, r[0]);
-  tmem_ld32(c.tmem_row + kTmemD0 + c.half * 64 + 32, r[1]);
+  tmem_ld32(c.tmem_row + kTmemD + c.half * 64, r[0]);
+  tmem_ld32(c.tmem_row + kTmemD + c.half * 64 + 32, r[1]);
   tmem_ld_wait();
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
@@ -340,9 +329,9 @@ __device__ __forceinline__ void epi_dir(EpiCtx& c, const float* dbias, const flo
     for (int j = 0; j < 8; ++j) {
       const int n = c.half * 64 + u * 32 + 4 * j;
       const float4 b = *reinterpret_cast<const float4*>(dbias + n);
-      const float4 wr = __ldg(reinterpret_cast<const float4*>(wrgb + n));
-      const float4 wg = __ldg(reinterpret_cast<const float4*>(wrgb + 128 + n));
-      const float4 wb = __ldg(reinterpret_cast<const float4*>(wrgb + 256 + n));
+      const float4 wr = *reinterpret_cast<const float4*>(wrgb + n);
+      const float4 wg = *reinterpret_cast<const float4*>(wrgb + 128 + n);
+      const float4 wb = *reinterpret_cast<const float4*>(wrgb + 256 + n);
       const float v0 = fmaxf(__uint_as_float(r[u][4 * j + 0]) + b.x, 0.f);
       const float v1 = fmaxf(__uint_as_float(r[u][4 * j + 1]) + b.y, 0.f);
       const float v2 = fmaxf(__uint_as_float(r[u][4 * j + 2]) + b.z, 0.f);
@@ -367,24 +356,24 @@ __device__ __forceinline__ void epi_dir(EpiCtx& c, const float* dbias, const flo
 __device__ __forceinline__ void epi_run_tile(EpiCtx& c, bool sigma_only, const float* dbias,
                                              const float* __restrict__ dir_row, float& sig_part,
                                              float (&rgb_part)[3]) {
-  const float* bias = c.f32 + kF32Bias;
-  const float* wsig = c.f32 + kF32WSigma;
+  const float* bias = c.cst + kF32Bias;
+  const float* wsig = c.cst + kF32WSigma;
   sig_part = 0.f;
   rgb_part[0] = rgb_part[1] = rgb_part[2] = 0.f;
   float dummy = 0.f;
   epi_signal_a(c, true);
   for (int l = 0; l < 7; ++l) {
-    epi_hidden<true, false, true>(c, l, bias + l * 256, nullptr, dummy);
+    epi_hidden<true, false, true>(c, bias + l * 256, nullptr, dummy);
     epi_signal_a(c, false);
   }
   if (sigma_only) {
-    epi_hidden<true, true, false>(c, 7, bias + 7 * 256, wsig, sig_part);
+    epi_hidden<true, true, false>(c, bias + 7 * 256, wsig, sig_part);
     return;   // next signal comes with the next tile's ENC write
   }
-  epi_hidden<true, true, true>(c, 7, bias + 7 * 256, wsig, sig_part);
+  epi_hidden<true, true, true>(c, bias + 7 * 256, wsig, sig_part);
   epi_signal_a(c, false);
   // xyz_encoding_final: bias only, no activation (models/nerf.py:116)
-  epi_hidden<false, false, true>(c, 8, bias + 8 * 256, nullptr, dummy);
+  epi_hidden<false, false, true>(c, bias + 8 * 256, nullptr, dummy);
   if (dir_row != nullptr) {
     // ENC tile is dead after layer 5: reuse it for the embedded direction (cols 27..63 zero)
     uint8_t* enc = c.smem + kSmemEnc;
@@ -395,8 +384,8 @@ __device__ __forceinline__ void epi_run_tile(EpiCtx& c, bool sigma_only, const f
     }
   }
   epi_signal_a(c, dir_row != nullptr);
-  epi_wait_d(c, 0, false);           // dir layer: only D0
-  epi_dir(c, dbias != nullptr ? dbias : (bias + 9 * 256), c.f32 + kF32WRgb, rgb_part);
+  epi_wait_d(c);
+  epi_dir(c, dbias != nullptr ? dbias : (bias + 9 * 256), c.cst + kF32WRgb, rgb_part);
 }
 
 __device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf(-x)); }

@@ -246,6 +246,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
     if (threadIdx.x == 0) atomicExch(p.status, 101);
     return;
   }
+  load_consts(smem, 0, p.net_coarse);
+  load_consts(smem, 1, p.net_fine);
+  __syncthreads();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int Sc = p.n_samples;
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
   } else if (warp == kMmaWarp) {
     if (lane == 0) {
       RingState rs;
-      uint32_t a_phase[2] = {0, 0};
+      uint32_t a_phase = 0;
       Timeline tlm{(blockIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
       for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
         for (int t = 0; t < tiles_c; ++t) mma_tile(rs, a_phase, smem, bars, coarse_sigma_only, false, &tlm);
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
     c.row = (warp & 3) * 32 + lane;
     c.half = warp >> 2;
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    c.d_count[0] = c.d_count[1] = 0;
+    c.d_phase = 0;
     Timeline tle{(blockIdx.x == 0 && threadIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
     c.tl = &tle;
     const int t = threadIdx.x;   // 0..255
@@ -328,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
         const bool sigma_only = (pass == 0) && coarse_sigma_only;
         const uint8_t* blob = pass ? p.net_fine : p.net_coarse;
         c.f32 = reinterpret_cast<const float*>(blob + kHalfRegionBytes);
+        c.cst = consts_ptr(smem, pass);
         if (!sigma_only) {
           // per-ray direction bias: b_dir + W_dir[:, 256:283] . dir_embedded   (fp32)
           const int r = t >> 7, n = t & 127;
@@ -353,12 +357,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
           }
           epi_bar();
           if (c.half == 0) {
-            sc->sigma[gr] = sc->sig_part[0][c.row] + sc->sig_part[1][c.row] + __ldg(c.f32 + kF32BSigma);
+            sc->sigma[gr] = sc->sig_part[0][c.row] + sc->sig_part[1][c.row] + c.cst[kF32BSigma];
             if (!sigma_only) {
 #pragma unroll
               for (int ch = 0; ch < 3; ++ch)
                 sc->rgb[ch][gr] = sigmoid_ref(sc->rgb_part[0][ch][c.row] + sc->rgb_part[1][ch][c.row] +
-                                              __ldg(c.f32 + kF32BRgb + ch));
+                                              c.cst[kF32BRgb + ch]);
             }
           }
           epi_bar();

@@ -47,24 +47,23 @@ def step_gemm():
     params = nb.nerf_parameters(m)
     a = torch.randn(128, 64, device="cuda")
     a16 = a.half().float()
-    # half-slice -> (weight, row offset, k offset, valid k)   (csrc/layout.h)
+    # slice -> (weight, k offset, valid k, N)   (csrc/layout.h)
     cases = {
-        0: (params[0], 0, 0, 63), 1: (params[0], 128, 0, 63),
-        2: (params[2], 0, 0, 64), 9: (params[2], 128, 192, 64),
-        26: (params[8], 0, 0, 63), 28: (params[8], 0, 63 + 64, 64), 35: (params[8], 128, 63 + 192, 64),
-        60: (params[16], 0, 0, 64), 68: (params[18], 0, 0, 64), 72: (params[18], 0, 256, 27),
+        0: (params[0], 0, 63, 256), 5: (params[4], 0, 64, 256), 8: (params[4], 192, 64, 256),
+        13: (params[8], 0, 63, 256), 15: (params[8], 63 + 64, 64, 256),
+        34: (params[18], 0, 64, 128), 38: (params[18], 256, 27, 128),
     }
     ok = True
     for mode in (0, 1):
-        for hs, (W, roff, koff, kval) in cases.items():
-            d = torch.zeros(128, 128, device="cuda")
-            rc = lib.nerfb200_debug_gemm(a.data_ptr(), blob.data_ptr(), hs, mode, d.data_ptr(), None)
+        for sl, (W, koff, kval, N) in cases.items():
+            d = torch.zeros(128, N, device="cuda")
+            rc = lib.nerfb200_debug_gemm(a.data_ptr(), blob.data_ptr(), sl, mode, d.data_ptr(), None)
             torch.cuda.synchronize()
-            Wk = torch.zeros(128, 64, device="cuda")
-            Wk[:, :kval] = W[roff:roff + 128, koff:koff + kval].detach().half().float()
+            Wk = torch.zeros(N, 64, device="cuda")
+            Wk[:, :kval] = W[:, koff:koff + kval].detach().half().float()
             ref = a16 @ Wk.t()
             err = (d - ref).abs().max().item()
-            print(f"gemm mode {mode} hs {hs:2d} rc={rc} max_abs_err={err:.3e} ref_absmax={ref.abs().max().item():.3f}")
+            print(f"gemm mode {mode} slice {sl:2d} N={N} rc={rc} max_abs_err={err:.3e} ref_absmax={ref.abs().max().item():.3f}")
             ok &= err < 1e-3
     print("GEMM_OK" if ok else "GEMM_FAIL")
 
