@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const MlpParam
   } else if (warp == kMmaWarp) {
     if (lane == 0) {
       RingState rs;
-      uint32_t a_phase = 0;
-      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) mma_tile(rs, a_phase, smem, bars, so, !so);
+      MmaPhases ph;
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) mma_tile(rs, ph, smem, bars, so, !so);
     }
   } else {
     EpiCtx c;
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_probe_kernel(const float* __
     }
   } else if (warp == kMmaWarp) {
     if (lane == 0) {
-      mbar_wait(smem_u32(&bars->a_ready), 0, 12);
+      mbar_wait(smem_u32(&bars->d_free), 0, 12);
       tc_fence_after();
       mbar_wait(smem_u32(&bars->full[0]), 0, 13);
       tc_fence_after();
@@ -356,7 +356,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_probe_kernel(const float* __
         h[i] = cvt_f16x2(a[c.row * 64 + c.half * 32 + 2 * i], a[c.row * 64 + c.half * 32 + 2 * i + 1]);
       tmem_st16(c.tmem_row + kTmemA + 16 * c.half, h);
     }
-    epi_signal_a(c, mode == 0);
+    tmem_st_wait();
+    epi_signal_tile_start(c);
     epi_wait_d(c);
     const int ncol = N / 2;
     for (int cc = 0; cc < ncol; cc += 32) {

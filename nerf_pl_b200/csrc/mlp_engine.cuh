@@ -18,8 +18,12 @@
 //   warp 9      MMA issuer (one thread): tcgen05.mma M=128, N=256|128, K=16; A from TMEM for
 //               hidden K blocks (139 cycles per K step measured, vs 129 from smem), from the
 //               ENC shared-memory tile for the encoded-input slices
-// MMA and epilogue of a tile alternate (the epilogue needs the whole accumulator, the next
-// layer needs the whole A); the producer keeps the following layer's weights resident.
+// MMA and epilogue of one tile cannot fully overlap (one accumulator), but the hand-over is
+// pipelined: the epilogue first drains the whole accumulator into registers (tcgen05.ld, ~130
+// cycles) and releases it ("d_free"), then produces the next A operand one 64-wide K block at a
+// time ("a_kb[k]"); the MMA issuer starts K block 0 of the next layer as soon as its columns
+// exist, while the epilogue warps are still converting blocks 1..3.
+// The producer keeps the following layer's weights resident.
 // Measured alternatives: A in shared memory costs 64 KiB of smem writes + reads per
 // layer; N=128 split accumulators with A in TMEM run the tensor core at half rate.
 #pragma once
@@ -35,12 +39,23 @@ constexpr int kEpiThreads = kEpiWarps * 32;   // 256
 constexpr int kProducerWarp = 8;
 constexpr int kMmaWarp = 9;
 constexpr int kThreads = 320;
-constexpr int kStages = 5;
+// Where the hidden activations (the next layer's A operand) live:
+//   true : tensor memory (tcgen05.st, TS MMA 139 cyc/K-step; epilogue stores contend with the
+//          MMA's TMEM reads when the two overlap)
+//   false: shared memory (st.shared into the SWIZZLE_128B tile, SS MMA 129 cyc/K-step)
+constexpr bool kAInTmem = true;
+// Hand the accumulator / A operand over to the MMA issuer K block by K block while the epilogue
+// is still converting (true), or all at once when the epilogue is done (false).  Measured on
+// B200: overlapping does not pay - the tensor core's TMEM (or smem) operand reads and
+// the epilogue's stores share one port, each slows the other by the overlap.
+constexpr bool kPipelinedHandover = false;
+constexpr int kStages = kAInTmem ? 5 : 3;
 constexpr int kTmemCols = 512;
 constexpr uint32_t kTmemD = 0, kTmemA = 256;
 
 constexpr uint32_t kSmemEnc = 0;                     // [128 x 64] fp16     16 KiB
-constexpr uint32_t kSmemRing = 16384;                // 5 x 32 KiB
+constexpr uint32_t kSmemA = 16384;                   // [4][128 x 64] fp16  64 KiB (only if !kAInTmem)
+constexpr uint32_t kSmemRing = kAInTmem ? 16384 : 81920;   // kStages x 32 KiB
 constexpr uint32_t kSmemConsts = kSmemRing + kStages * kSliceBytes256;    // 180224: fp32 biases + heads
 constexpr uint32_t kConstFloats = kF32WDirPart;      // biases, sigma head, rgb head of one network
 constexpr uint32_t kSmemScratch = kSmemConsts + 32768;                    // 212992
@@ -54,7 +69,9 @@ constexpr int kLayersSigma = 8;       // L1..L8
 struct Barriers {
   uint64_t full[kStages];
   uint64_t empty[kStages];
-  uint64_t a_ready;        // epilogue -> MMA : "A operand written, accumulator drained"
+  uint64_t d_free;         // epilogue (8 warps) -> MMA : "accumulator drained into registers"
+                           //   (at tile start: "ENC tile written")
+  uint64_t a_kb[4];        // epilogue (4 warps)  -> MMA : "A columns of K block kb written"
   uint64_t d_ready;        // MMA -> epilogue : "accumulator complete"
   uint32_t tmem_base;
   uint32_t pad[3];
@@ -93,7 +110,8 @@ __device__ __forceinline__ bool engine_setup(uint8_t* smem, Barriers* bars) {
       mbar_init(smem_u32(&bars->full[i]), 1);
       mbar_init(smem_u32(&bars->empty[i]), 1);
     }
-    mbar_init(smem_u32(&bars->a_ready), kEpiWarps);
+    mbar_init(smem_u32(&bars->d_free), kEpiWarps);
+    for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&bars->a_kb[k]), kEpiWarps / 2);
     mbar_init(smem_u32(&bars->d_ready), 1);
     fence_mbar_init();
   }
@@ -160,15 +178,17 @@ __device__ __forceinline__ void produce_tile(RingState& rs, uint8_t* smem, Barri
 
 // -------------------------------------------------------------------- MMA
 // One thread.  Issues all MMAs of one tile.
-__device__ __forceinline__ void mma_tile(RingState& rs, uint32_t& a_phase, uint8_t* smem,
+struct MmaPhases { uint32_t d_free = 0, a_kb = 0; };   // a_kb: the 4 K-block barriers flip together
+
+__device__ __forceinline__ void mma_tile(RingState& rs, MmaPhases& ph, uint8_t* smem,
                                          Barriers* bars, bool sigma_only, bool dir_slice,
                                          Timeline* tl = nullptr) {
   const uint32_t tmem = bars->tmem_base;
   const uint32_t enc_base = smem_u32(smem + kSmemEnc);
   const int n_layers = sigma_only ? kLayersSigma : kLayersFull;
   for (int l = 0; l < n_layers; ++l) {
-    mbar_wait(smem_u32(&bars->a_ready), a_phase, 3);
-    a_phase ^= 1;
+    mbar_wait(smem_u32(&bars->d_free), ph.d_free, 3);
+    ph.d_free ^= 1;
     tc_fence_after();
     tl_mark(tl, 1, 100 + l);
     const int n_slices = (l == 0) ? 1 : (l == 4) ? 5 : (l == 9 && dir_slice) ? 5 : 4;
@@ -178,6 +198,7 @@ __device__ __forceinline__ void mma_tile(RingState& rs, uint32_t& a_phase, uint8
       const int kb = (l == 4) ? s - 1 : s;
       const uint32_t b_addr = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
       mbar_wait(smem_u32(&bars->full[rs.stage]), rs.phase, 4);
+      if (!from_enc) mbar_wait(smem_u32(&bars->a_kb[kb]), ph.a_kb, 6);
       tc_fence_after();
       const uint64_t bdesc = make_desc_sw128(b_addr);
       if (from_enc) {
@@ -185,16 +206,22 @@ __device__ __forceinline__ void mma_tile(RingState& rs, uint32_t& a_phase, uint8
 #pragma unroll
         for (int j = 0; j < 4; ++j)   // +32 B per K=16 step inside the 128-byte swizzle row
           umma_f16(tmem + kTmemD, adesc + 2 * j, bdesc + 2 * j, idesc, (s | j) != 0 ? 1u : 0u);
-      } else {
+      } else if (kAInTmem) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)   // A: 64 K-values per block = 32 columns, 8 per K=16 step
           umma_f16_ts(tmem + kTmemD, tmem + kTmemA + kb * 32 + j * 8, bdesc + 2 * j, idesc,
                       (s | j) != 0 ? 1u : 0u);
+      } else {
+        const uint64_t adesc = make_desc_sw128(smem_u32(smem + kSmemA) + kb * 16384);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          umma_f16(tmem + kTmemD, adesc + 2 * j, bdesc + 2 * j, idesc, (s | j) != 0 ? 1u : 0u);
       }
       umma_commit(smem_u32(&bars->empty[rs.stage]));
       rs.advance();
     }
     umma_commit(smem_u32(&bars->d_ready));
+    if (l != 0) ph.a_kb ^= 1;
     tl_mark(tl, 1, 200 + l);
   }
 }
@@ -216,14 +243,28 @@ struct EpiCtx {
 __device__ __forceinline__ void epi_bar() {   // all 256 epilogue threads
   asm volatile("bar.sync 1, 256;" ::: "memory");
 }
-// `smem_written`: the ENC tile was written with generic stores (needs the async-proxy fence).
-__device__ __forceinline__ void epi_signal_a(EpiCtx& c, bool smem_written) {
-  if (smem_written) fence_proxy_async();
-  tmem_st_wait();
+// Tile start: the ENC tile has been written with generic stores (async-proxy fence needed) and
+// the previous tile's accumulator reads have retired.
+__device__ __forceinline__ void epi_signal_tile_start(EpiCtx& c) {
+  fence_proxy_async();
   tc_fence_before();
   __syncwarp();
-  if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_ready));
+  if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->d_free));
   tl_mark(c.tl, 0, 6);
+}
+// This warp's accumulator columns are in registers.
+__device__ __forceinline__ void epi_signal_d_free(EpiCtx& c) {
+  tc_fence_before();
+  __syncwarp();
+  if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->d_free));
+}
+// This warp's A columns of K block kb are stored in TMEM (and, optionally, ENC smem rewritten).
+__device__ __forceinline__ void epi_signal_kb(EpiCtx& c, int kb, bool smem_written) {
+  if (smem_written || !kAInTmem) fence_proxy_async();
+  if (kAInTmem) tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_kb[kb]));
 }
 __device__ __forceinline__ void epi_wait_d(EpiCtx& c) {
   mbar_wait(smem_u32(&c.bars->d_ready), c.d_phase, 5);
@@ -231,6 +272,11 @@ __device__ __forceinline__ void epi_wait_d(EpiCtx& c) {
   tc_fence_after();
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z,
+                                             uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w)
+               : "memory");
+}
 __device__ __forceinline__ void add_f32x2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
   asm("{ .reg .b64 a, b, d; mov.b64 a, {%2,%3}; mov.b64 b, {%4,%5}; add.rn.f32x2 d, a, b; mov.b64 {%0,%1}, d; }"
       : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
@@ -285,32 +331,67 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* 
       }
     }
   }
-  if (kStore) tmem_st16(a_dst, h);
+  if (kStore) {
+    if (kAInTmem) {
+      tmem_st16(a_dst, h);
+    } else {
+      // a_dst = smem address of this row inside K block 0; n0 selects K block and 16-byte chunk
+      const uint32_t kb = static_cast<uint32_t>(n0) >> 6;
+      const uint32_t c0 = (static_cast<uint32_t>(n0) & 63u) >> 3;      // first of 4 chunks
+      const uint32_t rsw = (a_dst >> 7) & 7u;                          // row & 7 (tile is 1024-aligned)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        st_shared_v4(a_dst + kb * 16384u + (((c0 + j) ^ rsw) << 4), h[4 * j], h[4 * j + 1], h[4 * j + 2],
+                     h[4 * j + 3]);
+    }
+  }
 }
 
-// Hidden-layer epilogue of this thread's 128 accumulator columns.
+// Hidden-layer epilogue of this thread's 128 accumulator columns: drain them into registers,
+// release the accumulator, then emit the next layer's A operand K block by K block.
+//   kStore = false: last layer of a sigma-only tile (nothing to hand to the tensor core).
+//   dir_row != nullptr (xyz_encoding_final in NeRF.forward mode): also rewrite the ENC tile with
+//   this row's embedded direction before the last signal.
 template <bool kRelu, bool kSigma, bool kStore>
 __device__ __forceinline__ void epi_hidden(EpiCtx& c, const float* bias, const float* wsig,
-                                           float& sig_acc) {
+                                           float& sig_acc, const float* __restrict__ dir_row = nullptr) {
   const int nb = c.half * 128;
-  const uint32_t a_dst = c.tmem_row + kTmemA + c.half * 64;   // 2 fp16 per column
+  const uint32_t a_row = smem_u32(c.smem + kSmemA) + static_cast<uint32_t>(c.row) * 128u;
+  const uint32_t a_tm = c.tmem_row + kTmemA + c.half * 64;    // 2 fp16 per column
   const uint32_t d_src = c.tmem_row + kTmemD + nb;
   tl_mark(c.tl, 0, 1);
   epi_wait_d(c);
   tl_mark(c.tl, 0, 2);
-  uint32_t r0[32], r1[32];
+  uint32_t r0[32], r1[32], r2[32], r3[32];
   tmem_ld32(d_src, r0);
   tmem_ld32(d_src + 32, r1);
+  tmem_ld32(d_src + 64, r2);
+  tmem_ld32(d_src + 96, r3);
   tmem_ld_wait();
+  if (kStore && kPipelinedHandover) epi_signal_d_free(c);
   tl_mark(c.tl, 0, 3);
-  epi_chunk<kRelu, kSigma, kStore>(r0, bias, nb, a_dst, wsig, sig_acc);
-  tmem_ld32(d_src + 64, r0);
-  epi_chunk<kRelu, kSigma, kStore>(r1, bias, nb + 32, a_dst + 16, wsig, sig_acc);
-  tmem_ld32(d_src + 96, r1);
-  tmem_ld_wait();
+  epi_chunk<kRelu, kSigma, kStore>(r0, bias, nb, kAInTmem ? a_tm : a_row, wsig, sig_acc);
+  epi_chunk<kRelu, kSigma, kStore>(r1, bias, nb + 32, kAInTmem ? a_tm + 16 : a_row, wsig, sig_acc);
+  if (kStore && kPipelinedHandover) epi_signal_kb(c, 2 * c.half, false);
   tl_mark(c.tl, 0, 4);
-  epi_chunk<kRelu, kSigma, kStore>(r0, bias, nb + 64, a_dst + 32, wsig, sig_acc);
-  epi_chunk<kRelu, kSigma, kStore>(r1, bias, nb + 96, a_dst + 48, wsig, sig_acc);
+  epi_chunk<kRelu, kSigma, kStore>(r2, bias, nb + 64, kAInTmem ? a_tm + 32 : a_row, wsig, sig_acc);
+  epi_chunk<kRelu, kSigma, kStore>(r3, bias, nb + 96, kAInTmem ? a_tm + 48 : a_row, wsig, sig_acc);
+  if (dir_row != nullptr) {
+    // ENC tile is dead after layer 5: reuse it for the embedded direction (cols 27..63 zero)
+    uint8_t* enc = c.smem + kSmemEnc;
+    const int k0 = c.half * 32;
+    for (int k = k0; k < k0 + 32; ++k) {
+      const float v = (k < kEncDir) ? __ldg(dir_row + k) : 0.f;
+      *reinterpret_cast<__half*>(enc + sw128_off(c.row, k)) = __float2half_rn(v);
+    }
+  }
+  if (kStore) {
+    if (!kPipelinedHandover) {
+      epi_signal_d_free(c);
+      epi_signal_kb(c, 2 * c.half, false);
+    }
+    epi_signal_kb(c, 2 * c.half + 1, dir_row != nullptr);
+  }
   tl_mark(c.tl, 0, 5);
 }
 
@@ -361,29 +442,15 @@ __device__ __forceinline__ void epi_run_tile(EpiCtx& c, bool sigma_only, const f
   sig_part = 0.f;
   rgb_part[0] = rgb_part[1] = rgb_part[2] = 0.f;
   float dummy = 0.f;
-  epi_signal_a(c, true);
-  for (int l = 0; l < 7; ++l) {
-    epi_hidden<true, false, true>(c, bias + l * 256, nullptr, dummy);
-    epi_signal_a(c, false);
-  }
+  epi_signal_tile_start(c);
+  for (int l = 0; l < 7; ++l) epi_hidden<true, false, true>(c, bias + l * 256, nullptr, dummy);
   if (sigma_only) {
     epi_hidden<true, true, false>(c, bias + 7 * 256, wsig, sig_part);
-    return;   // next signal comes with the next tile's ENC write
+    return;   // the accumulator is released with the next tile's ENC write
   }
   epi_hidden<true, true, true>(c, bias + 7 * 256, wsig, sig_part);
-  epi_signal_a(c, false);
   // xyz_encoding_final: bias only, no activation (models/nerf.py:116)
-  epi_hidden<false, false, true>(c, bias + 8 * 256, nullptr, dummy);
-  if (dir_row != nullptr) {
-    // ENC tile is dead after layer 5: reuse it for the embedded direction (cols 27..63 zero)
-    uint8_t* enc = c.smem + kSmemEnc;
-    const int k0 = c.half * 32;
-    for (int k = k0; k < k0 + 32; ++k) {
-      const float v = (k < kEncDir) ? __ldg(dir_row + k) : 0.f;
-      *reinterpret_cast<__half*>(enc + sw128_off(c.row, k)) = __float2half_rn(v);
-    }
-  }
-  epi_signal_a(c, dir_row != nullptr);
+  epi_hidden<false, false, true>(c, bias + 8 * 256, nullptr, dummy, dir_row);
   epi_wait_d(c);
   epi_dir(c, dbias != nullptr ? dbias : (bias + 9 * 256), c.cst + kF32WRgb, rgb_part);
 }

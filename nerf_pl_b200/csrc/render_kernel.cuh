@@ -272,11 +272,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
   } else if (warp == kMmaWarp) {
     if (lane == 0) {
       RingState rs;
-      uint32_t a_phase = 0;
+      MmaPhases ph;
       Timeline tlm{(blockIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
       for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        for (int t = 0; t < tiles_c; ++t) mma_tile(rs, a_phase, smem, bars, coarse_sigma_only, false, &tlm);
-        for (int t = 0; t < tiles_f; ++t) mma_tile(rs, a_phase, smem, bars, false, false, &tlm);
+        for (int t = 0; t < tiles_c; ++t) mma_tile(rs, ph, smem, bars, coarse_sigma_only, false, &tlm);
+        for (int t = 0; t < tiles_f; ++t) mma_tile(rs, ph, smem, bars, false, false, &tlm);
       }
     }
   } else {

