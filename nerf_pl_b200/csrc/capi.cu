@@ -122,6 +122,7 @@ struct Arena {
   }
 };
 Arena g_arena[64];
+std::mutex g_arena_mu;   // separate from g_mu: the host entry calls nerfb200_render_rays (device_info locks g_mu)
 
 }  // namespace
 
@@ -227,7 +228,7 @@ int nerfb200_render_rays_host(const nerfb200_render_args* h, void* stream_v) {
   // rays + 4 random inputs + 8 float outputs (+3 optional) + status, each rounded to 256 B
   size_t need = 16 * 256 + n * fl * (8 + Sc + Sc + K + Sf + 3 + 1 + 1 + 3 + 1 + 1 + Sf + Sc + Sf) + 256;
   Arena& ar = g_arena[dev];
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(g_arena_mu);
   rc = ar.reserve(need);
   if (rc) return rc;
   ar.off = 0;

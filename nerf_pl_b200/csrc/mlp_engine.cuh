@@ -362,20 +362,38 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, const float* bias, const f
   tl_mark(c.tl, 0, 1);
   epi_wait_d(c);
   tl_mark(c.tl, 0, 2);
-  uint32_t r0[32], r1[32], r2[32], r3[32];
-  tmem_ld32(d_src, r0);
-  tmem_ld32(d_src + 32, r1);
-  tmem_ld32(d_src + 64, r2);
-  tmem_ld32(d_src + 96, r3);
-  tmem_ld_wait();
-  if (kStore && kPipelinedHandover) epi_signal_d_free(c);
-  tl_mark(c.tl, 0, 3);
-  epi_chunk<kRelu, kSigma, kStore>(r0, bias, nb, kAInTmem ? a_tm : a_row, wsig, sig_acc);
-  epi_chunk<kRelu, kSigma, kStore>(r1, bias, nb + 32, kAInTmem ? a_tm + 16 : a_row, wsig, sig_acc);
-  if (kStore && kPipelinedHandover) epi_signal_kb(c, 2 * c.half, false);
-  tl_mark(c.tl, 0, 4);
-  epi_chunk<kRelu, kSigma, kStore>(r2, bias, nb + 64, kAInTmem ? a_tm + 32 : a_row, wsig, sig_acc);
-  epi_chunk<kRelu, kSigma, kStore>(r3, bias, nb + 96, kAInTmem ? a_tm + 48 : a_row, wsig, sig_acc);
+  if (kPipelinedHandover) {
+    // drain everything first so the accumulator can be released early
+    uint32_t r0[32], r1[32], r2[32], r3[32];
+    tmem_ld32(d_src, r0);
+    tmem_ld32(d_src + 32, r1);
+    tmem_ld32(d_src + 64, r2);
+    tmem_ld32(d_src + 96, r3);
+    tmem_ld_wait();
+    if (kStore) epi_signal_d_free(c);
+    tl_mark(c.tl, 0, 3);
+    epi_chunk<kRelu, kSigma, kStore>(r0, bias, nb, kAInTmem ? a_tm : a_row, wsig, sig_acc);
+    epi_chunk<kRelu, kSigma, kStore>(r1, bias, nb + 32, kAInTmem ? a_tm + 16 : a_row, wsig, sig_acc);
+    if (kStore) epi_signal_kb(c, 2 * c.half, false);
+    tl_mark(c.tl, 0, 4);
+    epi_chunk<kRelu, kSigma, kStore>(r2, bias, nb + 64, kAInTmem ? a_tm + 32 : a_row, wsig, sig_acc);
+    epi_chunk<kRelu, kSigma, kStore>(r3, bias, nb + 96, kAInTmem ? a_tm + 48 : a_row, wsig, sig_acc);
+  } else {
+    // two chunks in flight: the next tcgen05.ld overlaps the conversion of the previous chunk
+    uint32_t r0[32], r1[32];
+    tmem_ld32(d_src, r0);
+    tmem_ld32(d_src + 32, r1);
+    tmem_ld_wait();
+    tl_mark(c.tl, 0, 3);
+    epi_chunk<kRelu, kSigma, kStore>(r0, bias, nb, kAInTmem ? a_tm : a_row, wsig, sig_acc);
+    tmem_ld32(d_src + 64, r0);
+    epi_chunk<kRelu, kSigma, kStore>(r1, bias, nb + 32, kAInTmem ? a_tm + 16 : a_row, wsig, sig_acc);
+    tmem_ld32(d_src + 96, r1);
+    tmem_ld_wait();
+    tl_mark(c.tl, 0, 4);
+    epi_chunk<kRelu, kSigma, kStore>(r0, bias, nb + 64, kAInTmem ? a_tm + 32 : a_row, wsig, sig_acc);
+    epi_chunk<kRelu, kSigma, kStore>(r1, bias, nb + 96, kAInTmem ? a_tm + 48 : a_row, wsig, sig_acc);
+  }
   if (dir_row != nullptr) {
     // ENC tile is dead after layer 5: reuse it for the embedded direction (cols 27..63 zero)
     uint8_t* enc = c.smem + kSmemEnc;
