@@ -37,10 +37,19 @@ __global__ void pack_weights_kernel(const PackParams pp) {
     else if (slice == 13) { W = pp.p[8]; ld = 319; koff = 0; kvalid = 63; }
     else if (slice <= 17) { W = pp.p[8]; ld = 319; koff = 63 + (slice - 14) * 64; kvalid = 64; }
     else if (slice <= 29) { const int l = 5 + (slice - 18) / 4; W = pp.p[2 * l]; ld = 256; koff = ((slice - 18) % 4) * 64; kvalid = 64; }
-    else if (slice <= 33) { W = pp.p[16]; ld = 256; koff = (slice - 30) * 64; kvalid = 64; }
-    else if (slice <= 37) { W = pp.p[18]; ld = 283; koff = (slice - 34) * 64; kvalid = 64; }
+    else if (slice <= 33) { W = nullptr; ld = 0; koff = (slice - 30) * 64; kvalid = 64; }   // fused W' (below)
     else { W = pp.p[18]; ld = 283; koff = 256; kvalid = 27; }
-    const float v = (k < kvalid) ? W[static_cast<long long>(n) * ld + koff + k] : 0.f;
+    float v = 0.f;
+    if (W == nullptr) {
+      // W'[n][koff+k] = sum_m W_dir[n][m] * W_final[m][koff+k]   (fp32, layout.h)
+      const float* wd = pp.p[18] + static_cast<long long>(n) * 283;
+      const float* wf = pp.p[16] + koff + k;
+      float acc = 0.f;
+      for (int m = 0; m < 256; ++m) acc = fmaf(wd[m], wf[static_cast<long long>(m) * 256], acc);
+      v = acc;
+    } else if (k < kvalid) {
+      v = W[static_cast<long long>(n) * ld + koff + k];
+    }
     const uint32_t base = (slice < kNumSlices256) ? slice * kSliceBytes256
                                                    : kOffDir + (slice - kNumSlices256) * kSliceBytes128;
     (void)N;
@@ -55,15 +64,20 @@ __global__ void pack_weights_kernel(const PackParams pp) {
   if (i < kF32WSigma) {
     const int l = i / 256, n = i % 256;
     if (l < 8) v = pp.p[2 * l + 1][n];
-    else if (l == 8) v = pp.p[17][n];
-    else v = (n < 128) ? pp.p[19][n] : 0.f;
+    else if (n < 128) {
+      // b'[n] = b_dir[n] + sum_m W_dir[n][m] * b_final[m]
+      float acc = pp.p[19][n];
+      const float* wd = pp.p[18] + static_cast<long long>(n) * 283;
+      for (int m = 0; m < 256; ++m) acc = fmaf(wd[m], pp.p[17][m], acc);
+      v = acc;
+    }
   } else if (i < kF32BSigma) v = pp.p[20][i - kF32WSigma];
   else if (i < kF32WRgb) v = (i == kF32BSigma) ? pp.p[21][0] : 0.f;
   else if (i < kF32BRgb) v = pp.p[22][i - kF32WRgb];
   else if (i < kF32WDirPart) v = (i - kF32BRgb < 3) ? pp.p[23][i - kF32BRgb] : 0.f;
   else {
     const int j = i - kF32WDirPart;
-    const int n = j / 28, k = j % 28;
+    const int k = j / 128, n = j % 128;          // transposed: coalesced over n
     v = (k < 27) ? pp.p[18][static_cast<long long>(n) * 283 + 256 + k] : 0.f;
   }
   o[i] = v;

@@ -10,10 +10,14 @@
 //       slice 13       xyz_encoding_5  W[:, 0:63]  (skip: encoded-input part)   N=256
 //       slice 14..17   xyz_encoding_5  W[:, 63:319] (hidden part)               N=256
 //       slice 18..29   xyz_encoding_6..8                                        N=256
-//       slice 30..33   xyz_encoding_final                                       N=256
-//       slice 34..37   dir_encoding    W[:, 0:256]                              N=128
-//       slice 38       dir_encoding    W[:, 256:283] (cols 27..63 zero)         N=128
-//  [fp32 region]  biases (10 x 256), sigma head, rgb head, dir_encoding W[:, 256:283].
+//       slice 30..33   W' = W_dir[:, 0:256] . W_final   (see below)             N=128
+//       slice 34       dir_encoding    W[:, 256:283] (cols 27..63 zero)         N=128
+//  [fp32 region]  biases (9 x 256), sigma head, rgb head, dir_encoding W[:, 256:283] transposed.
+//
+//  xyz_encoding_final has no activation (models/nerf.py:70,116), so it is folded into the
+//  direction layer at pack time (fp32):  relu(W_dir . [W_f h + b_f, dir] + b_dir)
+//    = relu(W' h + W_dir[:, 256:283] dir + b'),  W' = W_dir[:, 0:256] W_f,  b' = W_dir[:, 0:256] b_f + b_dir.
+//  Same function, one 256->128 layer instead of 256->256->128 (65,536 fewer MACs per sample).
 #pragma once
 #include <cstdint>
 
@@ -26,22 +30,22 @@ constexpr int kDirW = 128;         // W//2                    (models/nerf.py:74
 
 constexpr uint32_t kSliceBytes256 = 256 * 128;   // 32 KiB
 constexpr uint32_t kSliceBytes128 = 128 * 128;   // 16 KiB
-constexpr int kNumSlices256 = 34;
+constexpr int kNumSlices256 = 30;                // layers 1..8
 constexpr int kNumSlicesSigmaOnly = 30;          // layers 1..8 only
-constexpr int kNumSlices128 = 5;                 // 4 hidden + 1 direction-part slice
+constexpr int kNumSlices128 = 5;                 // fused final.dir: 4 hidden + 1 direction-part slice
 
-constexpr uint32_t kOffDir = kNumSlices256 * kSliceBytes256;                 // 1,114,112
-constexpr uint32_t kHalfRegionBytes = kOffDir + kNumSlices128 * kSliceBytes128;  // 1,196,032
+constexpr uint32_t kOffDir = kNumSlices256 * kSliceBytes256;                 //   983,040
+constexpr uint32_t kHalfRegionBytes = kOffDir + kNumSlices128 * kSliceBytes128;  // 1,064,960
 
 // fp32 region (offsets in floats from the start of the region)
-constexpr int kNumBiasRows = 10;                 // b1..b8, b_final, b_dir(128 used)
-constexpr int kF32Bias = 0;                      // [10][256]
+constexpr int kNumBiasRows = 9;                  // b1..b8, b' (128 used)
+constexpr int kF32Bias = 0;                      // [9][256]
 constexpr int kF32WSigma = kF32Bias + kNumBiasRows * 256;   // [256]
 constexpr int kF32BSigma = kF32WSigma + 256;     // [4]  (1 used)
 constexpr int kF32WRgb = kF32BSigma + 4;         // [3][128]
 constexpr int kF32BRgb = kF32WRgb + 3 * 128;     // [4]  (3 used)
-constexpr int kF32WDirPart = kF32BRgb + 4;       // [128][28] (27 used)
-constexpr int kF32Count = kF32WDirPart + 128 * 28;
+constexpr int kF32WDirPart = kF32BRgb + 4;       // [28][128] transposed: [j][n] = W_dir[n][256+j] (27 used)
+constexpr int kF32Count = kF32WDirPart + 28 * 128;
 constexpr uint32_t kPackedBytes = kHalfRegionBytes + kF32Count * 4;
 
 // Parameter order of the 24 tensors handed to the pack routine

@@ -63,7 +63,7 @@ static_assert(2 * kConstFloats * 4 <= 32768, "constants of two networks must fit
 constexpr uint32_t kSmemTotal = 232448;              // 227 KiB (max opt-in)
 constexpr uint32_t kScratchBytes = kSmemTotal - kSmemScratch;       // 19456
 
-constexpr int kLayersFull = 10;       // L1..L8, final, dir
+constexpr int kLayersFull = 9;        // L1..L8, fused final.dir
 constexpr int kLayersSigma = 8;       // L1..L8
 
 struct Barriers {
@@ -191,10 +191,10 @@ __device__ __forceinline__ void mma_tile(RingState& rs, MmaPhases& ph, uint8_t* 
     ph.d_free ^= 1;
     tc_fence_after();
     tl_mark(tl, 1, 100 + l);
-    const int n_slices = (l == 0) ? 1 : (l == 4) ? 5 : (l == 9 && dir_slice) ? 5 : 4;
-    const uint32_t idesc = (l == 9) ? make_idesc_f16(128) : make_idesc_f16(256);
+    const int n_slices = (l == 0) ? 1 : (l == 4) ? 5 : (l == 8 && dir_slice) ? 5 : 4;
+    const uint32_t idesc = (l == 8) ? make_idesc_f16(128) : make_idesc_f16(256);
     for (int s = 0; s < n_slices; ++s) {
-      const bool from_enc = (l == 0) || (l == 4 && s == 0) || (l == 9 && s == 4);
+      const bool from_enc = (l == 0) || (l == 4 && s == 0) || (l == 8 && s == 4);
       const int kb = (l == 4) ? s - 1 : s;
       const uint32_t b_addr = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
       mbar_wait(smem_u32(&bars->full[rs.stage]), rs.phase, 4);
@@ -350,8 +350,8 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* 
 // Hidden-layer epilogue of this thread's 128 accumulator columns: drain them into registers,
 // release the accumulator, then emit the next layer's A operand K block by K block.
 //   kStore = false: last layer of a sigma-only tile (nothing to hand to the tensor core).
-//   dir_row != nullptr (xyz_encoding_final in NeRF.forward mode): also rewrite the ENC tile with
-//   this row's embedded direction before the last signal.
+//   dir_row != nullptr (layer 8 in NeRF.forward mode): also rewrite the ENC tile with this row's
+//   embedded direction before the last signal.
 template <bool kRelu, bool kSigma, bool kStore>
 __device__ __forceinline__ void epi_hidden(EpiCtx& c, const float* bias, const float* wsig,
                                            float& sig_acc, const float* __restrict__ dir_row = nullptr) {
@@ -466,11 +466,11 @@ __device__ __forceinline__ void epi_run_tile(EpiCtx& c, bool sigma_only, const f
     epi_hidden<true, true, false>(c, bias + 7 * 256, wsig, sig_part);
     return;   // the accumulator is released with the next tile's ENC write
   }
-  epi_hidden<true, true, true>(c, bias + 7 * 256, wsig, sig_part);
-  // xyz_encoding_final: bias only, no activation (models/nerf.py:116)
-  epi_hidden<false, false, true>(c, bias + 8 * 256, nullptr, dummy, dir_row);
+  // layer 8's activations feed the fused final.dir layer (layout.h); in NeRF.forward mode the ENC
+  // tile is rewritten with this row's embedded direction for the extra K slice
+  epi_hidden<true, true, true>(c, bias + 7 * 256, wsig, sig_part, dir_row);
   epi_wait_d(c);
-  epi_dir(c, dbias != nullptr ? dbias : (bias + 9 * 256), c.cst + kF32WRgb, rgb_part);
+  epi_dir(c, dbias != nullptr ? dbias : (bias + 8 * 256), c.cst + kF32WRgb, rgb_part);
 }
 
 __device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf(-x)); }

@@ -95,6 +95,18 @@ __device__ __forceinline__ void embed3(const float x[3], int n_freqs, float* out
   }
 }
 
+// sin / cos of arguments up to a few thousand radians (2^9 * |x|): two-constant Cody-Waite
+// reduction by 2 pi (6.28125 is exact in 8 bits, so n * 6.28125 is exact for n < 2^16), then the
+// MUFU approximations on [-pi, pi] (abs error 2^-21.4).  Total abs error ~1e-6, three orders of
+// magnitude below the fp16 rounding (4.9e-4) the encoded features receive anyway.
+__device__ __forceinline__ void fast_sincos(float a, float& s, float& c) {
+  const float n = rintf(a * 0.15915494309189535f);
+  float r = fmaf(n, -6.28125f, a);
+  r = fmaf(n, -1.9353071795864769e-3f, r);
+  s = __sinf(r);
+  c = __cosf(r);
+}
+
 // Encoded xyz of one sample row into the ENC tile; the two column-half threads of a row split
 // the ten frequencies.  Feature order models/nerf.py:33-38: [x, sin f0 x, cos f0 x, sin f1 x, ..].
 __device__ __forceinline__ void encode_row(uint8_t* enc, int row, int half, const float o[3],
@@ -111,12 +123,12 @@ __device__ __forceinline__ void encode_row(uint8_t* enc, int row, int half, cons
   }
   const int k0 = half * 5;
   float f = half ? 32.f : 1.f;
-#pragma unroll 1
+#pragma unroll
   for (int k = k0; k < k0 + 5; ++k, f *= 2.f) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float s, co;
-      sincosf(f * x[c], &s, &co);
+      fast_sincos(f * x[c], s, co);
       *reinterpret_cast<__half*>(enc + sw128_off(row, 3 + 6 * k + c)) = __float2half_rn(s);
       *reinterpret_cast<__half*>(enc + sw128_off(row, 3 + 6 * k + 3 + c)) = __float2half_rn(co);
     }
@@ -180,27 +192,25 @@ __device__ __forceinline__ RayOut composite_ray(int lane, int S, const float* z,
   return out;
 }
 
-// sample_pdf (models/rendering.py:14-55) for one ray by one warp.
-//   zc[0..S)      coarse depths (sorted)        w[0..S) coarse weights
-//   bins = mid-points (S-1), weights = w[1..S-2] (S-2)
-//   u[0..K)       sorted sample positions in [0,1]; overwritten with the K new depths.
-//   cdf[0..S-1)   scratch
-__device__ __forceinline__ void sample_pdf_ray(int lane, int S, int K, const float* zc,
-                                               const float* w, float* cdf, float* u) {
+// sample_pdf, first half (models/rendering.py:28-33) for one ray by one warp:
+//   weights = w[1..S-2] + 1e-5 -> pdf -> cdf[0..S-2] (cdf[0] = 0), S-1 entries.
+__device__ __forceinline__ void pdf_to_cdf_ray(int lane, int S, const float* w, float* cdf) {
   const int nw = S - 2;            // N_samples_
-  // pdf normaliser
   float part = 0.f;
   for (int i = lane; i < nw; i += 32) part += __fadd_rn(w[1 + i], 1e-5f);
   const float total = warp_sum(part);
-  // cdf[0] = 0, cdf[k] = sum_{i<k} pdf[i]: per-lane contiguous segments + warp scan
+  // per-lane contiguous segments + warp scan
   const int per = (nw + 31) >> 5;
   float loc[4];
   float run = 0.f;
-  for (int p = 0; p < per; ++p) {
-    const int i = lane * per + p;
-    const float pdf = (i < nw) ? __fdiv_rn(__fadd_rn(w[1 + i], 1e-5f), total) : 0.f;
-    run += pdf;
-    loc[p] = run;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    if (p < per) {
+      const int i = lane * per + p;
+      const float pdf = (i < nw) ? __fdiv_rn(__fadd_rn(w[1 + i], 1e-5f), total) : 0.f;
+      run += pdf;
+      loc[p] = run;
+    }
   }
   float incl = run;
 #pragma unroll
@@ -210,31 +220,34 @@ __device__ __forceinline__ void sample_pdf_ray(int lane, int S, int K, const flo
   }
   float excl = __shfl_up_sync(0xffffffffu, incl, 1);
   if (lane == 0) { excl = 0.f; cdf[0] = 0.f; }
-  for (int p = 0; p < per; ++p) {
-    const int i = lane * per + p;
-    if (i < nw) cdf[i + 1] = excl + loc[p];
-  }
-  __syncwarp();
-  const int ncdf = nw + 1;         // == S-1 entries, last valid index nw
-  for (int j = lane; j < K; j += 32) {
-    const float uj = u[j];
-    // searchsorted(cdf, u, side='right'): number of entries <= u
-    int lo = 0, hi = ncdf;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (cdf[mid] <= uj) lo = mid + 1; else hi = mid;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    if (p < per) {
+      const int i = lane * per + p;
+      if (i < nw) cdf[i + 1] = excl + loc[p];
     }
-    const int below = max(lo - 1, 0);
-    const int above = min(lo, nw);
-    const float c0 = cdf[below], c1 = cdf[above];
-    const float b0 = 0.5f * __fadd_rn(zc[below], zc[below + 1]);
-    const float b1 = 0.5f * __fadd_rn(zc[above], zc[above + 1]);
-    float denom = __fsub_rn(c1, c0);
-    if (denom < 1e-5f) denom = 1.f;
-    const float t = __fdiv_rn(__fsub_rn(uj, c0), denom);
-    u[j] = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
   }
-  __syncwarp();
+}
+
+// sample_pdf, second half (models/rendering.py:42-54) for one sample position u:
+//   inds = searchsorted(cdf, u, 'right'); below/above clamps; linear interpolation between the
+//   bin mid-points (bins[k] = 0.5 (z[k] + z[k+1])).
+__device__ __forceinline__ float inverse_cdf(int S, const float* zc, const float* cdf, float u) {
+  const int nw = S - 2;
+  int lo = 0, hi = nw + 1;         // S-1 cdf entries, last valid index nw
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  const int below = max(lo - 1, 0);
+  const int above = min(lo, nw);
+  const float c0 = cdf[below], c1 = cdf[above];
+  const float b0 = 0.5f * __fadd_rn(zc[below], zc[below + 1]);
+  const float b1 = 0.5f * __fadd_rn(zc[above], zc[above + 1]);
+  float denom = __fsub_rn(c1, c0);
+  if (denom < 1e-5f) denom = 1.f;
+  const float tt = __fdiv_rn(__fsub_rn(u, c0), denom);
+  return __fadd_rn(b0, __fmul_rn(tt, __fsub_rn(b1, b0)));
 }
 
 template <bool kDummy>
@@ -298,13 +311,24 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
       const bool valid1 = (ray0 + 1) < p.n_rays;
       const int rid[2] = {ray0, valid1 ? ray0 + 1 : ray0};
       // ---- rays, direction embedding (models/rendering.py:179-186)
+      tl_mark(c.tl, 0, 30);
       if (t < 16) sc->ray[t >> 3][t & 7] = __ldg(p.rays + static_cast<long long>(rid[t >> 3]) * p.ray_stride + (t & 7));
       epi_bar();
       if (t < 2) {
         const float* d = &sc->ray[t][3];
         sc->dnorm[t] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
-        embed3(d, 4, sc->direnc[t]);
-        sc->direnc[t][27] = 0.f;
+      } else if (t >= 32 && t < 32 + 30) {
+        // Embedding(3,4)(rays_d) (models/rendering.py:186): one (ray, coord, freq) per thread, accurate sincosf
+        const int q = t - 32, r = q / 15, cc = (q % 15) / 5, k = q % 5;     // k == 4: the raw value
+        const float dv = sc->ray[r][3 + cc];
+        if (k == 4) {
+          sc->direnc[r][cc] = dv;
+        } else {
+          float sn, cs;
+          sincosf(__fmul_rn(static_cast<float>(1 << k), dv), &sn, &cs);
+          sc->direnc[r][3 + 6 * k + cc] = sn;
+          sc->direnc[r][3 + 6 * k + 3 + cc] = cs;
+        }
       }
       // ---- coarse depths (models/rendering.py:189-204)
       for (int e = t; e < 2 * Sc; e += kEpiThreads) {
@@ -322,6 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
         sc->z[e] = z;
         sc->zc[r][i] = z;
       }
+      tl_mark(c.tl, 0, 31);
       epi_bar();
 
       // ================= two passes: coarse, fine =================
@@ -335,11 +360,15 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
         if (!sigma_only) {
           // per-ray direction bias: b_dir + W_dir[:, 256:283] . dir_embedded   (fp32)
           const int r = t >> 7, n = t & 127;
-          const float* wd = c.f32 + kF32WDirPart + n * 28;
-          float acc = __ldg(c.f32 + kF32Bias + 9 * 256 + n);
+          const float* wd = c.f32 + kF32WDirPart + n;           // [j][n]: coalesced over n
+          float wv[27];
 #pragma unroll
-          for (int j = 0; j < 27; ++j) acc = fmaf(__ldg(wd + j), sc->direnc[r][j], acc);
+          for (int j = 0; j < 27; ++j) wv[j] = __ldg(wd + j * 128);
+          float acc = c.cst[kF32Bias + 8 * 256 + n];
+#pragma unroll
+          for (int j = 0; j < 27; ++j) acc = fmaf(wv[j], sc->direnc[r][j], acc);
           sc->dirbias[r][n] = acc;
+          tl_mark(c.tl, 0, 27);
           epi_bar();
         }
         for (int tile = 0; tile < tiles; ++tile) {
@@ -378,6 +407,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
                                          sc->rgb[1] + r * S, sc->rgb[2] + r * S, nz, p.noise_std,
                                          sc->dnorm[r], !sigma_only, sc->w[r]);
           __syncwarp();
+          tl_mark(c.tl, 0, 22);
           const bool wr = (r == 0) || valid1;
           if (wr) {
             const long long ri = rid[r];
@@ -403,45 +433,50 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
               }
             }
           }
-          // ---- hierarchical resampling (models/rendering.py:223-229)
-          if (pass == 0 && fine) {
-            if (p.perturb > 0.f) {
-              // u ~ U[0,1): rank-sort so the new depths come out ascending
-              const float* ur = p.u_rand + static_cast<long long>(rid[r]) * K;
-              for (int j = lane; j < K; j += 32) {
-                const float uj = __ldg(ur + j);
-                int rank = 0;
-                for (int q = 0; q < K; ++q) {
-                  const float uq = __ldg(ur + q);
-                  rank += (uq < uj) || (uq == uj && q < j);
-                }
-                sc->znew[r][rank] = uj;
-              }
-            } else {
-              for (int j = lane; j < K; j += 32) sc->znew[r][j] = linspace01(j, K);
-            }
-            __syncwarp();
-            sample_pdf_ray(lane, Sc, K, sc->zc[r], sc->w[r], sc->cdf[r], sc->znew[r]);
-          }
+          tl_mark(c.tl, 0, 23);
+          // ---- hierarchical resampling, part 1 (models/rendering.py:28-33): pdf -> cdf
+          if (pass == 0 && fine) pdf_to_cdf_ray(lane, Sc, sc->w[r], sc->cdf[r]);
+          tl_mark(c.tl, 0, 24);
         }
         epi_bar();
         tl_mark(c.tl, 0, 21);
-        // ---- merge: z_fine = sort(cat(z_coarse, z_new))  (models/rendering.py:229), rank sort
         if (pass == 0 && fine) {
+          // ---- part 2 (:36-54): one u per thread -> inverse-CDF depth; u sorted first when random
+          if (t < 2 * K) {
+            const int r = t / K, j = t - r * K;
+            float uj;
+            int slot = j;
+            if (p.perturb > 0.f) {
+              const float* ur = p.u_rand + static_cast<long long>(rid[r]) * K;
+              uj = __ldg(ur + j);
+              slot = 0;
+#pragma unroll 8
+              for (int q = 0; q < K; ++q) {
+                const float uq = __ldg(ur + q);
+                slot += (uq < uj) || (uq == uj && q < j);
+              }
+            } else {
+              uj = linspace01(j, K);
+            }
+            sc->znew[r][slot] = inverse_cdf(Sc, sc->zc[r], sc->cdf[r], uj);
+          }
+          epi_bar();
+          // ---- merge: z_fine = sort(cat(z_coarse, z_new)) (:229) as a rank sort: position =
+          // number of elements that are smaller, ties broken by index in the concatenation (any
+          // tie order gives the same sorted VALUES, which is all torch.sort's output carries).
           for (int e = t; e < 2 * Sf; e += kEpiThreads) {
             const int r = e / Sf, i = e - r * Sf;
-            const float v = (i < Sc) ? sc->zc[r][i] : sc->znew[r][i - Sc];
+            const float* zc = sc->zc[r];
+            const float* zn = sc->znew[r];
+            const float v = (i < Sc) ? zc[i] : zn[i - Sc];
             int rank = 0;
-            for (int q = 0; q < Sc; ++q) {
-              const float x = sc->zc[r][q];
-              rank += (x < v) || (x == v && q < i);
-            }
-            for (int q = 0; q < K; ++q) {
-              const float x = sc->znew[r][q];
-              rank += (x < v) || (x == v && (q + Sc) < i);
-            }
+#pragma unroll 8
+            for (int q = 0; q < Sc; ++q) rank += (zc[q] < v) || (zc[q] == v && q < i);
+#pragma unroll 8
+            for (int q = 0; q < K; ++q) rank += (zn[q] < v) || (zn[q] == v && (q + Sc) < i);
             sc->z[r * Sf + rank] = v;
           }
+          tl_mark(c.tl, 0, 25);
           epi_bar();
           if (p.z_fine != nullptr) {
             for (int e = t; e < 2 * Sf; e += kEpiThreads) {

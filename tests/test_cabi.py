@@ -33,8 +33,8 @@ def test_header_symbols_exported(lib):
 
 def test_abi_basics(lib):
     assert lib.nerfb200_abi_version() == 1
-    # layout.h: 34 x 32 KiB + 5 x 16 KiB fp16 slices + fp32 tail
-    assert lib.nerfb200_packed_bytes() == 34 * 32768 + 5 * 16384 + 4 * (10 * 256 + 256 + 4 + 384 + 4 + 128 * 28)
+    # layout.h: 30 x 32 KiB + 5 x 16 KiB fp16 slices + fp32 tail
+    assert lib.nerfb200_packed_bytes() == 30 * 32768 + 5 * 16384 + 4 * (9 * 256 + 256 + 4 + 384 + 4 + 28 * 128)
     assert lib.nerfb200_launch_count() >= 0
 
 
