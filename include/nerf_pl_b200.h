@@ -132,6 +132,17 @@ int nerfb200_composite(const float* sigmas, const float* rgbs, const float* z_va
                        int64_t n_rays, int32_t n_samples, float* weights, float* rgb, float* depth,
                        float* opacity, void* stream);
 
+/* ---- ray generation ("next" row: the caller side of the path) ----------------------------
+ * Replaces: datasets/ray_utils.py:5-94 get_ray_directions + get_rays (+ get_ndc_rays as
+ * datasets/llff.py:236-241 applies it when ndc != 0: near plane 1.0, near/far columns 0/1) and
+ * the torch.cat of datasets/blender.py:97-102.  c2w_host: 12 HOST floats, row-major (3,4).
+ * rays: (H*W, 8) device rows [o(3) d(3) near far], pixel order row-major (j, i). */
+int nerfb200_generate_rays(int32_t H, int32_t W, float focal, const float c2w_host[12], float near, float far,
+                           int32_t ndc, float* rays, void* stream);
+
+/* Replaces: eval.py:126-128 (clip(img,0,1)*255).astype(uint8) on the rendered image, on device. */
+int nerfb200_to_uint8(const float* src, int64_t n, uint8_t* dst, void* stream);
+
 /* ---- diagnostics -------------------------------------------------------------------------
  * Number of kernels this library has launched on the calling process so far (all entry
  * points).  bench.py reports the delta as `gpu_launches`. */

@@ -38,6 +38,8 @@ EXPORTS = [
     "nerfb200_searchsorted",
     "nerfb200_sample_pdf",
     "nerfb200_composite",
+    "nerfb200_generate_rays",
+    "nerfb200_to_uint8",
     "nerfb200_launch_count",
     "nerfb200_debug_gemm",
     "nerfb200_debug_timeline",
@@ -134,6 +136,11 @@ def _declare(lib: ctypes.CDLL) -> None:
                                        c_void_p, c_void_p]
     lib.nerfb200_debug_gemm.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
     lib.nerfb200_debug_gemm.restype = c_int32
+    lib.nerfb200_generate_rays.argtypes = [c_int32, c_int32, c_float, POINTER(c_float), c_float, c_float, c_int32,
+                                           c_void_p, c_void_p]
+    lib.nerfb200_generate_rays.restype = c_int32
+    lib.nerfb200_to_uint8.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
+    lib.nerfb200_to_uint8.restype = c_int32
     lib.nerfb200_debug_mma_bench.argtypes = [c_void_p, c_int32, c_int32, c_void_p]
     lib.nerfb200_debug_mma_bench.restype = c_int32
     lib.nerfb200_debug_timeline.argtypes = [c_void_p, c_int64]

@@ -384,6 +384,67 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_probe_kernel(const float* __
   engine_teardown(bars);
 }
 
+// ------------------------------------------------ ray generation (datasets/ray_utils.py:5-94)
+// One thread per pixel: get_ray_directions (:16-22, no +0.5 pixel centre), get_rays (:41-46:
+// rotate by c2w[:, :3], normalise, origin = c2w[:, 3]) and optionally get_ndc_rays (:75-92, as
+// datasets/llff.py:236-241 applies it: near plane 1.0, then near/far columns 0/1).
+// Writes the (H*W, 8) ray rows [o, d, near, far] the renderer consumes, so rays never cross PCIe.
+struct RayGenParams {
+  int H, W;
+  float focal;
+  float c2w[12];      // row-major (3, 4)
+  float near, far;
+  int ndc;
+  float* rays;
+};
+__global__ void generate_rays_kernel(const RayGenParams p) {
+  const long long total = static_cast<long long>(p.H) * p.W;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(idx / p.W), i = static_cast<int>(idx - static_cast<long long>(j) * p.W);
+    const float dx = __fdiv_rn(static_cast<float>(i) - 0.5f * p.W, p.focal);
+    const float dy = -__fdiv_rn(static_cast<float>(j) - 0.5f * p.H, p.focal);
+    const float dz = -1.f;
+    float d[3], o[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      d[r] = __fadd_rn(__fadd_rn(__fmul_rn(dx, p.c2w[4 * r + 0]), __fmul_rn(dy, p.c2w[4 * r + 1])),
+                       __fmul_rn(dz, p.c2w[4 * r + 2]));
+      o[r] = p.c2w[4 * r + 3];
+    }
+    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+#pragma unroll
+    for (int r = 0; r < 3; ++r) d[r] = __fdiv_rn(d[r], nrm);
+    float near = p.near, far = p.far;
+    if (p.ndc) {
+      const float n1 = 1.0f;                                   // llff.py:238 near plane at 1.0
+      const float tt = -__fdiv_rn(__fadd_rn(n1, o[2]), d[2]);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) o[r] = __fadd_rn(o[r], __fmul_rn(tt, d[r]));
+      const float ox_oz = __fdiv_rn(o[0], o[2]), oy_oz = __fdiv_rn(o[1], o[2]);
+      const float sx = -1.f / (p.W / (2.f * p.focal)), sy = -1.f / (p.H / (2.f * p.focal));
+      const float o0 = sx * ox_oz, o1 = sy * oy_oz, o2 = 1.f + 2.f * n1 / o[2];
+      const float d0 = sx * (__fdiv_rn(d[0], d[2]) - ox_oz), d1 = sy * (__fdiv_rn(d[1], d[2]) - oy_oz);
+      const float d2 = 1.f - o2;
+      o[0] = o0; o[1] = o1; o[2] = o2; d[0] = d0; d[1] = d1; d[2] = d2;
+      near = 0.f; far = 1.f;
+    }
+    float4* out = reinterpret_cast<float4*>(p.rays + idx * 8);
+    out[0] = make_float4(o[0], o[1], o[2], d[0]);
+    out[1] = make_float4(d[1], d[2], near, far);
+  }
+}
+
+// ------------------------------------------------ float image -> uint8 (eval.py:126-128)
+// img_pred_ = (clip(img_pred, 0, 1) * 255).astype(uint8)  (truncation, as numpy's astype does)
+__global__ void to_uint8_kernel(const float* __restrict__ src, long long n, uint8_t* __restrict__ dst) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = fminf(fmaxf(src[i], 0.f), 1.f) * 255.f;
+    dst[i] = static_cast<uint8_t>(v);
+  }
+}
+
 // ------------------------------------------------ diagnostics: raw tcgen05.mma issue rate
 // out[block*8 + v] = SM cycles for `reps` x 16 back-to-back MMAs (K=16 each) of variant v:
 //   0: SS N=256   1: SS N=128   2: TS N=128   3: TS N=256   4: TS N=128 alternating D0/D1

@@ -205,7 +205,7 @@ int nerfb200_render_rays(const nerfb200_render_args* a, void* stream) {
       p.timeline = d->timeline;
     }
   }
-  const int n_groups = (p.n_rays + 1) / 2;
+  const int n_groups = (p.n_rays + 1) / 2;     // two rays share the coarse tile
   int ctas = d->sm_count;
   if (a->max_ctas > 0 && a->max_ctas < ctas) ctas = a->max_ctas;
   if (n_groups < ctas) ctas = n_groups;
@@ -399,6 +399,35 @@ int nerfb200_debug_timeline(int64_t* host_out, int64_t n_values) {
   CUDA_TRY(cudaDeviceSynchronize(), "timeline sync");
   CUDA_TRY(cudaMemcpy(host_out, di->timeline, sizeof(long long) * (n_values < cap ? n_values : cap),
                       cudaMemcpyDeviceToHost), "timeline copy");
+  return 0;
+}
+
+int nerfb200_generate_rays(int32_t H, int32_t W, float focal, const float c2w_host[12], float near, float far,
+                           int32_t ndc, float* rays, void* stream) {
+  if (H <= 0 || W <= 0 || !(focal > 0.f)) return fail(NERFB200_EINVAL, "generate_rays: bad H / W / focal%s");
+  if (!c2w_host || !rays) return fail(NERFB200_EINVAL, "generate_rays: NULL argument%s");
+  if (reinterpret_cast<uintptr_t>(rays) & 15) return fail(NERFB200_EINVAL, "generate_rays: rays must be 16-byte aligned%s");
+  RayGenParams p;
+  p.H = H; p.W = W; p.focal = focal; p.near = near; p.far = far; p.ndc = ndc; p.rays = rays;
+  for (int i = 0; i < 12; ++i) p.c2w[i] = c2w_host[i];
+  const long long total = static_cast<long long>(H) * W;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  generate_rays_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "generate_rays launch");
+  return 0;
+}
+
+int nerfb200_to_uint8(const float* src, int64_t n, uint8_t* dst, void* stream) {
+  if (n < 0) return fail(NERFB200_EINVAL, "to_uint8: n < 0%s");
+  if (n == 0) return 0;
+  if (!src || !dst) return fail(NERFB200_EINVAL, "to_uint8: NULL argument%s");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  to_uint8_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, n, dst);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "to_uint8 launch");
   return 0;
 }
 

@@ -269,17 +269,24 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
   const int Sf = Sc + K;
   const bool fine = K > 0;
   const bool coarse_sigma_only = p.test_time != 0;
-  const int tiles_c = (2 * Sc) >> 7;
-  const int tiles_f = fine ? ((2 * Sf) >> 7) : 0;
-  const int n_groups = (p.n_rays + 1) >> 1;
+  // Balanced contiguous ray ranges: CTA b renders rays [my_lo, my_lo + my_n), two at a time; an odd
+  // count ends with a single-ray group that only runs the tiles it needs.
+  const int per_cta = p.n_rays / static_cast<int>(gridDim.x), rem_cta = p.n_rays % static_cast<int>(gridDim.x);
+  const int my_lo = static_cast<int>(blockIdx.x) * per_cta + min(static_cast<int>(blockIdx.x), rem_cta);
+  const int my_n = per_cta + (static_cast<int>(blockIdx.x) < rem_cta ? 1 : 0);
+  const int n_groups = (my_n + 1) >> 1;
+  auto rays_in_group = [&](int g) { return min(2, my_n - 2 * g); };
+  auto tiles_of = [](int n_r, int S) { return (n_r * S + 127) >> 7; };
 
   if (warp == kProducerWarp) {
     if (lane == 0) {
       RingState rs;
-      for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        for (int t = 0; t < tiles_c; ++t)
+      for (int g = 0; g < n_groups; ++g) {
+        const int nr = rays_in_group(g);
+        for (int t = 0; t < tiles_of(nr, Sc); ++t)
           produce_tile(rs, smem, bars, p.net_coarse, coarse_sigma_only, false);
-        for (int t = 0; t < tiles_f; ++t) produce_tile(rs, smem, bars, p.net_fine, false, false);
+        if (fine)
+          for (int t = 0; t < tiles_of(nr, Sf); ++t) produce_tile(rs, smem, bars, p.net_fine, false, false);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -287,9 +294,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
       RingState rs;
       MmaPhases ph;
       Timeline tlm{(blockIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
-      for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        for (int t = 0; t < tiles_c; ++t) mma_tile(rs, ph, smem, bars, coarse_sigma_only, false, &tlm);
-        for (int t = 0; t < tiles_f; ++t) mma_tile(rs, ph, smem, bars, false, false, &tlm);
+      for (int g = 0; g < n_groups; ++g) {
+        const int nr = rays_in_group(g);
+        for (int t = 0; t < tiles_of(nr, Sc); ++t) mma_tile(rs, ph, smem, bars, coarse_sigma_only, false, &tlm);
+        if (fine)
+          for (int t = 0; t < tiles_of(nr, Sf); ++t) mma_tile(rs, ph, smem, bars, false, false, &tlm);
       }
     }
   } else {
@@ -306,9 +315,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
     const int t = threadIdx.x;   // 0..255
     uint8_t* enc = smem + kSmemEnc;
 
-    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-      const int ray0 = 2 * g;
-      const bool valid1 = (ray0 + 1) < p.n_rays;
+    for (int g = 0; g < n_groups; ++g) {
+      const int ray0 = my_lo + 2 * g;
+      const bool valid1 = rays_in_group(g) == 2;
       const int rid[2] = {ray0, valid1 ? ray0 + 1 : ray0};
       // ---- rays, direction embedding (models/rendering.py:179-186)
       tl_mark(c.tl, 0, 30);
@@ -352,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
       // ================= two passes: coarse, fine =================
       for (int pass = 0; pass < (fine ? 2 : 1); ++pass) {
         const int S = pass ? Sf : Sc;
-        const int tiles = pass ? tiles_f : tiles_c;
+        const int tiles = tiles_of(valid1 ? 2 : 1, S);
         const bool sigma_only = (pass == 0) && coarse_sigma_only;
         const uint8_t* blob = pass ? p.net_fine : p.net_coarse;
         c.f32 = reinterpret_cast<const float*>(blob + kHalfRegionBytes);
@@ -461,20 +470,52 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
             sc->znew[r][slot] = inverse_cdf(Sc, sc->zc[r], sc->cdf[r], uj);
           }
           epi_bar();
-          // ---- merge: z_fine = sort(cat(z_coarse, z_new)) (:229) as a rank sort: position =
-          // number of elements that are smaller, ties broken by index in the concatenation (any
-          // tie order gives the same sorted VALUES, which is all torch.sort's output carries).
-          for (int e = t; e < 2 * Sf; e += kEpiThreads) {
-            const int r = e / Sf, i = e - r * Sf;
-            const float* zc = sc->zc[r];
-            const float* zn = sc->znew[r];
-            const float v = (i < Sc) ? zc[i] : zn[i - Sc];
-            int rank = 0;
+          // ---- merge: z_fine = sort(cat(z_coarse, z_new)) (:229) as a rank computation:
+          // position = number of elements that are smaller, ties broken by index in the
+          // concatenation (any tie order gives the same sorted VALUES, which is all torch.sort's
+          // output carries).  Both lists are sorted except for possible 1-ulp inversions from
+          // rounding, so every element first checks its predecessor; if no inversion exists
+          // anywhere (the common case) ranks come from two binary searches, otherwise from
+          // exhaustive counting.  Both paths give identical results on sorted input.
+          {
+            bool inv = false;
+            for (int e = t; e < 2 * Sf; e += kEpiThreads) {
+              const int r = e / Sf, i = e - r * Sf;
+              if (i != 0 && i != Sc)
+                inv |= (i < Sc) ? (sc->zc[r][i] < sc->zc[r][i - 1]) : (sc->znew[r][i - Sc] < sc->znew[r][i - Sc - 1]);
+            }
+            int any_inv;
+            asm volatile(
+                "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                "barrier.red.or.pred p, 1, 256, q;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                : "=r"(any_inv) : "r"(static_cast<int>(inv)) : "memory");
+            for (int e = t; e < 2 * Sf; e += kEpiThreads) {
+              const int r = e / Sf, i = e - r * Sf;
+              const float* zc = sc->zc[r];
+              const float* zn = sc->znew[r];
+              const float v = (i < Sc) ? zc[i] : zn[i - Sc];
+              int rank;
+              if (!any_inv) {
+                // lower_bound in the other list for coarse elements (coarse first on ties),
+                // upper_bound for new elements
+                const float* other = (i < Sc) ? zn : zc;
+                int lo = 0, hi = (i < Sc) ? K : Sc;
+                while (lo < hi) {
+                  const int mid = (lo + hi) >> 1;
+                  const float x = other[mid];
+                  const bool right = (i < Sc) ? (x < v) : (x <= v);
+                  if (right) lo = mid + 1; else hi = mid;
+                }
+                rank = lo + ((i < Sc) ? i : i - Sc);
+              } else {
+                rank = 0;
 #pragma unroll 8
-            for (int q = 0; q < Sc; ++q) rank += (zc[q] < v) || (zc[q] == v && q < i);
+                for (int q = 0; q < Sc; ++q) rank += (zc[q] < v) || (zc[q] == v && q < i);
 #pragma unroll 8
-            for (int q = 0; q < K; ++q) rank += (zn[q] < v) || (zn[q] == v && (q + Sc) < i);
-            sc->z[r * Sf + rank] = v;
+                for (int q = 0; q < K; ++q) rank += (zn[q] < v) || (zn[q] == v && (q + Sc) < i);
+              }
+              sc->z[r * Sf + rank] = v;
+            }
           }
           tl_mark(c.tl, 0, 25);
           epi_bar();

@@ -244,6 +244,35 @@ def render_rays(weights: List[Dict[str, np.ndarray]], rays: np.ndarray, N_sample
     return res
 
 
+# ------------------------------------------------------------------ datasets/ray_utils.py ("next" rows)
+def generate_rays(H: int, W: int, focal: float, c2w: np.ndarray, near: float, far: float, ndc: bool = False):
+    """get_ray_directions (datasets/ray_utils.py:16-22) + get_rays (:41-51) [+ get_ndc_rays (:75-92)
+    with near plane 1.0 and near/far = 0/1 as datasets/llff.py:236-241] -> (H*W, 8) rays."""
+    j, i = np.meshgrid(np.arange(H, dtype=F32), np.arange(W, dtype=F32), indexing="ij")
+    dirs = np.stack([(i - F32(W / 2)) / F32(focal), -(j - F32(H / 2)) / F32(focal), -np.ones_like(i)], -1)
+    c2w = np.asarray(c2w, dtype=F32).reshape(3, 4)
+    d = (dirs.reshape(-1, 3) @ c2w[:, :3].T).astype(F32)
+    d = (d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(F32)
+    o = np.broadcast_to(c2w[:, 3], d.shape).astype(F32)
+    if ndc:
+        n1 = F32(1.0)
+        t = -(n1 + o[:, 2]) / d[:, 2]
+        o = (o + t[:, None] * d).astype(F32)
+        ox_oz, oy_oz = o[:, 0] / o[:, 2], o[:, 1] / o[:, 2]
+        sx, sy = F32(-1.0 / (W / (2.0 * focal))), F32(-1.0 / (H / (2.0 * focal)))
+        o2 = F32(1) + F32(2) * n1 / o[:, 2]
+        o_n = np.stack([sx * ox_oz, sy * oy_oz, o2], -1)
+        d_n = np.stack([sx * (d[:, 0] / d[:, 2] - ox_oz), sy * (d[:, 1] / d[:, 2] - oy_oz), F32(1) - o2], -1)
+        o, d, near, far = o_n.astype(F32), d_n.astype(F32), 0.0, 1.0
+    nf = np.broadcast_to(np.array([near, far], F32), (d.shape[0], 2))
+    return np.concatenate([o, d, nf], -1).astype(F32)
+
+
+def to_uint8(img: np.ndarray) -> np.ndarray:
+    """eval.py:126-128."""
+    return (np.clip(img, 0, 1) * 255).astype(np.uint8)
+
+
 def psnr(a: np.ndarray, b: np.ndarray) -> float:
     """metrics.py:4-13: -10 log10(mse)."""
     mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))

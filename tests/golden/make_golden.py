@@ -29,6 +29,16 @@ def import_reference():
     shim.searchsorted = lambda a, v, out=None, side="left": torch.searchsorted(
         a.contiguous(), v.contiguous(), right=(side == "right"))
     sys.modules["torchsearchsorted"] = shim
+    # datasets/ray_utils.py:2 imports kornia.create_meshgrid (kornia is not installed here): the one
+    # function it uses is restated (pixel grid, x = column index, y = row index, un-normalised)
+    kor = types.ModuleType("kornia")
+
+    def create_meshgrid(H, W, normalized_coordinates=False):
+        assert not normalized_coordinates
+        ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+        return torch.stack([xs, ys], -1)[None]
+    kor.create_meshgrid = create_meshgrid
+    sys.modules["kornia"] = kor
     sys.path.insert(0, REF)
     from models.nerf import Embedding, NeRF
     from models.rendering import render_rays, sample_pdf
@@ -109,6 +119,23 @@ def main():
                         pdf_u=u_ref, pdf_rand=sp_rand, linspace64=torch.linspace(0, 1, 64).numpy(),
                         linspace128=torch.linspace(0, 1, 128).numpy())
     print("units ok")
+
+    # ray generation ("next" row): datasets/ray_utils.py run as datasets/blender.py / llff.py use it
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_ray_utils", os.path.join(REF, "datasets", "ray_utils.py"))
+    ru = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ru)
+    H, W, focal = 24, 36, 41.5
+    th = 0.7
+    c2w = np.array([[np.cos(th), 0, np.sin(th), 1.5], [0.2, 0.96, -0.1, -0.3], [-np.sin(th), 0.1, np.cos(th), 3.2]],
+                   dtype=np.float32)
+    dirs = ru.get_ray_directions(H, W, focal)
+    ro, rd = ru.get_rays(dirs, torch.from_numpy(c2w))
+    blender = torch.cat([ro, rd, 2.0 * torch.ones_like(ro[:, :1]), 6.0 * torch.ones_like(ro[:, :1])], 1).numpy()
+    no, nd = ru.get_ndc_rays(H, W, focal, 1.0, ro, rd)
+    ndc = torch.cat([no, nd, 0 * torch.ones_like(ro[:, :1]), 1 * torch.ones_like(ro[:, :1])], 1).numpy()
+    np.savez_compressed(os.path.join(HERE, "raygen.npz"), H=H, W=W, focal=focal, c2w=c2w, blender=blender, ndc=ndc)
+    print("raygen ok", blender.shape)
 
 
 if __name__ == "__main__":

@@ -253,3 +253,23 @@ def test_unsupported_shapes_fail_loudly(models, emb, dev):
         nb.render_rays(models[:1], emb, rays, 64, False, 0, 0, 64)
     out = nb.render_rays(models[:1], emb, rays[:0], 64, False, 0, 0, 0)          # empty input
     assert out["rgb_coarse"].shape == (0, 3)
+
+
+def test_ray_generation_and_image_driver(models, emb, ws, dev):
+    """on-GPU rays (vs reference ray_utils golden), one-launch image render,
+    uint8 conversion (eval.py:58-86, 119-128)."""
+    g = np.load(os.path.join(cases.GOLDEN, "raygen.npz"))
+    H, W, focal = int(g["H"]), int(g["W"]), float(g["focal"])
+    r = nb.generate_rays(H, W, focal, g["c2w"], 2.0, 6.0, device=dev)
+    np.testing.assert_allclose(r.cpu().numpy(), g["blender"], atol=2e-6, rtol=0)
+    rn = nb.generate_rays(H, W, focal, g["c2w"], 2.0, 6.0, ndc=True, device=dev)
+    np.testing.assert_allclose(rn.cpu().numpy(), g["ndc"], atol=5e-6, rtol=1e-5)
+    out = nb.render_image(models, emb, H, W, focal, g["c2w"], 2.0, 6.0, 64, 64, white_back=True, device=dev)
+    assert out["rgb"].shape == (H, W, 3) and out["rgb_uint8"].dtype == torch.uint8
+    ref = orc.render_rays(ws, g["blender"], 64, False, 0.0, 0.0, 64, True, True)
+    assert np.abs(out["rgb"].reshape(-1, 3).cpu().numpy() - ref["rgb_fine"]).max() < 1e-3
+    exp8 = orc.to_uint8(out["rgb"].cpu().numpy())
+    assert np.abs(out["rgb_uint8"].cpu().numpy().astype(int) - exp8.astype(int)).max() <= 1
+    bi = nb.batched_inference(models, emb, r, 64, 64, False, 32768, True)
+    assert set(bi) == {"opacity_coarse", "rgb_fine", "depth_fine", "opacity_fine"}
+    assert torch.equal(bi["rgb_fine"].view(H, W, 3), out["rgb"])

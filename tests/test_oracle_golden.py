@@ -70,3 +70,13 @@ def test_searchsorted_grid(side):
                 assert out.dtype == np.int64 and out.shape == (max(Ba, Bv), V)
                 r = max(Ba, Bv) - 1
                 np.testing.assert_array_equal(out[r], np.searchsorted(a[min(r, Ba - 1)], v[min(r, Bv - 1)], side))
+
+
+def test_ray_generation_matches_reference():
+    """datasets/ray_utils.py get_ray_directions/get_rays/get_ndc_rays (run by make_golden.py)."""
+    g = np.load(os.path.join(cases.GOLDEN, "raygen.npz"))
+    H, W, focal = int(g["H"]), int(g["W"]), float(g["focal"])
+    np.testing.assert_allclose(orc.generate_rays(H, W, focal, g["c2w"], 2.0, 6.0), g["blender"], atol=2e-6, rtol=0)
+    np.testing.assert_allclose(orc.generate_rays(H, W, focal, g["c2w"], 2.0, 6.0, ndc=True), g["ndc"], atol=5e-6, rtol=1e-5)
+    img = np.linspace(-0.2, 1.2, 97, dtype=np.float32)
+    assert orc.to_uint8(img).dtype == np.uint8 and orc.to_uint8(img).max() == 255 and orc.to_uint8(img).min() == 0

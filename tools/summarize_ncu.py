@@ -1,0 +1,78 @@
+"""Summarise ncu captures brought back in gpurun_out/ into profiles/ (text, committed).
+
+    python tools/summarize_ncu.py <round-tag>   e.g. r01
+Reads gpurun_out/launches_<tag>.csv (per-launch gpu__time_duration) and
+gpurun_out/prof_<tag>_render.ncu-rep (--set full capture of render_rays_kernel)."""
+import csv
+import io
+import os
+import subprocess
+import sys
+from collections import defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+out = []
+
+lp = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
+if os.path.exists(lp):
+    rows = [r for r in csv.reader(open(lp)) if len(r) > 5 and r[0].strip('"').isdigit()]
+    tot = defaultdict(lambda: [0, 0.0])
+    for r in rows:
+        name = r[4].split("(")[0].split("<")[0].strip()
+        if "distribution" in r[4]:
+            name = "at::distribution_elementwise (torch.rand/randn)"
+        if "vectorized_elementwise" in r[4] or "FillFunctor" in r[4]:
+            name = "at::vectorized_elementwise (fill / L2 flush)"
+        tot[name][0] += 1
+        tot[name][1] += float(r[-1])
+    total = sum(v[1] for v in tot.values())
+    out.append(f"## Launch list ({os.path.basename(lp)}; ncu --metrics gpu__time_duration.sum, cold-cache, serialised)\n")
+    out.append("| kernel | launches | total ns | share |\n|---|---|---|---|")
+    for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+        out.append(f"| `{k}` | {v[0]} | {v[1]:.0f} | {100 * v[1] / total:.1f}% |")
+    rr = [float(r[-1]) for r in rows if "render_rays_kernel" in r[4]]
+    if rr:
+        out.append(f"\nrender_rays_kernel: {len(rr)} launches, mean {sum(rr) / len(rr) / 1e3:.1f} us "
+                   f"(1024 rays x 192 samples each; excludes the 256 MiB L2-flush fill between bench steps).\n")
+
+rp = os.path.join(ROOT, "gpurun_out", f"prof_{tag}_render.ncu-rep")
+if os.path.exists(rp):
+    raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+            "smsp__inst_executed.sum", "launch__shared_mem_per_block_dynamic"]
+    out.append(f"## Full capture ({os.path.basename(rp)}; ncu --set full --clock-control none, one launch: "
+               f"32768 rays, 64+64 samples, training-mode forward)\n")
+    out.append("| metric | unit | value |\n|---|---|---|")
+    for h, u, v in zip(hdr, units, vals):
+        if h in want:
+            out.append(f"| `{h}` | {u} | {v} |")
+    src = subprocess.run(["ncu", "-i", rp, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    srows = list(csv.reader(io.StringIO(src)))
+    shdr, data = srows[1], srows[2:]
+    i_s = shdr.index("# Samples")
+    stall = [i for i, h in enumerate(shdr) if h.startswith("stall_") and "Not Issued" not in h]
+    total = sum(int(r[i_s]) for r in data)
+    out.append(f"\nWarp-stall samples (all warps incl. the spinning producer / MMA-issuer threads), total {total}:\n")
+    out.append("| stall | share |\n|---|---|")
+    for i in sorted(stall, key=lambda i: -sum(int(r[i]) for r in data)):
+        sh = sum(int(r[i]) for r in data)
+        if sh > 0.01 * total:
+            out.append(f"| {shdr[i]} | {100 * sh / total:.1f}% |")
+    sass = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "nerf_pl_b200", "libnerf_pl_b200.so")],
+                          capture_output=True, text=True).stdout
+    cnt = {k: sass.count(k) for k in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTCBAR", "SYNCS.PHASECHK", "FADD2", "F2FP.RELU", "HMMA.")}
+    out.append("\nSASS mnemonics in libnerf_pl_b200.so (cuobjdump): " + ", ".join(f"{k} x{v}" for k, v in cnt.items()) + "\n")
+
+os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+dst = os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md")
+open(dst, "w").write(f"# ncu summary {tag}\n\n" + "\n".join(out) + "\n")
+print(open(dst).read())
