@@ -56,7 +56,7 @@ int nerfb200_pack_weights(const float* const params[24], void* packed, void* str
  *   opacity_coarse (n); rgb_fine (n,3), depth_fine (n), opacity_fine (n) iff N_importance > 0
  * Optional outputs (NULL to skip): z_fine (n, N_samples+N_importance) merged sorted depths,
  *   weights_coarse (n,N_samples), weights_fine (n,N_samples+N_importance).
- * Supported shapes: N_samples in {64,128}; N_importance in {0,64,128}; total <= 192.
+ * Supported shapes: N_samples = 64; N_importance in {0,64,128}.
  * `status` is a device int32 the kernel sets non-zero on a device-side fault (may be NULL,
  * then an internal one is used and checked with a synchronising copy). */
 typedef struct nerfb200_render_args {

@@ -123,9 +123,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const MlpParam
     EpiCtx c;
     c.smem = smem; c.bars = bars; c.lane = lane;
     c.row = (warp & 3) * 32 + lane;
-    c.half = warp >> 2;
+    c.part = warp >> 2;
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     c.d_phase = 0;
+    c.flags = 0;
     c.tl = nullptr;
     c.f32 = reinterpret_cast<const float*>(p.net + kHalfRegionBytes);
     c.cst = consts_ptr(smem, 0);
@@ -134,29 +135,34 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const MlpParam
       const long long gi = tile * 128 + c.row;
       const bool valid = gi < p.n;
       const float* xr = p.x + (valid ? gi : (p.n - 1)) * p.x_stride;
-      const int k0 = c.half * 32;
-      for (int k = k0; k < k0 + 32; ++k) {
+      const int k0 = c.part * (64 / kColSplit);
+      for (int k = k0; k < k0 + 64 / kColSplit; ++k) {
         const float v = (k < kEncXyz) ? __ldg(xr + k) : 0.f;
         *reinterpret_cast<__half*>(enc + sw128_off(c.row, k)) = __float2half_rn(v);
       }
       float sig_part, rgb_part[3];
       epi_run_tile(c, so, nullptr, so ? nullptr : xr + kEncXyz, sig_part, rgb_part);
-      sc->sig_part[c.half][c.row] = sig_part;
+      sc->sig_part[c.part][c.row] = sig_part;
       if (!so) {
-        sc->rgb_part[c.half][0][c.row] = rgb_part[0];
-        sc->rgb_part[c.half][1][c.row] = rgb_part[1];
-        sc->rgb_part[c.half][2][c.row] = rgb_part[2];
+        sc->rgb_part[c.part][0][c.row] = rgb_part[0];
+        sc->rgb_part[c.part][1][c.row] = rgb_part[1];
+        sc->rgb_part[c.part][2][c.row] = rgb_part[2];
       }
       epi_bar();
-      if (c.half == 0 && valid) {
-        const float sg = sc->sig_part[0][c.row] + sc->sig_part[1][c.row] + c.cst[kF32BSigma];
+      if (c.part == 0 && valid) {
+        float sg = c.cst[kF32BSigma];
+        float pre[3] = {c.cst[kF32BRgb + 0], c.cst[kF32BRgb + 1], c.cst[kF32BRgb + 2]};
+        for (int q = 0; q < kColSplit; ++q) {
+          sg += sc->sig_part[q][c.row];
+          if (!so) { pre[0] += sc->rgb_part[q][0][c.row]; pre[1] += sc->rgb_part[q][1][c.row]; pre[2] += sc->rgb_part[q][2][c.row]; }
+        }
         if (so) {
           p.out[gi] = sg;
         } else {
           float4 o;
-          o.x = sigmoid_ref(sc->rgb_part[0][0][c.row] + sc->rgb_part[1][0][c.row] + c.cst[kF32BRgb + 0]);
-          o.y = sigmoid_ref(sc->rgb_part[0][1][c.row] + sc->rgb_part[1][1][c.row] + c.cst[kF32BRgb + 1]);
-          o.z = sigmoid_ref(sc->rgb_part[0][2][c.row] + sc->rgb_part[1][2][c.row] + c.cst[kF32BRgb + 2]);
+          o.x = sigmoid_ref(pre[0]);
+          o.y = sigmoid_ref(pre[1]);
+          o.z = sigmoid_ref(pre[2]);
           o.w = sg;
           *reinterpret_cast<float4*>(p.out + gi * 4) = o;
         }
@@ -337,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_probe_kernel(const float* __
     }
   } else if (warp == kMmaWarp) {
     if (lane == 0) {
-      mbar_wait(smem_u32(&bars->d_free), 0, 12);
+      mbar_wait(smem_u32(kPipelinedHandover ? &bars->d_free : &bars->a_ready), 0, 12);
       tc_fence_after();
       mbar_wait(smem_u32(&bars->full[0]), 0, 13);
       tc_fence_after();
@@ -356,29 +362,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_probe_kernel(const float* __
     EpiCtx c;
     c.smem = smem; c.bars = bars; c.lane = lane;
     c.row = (warp & 3) * 32 + lane;
-    c.half = warp >> 2;
+    c.part = warp >> 2;
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     c.d_phase = 0;
+    c.flags = 0;
     c.tl = nullptr;
     if (mode == 0) {
       uint8_t* enc = smem + kSmemEnc;
-      for (int k = c.half * 32; k < c.half * 32 + 32; ++k)
+      for (int k = c.part * (64 / kColSplit); k < (c.part + 1) * (64 / kColSplit); ++k)
         *reinterpret_cast<__half*>(enc + sw128_off(c.row, k)) = __float2half_rn(a[c.row * 64 + k]);
-    } else {
-      uint32_t h[16];   // this thread's 32 K-values -> 16 packed columns at A + 16*half
+    } else if (c.part < 2) {
+      uint32_t h[16];   // parts 0,1: 32 K-values each -> 16 packed columns at A + 16*part
       for (int i = 0; i < 16; ++i)
-        h[i] = cvt_f16x2(a[c.row * 64 + c.half * 32 + 2 * i], a[c.row * 64 + c.half * 32 + 2 * i + 1]);
-      tmem_st16(c.tmem_row + kTmemA + 16 * c.half, h);
+        h[i] = cvt_f16x2(a[c.row * 64 + c.part * 32 + 2 * i], a[c.row * 64 + c.part * 32 + 2 * i + 1]);
+      tmem_st16(c.tmem_row + kTmemA + 16 * c.part, h);
     }
     tmem_st_wait();
     epi_signal_tile_start(c);
     epi_wait_d(c);
-    const int ncol = N / 2;
+    const int ncol = N / kColSplit;
     for (int cc = 0; cc < ncol; cc += 32) {
       uint32_t r[32];
-      tmem_ld32(c.tmem_row + kTmemD + c.half * ncol + cc, r);
+      tmem_ld32(c.tmem_row + kTmemD + c.part * ncol + cc, r);
       tmem_ld_wait();
-      for (int i = 0; i < 32; ++i) d[c.row * N + c.half * ncol + cc + i] = __uint_as_float(r[i]);
+      for (int i = 0; i < 32; ++i) d[c.row * N + c.part * ncol + cc + i] = __uint_as_float(r[i]);
     }
   }
   engine_teardown(bars);

@@ -34,11 +34,13 @@
 
 namespace nerfb200 {
 
-constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = kEpiWarps * 32;   // 256
-constexpr int kProducerWarp = 8;
-constexpr int kMmaWarp = 9;
-constexpr int kThreads = 320;
+constexpr int kEpiWarps = 16;                 // 4 per scheduler: latency hiding for the serial epilogue
+constexpr int kEpiThreads = kEpiWarps * 32;   // 512
+constexpr int kColSplit = kEpiWarps / 4;      // column groups per accumulator row (4 lane quadrants each)
+constexpr int kColsPer = 256 / kColSplit;     // accumulator columns per epilogue thread (64)
+constexpr int kProducerWarp = kEpiWarps;
+constexpr int kMmaWarp = kEpiWarps + 1;
+constexpr int kThreads = (kEpiWarps + 2) * 32;   // 576
 // Where the hidden activations (the next layer's A operand) live:
 //   true : tensor memory (tcgen05.st, TS MMA 139 cyc/K-step; epilogue stores contend with the
 //          MMA's TMEM reads when the two overlap)
@@ -69,12 +71,13 @@ constexpr int kLayersSigma = 8;       // L1..L8
 struct Barriers {
   uint64_t full[kStages];
   uint64_t empty[kStages];
-  uint64_t d_free;         // epilogue (8 warps) -> MMA : "accumulator drained into registers"
+  uint64_t a_ready;        // sequential hand-over: all epilogue warps -> MMA : "A written, D drained"
                            //   (at tile start: "ENC tile written")
-  uint64_t a_kb[4];        // epilogue (4 warps)  -> MMA : "A columns of K block kb written"
+  uint64_t d_free;         // pipelined hand-over: all epilogue warps -> MMA : "D drained into registers"
+  uint64_t a_kb[4];        // pipelined hand-over: 4 warps -> MMA : "A columns of K block kb written"
   uint64_t d_ready;        // MMA -> epilogue : "accumulator complete"
   uint32_t tmem_base;
-  uint32_t pad[3];
+  uint32_t pad[1];
 };
 static_assert(sizeof(Barriers) % 16 == 0, "Barriers must keep 16-byte alignment of what follows");
 
@@ -110,8 +113,9 @@ __device__ __forceinline__ bool engine_setup(uint8_t* smem, Barriers* bars) {
       mbar_init(smem_u32(&bars->full[i]), 1);
       mbar_init(smem_u32(&bars->empty[i]), 1);
     }
+    mbar_init(smem_u32(&bars->a_ready), kEpiWarps);
     mbar_init(smem_u32(&bars->d_free), kEpiWarps);
-    for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&bars->a_kb[k]), kEpiWarps / 2);
+    for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&bars->a_kb[k]), 4);   // one K block = 64 columns = 4 warps' work
     mbar_init(smem_u32(&bars->d_ready), 1);
     fence_mbar_init();
   }
@@ -187,7 +191,7 @@ __device__ __forceinline__ void mma_tile(RingState& rs, MmaPhases& ph, uint8_t* 
   const uint32_t enc_base = smem_u32(smem + kSmemEnc);
   const int n_layers = sigma_only ? kLayersSigma : kLayersFull;
   for (int l = 0; l < n_layers; ++l) {
-    mbar_wait(smem_u32(&bars->d_free), ph.d_free, 3);
+    mbar_wait(smem_u32(kPipelinedHandover ? &bars->d_free : &bars->a_ready), ph.d_free, 3);
     ph.d_free ^= 1;
     tc_fence_after();
     tl_mark(tl, 1, 100 + l);
@@ -198,7 +202,7 @@ __device__ __forceinline__ void mma_tile(RingState& rs, MmaPhases& ph, uint8_t* 
       const int kb = (l == 4) ? s - 1 : s;
       const uint32_t b_addr = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
       mbar_wait(smem_u32(&bars->full[rs.stage]), rs.phase, 4);
-      if (!from_enc) mbar_wait(smem_u32(&bars->a_kb[kb]), ph.a_kb, 6);
+      if (kPipelinedHandover && !from_enc) mbar_wait(smem_u32(&bars->a_kb[kb]), ph.a_kb, 6);
       tc_fence_after();
       const uint64_t bdesc = make_desc_sw128(b_addr);
       if (from_enc) {
@@ -235,13 +239,14 @@ struct EpiCtx {
   uint32_t tmem_row;               // tmem base + (lane quadrant << 16)
   uint32_t d_phase;
   int row;                         // 0..127 : tile row == TMEM lane
-  int half;                        // 0/1    : which accumulator column half this warp drains
+  int part;                        // 0..kColSplit-1 : which accumulator column group this warp drains
   int lane;
   Timeline* tl;                    // non-null only for the one traced thread
+  unsigned flags;                  // experiment switches (0 in production)
 };
 
 __device__ __forceinline__ void epi_bar() {   // all 256 epilogue threads
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 }
 // Tile start: the ENC tile has been written with generic stores (async-proxy fence needed) and
 // the previous tile's accumulator reads have retired.
@@ -249,8 +254,16 @@ __device__ __forceinline__ void epi_signal_tile_start(EpiCtx& c) {
   fence_proxy_async();
   tc_fence_before();
   __syncwarp();
-  if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->d_free));
+  if (c.lane == 0) mbar_arrive(smem_u32(kPipelinedHandover ? &c.bars->d_free : &c.bars->a_ready));
   tl_mark(c.tl, 0, 6);
+}
+// Sequential hand-over: this warp's accumulator columns are drained and its A columns stored.
+__device__ __forceinline__ void epi_signal_a_ready(EpiCtx& c, bool smem_written) {
+  if (smem_written || !kAInTmem) fence_proxy_async();
+  if (kAInTmem) tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_ready));
 }
 // This warp's accumulator columns are in registers.
 __device__ __forceinline__ void epi_signal_d_free(EpiCtx& c) {
@@ -347,86 +360,92 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* 
   }
 }
 
-// Hidden-layer epilogue of this thread's 128 accumulator columns: drain them into registers,
-// release the accumulator, then emit the next layer's A operand K block by K block.
+// NeRF.forward mode: the ENC tile is dead after layer 5; reuse it for this row's embedded direction
+// (27 values, columns 27..63 zero), each column group writes its share of the 64 columns.
+__device__ __forceinline__ void write_dir_row(EpiCtx& c, const float* __restrict__ dir_row) {
+  uint8_t* enc = c.smem + kSmemEnc;
+  constexpr int kPer = 64 / kColSplit;
+  const int k0 = c.part * kPer;
+#pragma unroll 4
+  for (int k = k0; k < k0 + kPer; ++k) {
+    const float v = (k < kEncDir) ? __ldg(dir_row + k) : 0.f;
+    *reinterpret_cast<__half*>(enc + sw128_off(c.row, k)) = __float2half_rn(v);
+  }
+}
+
+// Hidden-layer epilogue of this thread's kColsPer accumulator columns.
 //   kStore = false: last layer of a sigma-only tile (nothing to hand to the tensor core).
 //   dir_row != nullptr (layer 8 in NeRF.forward mode): also rewrite the ENC tile with this row's
 //   embedded direction before the last signal.
 template <bool kRelu, bool kSigma, bool kStore>
 __device__ __forceinline__ void epi_hidden(EpiCtx& c, const float* bias, const float* wsig,
                                            float& sig_acc, const float* __restrict__ dir_row = nullptr) {
-  const int nb = c.half * 128;
+  const int nb = c.part * kColsPer;
   const uint32_t a_row = smem_u32(c.smem + kSmemA) + static_cast<uint32_t>(c.row) * 128u;
-  const uint32_t a_tm = c.tmem_row + kTmemA + c.half * 64;    // 2 fp16 per column
+  const uint32_t a_tm = c.tmem_row + kTmemA + nb / 2;         // 2 fp16 per column
   const uint32_t d_src = c.tmem_row + kTmemD + nb;
   tl_mark(c.tl, 0, 1);
   epi_wait_d(c);
   tl_mark(c.tl, 0, 2);
+  constexpr int kPairs = kColsPer / 64;                       // 64 columns = one K block of the next layer
   if (kPipelinedHandover) {
     // drain everything first so the accumulator can be released early
-    uint32_t r0[32], r1[32], r2[32], r3[32];
-    tmem_ld32(d_src, r0);
-    tmem_ld32(d_src + 32, r1);
-    tmem_ld32(d_src + 64, r2);
-    tmem_ld32(d_src + 96, r3);
+    uint32_t r[kPairs][2][32];
+#pragma unroll
+    for (int pr = 0; pr < kPairs; ++pr) {
+      tmem_ld32(d_src + 64 * pr, r[pr][0]);
+      tmem_ld32(d_src + 64 * pr + 32, r[pr][1]);
+    }
     tmem_ld_wait();
     if (kStore) epi_signal_d_free(c);
     tl_mark(c.tl, 0, 3);
-    epi_chunk<kRelu, kSigma, kStore>(r0, bias, nb, kAInTmem ? a_tm : a_row, wsig, sig_acc);
-    epi_chunk<kRelu, kSigma, kStore>(r1, bias, nb + 32, kAInTmem ? a_tm + 16 : a_row, wsig, sig_acc);
-    if (kStore) epi_signal_kb(c, 2 * c.half, false);
-    tl_mark(c.tl, 0, 4);
-    epi_chunk<kRelu, kSigma, kStore>(r2, bias, nb + 64, kAInTmem ? a_tm + 32 : a_row, wsig, sig_acc);
-    epi_chunk<kRelu, kSigma, kStore>(r3, bias, nb + 96, kAInTmem ? a_tm + 48 : a_row, wsig, sig_acc);
+#pragma unroll
+    for (int pr = 0; pr < kPairs; ++pr) {
+      epi_chunk<kRelu, kSigma, kStore>(r[pr][0], bias, nb + 64 * pr, kAInTmem ? a_tm + 32 * pr : a_row, wsig, sig_acc);
+      epi_chunk<kRelu, kSigma, kStore>(r[pr][1], bias, nb + 64 * pr + 32, kAInTmem ? a_tm + 32 * pr + 16 : a_row, wsig, sig_acc);
+      if (pr == kPairs - 1 && dir_row != nullptr) write_dir_row(c, dir_row);
+      if (kStore) epi_signal_kb(c, nb / 64 + pr, pr == kPairs - 1 && dir_row != nullptr);
+    }
   } else {
-    // two chunks in flight: the next tcgen05.ld overlaps the conversion of the previous chunk
     uint32_t r0[32], r1[32];
     tmem_ld32(d_src, r0);
     tmem_ld32(d_src + 32, r1);
     tmem_ld_wait();
     tl_mark(c.tl, 0, 3);
-    epi_chunk<kRelu, kSigma, kStore>(r0, bias, nb, kAInTmem ? a_tm : a_row, wsig, sig_acc);
-    tmem_ld32(d_src + 64, r0);
-    epi_chunk<kRelu, kSigma, kStore>(r1, bias, nb + 32, kAInTmem ? a_tm + 16 : a_row, wsig, sig_acc);
-    tmem_ld32(d_src + 96, r1);
-    tmem_ld_wait();
+#pragma unroll
+    for (int pr = 0; pr < kPairs; ++pr) {
+      epi_chunk<kRelu, kSigma, kStore>(r0, bias, nb + 64 * pr, kAInTmem ? a_tm + 32 * pr : a_row, wsig, sig_acc);
+      if (pr + 1 < kPairs) tmem_ld32(d_src + 64 * (pr + 1), r0);
+      epi_chunk<kRelu, kSigma, kStore>(r1, bias, nb + 64 * pr + 32, kAInTmem ? a_tm + 32 * pr + 16 : a_row, wsig, sig_acc);
+      if (pr + 1 < kPairs) {
+        tmem_ld32(d_src + 64 * (pr + 1) + 32, r1);
+        tmem_ld_wait();
+      }
+    }
     tl_mark(c.tl, 0, 4);
-    epi_chunk<kRelu, kSigma, kStore>(r0, bias, nb + 64, kAInTmem ? a_tm + 32 : a_row, wsig, sig_acc);
-    epi_chunk<kRelu, kSigma, kStore>(r1, bias, nb + 96, kAInTmem ? a_tm + 48 : a_row, wsig, sig_acc);
-  }
-  if (dir_row != nullptr) {
-    // ENC tile is dead after layer 5: reuse it for the embedded direction (cols 27..63 zero)
-    uint8_t* enc = c.smem + kSmemEnc;
-    const int k0 = c.half * 32;
-    for (int k = k0; k < k0 + 32; ++k) {
-      const float v = (k < kEncDir) ? __ldg(dir_row + k) : 0.f;
-      *reinterpret_cast<__half*>(enc + sw128_off(c.row, k)) = __float2half_rn(v);
-    }
-  }
-  if (kStore) {
-    if (!kPipelinedHandover) {
-      epi_signal_d_free(c);
-      epi_signal_kb(c, 2 * c.half, false);
-    }
-    epi_signal_kb(c, 2 * c.half + 1, dir_row != nullptr);
+    if (dir_row != nullptr) write_dir_row(c, dir_row);
+    if (kStore) epi_signal_a_ready(c, dir_row != nullptr);
   }
   tl_mark(c.tl, 0, 5);
 }
 
-// dir_encoding epilogue (N=128; this thread's 64 columns) fused with the rgb head
+// dir_encoding epilogue (N=128; this thread's 128/kColSplit columns) fused with the rgb head
 // (models/nerf.py:119-120): d = relu(acc + dbias[n]); rgb_acc[c] += d * w_rgb[c][n].
-// dbias is either the per-ray vector (bias + direction part, shared memory) or b_dir (global).
+// dbias is either the per-ray vector (bias + direction part, shared memory) or b' (shared memory).
 __device__ __forceinline__ void epi_dir(EpiCtx& c, const float* dbias, const float* wrgb,
                                         float (&rgb_acc)[3]) {
-  uint32_t r[2][32];
-  tmem_ld32(c.tmem_row + kTmemD + c.half * 64, r[0]);
-  tmem_ld32(c.tmem_row + kTmemD + c.half * 64 + 32, r[1]);
+  constexpr int kCols = 128 / kColSplit;     // 32 or 64
+  constexpr int kChunks = kCols / 32;
+  const int n0 = c.part * kCols;
+  uint32_t r[kChunks][32];
+#pragma unroll
+  for (int u = 0; u < kChunks; ++u) tmem_ld32(c.tmem_row + kTmemD + n0 + 32 * u, r[u]);
   tmem_ld_wait();
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
+  for (int u = 0; u < kChunks; ++u) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int n = c.half * 64 + u * 32 + 4 * j;
+      const int n = n0 + u * 32 + 4 * j;
       const float4 b = *reinterpret_cast<const float4*>(dbias + n);
       const float4 wr = *reinterpret_cast<const float4*>(wrgb + n);
       const float4 wg = *reinterpret_cast<const float4*>(wrgb + 128 + n);
@@ -451,7 +470,7 @@ __device__ __forceinline__ void epi_dir(EpiCtx& c, const float* dbias, const flo
 //                nullptr to use b_dir from the image (dir_slice mode adds the direction
 //                part through the tensor core instead).
 //   dir_row    : dir_slice mode only - this row's 27 embedded direction values (global).
-// Outputs partial sums (this thread's column half): sigma and rgb pre-activation.
+// Outputs partial sums (this thread's column group): sigma and rgb pre-activation.
 __device__ __forceinline__ void epi_run_tile(EpiCtx& c, bool sigma_only, const float* dbias,
                                              const float* __restrict__ dir_row, float& sig_part,
                                              float (&rgb_part)[3]) {

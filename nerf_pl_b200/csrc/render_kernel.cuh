@@ -7,7 +7,7 @@
 
 namespace nerfb200 {
 
-constexpr int kMaxSc = 128;     // max coarse samples / ray
+constexpr int kMaxSc = 64;      // max coarse samples / ray
 constexpr int kMaxImp = 128;    // max importance samples / ray
 constexpr int kMaxSf = 192;     // max fine samples / ray (N_samples + N_importance)
 constexpr int kMaxRows = 2 * kMaxSf;
@@ -46,19 +46,19 @@ struct RenderParams {
 struct alignas(16) Scratch {
   Barriers bars;                       //   96
   alignas(16) float dirbias[2][kDirW]; // 1024   per-ray b_dir + W_dir[:,256:283] . dir_enc
-  float sig_part[2][128];              // 1024   [half][row]
-  float rgb_part[2][3][128];           // 3072
+  float sig_part[kColSplit][128];      // [column group][row] partial sigma-head sums
+  float rgb_part[kColSplit][3][128];   // partial rgb-head sums
   float ray[2][8];                     //   64
   float dnorm[2];
   float pad0[2];
   float direnc[2][28];                 //  224
   float z[kMaxRows];                   // 1536   depths of the current pass, [ray][S]
-  float sigma[kMaxRows];               // 1536
+  float sigma[kMaxRows];               // 1536   sigma of the current pass; overwritten in place by the
+                                       //        compositing weights (same index, same lane)
   float rgb[3][kMaxRows];              // 4608
-  float w[2][kMaxSf];                  // 1536   compositing weights of the current pass
-  float cdf[2][kMaxSc];                // 1024
+  float cdf[2][kMaxSc];                //  512
   float znew[2][kMaxImp];              // 1024   u (sorted) then the new depths
-  float zc[2][kMaxSc];                 // 1024   coarse depths kept for the merge
+  float zc[2][kMaxSc];                 //  512   coarse depths kept for the merge
 };
 static_assert(sizeof(Scratch) <= kScratchBytes, "scratch does not fit");
 
@@ -107,24 +107,25 @@ __device__ __forceinline__ void fast_sincos(float a, float& s, float& c) {
   c = __cosf(r);
 }
 
-// Encoded xyz of one sample row into the ENC tile; the two column-half threads of a row split
-// the ten frequencies.  Feature order models/nerf.py:33-38: [x, sin f0 x, cos f0 x, sin f1 x, ..].
-__device__ __forceinline__ void encode_row(uint8_t* enc, int row, int half, const float o[3],
+// Encoded xyz of one sample row into the ENC tile; the kColSplit threads of a row split the ten
+// frequencies.  Feature order models/nerf.py:33-38: [x, sin f0 x, cos f0 x, sin f1 x, ..].
+__device__ __forceinline__ void encode_row(uint8_t* enc, int row, int part, const float o[3],
                                            const float d[3], float z) {
   float x[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(o[c], __fmul_rn(d[c], z));   // rendering.py:206
-  if (half == 0) {
+  if (part == 0) {
 #pragma unroll
     for (int c = 0; c < 3; ++c)
       *reinterpret_cast<__half*>(enc + sw128_off(row, c)) = __float2half_rn(x[c]);
-  } else {
+  } else if (part == kColSplit - 1) {
     *reinterpret_cast<__half*>(enc + sw128_off(row, 63)) = __float2half_rn(0.f);
   }
-  const int k0 = half * 5;
-  float f = half ? 32.f : 1.f;
-#pragma unroll
-  for (int k = k0; k < k0 + 5; ++k, f *= 2.f) {
+  // frequencies [k0, k1): 2 groups -> 5+5, 4 groups -> 3+3+2+2
+  const int k0 = (kColSplit == 2) ? part * 5 : (part < 2 ? part * 3 : 6 + (part - 2) * 2);
+  const int k1 = (kColSplit == 2) ? k0 + 5 : (part < 2 ? k0 + 3 : k0 + 2);
+  float f = static_cast<float>(1 << k0);
+  for (int k = k0; k < k1; ++k, f *= 2.f) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float s, co;
@@ -307,9 +308,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
     c.bars = bars;
     c.lane = lane;
     c.row = (warp & 3) * 32 + lane;
-    c.half = warp >> 2;
+    c.part = warp >> 2;
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     c.d_phase = 0;
+    c.flags = p.flags;
     Timeline tle{(blockIdx.x == 0 && threadIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
     c.tl = &tle;
     const int t = threadIdx.x;   // 0..255
@@ -368,15 +370,17 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
         c.cst = consts_ptr(smem, pass);
         if (!sigma_only) {
           // per-ray direction bias: b_dir + W_dir[:, 256:283] . dir_embedded   (fp32)
-          const int r = t >> 7, n = t & 127;
-          const float* wd = c.f32 + kF32WDirPart + n;           // [j][n]: coalesced over n
-          float wv[27];
+          if (t < 256) {
+            const int r = t >> 7, n = t & 127;
+            const float* wd = c.f32 + kF32WDirPart + n;           // [j][n]: coalesced over n
+            float wv[27];
 #pragma unroll
-          for (int j = 0; j < 27; ++j) wv[j] = __ldg(wd + j * 128);
-          float acc = c.cst[kF32Bias + 8 * 256 + n];
+            for (int j = 0; j < 27; ++j) wv[j] = __ldg(wd + j * 128);
+            float acc = c.cst[kF32Bias + 8 * 256 + n];
 #pragma unroll
-          for (int j = 0; j < 27; ++j) acc = fmaf(wv[j], sc->direnc[r][j], acc);
-          sc->dirbias[r][n] = acc;
+            for (int j = 0; j < 27; ++j) acc = fmaf(wv[j], sc->direnc[r][j], acc);
+            sc->dirbias[r][n] = acc;
+          }
           tl_mark(c.tl, 0, 27);
           epi_bar();
         }
@@ -384,23 +388,30 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
           const int gr = tile * 128 + c.row;
           const int r = gr / S;
           tl_mark(c.tl, 0, 10);
-          encode_row(enc, c.row, c.half, &sc->ray[r][0], &sc->ray[r][3], sc->z[gr]);
+          encode_row(enc, c.row, c.part, &sc->ray[r][0], &sc->ray[r][3], sc->z[gr]);
           float sig_part, rgb_part[3];
           epi_run_tile(c, sigma_only, sc->dirbias[r], nullptr, sig_part, rgb_part);
-          sc->sig_part[c.half][c.row] = sig_part;
+          sc->sig_part[c.part][c.row] = sig_part;
           if (!sigma_only) {
-            sc->rgb_part[c.half][0][c.row] = rgb_part[0];
-            sc->rgb_part[c.half][1][c.row] = rgb_part[1];
-            sc->rgb_part[c.half][2][c.row] = rgb_part[2];
+            sc->rgb_part[c.part][0][c.row] = rgb_part[0];
+            sc->rgb_part[c.part][1][c.row] = rgb_part[1];
+            sc->rgb_part[c.part][2][c.row] = rgb_part[2];
           }
           epi_bar();
-          if (c.half == 0) {
-            sc->sigma[gr] = sc->sig_part[0][c.row] + sc->sig_part[1][c.row] + c.cst[kF32BSigma];
-            if (!sigma_only) {
+          // combine the column groups' partial head sums: group 0 -> sigma, groups 1..3 -> r, g, b
+          if (c.part == 0) {
+            float sg = c.cst[kF32BSigma];
 #pragma unroll
-              for (int ch = 0; ch < 3; ++ch)
-                sc->rgb[ch][gr] = sigmoid_ref(sc->rgb_part[0][ch][c.row] + sc->rgb_part[1][ch][c.row] +
-                                              c.cst[kF32BRgb + ch]);
+            for (int q = 0; q < kColSplit; ++q) sg += sc->sig_part[q][c.row];
+            sc->sigma[gr] = sg;
+          }
+          if (!sigma_only) {
+            for (int ch = c.part - (kColSplit == 4 ? 1 : 0); ch < 3 && ch >= 0; ch += (kColSplit == 4 ? 3 : 1)) {
+              if (kColSplit == 2 && c.part != 0) break;
+              float pre = c.cst[kF32BRgb + ch];
+#pragma unroll
+              for (int q = 0; q < kColSplit; ++q) pre += sc->rgb_part[q][ch][c.row];
+              sc->rgb[ch][gr] = sigmoid_ref(pre);
             }
           }
           epi_bar();
@@ -414,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
             nz = (pass ? p.noise_fine : p.noise_coarse) + static_cast<long long>(rid[r]) * S;
           const RayOut o = composite_ray(lane, S, sc->z + r * S, sc->sigma + r * S, sc->rgb[0] + r * S,
                                          sc->rgb[1] + r * S, sc->rgb[2] + r * S, nz, p.noise_std,
-                                         sc->dnorm[r], !sigma_only, sc->w[r]);
+                                         sc->dnorm[r], !sigma_only, sc->sigma + r * S);
           __syncwarp();
           tl_mark(c.tl, 0, 22);
           const bool wr = (r == 0) || valid1;
@@ -422,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
             const long long ri = rid[r];
             float* wout = pass ? p.weights_fine : p.weights_coarse;
             if (wout != nullptr)
-              for (int i = lane; i < S; i += 32) wout[ri * S + i] = sc->w[r][i];
+              for (int i = lane; i < S; i += 32) wout[ri * S + i] = sc->sigma[r * S + i];
             if (lane == 0) {
               float add = (p.white_back != 0) ? __fsub_rn(1.f, o.opac) : 0.f;
               if (pass == 0) {
@@ -444,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
           }
           tl_mark(c.tl, 0, 23);
           // ---- hierarchical resampling, part 1 (models/rendering.py:28-33): pdf -> cdf
-          if (pass == 0 && fine) pdf_to_cdf_ray(lane, Sc, sc->w[r], sc->cdf[r]);
+          if (pass == 0 && fine) pdf_to_cdf_ray(lane, Sc, sc->sigma + r * Sc, sc->cdf[r]);
           tl_mark(c.tl, 0, 24);
         }
         epi_bar();
@@ -487,8 +498,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
             int any_inv;
             asm volatile(
                 "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
-                "barrier.red.or.pred p, 1, 256, q;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                : "=r"(any_inv) : "r"(static_cast<int>(inv)) : "memory");
+                "barrier.red.or.pred p, 1, %2, q;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                : "=r"(any_inv) : "r"(static_cast<int>(inv)), "n"(kEpiThreads) : "memory");
             for (int e = t; e < 2 * Sf; e += kEpiThreads) {
               const int r = e / Sf, i = e - r * Sf;
               const float* zc = sc->zc[r];

@@ -219,13 +219,17 @@ def test_host_buffer_entry_matches_device_path(models, emb, dev):
 
 
 def test_weight_cache_tracks_parameter_updates(ws, emb, dev):
-    m = [nb.NeRF().to(dev), nb.NeRF().to(dev)]
+    m = []
+    for w in ws:                  # pseudo-trained weights: non-zero opacity, so colours matter
+        net = nb.NeRF()
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+        m.append(net.to(dev))
     rays = torch.from_numpy(orc.make_rays(64, 1)).to(dev)
     with torch.no_grad():
         a = nb.render_rays(m, emb, rays, 64, False, 0, 0, 64)["rgb_fine"].clone()
         m[1].rgb[0].bias.add_(1.0)            # in-place update bumps _version, like an optimizer step
         b = nb.render_rays(m, emb, rays, 64, False, 0, 0, 64)["rgb_fine"]
-    assert not torch.equal(a, b)
+    assert float((a - b).abs().max()) > 1e-2
 
 
 def test_training_path_produces_gradients(ws, emb, dev):

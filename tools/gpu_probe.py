@@ -51,7 +51,8 @@ def step_gemm():
     cases = {
         0: (params[0], 0, 63, 256), 5: (params[4], 0, 64, 256), 8: (params[4], 192, 64, 256),
         13: (params[8], 0, 63, 256), 15: (params[8], 63 + 64, 64, 256),
-        34: (params[18], 0, 64, 128), 38: (params[18], 256, 27, 128),
+        31: ((params[18][:, :256].double() @ params[16].double()).float(), 64, 64, 128),   # fused W' k-block 1
+        34: (params[18], 256, 27, 128),
     }
     ok = True
     for mode in (0, 1):
@@ -147,6 +148,29 @@ def step_mmabench():
     print("MMABENCH_DONE")
 
 
+def step_cache():
+    import numpy as np
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import nerf_oracle as orc
+    dev = torch.device("cuda:0")
+    emb = [nb.Embedding(3, 10), nb.Embedding(3, 4)]
+    m = [nb.NeRF().to(dev), nb.NeRF().to(dev)]
+    rays = torch.from_numpy(orc.make_rays(64, 1)).to(dev)
+    with torch.no_grad():
+        o1 = nb.render_rays(m, emb, rays, 64, False, 0, 0, 64)
+        a = o1["rgb_fine"].clone()
+        v0 = m[1].rgb[0].bias._version
+        m[1].rgb[0].bias.add_(1.0)
+        print("version", v0, "->", m[1].rgb[0].bias._version)
+        o2 = nb.render_rays(m, emb, rays, 64, False, 0, 0, 64)
+        b = o2["rgb_fine"]
+    torch.cuda.synchronize()
+    print("a[:4]", a[:4].cpu().numpy())
+    print("b[:4]", b[:4].cpu().numpy())
+    print("opacity_fine", o2["opacity_fine"][:8].cpu().numpy())
+    print("equal:", torch.equal(a, b), "nan:", bool(torch.isnan(a).any()), bool(torch.isnan(b).any()))
+
+
 def step_timeline():
     import numpy as np
     os.environ["NERFB200_FLAGS"] = str(int(os.environ.get("NERFB200_FLAGS", "0")) | 2)
@@ -177,5 +201,5 @@ def step_timeline():
 
 if __name__ == "__main__":
     t0 = time.time()
-    {"gemm": step_gemm, "mlp": step_mlp, "render": step_render, "speed": step_speed, "timeline": step_timeline, "mmabench": step_mmabench}[sys.argv[1]]()
+    {"gemm": step_gemm, "mlp": step_mlp, "render": step_render, "speed": step_speed, "timeline": step_timeline, "mmabench": step_mmabench, "cache": step_cache}[sys.argv[1]]()
     print(f"[{sys.argv[1]}] {time.time() - t0:.1f}s")
