@@ -50,7 +50,7 @@ constexpr bool kAInTmem = true;
 // is still converting (true), or all at once when the epilogue is done (false).  Measured on
 // B200: overlapping does not pay - the tensor core's TMEM (or smem) operand reads and
 // the epilogue's stores share one port, each slows the other by the overlap.
-constexpr bool kPipelinedHandover = false;
+constexpr bool kPipelinedHandover = true;
 constexpr int kStages = kAInTmem ? 5 : 3;
 constexpr int kTmemCols = 512;
 constexpr uint32_t kTmemD = 0, kTmemA = 256;
@@ -73,8 +73,9 @@ struct Barriers {
   uint64_t empty[kStages];
   uint64_t a_ready;        // sequential hand-over: all epilogue warps -> MMA : "A written, D drained"
                            //   (at tile start: "ENC tile written")
-  uint64_t d_free;         // pipelined hand-over: all epilogue warps -> MMA : "D drained into registers"
-  uint64_t a_kb[4];        // pipelined hand-over: 4 warps -> MMA : "A columns of K block kb written"
+  uint64_t d_free;         // pipelined hand-over: all epilogue warps -> MMA : "tile start: ENC written, D free"
+  uint64_t a_kb[4];        // pipelined hand-over: all warps -> MMA : "A columns of K block kb written"
+                           //   (every warp has drained its accumulator columns before its first arrive)
   uint64_t d_ready;        // MMA -> epilogue : "accumulator complete"
   uint32_t tmem_base;
   uint32_t pad[1];
@@ -115,7 +116,7 @@ __device__ __forceinline__ bool engine_setup(uint8_t* smem, Barriers* bars) {
     }
     mbar_init(smem_u32(&bars->a_ready), kEpiWarps);
     mbar_init(smem_u32(&bars->d_free), kEpiWarps);
-    for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&bars->a_kb[k]), 4);   // one K block = 64 columns = 4 warps' work
+    for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&bars->a_kb[k]), kEpiWarps);   // all warps work on one K block at a time
     mbar_init(smem_u32(&bars->d_ready), 1);
     fence_mbar_init();
   }
@@ -191,8 +192,18 @@ __device__ __forceinline__ void mma_tile(RingState& rs, MmaPhases& ph, uint8_t* 
   const uint32_t enc_base = smem_u32(smem + kSmemEnc);
   const int n_layers = sigma_only ? kLayersSigma : kLayersFull;
   for (int l = 0; l < n_layers; ++l) {
-    mbar_wait(smem_u32(kPipelinedHandover ? &bars->d_free : &bars->a_ready), ph.d_free, 3);
-    ph.d_free ^= 1;
+    if (kPipelinedHandover) {
+      // layer 0 reads the ENC tile: wait for "tile start" (d_free, once per tile).  Later layers:
+      // a_kb[0] - on which every warp arrives after draining its columns - implies the
+      // accumulator is free.
+      if (l == 0) {
+        mbar_wait(smem_u32(&bars->d_free), ph.d_free, 3);
+        ph.d_free ^= 1;
+      }
+    } else {
+      mbar_wait(smem_u32(&bars->a_ready), ph.d_free, 3);
+      ph.d_free ^= 1;
+    }
     tc_fence_after();
     tl_mark(tl, 1, 100 + l);
     const int n_slices = (l == 0) ? 1 : (l == 4) ? 5 : (l == 8 && dir_slice) ? 5 : 4;
@@ -264,12 +275,6 @@ __device__ __forceinline__ void epi_signal_a_ready(EpiCtx& c, bool smem_written)
   tc_fence_before();
   __syncwarp();
   if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_ready));
-}
-// This warp's accumulator columns are in registers.
-__device__ __forceinline__ void epi_signal_d_free(EpiCtx& c) {
-  tc_fence_before();
-  __syncwarp();
-  if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->d_free));
 }
 // This warp's A columns of K block kb are stored in TMEM (and, optionally, ENC smem rewritten).
 __device__ __forceinline__ void epi_signal_kb(EpiCtx& c, int kb, bool smem_written) {
@@ -389,22 +394,51 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, const float* bias, const f
   tl_mark(c.tl, 0, 2);
   constexpr int kPairs = kColsPer / 64;                       // 64 columns = one K block of the next layer
   if (kPipelinedHandover) {
-    // drain everything first so the accumulator can be released early
-    uint32_t r[kPairs][2][32];
+    // K-block interleaved: every warp owns kColsPer/4 columns of EACH 64-wide K block, so the
+    // blocks complete one after the other and the MMA of the next layer can start on block 0
+    // while blocks 1..3 are still being converted.  Requires the TMEM A operand.
+    static_assert(kAInTmem || !kPipelinedHandover, "pipelined hand-over is implemented for the TMEM operand");
+    constexpr int kW16 = kColsPer / 4;                        // 16 columns per K block per thread
+    static_assert(kW16 == 16, "pipelined hand-over assumes 16 epilogue warps");
+    uint32_t r[4][16];
 #pragma unroll
-    for (int pr = 0; pr < kPairs; ++pr) {
-      tmem_ld32(d_src + 64 * pr, r[pr][0]);
-      tmem_ld32(d_src + 64 * pr + 32, r[pr][1]);
-    }
+    for (int kb = 0; kb < 4; ++kb) tmem_ld16(c.tmem_row + kTmemD + kb * 64 + c.part * 16, r[kb]);
     tmem_ld_wait();
-    if (kStore) epi_signal_d_free(c);
     tl_mark(c.tl, 0, 3);
 #pragma unroll
-    for (int pr = 0; pr < kPairs; ++pr) {
-      epi_chunk<kRelu, kSigma, kStore>(r[pr][0], bias, nb + 64 * pr, kAInTmem ? a_tm + 32 * pr : a_row, wsig, sig_acc);
-      epi_chunk<kRelu, kSigma, kStore>(r[pr][1], bias, nb + 64 * pr + 32, kAInTmem ? a_tm + 32 * pr + 16 : a_row, wsig, sig_acc);
-      if (pr == kPairs - 1 && dir_row != nullptr) write_dir_row(c, dir_row);
-      if (kStore) epi_signal_kb(c, nb / 64 + pr, pr == kPairs - 1 && dir_row != nullptr);
+    for (int kb = 0; kb < 4; ++kb) {
+      const int n0 = kb * 64 + c.part * 16;
+      uint32_t h[8];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + n0 + 8 * j);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + n0 + 8 * j + 4);
+        float v[8];
+        add_f32x2(v[0], v[1], __uint_as_float(r[kb][8 * j + 0]), __uint_as_float(r[kb][8 * j + 1]), b0.x, b0.y);
+        add_f32x2(v[2], v[3], __uint_as_float(r[kb][8 * j + 2]), __uint_as_float(r[kb][8 * j + 3]), b0.z, b0.w);
+        add_f32x2(v[4], v[5], __uint_as_float(r[kb][8 * j + 4]), __uint_as_float(r[kb][8 * j + 5]), b1.x, b1.y);
+        add_f32x2(v[6], v[7], __uint_as_float(r[kb][8 * j + 6]), __uint_as_float(r[kb][8 * j + 7]), b1.z, b1.w);
+        if (kSigma) {
+          const float4 w0 = *reinterpret_cast<const float4*>(wsig + n0 + 8 * j);
+          const float4 w1 = *reinterpret_cast<const float4*>(wsig + n0 + 8 * j + 4);
+          sig_acc = fmaf(fmaxf(v[0], 0.f), w0.x, sig_acc); sig_acc = fmaf(fmaxf(v[1], 0.f), w0.y, sig_acc);
+          sig_acc = fmaf(fmaxf(v[2], 0.f), w0.z, sig_acc); sig_acc = fmaf(fmaxf(v[3], 0.f), w0.w, sig_acc);
+          sig_acc = fmaf(fmaxf(v[4], 0.f), w1.x, sig_acc); sig_acc = fmaf(fmaxf(v[5], 0.f), w1.y, sig_acc);
+          sig_acc = fmaf(fmaxf(v[6], 0.f), w1.z, sig_acc); sig_acc = fmaf(fmaxf(v[7], 0.f), w1.w, sig_acc);
+        }
+        if (kRelu) {
+          h[4 * j + 0] = cvt_f16x2_relu(v[0], v[1]); h[4 * j + 1] = cvt_f16x2_relu(v[2], v[3]);
+          h[4 * j + 2] = cvt_f16x2_relu(v[4], v[5]); h[4 * j + 3] = cvt_f16x2_relu(v[6], v[7]);
+        } else {
+          h[4 * j + 0] = cvt_f16x2(v[0], v[1]); h[4 * j + 1] = cvt_f16x2(v[2], v[3]);
+          h[4 * j + 2] = cvt_f16x2(v[4], v[5]); h[4 * j + 3] = cvt_f16x2(v[6], v[7]);
+        }
+      }
+      if (kStore) {
+        tmem_st8(c.tmem_row + kTmemA + n0 / 2, h);
+        if (kb == 3 && dir_row != nullptr) write_dir_row(c, dir_row);
+        epi_signal_kb(c, kb, kb == 3 && dir_row != nullptr);
+      }
     }
   } else {
     uint32_t r0[32], r1[32];
