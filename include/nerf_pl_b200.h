@@ -104,6 +104,20 @@ int nerfb200_render_rays_host(const nerfb200_render_args* host_args, void* strea
 int nerfb200_nerf_forward(const float* x, int64_t n, int64_t x_stride, const void* packed,
                           int32_t sigma_only, float* out, void* stream);
 
+/* ---- dense sigma query ("next" row: mesh extraction) -------------------------------------
+ * Replaces: extract_color_mesh.py:127-140 (embedding_xyz + embedding_dir + cat + nerf(...)[:, -1]
+ * per chunk): raw positions xyz (n, xyz_stride >= 3) -> raw sigma (n); the positional encoding is
+ * computed in the kernel, the direction does not enter sigma (models/nerf.py:112). */
+int nerfb200_query_sigma(const float* xyz, int64_t n, int64_t xyz_stride, const void* packed, float* sigma,
+                         void* stream);
+
+/* ---- loss / metric epilogue ("next" row) -------------------------------------------------
+ * Replaces: losses.py:9-14 MSELoss.forward and metrics.py:4-13 psnr on the rendered batch.
+ * rgb_coarse / rgb_fine: (n_rays,3), either may be NULL; target (n_rays,3).
+ * out4 (device): [mse_coarse, mse_fine, mse_coarse + mse_fine, psnr of the finest pass]. */
+int nerfb200_mse_psnr(const float* rgb_coarse, const float* rgb_fine, const float* target, int64_t n_rays,
+                      float* out4, void* stream);
+
 /* ---- Embedding.forward -------------------------------------------------------------------
  * Replaces: models/nerf.py:21-38.  x: (n,3) -> out: (n, 3 + 6*n_freqs). */
 int nerfb200_embed(const float* x, int64_t n, int32_t n_freqs, float* out, void* stream);

@@ -38,6 +38,8 @@ EXPORTS = [
     "nerfb200_searchsorted",
     "nerfb200_sample_pdf",
     "nerfb200_composite",
+    "nerfb200_query_sigma",
+    "nerfb200_mse_psnr",
     "nerfb200_generate_rays",
     "nerfb200_to_uint8",
     "nerfb200_launch_count",
@@ -136,6 +138,10 @@ def _declare(lib: ctypes.CDLL) -> None:
                                        c_void_p, c_void_p]
     lib.nerfb200_debug_gemm.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
     lib.nerfb200_debug_gemm.restype = c_int32
+    lib.nerfb200_query_sigma.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.nerfb200_query_sigma.restype = c_int32
+    lib.nerfb200_mse_psnr.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
+    lib.nerfb200_mse_psnr.restype = c_int32
     lib.nerfb200_generate_rays.argtypes = [c_int32, c_int32, c_float, POINTER(c_float), c_float, c_float, c_int32,
                                            c_void_p, c_void_p]
     lib.nerfb200_generate_rays.restype = c_int32

@@ -85,6 +85,7 @@ __global__ void pack_weights_kernel(const PackParams pp) {
 
 // ------------------------------------------------ NeRF.forward (models/nerf.py:83-124)
 struct MlpParams {
+  int raw_xyz;             // 1: x is (n, x_stride>=3) raw positions, encoded in-kernel; sigma only
   const float* x;          // (n, x_stride): embedded xyz (63) [+ embedded dir (27)]
   long long x_stride;
   long long n;
@@ -135,10 +136,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const MlpParam
       const long long gi = tile * 128 + c.row;
       const bool valid = gi < p.n;
       const float* xr = p.x + (valid ? gi : (p.n - 1)) * p.x_stride;
-      const int k0 = c.part * (64 / kColSplit);
-      for (int k = k0; k < k0 + 64 / kColSplit; ++k) {
-        const float v = (k < kEncXyz) ? __ldg(xr + k) : 0.f;
-        *reinterpret_cast<__half*>(enc + sw128_off(c.row, k)) = __float2half_rn(v);
+      if (p.raw_xyz) {
+        // dense-grid sigma query (extract_color_mesh.py:127-140): encode the raw position here
+        const float o[3] = {__ldg(xr), __ldg(xr + 1), __ldg(xr + 2)};
+        const float zero[3] = {0.f, 0.f, 0.f};
+        encode_row(enc, c.row, c.part, o, zero, 0.f);
+      } else {
+        const int k0 = c.part * (64 / kColSplit);
+        for (int k = k0; k < k0 + 64 / kColSplit; ++k) {
+          const float v = (k < kEncXyz) ? __ldg(xr + k) : 0.f;
+          *reinterpret_cast<__half*>(enc + sw128_off(c.row, k)) = __float2half_rn(v);
+        }
       }
       float sig_part, rgb_part[3];
       epi_run_tile(c, so, nullptr, so ? nullptr : xr + kEncXyz, sig_part, rgb_part);
@@ -449,6 +457,37 @@ __global__ void to_uint8_kernel(const float* __restrict__ src, long long n, uint
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float v = fminf(fmaxf(src[i], 0.f), 1.f) * 255.f;
     dst[i] = static_cast<uint8_t>(v);
+  }
+}
+
+// ------------------------------------------------ loss / metric epilogue (losses.py:9-14, metrics.py:4-13)
+// out[0] = mean((rgb_coarse - t)^2), out[1] = mean((rgb_fine - t)^2) (0 if rgb_fine is null),
+// out[2] = out[0] + out[1] (MSELoss.forward), out[3] = -10 log10(mse of the finest available)  (psnr).
+// One block, fixed summation order (deterministic).
+__global__ void __launch_bounds__(1024, 1) mse_psnr_kernel(const float* __restrict__ rgb_c,
+                                                           const float* __restrict__ rgb_f,
+                                                           const float* __restrict__ target, long long n_elem,
+                                                           float* __restrict__ out) {
+  __shared__ double red[2][32];
+  double ac = 0.0, af = 0.0;
+  for (long long i = threadIdx.x; i < n_elem; i += blockDim.x) {
+    const float t = target[i];
+    if (rgb_c != nullptr) { const float d = rgb_c[i] - t; ac += static_cast<double>(d) * d; }
+    if (rgb_f != nullptr) { const float d = rgb_f[i] - t; af += static_cast<double>(d) * d; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    ac += __shfl_xor_sync(0xffffffffu, ac, o);
+    af += __shfl_xor_sync(0xffffffffu, af, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ac; red[1][threadIdx.x >> 5] = af; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sc = 0.0, sf = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { sc += red[0][w]; sf += red[1][w]; }
+    const float mc = static_cast<float>(sc / static_cast<double>(n_elem));
+    const float mf = static_cast<float>(sf / static_cast<double>(n_elem));
+    out[0] = mc; out[1] = mf; out[2] = mc + mf;
+    out[3] = -10.f * log10f(rgb_f != nullptr ? mf : mc);
   }
 }
 

@@ -303,6 +303,7 @@ int nerfb200_nerf_forward(const float* x, int64_t n, int64_t x_stride, const voi
   int rc = device_info(&d);
   if (rc) return rc;
   MlpParams p;
+  p.raw_xyz = 0;
   p.x = x; p.x_stride = x_stride; p.n = n;
   p.net = static_cast<const uint8_t*>(packed);
   p.sigma_only = sigma_only;
@@ -313,6 +314,40 @@ int nerfb200_nerf_forward(const float* x, int64_t n, int64_t x_stride, const voi
   mlp_forward_kernel<<<ctas, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
   g_launches++;
   CUDA_TRY(cudaGetLastError(), "nerf_forward launch");
+  return 0;
+}
+
+int nerfb200_query_sigma(const float* xyz, int64_t n, int64_t xyz_stride, const void* packed, float* sigma,
+                         void* stream) {
+  if (n < 0) return fail(NERFB200_EINVAL, "query_sigma: n < 0%s");
+  if (n == 0) return 0;
+  if (!xyz || !packed || !sigma) return fail(NERFB200_EINVAL, "query_sigma: NULL argument%s");
+  if (xyz_stride < 3) return fail(NERFB200_EINVAL, "query_sigma: xyz_stride < 3%s");
+  DeviceInfo* d = nullptr;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  MlpParams p;
+  p.raw_xyz = 1;
+  p.x = xyz; p.x_stride = xyz_stride; p.n = n;
+  p.net = static_cast<const uint8_t*>(packed);
+  p.sigma_only = 1;
+  p.out = sigma;
+  p.status = d->status;
+  const long long tiles = (n + 127) / 128;
+  const int ctas = static_cast<int>(tiles < d->sm_count ? tiles : d->sm_count);
+  mlp_forward_kernel<<<ctas, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "query_sigma launch");
+  return 0;
+}
+
+int nerfb200_mse_psnr(const float* rgb_coarse, const float* rgb_fine, const float* target, int64_t n_rays,
+                      float* out4, void* stream) {
+  if (n_rays <= 0) return fail(NERFB200_EINVAL, "mse_psnr: n_rays <= 0%s");
+  if ((!rgb_coarse && !rgb_fine) || !target || !out4) return fail(NERFB200_EINVAL, "mse_psnr: NULL argument%s");
+  mse_psnr_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(rgb_coarse, rgb_fine, target, n_rays * 3, out4);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "mse_psnr launch");
   return 0;
 }
 

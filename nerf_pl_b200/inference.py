@@ -12,7 +12,7 @@ from typing import Dict, Optional, Sequence
 import torch
 
 from . import _lib
-from .nerf import _stream_ptr
+from .nerf import _stream_ptr, packed_weights
 from .rendering import render_rays
 from .sharded import render_rays_sharded
 
@@ -85,3 +85,39 @@ def render_image(models, embeddings, H: int, W: int, focal: float, c2w, near: fl
         out["depth"] = res[f"depth_{typ}"].view(H, W)
         out["rgb_uint8"] = to_uint8(out["rgb"])
     return out
+
+
+@torch.no_grad()
+def query_sigma(model: torch.nn.Module, xyz: torch.Tensor) -> torch.Tensor:
+    """Raw sigma at positions xyz (N,3) with one fused launch (encoding in-kernel, sigma-only MLP).
+    Equivalent to extract_color_mesh.py:127-140 `nerf(cat(embedding_xyz(x), embedding_dir(0)))[:, -1]`."""
+    if not xyz.is_cuda or xyz.dim() != 2 or xyz.shape[1] != 3:
+        raise ValueError("xyz must be a (N, 3) CUDA tensor")
+    x = xyz.detach().to(torch.float32).contiguous()
+    out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    blob = packed_weights(model)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.nerfb200_query_sigma(x.data_ptr(), x.shape[0], 3, blob.data_ptr(), out.data_ptr(),
+                                            _stream_ptr()), "nerfb200_query_sigma")
+    return out
+
+
+@torch.no_grad()
+def mse_psnr(results: Dict[str, torch.Tensor], targets: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """losses.py:9-14 MSELoss + metrics.py:12-13 psnr of a render_rays result in one launch.
+    Returns {'loss': mse_coarse (+ mse_fine), 'psnr': of rgb_fine if present else rgb_coarse}."""
+    rc, rf = results.get("rgb_coarse"), results.get("rgb_fine")
+    ref = rf if rf is not None else rc
+    if ref is None or not ref.is_cuda:
+        raise ValueError("results must hold CUDA rgb_coarse and/or rgb_fine")
+    t = targets.detach().to(torch.float32).contiguous()
+    out = torch.empty(4, dtype=torch.float32, device=ref.device)
+    lib = _lib.load()
+    keep = [None if v is None else v.detach().float().contiguous() for v in (rc, rf)]
+    with torch.cuda.device(ref.device):
+        _lib.check(lib.nerfb200_mse_psnr(None if keep[0] is None else keep[0].data_ptr(),
+                                         None if keep[1] is None else keep[1].data_ptr(),
+                                         t.data_ptr(), t.shape[0], out.data_ptr(), _stream_ptr()),
+                   "nerfb200_mse_psnr")
+    return {"loss": out[2] if rc is not None else out[1], "psnr": out[3], "mse_coarse": out[0], "mse_fine": out[1]}

@@ -277,3 +277,27 @@ def test_ray_generation_and_image_driver(models, emb, ws, dev):
     bi = nb.batched_inference(models, emb, r, 64, 64, False, 32768, True)
     assert set(bi) == {"opacity_coarse", "rgb_fine", "depth_fine", "opacity_fine"}
     assert torch.equal(bi["rgb_fine"].view(H, W, 3), out["rgb"])
+
+
+def test_sigma_query_and_loss_epilogue(models, emb, ws, dev):
+    """dense sigma query (extract_color_mesh.py:127-140) and MSE/PSNR
+    (losses.py:9-14, metrics.py:4-13)."""
+    rs = np.random.RandomState(5)
+    xyz = rs.uniform(-1.5, 1.5, (3000, 3)).astype(np.float32)
+    got = nb.query_sigma(models[1], torch.from_numpy(xyz).to(dev)).cpu().numpy()
+    x = np.concatenate([orc.embed(xyz, 10), orc.embed(np.zeros_like(xyz), 4)], -1)
+    ref = orc.nerf_forward(ws[1], x)[:, -1]
+    assert got.shape == (3000,)
+    assert (np.abs(got - ref) / (1 + np.abs(ref))).max() < 2e-3
+    # drop-in two-step path gives the same numbers to the same tolerance
+    two = models[1](torch.cat([emb[0](torch.from_numpy(xyz).to(dev)), emb[1](torch.zeros(3000, 3, device=dev))], 1))
+    assert (np.abs(two[:, -1].cpu().numpy() - ref) / (1 + np.abs(ref))).max() < 2e-3
+    rays = torch.from_numpy(orc.make_rays(500, 4)).to(dev)
+    with torch.no_grad():
+        res = nb.render_rays(models, emb, rays, 64, False, 0, 0, 64, 32768, True)
+    tgt = torch.rand(500, 3, device=dev)
+    m = nb.mse_psnr(res, tgt)
+    mc = float(((res["rgb_coarse"] - tgt) ** 2).mean())
+    mf = float(((res["rgb_fine"] - tgt) ** 2).mean())
+    assert abs(float(m["loss"]) - (mc + mf)) < 1e-5 * (mc + mf) + 1e-9
+    assert abs(float(m["psnr"]) - (-10 * np.log10(mf))) < 1e-4
