@@ -87,6 +87,20 @@ typedef struct nerfb200_render_args {
   float* weights_fine;
   int32_t* status;
   int32_t max_ctas; /* 0 = one CTA per SM */
+  /* Training mode (all NULL = inference; requires test_time == 0): per-sample intermediates the
+   * backward pass needs, written by the same fused launch.  n_c = n_rays*N_samples,
+   * n_f = n_rays*(N_samples+N_importance); sample row = ray*S + index along the (sorted) ray.
+   *   save_act_*   fp16 (8, n, 256): outputs of xyz_encoding_1..8 (post-ReLU)
+   *   save_dir_*   fp16 (n, 128):    output of dir_encoding (post-ReLU)
+   *   save_sigma_* fp32 (n):         raw sigma          save_rgb_* fp32 (n, 3): sigmoid(rgb) */
+  void* save_act_coarse;
+  void* save_act_fine;
+  void* save_dir_coarse;
+  void* save_dir_fine;
+  float* save_sigma_coarse;
+  float* save_sigma_fine;
+  float* save_rgb_coarse;
+  float* save_rgb_fine;
 } nerfb200_render_args;
 
 int nerfb200_render_rays(const nerfb200_render_args* args, void* stream);

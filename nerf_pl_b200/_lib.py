@@ -81,6 +81,14 @@ class RenderArgs(ctypes.Structure):
         ("weights_fine", c_void_p),
         ("status", c_void_p),
         ("max_ctas", c_int32),
+        ("save_act_coarse", c_void_p),
+        ("save_act_fine", c_void_p),
+        ("save_dir_coarse", c_void_p),
+        ("save_dir_fine", c_void_p),
+        ("save_sigma_coarse", c_void_p),
+        ("save_sigma_fine", c_void_p),
+        ("save_rgb_coarse", c_void_p),
+        ("save_rgb_fine", c_void_p),
     ]
 
 

@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const MlpParam
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     c.d_phase = 0;
     c.flags = 0;
+    c.save_act = nullptr; c.save_d = nullptr; c.save_n = 0; c.save_row = -1;
     c.tl = nullptr;
     c.f32 = reinterpret_cast<const float*>(p.net + kHalfRegionBytes);
     c.cst = consts_ptr(smem, 0);
@@ -374,6 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_probe_kernel(const float* __
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     c.d_phase = 0;
     c.flags = 0;
+    c.save_act = nullptr; c.save_d = nullptr; c.save_n = 0; c.save_row = -1;
     c.tl = nullptr;
     if (mode == 0) {
       uint8_t* enc = smem + kSmemEnc;

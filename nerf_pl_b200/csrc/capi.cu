@@ -53,6 +53,8 @@ int device_info(DeviceInfo** out) {
   if (!d.attrs_set) {
     CUDA_TRY(cudaFuncSetAttribute(render_rays_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kSmemTotal)), "smem attr render");
+    CUDA_TRY(cudaFuncSetAttribute(render_rays_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kSmemTotal)), "smem attr render(save)");
     CUDA_TRY(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kSmemTotal)), "smem attr mlp");
     CUDA_TRY(cudaFuncSetAttribute(gemm_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -193,6 +195,17 @@ int nerfb200_render_rays(const nerfb200_render_args* a, void* stream) {
   p.weights_coarse = a->weights_coarse;
   p.weights_fine = a->weights_fine;
   p.status = a->status ? a->status : d->status;
+  p.save_act_c = static_cast<__half*>(a->save_act_coarse);
+  p.save_act_f = static_cast<__half*>(a->save_act_fine);
+  p.save_d_c = static_cast<__half*>(a->save_dir_coarse);
+  p.save_d_f = static_cast<__half*>(a->save_dir_fine);
+  p.save_sig_c = a->save_sigma_coarse;
+  p.save_sig_f = a->save_sigma_fine;
+  p.save_rgb_c = a->save_rgb_coarse;
+  p.save_rgb_f = a->save_rgb_fine;
+  const bool save = p.save_act_c || p.save_act_f || p.save_d_c || p.save_d_f || p.save_sig_c || p.save_sig_f ||
+                    p.save_rgb_c || p.save_rgb_f;
+  if (save && a->test_time) return fail(NERFB200_EINVAL, "save_* buffers need test_time = 0%s");
   {
     const char* f = std::getenv("NERFB200_FLAGS");   // experiment switches; unset in production
     p.flags = f ? static_cast<unsigned>(std::strtoul(f, nullptr, 0)) : 0u;
@@ -209,7 +222,10 @@ int nerfb200_render_rays(const nerfb200_render_args* a, void* stream) {
   int ctas = d->sm_count;
   if (a->max_ctas > 0 && a->max_ctas < ctas) ctas = a->max_ctas;
   if (n_groups < ctas) ctas = n_groups;
-  render_rays_kernel<false><<<ctas, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
+  if (save)
+    render_rays_kernel<true><<<ctas, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
+  else
+    render_rays_kernel<false><<<ctas, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
   g_launches++;
   CUDA_TRY(cudaGetLastError(), "render_rays launch");
   return 0;
@@ -234,6 +250,9 @@ int nerfb200_render_rays_host(const nerfb200_render_args* h, void* stream_v) {
   ar.off = 0;
   nerfb200_render_args a = *h;
   a.ray_stride = 8;
+  if (h->save_act_coarse || h->save_act_fine || h->save_dir_coarse || h->save_dir_fine || h->save_sigma_coarse ||
+      h->save_sigma_fine || h->save_rgb_coarse || h->save_rgb_fine)
+    return fail(NERFB200_EINVAL, "render_rays_host: save_* buffers are device-only%s");
   auto up = [&](const float* src, size_t count, size_t src_stride, size_t width) -> const float* {
     if (!src) return nullptr;
     float* dst = static_cast<float*>(ar.take(count * fl));

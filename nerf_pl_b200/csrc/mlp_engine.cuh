@@ -254,6 +254,12 @@ struct EpiCtx {
   int lane;
   Timeline* tl;                    // non-null only for the one traced thread
   unsigned flags;                  // experiment switches (0 in production)
+  // training mode ("save"): post-activation outputs of layers 1..8 and of the direction layer
+  // are also written to HBM for the backward pass
+  __half* save_act;                // [8][save_n][256] fp16 (null = off)
+  __half* save_d;                  // [save_n][128] fp16
+  long long save_n;                // samples in the pass (rows per layer)
+  long long save_row;              // this thread's global sample row, -1 = padding row
 };
 
 __device__ __forceinline__ void epi_bar() {   // all 256 epilogue threads
@@ -382,8 +388,8 @@ __device__ __forceinline__ void write_dir_row(EpiCtx& c, const float* __restrict
 //   kStore = false: last layer of a sigma-only tile (nothing to hand to the tensor core).
 //   dir_row != nullptr (layer 8 in NeRF.forward mode): also rewrite the ENC tile with this row's
 //   embedded direction before the last signal.
-template <bool kRelu, bool kSigma, bool kStore>
-__device__ __forceinline__ void epi_hidden(EpiCtx& c, const float* bias, const float* wsig,
+template <bool kRelu, bool kSigma, bool kStore, bool kSave = false>
+__device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, const float* wsig,
                                            float& sig_acc, const float* __restrict__ dir_row = nullptr) {
   const int nb = c.part * kColsPer;
   const uint32_t a_row = smem_u32(c.smem + kSmemA) + static_cast<uint32_t>(c.row) * 128u;
@@ -439,6 +445,11 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, const float* bias, const f
         if (kb == 3 && dir_row != nullptr) write_dir_row(c, dir_row);
         epi_signal_kb(c, kb, kb == 3 && dir_row != nullptr);
       }
+      if (kSave && c.save_act != nullptr && c.save_row >= 0) {
+        uint4* dst = reinterpret_cast<uint4*>(c.save_act + (static_cast<long long>(l) * c.save_n + c.save_row) * 256 + n0);
+        dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
+        dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
+      }
     }
   } else {
     uint32_t r0[32], r1[32];
@@ -466,6 +477,7 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, const float* bias, const f
 // dir_encoding epilogue (N=128; this thread's 128/kColSplit columns) fused with the rgb head
 // (models/nerf.py:119-120): d = relu(acc + dbias[n]); rgb_acc[c] += d * w_rgb[c][n].
 // dbias is either the per-ray vector (bias + direction part, shared memory) or b' (shared memory).
+template <bool kSave = false>
 __device__ __forceinline__ void epi_dir(EpiCtx& c, const float* dbias, const float* wrgb,
                                         float (&rgb_acc)[3]) {
   constexpr int kCols = 128 / kColSplit;     // 32 or 64
@@ -494,6 +506,10 @@ __device__ __forceinline__ void epi_dir(EpiCtx& c, const float* dbias, const flo
       rgb_acc[1] = fmaf(v2, wg.z, rgb_acc[1]); rgb_acc[1] = fmaf(v3, wg.w, rgb_acc[1]);
       rgb_acc[2] = fmaf(v0, wb.x, rgb_acc[2]); rgb_acc[2] = fmaf(v1, wb.y, rgb_acc[2]);
       rgb_acc[2] = fmaf(v2, wb.z, rgb_acc[2]); rgb_acc[2] = fmaf(v3, wb.w, rgb_acc[2]);
+      if (kSave && c.save_d != nullptr && c.save_row >= 0) {
+        uint2* dst = reinterpret_cast<uint2*>(c.save_d + c.save_row * 128 + n);
+        *dst = make_uint2(cvt_f16x2(v0, v1), cvt_f16x2(v2, v3));
+      }
     }
   }
 }
@@ -505,6 +521,7 @@ __device__ __forceinline__ void epi_dir(EpiCtx& c, const float* dbias, const flo
 //                part through the tensor core instead).
 //   dir_row    : dir_slice mode only - this row's 27 embedded direction values (global).
 // Outputs partial sums (this thread's column group): sigma and rgb pre-activation.
+template <bool kSave = false>
 __device__ __forceinline__ void epi_run_tile(EpiCtx& c, bool sigma_only, const float* dbias,
                                              const float* __restrict__ dir_row, float& sig_part,
                                              float (&rgb_part)[3]) {
@@ -514,16 +531,16 @@ __device__ __forceinline__ void epi_run_tile(EpiCtx& c, bool sigma_only, const f
   rgb_part[0] = rgb_part[1] = rgb_part[2] = 0.f;
   float dummy = 0.f;
   epi_signal_tile_start(c);
-  for (int l = 0; l < 7; ++l) epi_hidden<true, false, true>(c, bias + l * 256, nullptr, dummy);
+  for (int l = 0; l < 7; ++l) epi_hidden<true, false, true, kSave>(c, l, bias + l * 256, nullptr, dummy);
   if (sigma_only) {
-    epi_hidden<true, true, false>(c, bias + 7 * 256, wsig, sig_part);
+    epi_hidden<true, true, false, kSave>(c, 7, bias + 7 * 256, wsig, sig_part);
     return;   // the accumulator is released with the next tile's ENC write
   }
   // layer 8's activations feed the fused final.dir layer (layout.h); in NeRF.forward mode the ENC
   // tile is rewritten with this row's embedded direction for the extra K slice
-  epi_hidden<true, true, true>(c, bias + 7 * 256, wsig, sig_part, dir_row);
+  epi_hidden<true, true, true, kSave>(c, 7, bias + 7 * 256, wsig, sig_part, dir_row);
   epi_wait_d(c);
-  epi_dir(c, dbias != nullptr ? dbias : (bias + 8 * 256), c.cst + kF32WRgb, rgb_part);
+  epi_dir<kSave>(c, dbias != nullptr ? dbias : (bias + 8 * 256), c.cst + kF32WRgb, rgb_part);
 }
 
 __device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf(-x)); }

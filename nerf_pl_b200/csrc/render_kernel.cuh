@@ -39,6 +39,15 @@ struct RenderParams {
   float* weights_coarse;        // (n_rays, S_c) optional
   float* weights_fine;          // (n_rays, S_f) optional
   int* status;                  // device int: nonzero on device-detected error
+  // training mode: per-sample intermediates for the backward pass (all null = inference)
+  __half* save_act_c;           // [8][n_rays*S_c][256] fp16: coarse h1..h8
+  __half* save_act_f;           // [8][n_rays*S_f][256]
+  __half* save_d_c;             // [n_rays*S_c][128] fp16: direction-layer activation
+  __half* save_d_f;             // [n_rays*S_f][128]
+  float* save_sig_c;            // [n_rays*S_c] raw sigma
+  float* save_sig_f;            // [n_rays*S_f]
+  float* save_rgb_c;            // [n_rays*S_c][3] sigmoid(rgb)
+  float* save_rgb_f;            // [n_rays*S_f][3]
   unsigned flags;               // experiment switches (NERFB200_FLAGS), 0 in production
   long long* timeline;          // experiment: device timeline buffer (flags & 2), else null
 };
@@ -251,7 +260,7 @@ __device__ __forceinline__ float inverse_cdf(int S, const float* zc, const float
   return __fadd_rn(b0, __fmul_rn(tt, __fsub_rn(b1, b0)));
 }
 
-template <bool kDummy>
+template <bool kSave>
 __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Scratch* sc = reinterpret_cast<Scratch*>(smem + kSmemScratch);
@@ -312,6 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     c.d_phase = 0;
     c.flags = p.flags;
+    c.save_act = nullptr; c.save_d = nullptr; c.save_n = 0; c.save_row = -1;
     Timeline tle{(blockIdx.x == 0 && threadIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
     c.tl = &tle;
     const int t = threadIdx.x;   // 0..255
@@ -368,6 +378,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
         const uint8_t* blob = pass ? p.net_fine : p.net_coarse;
         c.f32 = reinterpret_cast<const float*>(blob + kHalfRegionBytes);
         c.cst = consts_ptr(smem, pass);
+        c.save_act = kSave ? (pass ? p.save_act_f : p.save_act_c) : nullptr;
+        c.save_d = kSave ? (pass ? p.save_d_f : p.save_d_c) : nullptr;
+        c.save_n = static_cast<long long>(p.n_rays) * S;
         if (!sigma_only) {
           // per-ray direction bias: b_dir + W_dir[:, 256:283] . dir_embedded   (fp32)
           if (t < 256) {
@@ -389,8 +402,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
           const int r = gr / S;
           tl_mark(c.tl, 0, 10);
           encode_row(enc, c.row, c.part, &sc->ray[r][0], &sc->ray[r][3], sc->z[gr]);
+          const long long grow = (r == 0 || valid1) ? static_cast<long long>(rid[r]) * S + (gr - r * S) : -1;
+          c.save_row = grow;
           float sig_part, rgb_part[3];
-          epi_run_tile(c, sigma_only, sc->dirbias[r], nullptr, sig_part, rgb_part);
+          epi_run_tile<kSave>(c, sigma_only, sc->dirbias[r], nullptr, sig_part, rgb_part);
           sc->sig_part[c.part][c.row] = sig_part;
           if (!sigma_only) {
             sc->rgb_part[c.part][0][c.row] = rgb_part[0];
@@ -404,6 +419,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
 #pragma unroll
             for (int q = 0; q < kColSplit; ++q) sg += sc->sig_part[q][c.row];
             sc->sigma[gr] = sg;
+            if (kSave && grow >= 0) {
+              float* ss = pass ? p.save_sig_f : p.save_sig_c;
+              if (ss != nullptr) ss[grow] = sg;
+            }
           }
           if (!sigma_only) {
             for (int ch = c.part - (kColSplit == 4 ? 1 : 0); ch < 3 && ch >= 0; ch += (kColSplit == 4 ? 3 : 1)) {
@@ -411,7 +430,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
               float pre = c.cst[kF32BRgb + ch];
 #pragma unroll
               for (int q = 0; q < kColSplit; ++q) pre += sc->rgb_part[q][ch][c.row];
-              sc->rgb[ch][gr] = sigmoid_ref(pre);
+              const float col = sigmoid_ref(pre);
+              sc->rgb[ch][gr] = col;
+              if (kSave && grow >= 0) {
+                float* sr = pass ? p.save_rgb_f : p.save_rgb_c;
+                if (sr != nullptr) sr[grow * 3 + ch] = col;
+              }
             }
           }
           epi_bar();

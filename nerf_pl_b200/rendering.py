@@ -151,7 +151,8 @@ def render_rays(models: List[torch.nn.Module],
                 *,
                 randoms: Optional[Dict[str, torch.Tensor]] = None,
                 match_reference_rng: bool = True,
-                extras: bool = False) -> Dict[str, torch.Tensor]:
+                extras: bool = False,
+                autograd_impl: str = "fused") -> Dict[str, torch.Tensor]:
     """Render rays with the coarse (and fine) NeRF.  Drop-in for reference
     ``models.rendering.render_rays`` (models/rendering.py:58-244): same positional arguments,
     defaults and result keys/shapes/dtypes:
@@ -163,7 +164,10 @@ def render_rays(models: List[torch.nn.Module],
     ``chunk`` is accepted and ignored (nothing is materialised per point, so there is nothing to
     chunk).  Keyword-only extensions: ``randoms`` supplies pre-drawn ``perturb_rand``,
     ``noise_coarse``, ``u_rand``, ``noise_fine`` tensors; ``extras=True`` adds ``z_vals_fine``,
-    ``weights_coarse``, ``weights_fine`` to the result.
+    ``weights_coarse``, ``weights_fine`` to the result.  When a gradient graph is needed the
+    result comes from ``nerf_pl_b200.training.FusedRenderFunction`` (fused forward with activation
+    capture + hand-written backward); ``autograd_impl="torch"`` selects the plain torch-op
+    evaluation instead (the gradient reference used by the tests).
     """
     del chunk
     if rays.dim() != 2 or rays.shape[1] != 8:
@@ -191,6 +195,10 @@ def render_rays(models: List[torch.nn.Module],
         ur, nf = randoms.get("u_rand"), randoms.get("noise_fine")
     keep = [t.to(torch.float32).contiguous() if t is not None else None for t in (pr, nc, ur, nf)]
     pr, nc, ur, nf = keep
+
+    if needs_graph and autograd_impl == "fused" and not test_time and not extras and n > 0:
+        from .training import render_rays_train
+        return render_rays_train(models, rays_c, S_c, use_disp, perturb, noise_std, K, white_back, pr, nc, ur, nf)
 
     f32 = dict(dtype=torch.float32, device=dev)
     coarse_rgb = not test_time

@@ -290,7 +290,8 @@ def test_sigma_query_and_loss_epilogue(models, emb, ws, dev):
     assert got.shape == (3000,)
     assert (np.abs(got - ref) / (1 + np.abs(ref))).max() < 2e-3
     # drop-in two-step path gives the same numbers to the same tolerance
-    two = models[1](torch.cat([emb[0](torch.from_numpy(xyz).to(dev)), emb[1](torch.zeros(3000, 3, device=dev))], 1))
+    with torch.no_grad():
+        two = models[1](torch.cat([emb[0](torch.from_numpy(xyz).to(dev)), emb[1](torch.zeros(3000, 3, device=dev))], 1))
     assert (np.abs(two[:, -1].cpu().numpy() - ref) / (1 + np.abs(ref))).max() < 2e-3
     rays = torch.from_numpy(orc.make_rays(500, 4)).to(dev)
     with torch.no_grad():
@@ -301,3 +302,42 @@ def test_sigma_query_and_loss_epilogue(models, emb, ws, dev):
     mf = float(((res["rgb_fine"] - tgt) ** 2).mean())
     assert abs(float(m["loss"]) - (mc + mf)) < 1e-5 * (mc + mf) + 1e-9
     assert abs(float(m["psnr"]) - (-10 * np.log10(mf))) < 1e-4
+
+
+def test_fused_training_gradients_match_torch_autograd(ws, emb, dev):
+    """FusedRenderFunction (fused forward with activation capture + hand-written fp16 backward) against
+    plain torch fp32 autograd through the same maths (the reference's graph, models/rendering.py +
+    models/nerf.py), same pre-drawn randoms.  Per-parameter relative L2 error and cosine."""
+    def build():
+        out = []
+        for w in ws:
+            net = nb.NeRF()
+            net.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+            out.append(net.to(dev))
+        return out
+    n = 256
+    rays = torch.from_numpy(orc.make_rays(n, 12)).to(dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    rnd = {"perturb_rand": torch.rand(n, 64, device=dev, generator=g), "u_rand": torch.rand(n, 64, device=dev, generator=g),
+           "noise_coarse": torch.randn(n, 64, device=dev, generator=g), "noise_fine": torch.randn(n, 128, device=dev, generator=g)}
+    tgt = torch.rand(n, 3, device=dev, generator=g)
+    grads = {}
+    outs = {}
+    for impl in ("fused", "torch"):
+        m = build()
+        out = nb.render_rays(m, emb, rays, 64, False, 1.0, 0.5, 64, 32768, True, randoms=rnd, autograd_impl=impl)
+        loss = ((out["rgb_coarse"] - tgt) ** 2).mean() + ((out["rgb_fine"] - tgt) ** 2).mean()    # losses.py:9-14
+        loss.backward()
+        grads[impl] = [p.grad.detach().clone() for net in m for p in net.parameters()]
+        outs[impl] = {k: v.detach() for k, v in out.items()}
+    for k in outs["torch"]:
+        assert float((outs["fused"][k] - outs["torch"][k]).abs().max()) < (2e-2 if k.startswith("depth") else 1e-3), k
+    names = [f"{i}.{k}" for i in range(2) for k in orc.PARAM_KEYS]
+    worst = 0.0
+    for name, a, b in zip(names, grads["fused"], grads["torch"]):
+        assert a.shape == b.shape and torch.isfinite(a).all(), name
+        rel = float((a - b).norm() / (b.norm() + 1e-12))
+        cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-20))
+        worst = max(worst, rel)
+        assert rel < 5e-2 and cos > 0.998, f"{name}: rel {rel:.3e} cos {cos:.5f}"
+    print(f"worst relative gradient error {worst:.3e}")

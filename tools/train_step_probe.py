@@ -23,9 +23,12 @@ rays = torch.from_numpy(bench.blender_rays(1024, 0)).to(dev)
 tgt = torch.rand(1024, 3, device=dev)
 
 
+IMPL = sys.argv[1] if len(sys.argv) > 1 else "fused"
+
+
 def step():
     opt.zero_grad(set_to_none=True)
-    out = nb.render_rays(models, emb, rays, 64, False, 1.0, 0.0, 64, 32768, True)
+    out = nb.render_rays(models, emb, rays, 64, False, 1.0, 0.0, 64, 32768, True, autograd_impl=IMPL)
     loss = ((out["rgb_coarse"] - tgt) ** 2).mean() + ((out["rgb_fine"] - tgt) ** 2).mean()
     loss.backward()
     opt.step()
@@ -41,5 +44,5 @@ for _ in range(n):
     l = step()
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / n
-print(f"train step (fused sampling + torch autograd MLP): {dt * 1e3:.2f} ms/step, "
+print(f"train step [{IMPL}] fwd+bwd+Adam: {dt * 1e3:.2f} ms/step, "
       f"{1024 * 192 / dt:.3e} ray-samples/s, loss {float(l):.4f}")
