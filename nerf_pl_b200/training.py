@@ -95,20 +95,20 @@ def _mlp_backward(params: List[torch.Tensor], acts: torch.Tensor, d_act: torch.T
     h8 = acts[7]
 
     # rgb head: pre = W_rgb d + b_rgb
-    grads[22] = _mm32(g3.t(), d_act) * inv                   # (3,128)
+    grads[22] = _mm32(g3.t().contiguous(), d_act) * inv                   # (3,128)
     grads[23] = g3.float().sum(0) * inv
     dd = torch.mm(g3, W[11].half())                                      # (S,128)
     dd = dd * (d_act > 0)
     # dir_encoding: d = relu(W_d [final, dir] + b_d), final = W_f h8 + b_f (no activation)
     final = torch.addmm(params[17].half(), h8, W[8].half().t())          # (S,256) fp16
     gWd = torch.empty_like(W[9])
-    gWd[:, :256] = _mm32(dd.t(), final) * inv
+    gWd[:, :256] = _mm32(dd.t().contiguous(), final) * inv
     dd_ray = dd.view(R, samples_per_ray, 128).float().sum(1)             # direction is constant per ray
     gWd[:, 256:] = (dd_ray.t() @ dir_enc) * inv
     grads[18] = gWd
     grads[19] = _mm32(ones, dd).view(-1) * inv
     dfinal = torch.mm(dd, W[9][:, :256].half())                          # (S,256)
-    grads[16] = _mm32(dfinal.t(), h8) * inv
+    grads[16] = _mm32(dfinal.t().contiguous(), h8) * inv
     grads[17] = _mm32(ones, dfinal).view(-1) * inv
     # sigma head + layer 8
     grads[20] = _mm32(gs.view(1, S), h8) * inv
@@ -116,7 +116,7 @@ def _mlp_backward(params: List[torch.Tensor], acts: torch.Tensor, d_act: torch.T
     dh = torch.addmm(gs.view(S, 1) * W[10].half().view(1, 256), dfinal, W[8].half())   # (S,256)
     for l in range(7, -1, -1):                                           # xyz_encoding_{l+1}
         dpre = dh * (acts[l] > 0)
-        dpre_t = dpre.t()
+        dpre_t = dpre.t().contiguous()
         grads[2 * l + 1] = _mm32(ones, dpre).view(-1) * inv
         if l == 0:
             grads[0] = (_mm32(dpre_t, enc) * inv)[:, :63].contiguous()

@@ -332,8 +332,11 @@ def test_fused_training_gradients_match_torch_autograd(ws, emb, dev):
         loss.backward()
         grads[impl] = [p.grad.detach().clone() for net in m for p in net.parameters()]
         outs[impl] = {k: v.detach() for k, v in out.items()}
+    # forward values: fp16 tensor-core path vs torch fp32 at random (perturbed) depths; rays whose
+    # far-plane sigma is ~0 flip alpha_last and move by T_last, hence 5e-3 here
+    # (reference parity proper is pinned by the golden tests above)
     for k in outs["torch"]:
-        assert float((outs["fused"][k] - outs["torch"][k]).abs().max()) < (2e-2 if k.startswith("depth") else 1e-3), k
+        assert float((outs["fused"][k] - outs["torch"][k]).abs().max()) < (2e-2 if k.startswith("depth") else 5e-3), k
     names = [f"{i}.{k}" for i in range(2) for k in orc.PARAM_KEYS]
     worst = 0.0
     for name, a, b in zip(names, grads["fused"], grads["torch"]):
