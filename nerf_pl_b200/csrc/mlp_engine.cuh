@@ -193,12 +193,15 @@ __device__ __forceinline__ void mma_tile(RingState& rs, MmaPhases& ph, uint8_t* 
   const int n_layers = sigma_only ? kLayersSigma : kLayersFull;
   for (int l = 0; l < n_layers; ++l) {
     if (kPipelinedHandover) {
-      // layer 0 reads the ENC tile: wait for "tile start" (d_free, once per tile).  Later layers:
-      // a_kb[0] - on which every warp arrives after draining its columns - implies the
-      // accumulator is free.
+      // The first MMA of a layer overwrites the accumulator, so the previous epilogue must have
+      // drained it.  Layer 0: "tile start" (d_free, once per tile).  Later layers: a_kb[0] - every
+      // warp arrives on it only after its tcgen05.ld of the whole accumulator has completed.  This
+      // also covers layer 4, whose first slice (encoded input) needs no A columns at all.
       if (l == 0) {
         mbar_wait(smem_u32(&bars->d_free), ph.d_free, 3);
         ph.d_free ^= 1;
+      } else {
+        mbar_wait(smem_u32(&bars->a_kb[0]), ph.a_kb, 6);
       }
     } else {
       mbar_wait(smem_u32(&bars->a_ready), ph.d_free, 3);
@@ -213,7 +216,7 @@ __device__ __forceinline__ void mma_tile(RingState& rs, MmaPhases& ph, uint8_t* 
       const int kb = (l == 4) ? s - 1 : s;
       const uint32_t b_addr = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
       mbar_wait(smem_u32(&bars->full[rs.stage]), rs.phase, 4);
-      if (kPipelinedHandover && !from_enc) mbar_wait(smem_u32(&bars->a_kb[kb]), ph.a_kb, 6);
+      if (kPipelinedHandover && !from_enc && kb > 0) mbar_wait(smem_u32(&bars->a_kb[kb]), ph.a_kb, 6);
       tc_fence_after();
       const uint64_t bdesc = make_desc_sw128(b_addr);
       if (from_enc) {
