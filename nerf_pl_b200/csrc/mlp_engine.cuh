@@ -9,23 +9,25 @@
 //   TMEM (512 columns allocated, lane = tile row):
 //     [  0,256) D   fp32 accumulator, 256 output features
 //     [256,384) A   fp16 activations (2 per 32-bit column), the next layer's A operand;
-//                   rewritten in place by the epilogue once the layer's MMAs have retired
-//   warps 0..7  epilogue: warp w owns TMEM lanes 32(w&3).. and accumulator columns 128(w>>2)..
-//   warp 8      weight producer: streams the packed 32 KiB K-slices (layout.h) through a
+//                   rewritten by the epilogue once the layer's MMAs have retired
+//   warps 0..15 epilogue: warp w owns TMEM lanes 32(w&3).. and column group w>>2
+//   warp 16     weight producer: streams the packed 32 KiB K-slices (layout.h) through a
 //               5-stage ring with cp.async.bulk + mbarriers, up to 1.25 layers ahead
-//   smem also keeps the fp32 biases and head weights of both networks resident (25 KiB), so the
-//   epilogue reads them with broadcast LDS instead of L1/L2 loads
-//   warp 9      MMA issuer (one thread): tcgen05.mma M=128, N=256|128, K=16; A from TMEM for
+//   warp 17     MMA issuer (one thread): tcgen05.mma M=128, N=256|128, K=16; A from TMEM for
 //               hidden K blocks (139 cycles per K step measured, vs 129 from smem), from the
 //               ENC shared-memory tile for the encoded-input slices
-// MMA and epilogue of one tile cannot fully overlap (one accumulator), but the hand-over is
-// pipelined: the epilogue first drains the whole accumulator into registers (tcgen05.ld, ~130
-// cycles) and releases it ("d_free"), then produces the next A operand one 64-wide K block at a
-// time ("a_kb[k]"); the MMA issuer starts K block 0 of the next layer as soon as its columns
-// exist, while the epilogue warps are still converting blocks 1..3.
-// The producer keeps the following layer's weights resident.
-// Measured alternatives: A in shared memory costs 64 KiB of smem writes + reads per
-// layer; N=128 split accumulators with A in TMEM run the tensor core at half rate.
+//   smem also keeps the fp32 biases and head weights of both networks resident (25 KiB), so the
+//   epilogue reads them with broadcast LDS instead of L1/L2 loads
+//
+// Hand-over between layers (kPipelinedHandover): a tile has ONE accumulator, so its MMA and
+// epilogue cannot fully overlap, but the hand-over is pipelined at K-block granularity: every
+// epilogue warp first drains its 4 x 16 accumulator columns into registers (tcgen05.ld), then
+// converts the 16 columns belonging to K block 0, stores them (tcgen05.st) and arrives on
+// a_kb[0]; then K block 1, ...  The MMA issuer starts the next layer's K block 0 as soon as
+// a_kb[0] completes (which also proves that every warp has drained the accumulator, so the first
+// MMA may overwrite it) while the warps are still converting blocks 1..3.
+// Measured alternatives are recorded in DESIGN.md section 4 (A in shared memory; N=128 split
+// accumulators; sequential hand-over).
 #pragma once
 #include <cuda_fp16.h>
 
