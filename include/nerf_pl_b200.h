@@ -125,6 +125,14 @@ int nerfb200_nerf_forward(const float* x, int64_t n, int64_t x_stride, const voi
 int nerfb200_query_sigma(const float* xyz, int64_t n, int64_t xyz_stride, const void* packed, float* sigma,
                          void* stream);
 
+/* ---- backward glue --------------------------------------------------------------------------
+ * dpre = dh * (act > 0) for one ReLU layer of the hand-written MLP backward
+ * (nerf_pl_b200/training.py; the derivative of models/nerf.py:68 nn.ReLU), fp16 (n_rows, n_cols),
+ * written row-major (dpre, for the dgrad GEMM) and transposed (dpre_t (n_cols, n_rows), for the
+ * wgrad GEMM) in one pass.  n_cols % 64 == 0, n_rows even. */
+int nerfb200_relu_backward(const void* dh, const void* act, int64_t n_rows, int32_t n_cols, void* dpre,
+                           void* dpre_t, void* stream);
+
 /* ---- loss / metric epilogue ("next" row) -------------------------------------------------
  * Replaces: losses.py:9-14 MSELoss.forward and metrics.py:4-13 psnr on the rendered batch.
  * rgb_coarse / rgb_fine: (n_rays,3), either may be NULL; target (n_rays,3).

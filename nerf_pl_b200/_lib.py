@@ -40,6 +40,7 @@ EXPORTS = [
     "nerfb200_composite",
     "nerfb200_query_sigma",
     "nerfb200_mse_psnr",
+    "nerfb200_relu_backward",
     "nerfb200_generate_rays",
     "nerfb200_to_uint8",
     "nerfb200_launch_count",
@@ -148,6 +149,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.nerfb200_debug_gemm.restype = c_int32
     lib.nerfb200_query_sigma.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
     lib.nerfb200_query_sigma.restype = c_int32
+    lib.nerfb200_relu_backward.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.nerfb200_relu_backward.restype = c_int32
     lib.nerfb200_mse_psnr.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
     lib.nerfb200_mse_psnr.restype = c_int32
     lib.nerfb200_generate_rays.argtypes = [c_int32, c_int32, c_float, POINTER(c_float), c_float, c_float, c_int32,

@@ -360,6 +360,21 @@ int nerfb200_query_sigma(const float* xyz, int64_t n, int64_t xyz_stride, const 
   return 0;
 }
 
+int nerfb200_relu_backward(const void* dh, const void* act, int64_t n_rows, int32_t n_cols, void* dpre,
+                           void* dpre_t, void* stream) {
+  if (n_rows < 0 || n_cols <= 0 || (n_cols % 64) != 0) return fail(NERFB200_EINVAL, "relu_backward: n_cols must be a multiple of 64%s");
+  if (n_rows == 0) return 0;
+  if ((n_rows & 1) != 0) return fail(NERFB200_EINVAL, "relu_backward: n_rows must be even%s");
+  if (!dh || !act || !dpre || !dpre_t) return fail(NERFB200_EINVAL, "relu_backward: NULL argument%s");
+  dim3 grid(static_cast<unsigned>((n_rows + 63) / 64), static_cast<unsigned>(n_cols / 64));
+  relu_bwd_transpose_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(dh), static_cast<const __half*>(act), n_rows, n_cols, static_cast<__half*>(dpre),
+      static_cast<__half*>(dpre_t));
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "relu_backward launch");
+  return 0;
+}
+
 int nerfb200_mse_psnr(const float* rgb_coarse, const float* rgb_fine, const float* target, int64_t n_rays,
                       float* out4, void* stream) {
   if (n_rays <= 0) return fail(NERFB200_EINVAL, "mse_psnr: n_rays <= 0%s");

@@ -72,6 +72,18 @@ def _mm32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return torch.mm(a, b, out_dtype=torch.float32)
 
 
+def _relu_backward(dh: torch.Tensor, act: torch.Tensor):
+    """dpre = dh * (act > 0) plus its transpose, one fused kernel (C ABI nerfb200_relu_backward)."""
+    S, C = dh.shape
+    dpre = torch.empty_like(dh)
+    dpre_t = torch.empty(C, S, dtype=dh.dtype, device=dh.device)
+    lib = _lib.load()
+    with torch.cuda.device(dh.device):
+        _lib.check(lib.nerfb200_relu_backward(dh.data_ptr(), act.data_ptr(), S, C, dpre.data_ptr(), dpre_t.data_ptr(),
+                                              _stream_ptr()), "nerfb200_relu_backward")
+    return dpre, dpre_t
+
+
 def _mlp_backward(params: List[torch.Tensor], acts: torch.Tensor, d_act: torch.Tensor, enc: torch.Tensor,
                   dir_enc: torch.Tensor, samples_per_ray: int, dsig: torch.Tensor, dpre_rgb: torch.Tensor
                   ) -> List[torch.Tensor]:
@@ -97,12 +109,11 @@ def _mlp_backward(params: List[torch.Tensor], acts: torch.Tensor, d_act: torch.T
     # rgb head: pre = W_rgb d + b_rgb
     grads[22] = _mm32(g3.t().contiguous(), d_act) * inv                   # (3,128)
     grads[23] = g3.float().sum(0) * inv
-    dd = torch.mm(g3, W[11].half())                                      # (S,128)
-    dd = dd * (d_act > 0)
+    dd, dd_t = _relu_backward(torch.mm(g3, W[11].half()), d_act)         # (S,128), (128,S)
     # dir_encoding: d = relu(W_d [final, dir] + b_d), final = W_f h8 + b_f (no activation)
     final = torch.addmm(params[17].half(), h8, W[8].half().t())          # (S,256) fp16
     gWd = torch.empty_like(W[9])
-    gWd[:, :256] = _mm32(dd.t().contiguous(), final) * inv
+    gWd[:, :256] = _mm32(dd_t, final) * inv
     dd_ray = dd.view(R, samples_per_ray, 128).float().sum(1)             # direction is constant per ray
     gWd[:, 256:] = (dd_ray.t() @ dir_enc) * inv
     grads[18] = gWd
@@ -115,8 +126,7 @@ def _mlp_backward(params: List[torch.Tensor], acts: torch.Tensor, d_act: torch.T
     grads[21] = (gs.float().sum() * inv).view(1)
     dh = torch.addmm(gs.view(S, 1) * W[10].half().view(1, 256), dfinal, W[8].half())   # (S,256)
     for l in range(7, -1, -1):                                           # xyz_encoding_{l+1}
-        dpre = dh * (acts[l] > 0)
-        dpre_t = dpre.t().contiguous()
+        dpre, dpre_t = _relu_backward(dh.contiguous(), acts[l])
         grads[2 * l + 1] = _mm32(ones, dpre).view(-1) * inv
         if l == 0:
             grads[0] = (_mm32(dpre_t, enc) * inv)[:, :63].contiguous()
