@@ -192,6 +192,11 @@ int nerfb200_debug_gemm(const float* a, const void* packed, int32_t slice, int32
 /* Raw tcgen05.mma issue-rate microbenchmark (timing only): out_dev (n_ctas, 8) int64 device
  * buffer; column v = SM cycles for reps x 16 MMAs of variant v (csrc/aux_kernels.cuh). */
 int nerfb200_debug_mma_bench(int64_t* out_dev, int32_t n_ctas, int32_t reps, void* stream);
+/* tcgen05.mma vs. concurrent tcgen05.ld/st microbenchmark (timing only): out_dev (n_ctas, 4)
+ * int64; [0] = SM cycles of reps x 16 MMAs, [1] = background iterations meanwhile
+ * (bg / variant codes: csrc/aux_kernels.cuh mma_contention_kernel). */
+int nerfb200_debug_mma_contention(int64_t* out_dev, int32_t n_ctas, int32_t reps, int32_t bg, int32_t variant,
+                                  void* stream);
 /* Experiment hook: with NERFB200_FLAGS bit 1 set, CTA 0 of the last render launch records
  * (tag, SM clock) pairs for its epilogue / MMA roles; this copies 3*512*2 int64 to host. */
 int nerfb200_debug_timeline(int64_t* host_out, int64_t n_values);

@@ -16,6 +16,8 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_size_t, c_voi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libnerf_pl_b200.so")
+if os.environ.get("NERFB200_LIB"):          # experiment builds (tools/build_variants.py); unset in production
+    LIB_PATH = os.path.abspath(os.environ["NERFB200_LIB"])
 SOURCES = ["capi.cu"]
 HEADERS = ["ptx.cuh", "layout.h", "mlp_engine.cuh", "render_kernel.cuh", "aux_kernels.cuh"]
 NVCC_FLAGS = [
@@ -47,6 +49,7 @@ EXPORTS = [
     "nerfb200_debug_gemm",
     "nerfb200_debug_timeline",
     "nerfb200_debug_mma_bench",
+    "nerfb200_debug_mma_contention",
     "nerfb200_sm_count",
 ]
 
@@ -160,6 +163,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.nerfb200_to_uint8.restype = c_int32
     lib.nerfb200_debug_mma_bench.argtypes = [c_void_p, c_int32, c_int32, c_void_p]
     lib.nerfb200_debug_mma_bench.restype = c_int32
+    lib.nerfb200_debug_mma_contention.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.nerfb200_debug_mma_contention.restype = c_int32
     lib.nerfb200_debug_timeline.argtypes = [c_void_p, c_int64]
     lib.nerfb200_debug_timeline.restype = c_int32
     lib.nerfb200_launch_count.restype = c_int64

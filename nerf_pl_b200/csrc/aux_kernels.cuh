@@ -579,4 +579,217 @@ __global__ void __launch_bounds__(kThreads, 1) mma_bench_kernel(long long* __res
   engine_teardown(bars);
 }
 
+// ------------------------------------------------ tcgen05 / TMEM contention microbenchmark
+// The MMA thread issues `reps` x 16 MMAs (K=16, M=128, N=256) into accumulator region 0 while
+// the 16 epilogue warps run an epilogue-shaped background load on region 1 (columns 256..511):
+//   bg 0: idle   1: tcgen05.ld only (4 x16 per iteration = this warp's share of a 128x256 fp32
+//   accumulator)   2: ld + bias/ReLU/convert + tcgen05.st (in place, 8 columns per K block)
+//   3: tcgen05.st only   4: as 2 but one K block at a time (ld 16, convert, st 8)
+// variant 0: SS (A from smem)   1: TS, A read from region 1 in the in-place layout
+//   (K block kb, step j -> columns 256 + kb*64 + j*16)   2: TS, A from columns 256 + kb*32 + j*8
+// out[block*4 + 0] = cycles of the MMA loop, [1] = background iterations of warp 0 during it,
+// [2] = checksum (keeps the loads alive).
+__global__ void __launch_bounds__(kThreads, 1) mma_contention_kernel(long long* __restrict__ out, int reps,
+                                                                     int bg, int variant, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Scratch* sc = reinterpret_cast<Scratch*>(smem + kSmemScratch);
+  Barriers* bars = &sc->bars;
+  if (!engine_setup(smem, bars)) {
+    if (threadIdx.x == 0) atomicExch(status, 101);
+    return;
+  }
+  for (uint32_t i = threadIdx.x; i < kSmemScratch / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  volatile int* stop = reinterpret_cast<volatile int*>(&sc->z[0]);
+  volatile int* go = reinterpret_cast<volatile int*>(&sc->z[1]);
+  if (threadIdx.x == 0) { *stop = 0; *go = 0; }
+  fence_proxy_async();
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem = bars->tmem_base;
+  if (warp < kEpiWarps) {
+    // zero both regions once (defined operands)
+    const uint32_t row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const int part = warp >> 2;
+    uint32_t zero[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) zero[i] = 0;
+    for (int cg = 0; cg < 8; ++cg) tmem_st16(row + part * 128 + cg * 16, zero);
+    tmem_st_wait();
+    tc_fence_before();
+    epi_bar();
+    if (threadIdx.x == 0) *go = 1;
+    long long iters = 0;
+    uint32_t chk = 0;
+    uint32_t r[4][16];
+    uint32_t h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = 0;
+    while (*stop == 0) {
+      if (bg == 1 || bg == 2) {
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) tmem_ld16(row + 256 + kb * 64 + part * 16, r[kb]);
+        tmem_ld_wait();
+        if (bg == 1) {
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) chk ^= r[kb][0] ^ r[kb][7] ^ r[kb][15];
+        }
+      }
+      if (bg == 2) {
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float a, b;
+            add_f32x2(a, b, __uint_as_float(r[kb][2 * i]), __uint_as_float(r[kb][2 * i + 1]), 0.25f, 0.5f);
+            h[i] = cvt_f16x2_relu(a, b);
+          }
+          tmem_st8(row + 256 + kb * 64 + part * 16, h);
+          tmem_st_wait();
+        }
+      }
+      if (bg == 3) {
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          tmem_st8(row + 256 + kb * 64 + part * 16, h);
+          tmem_st_wait();
+        }
+      }
+      if (bg == 4) {
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          tmem_ld16(row + 256 + kb * 64 + part * 16, r[0]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float a, b;
+            add_f32x2(a, b, __uint_as_float(r[0][2 * i]), __uint_as_float(r[0][2 * i + 1]), 0.25f, 0.5f);
+            h[i] = cvt_f16x2_relu(a, b);
+          }
+          tmem_st8(row + 256 + kb * 64 + part * 16, h);
+          tmem_st_wait();
+        }
+      }
+      if (bg == 5) {   // what the real epilogue does while the MMA runs: poll an mbarrier that does not flip
+        uint32_t done;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(&bars->a_ready)), "r"(0u) : "memory");
+        chk ^= done;
+      }
+      if (bg == 6) {   // st8 + wait + fence + elected arrive, the real hand-over sequence
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          tmem_st8(row + 256 + kb * 64 + part * 16, h);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->a_kb[kb]));
+        }
+      }
+      if (bg == 0) __nanosleep(200);
+      ++iters;
+    }
+    tc_fence_before();
+    if (threadIdx.x == 0) {
+      out[blockIdx.x * 4 + 1] = iters;
+      out[blockIdx.x * 4 + 2] = chk;
+    }
+  } else if (threadIdx.x == kMmaWarp * 32) {
+    while (*go == 0) {}
+    tc_fence_after();
+    const uint64_t adesc = make_desc_sw128(smem_u32(smem + kSmemEnc));
+    const uint64_t bdesc = make_desc_sw128(smem_u32(smem + kSmemRing));
+    const uint32_t idesc = make_idesc_f16(256);
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t j = i & 3, kb = i >> 2;
+        const uint64_t b = bdesc + 2 * j + (kb * 2048);
+        if (variant == 0) umma_f16(tmem + kTmemD, adesc + 2 * j, b, idesc, 1u);
+        else if (variant == 1) umma_f16_ts(tmem + kTmemD, tmem + 256 + kb * 64 + j * 16, b, idesc, 1u);
+        else umma_f16_ts(tmem + kTmemD, tmem + 256 + kb * 32 + j * 8, b, idesc, 1u);
+      }
+    }
+    umma_commit(smem_u32(&bars->d_ready));
+    mbar_wait(smem_u32(&bars->d_ready), 0, 21);
+    out[blockIdx.x * 4 + 0] = clock64() - t0;
+    *stop = 1;
+  }
+  engine_teardown(bars);
+}
+
+// ------------------------------------------------ tcgen05 issue-pattern microbenchmark
+// One thread issues reps x 16 TS MMAs (M=128, N=256, K=16) with bookkeeping around them, to find
+// how far the issuing thread may run ahead of the tensor pipe (queue depth) and what the engine's
+// per-slice waits cost.  MODE (compile time, so the loop stays lean):
+//   0 back-to-back                         1 commit after every 4
+//   2 busy-wait `arg` cycles after every 4th MMA        3 busy-wait `arg` cycles after every MMA
+//   4 two mbarrier waits (already complete) + fence BEFORE every 4
+//   5 the same waits + fence between MMA 0 and MMA 1 of every 4 (software-pipelined)
+//   6 as 5, between MMA 1 and MMA 2       7 as 5, between MMA 2 and 3
+//   8 one mbarrier wait + fence before every 4
+// out[block*4+0] = cycles.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) mma_issue_kernel(long long* __restrict__ out, int reps, int arg,
+                                                                int* status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Scratch* sc = reinterpret_cast<Scratch*>(smem + kSmemScratch);
+  Barriers* bars = &sc->bars;
+  if (!engine_setup(smem, bars)) {
+    if (threadIdx.x == 0) atomicExch(status, 101);
+    return;
+  }
+  for (uint32_t i = threadIdx.x; i < kSmemScratch / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  const uint32_t tmem = bars->tmem_base;
+  if (warp < kEpiWarps) {
+    const uint32_t row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    uint32_t zero[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) zero[i] = 0;
+    for (int cg = 0; cg < 8; ++cg) tmem_st16(row + (warp >> 2) * 128 + cg * 16, zero);
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (threadIdx.x == kMmaWarp * 32) {
+    tc_fence_after();
+    const uint64_t bdesc = make_desc_sw128(smem_u32(smem + kSmemRing));
+    const uint32_t idesc = make_idesc_f16(256);
+    const uint32_t bar_a = smem_u32(&bars->a_ready), bar_b = smem_u32(&bars->d_free);
+    auto waits = [&]() {
+      mbar_wait(bar_a, 1, 31);        // fresh barrier: parity 1 is "already complete"
+      if (MODE != 8) mbar_wait(bar_b, 1, 32);
+      tc_fence_after();
+    };
+    auto spin = [&](int n) {
+      const long long t = clock64();
+      while (clock64() - t < n) {}
+    };
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        if (MODE == 4 || MODE == 8) waits();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          umma_f16_ts(tmem + kTmemD, tmem + kTmemA + kb * 32 + j * 8, bdesc + kb * 2048 + 2 * j, idesc, 1u);
+          if (MODE == 3) spin(arg);
+          if ((MODE == 5 && j == 0) || (MODE == 6 && j == 1) || (MODE == 7 && j == 2)) waits();
+        }
+        if (MODE == 2) spin(arg);
+        if (MODE >= 1) umma_commit(smem_u32(&bars->empty[kb]));
+      }
+    }
+    umma_commit(smem_u32(&bars->d_ready));
+    mbar_wait(smem_u32(&bars->d_ready), 0, 21);
+    out[blockIdx.x * 4 + 0] = clock64() - t0;
+  }
+  engine_teardown(bars);
+}
+
 }  // namespace nerfb200

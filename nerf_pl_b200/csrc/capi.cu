@@ -61,6 +61,8 @@ int device_info(DeviceInfo** out) {
                                   static_cast<int>(kSmemTotal)), "smem attr probe");
     CUDA_TRY(cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kSmemTotal)), "smem attr bench");
+    CUDA_TRY(cudaFuncSetAttribute(mma_contention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kSmemTotal)), "smem attr contention");
     CUDA_TRY(cudaMalloc(&d.status, sizeof(int)), "status alloc");
     CUDA_TRY(cudaMemset(d.status, 0, sizeof(int)), "status memset");
     d.attrs_set = true;
@@ -221,6 +223,10 @@ int nerfb200_render_rays(const nerfb200_render_args* a, void* stream) {
   const int n_groups = (p.n_rays + 1) / 2;     // two rays share the coarse tile
   int ctas = d->sm_count;
   if (a->max_ctas > 0 && a->max_ctas < ctas) ctas = a->max_ctas;
+  if (const char* mc = std::getenv("NERFB200_MAX_CTAS")) {   // experiment switch; unset in production
+    const int v = std::atoi(mc);
+    if (v > 0 && v < ctas) ctas = v;
+  }
   if (n_groups < ctas) ctas = n_groups;
   if (save)
     render_rays_kernel<true><<<ctas, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
@@ -509,6 +515,38 @@ int nerfb200_debug_mma_bench(int64_t* out_dev, int32_t n_ctas, int32_t reps, voi
       reinterpret_cast<long long*>(out_dev), reps, di->status);
   g_launches++;
   CUDA_TRY(cudaGetLastError(), "debug_mma_bench launch");
+  return 0;
+}
+
+int nerfb200_debug_mma_contention(int64_t* out_dev, int32_t n_ctas, int32_t reps, int32_t bg, int32_t variant,
+                                  void* stream) {
+  if (!out_dev || n_ctas < 1 || reps < 1) return fail(NERFB200_EINVAL, "debug_mma_contention: bad argument%s");
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (bg < 0) {     // issue-pattern benchmark: variant = mode, -bg - 1 = arg
+    const int arg = -bg - 1;
+    long long* o = reinterpret_cast<long long*>(out_dev);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define NERFB200_ISSUE_CASE(M)                                                                      \
+  case M:                                                                                           \
+    CUDA_TRY(cudaFuncSetAttribute(mma_issue_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  static_cast<int>(kSmemTotal)), "smem attr issue");                \
+    mma_issue_kernel<M><<<n_ctas, kThreads, kSmemTotal, st>>>(o, reps, arg, di->status);            \
+    break;
+    switch (variant) {
+      NERFB200_ISSUE_CASE(0) NERFB200_ISSUE_CASE(1) NERFB200_ISSUE_CASE(2) NERFB200_ISSUE_CASE(3)
+      NERFB200_ISSUE_CASE(4) NERFB200_ISSUE_CASE(5) NERFB200_ISSUE_CASE(6) NERFB200_ISSUE_CASE(7)
+      NERFB200_ISSUE_CASE(8)
+      default: return fail(NERFB200_EINVAL, "debug_mma_contention: bad issue mode%s");
+    }
+#undef NERFB200_ISSUE_CASE
+  } else {
+    mma_contention_kernel<<<n_ctas, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<long long*>(out_dev), reps, bg, variant, di->status);
+  }
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "debug_mma_contention launch");
   return 0;
 }
 

@@ -53,7 +53,10 @@ constexpr bool kAInTmem = true;
 // B200: overlapping does not pay - the tensor core's TMEM (or smem) operand reads and
 // the epilogue's stores share one port, each slows the other by the overlap.
 constexpr bool kPipelinedHandover = true;
-constexpr int kStages = kAInTmem ? 5 : 3;
+#ifndef NERFB200_STAGES
+#define NERFB200_STAGES 5
+#endif
+constexpr int kStages = kAInTmem ? NERFB200_STAGES : 3;
 constexpr int kTmemCols = 512;
 constexpr uint32_t kTmemD = 0, kTmemA = 256;
 
@@ -98,9 +101,20 @@ __device__ __forceinline__ void tl_mark(Timeline* tl, int role, int tag) {
   tl->buf[(role * kTlMax + i) * 2 + 1] = clock64();
   tl->n[role] = i + 1;
 }
+__device__ __forceinline__ void tl_val(Timeline* tl, int role, int tag, long long value) {
+  if (tl == nullptr || tl->buf == nullptr) return;
+  int i = tl->n[role];
+  if (i >= kTlMax) return;
+  tl->buf[(role * kTlMax + i) * 2 + 0] = tag;
+  tl->buf[(role * kTlMax + i) * 2 + 1] = value;
+  tl->n[role] = i + 1;
+}
 
 struct RingState {
   uint32_t stage = 0, phase = 0;
+#ifdef NERFB200_EXP_NOLOAD
+  uint32_t filled = 0;      // timing experiment: only the first kStages slices are really fetched
+#endif
   __device__ __forceinline__ void advance() {
     if (++stage == kStages) { stage = 0; phase ^= 1; }
   }
@@ -162,6 +176,10 @@ __device__ __forceinline__ void produce_tile(RingState& rs, uint8_t* smem, Barri
     mbar_wait(smem_u32(&bars->empty[rs.stage]), rs.phase ^ 1, 1);
     const uint32_t full = smem_u32(&bars->full[rs.stage]);
     const uint32_t dst = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
+#ifdef NERFB200_EXP_NOLOAD
+    if (rs.filled >= static_cast<uint32_t>(kStages)) { mbar_arrive(full); rs.advance(); continue; }
+    ++rs.filled;
+#endif
     mbar_arrive_expect_tx(full, kSliceBytes256);
     const uint8_t* src = blob + static_cast<size_t>(i) * kSliceBytes256;
 #pragma unroll
@@ -174,6 +192,10 @@ __device__ __forceinline__ void produce_tile(RingState& rs, uint8_t* smem, Barri
       mbar_wait(smem_u32(&bars->empty[rs.stage]), rs.phase ^ 1, 2);
       const uint32_t full = smem_u32(&bars->full[rs.stage]);
       const uint32_t dst = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
+#ifdef NERFB200_EXP_NOLOAD
+      if (rs.filled >= static_cast<uint32_t>(kStages)) { mbar_arrive(full); rs.advance(); continue; }
+      ++rs.filled;
+#endif
       mbar_arrive_expect_tx(full, kSliceBytes128);
       const uint8_t* src = blob + kOffDir + static_cast<size_t>(i) * kSliceBytes128;
 #pragma unroll
@@ -185,65 +207,88 @@ __device__ __forceinline__ void produce_tile(RingState& rs, uint8_t* smem, Barri
 
 // -------------------------------------------------------------------- MMA
 // One thread.  Issues all MMAs of one tile.
+//
+// The tensor pipe queues only about two MMAs ahead of the one it executes (measured with
+// nerfb200_debug_mma_contention: ~200 cycles of issuer-side work per four MMAs are hidden, 400 are
+// not), so every instruction between two tcgen05.mma counts: the layer / slice structure is fully
+// unrolled at compile time (template flags instead of run-time ones), the descriptors are formed
+// from one per-stage add, and the only run-time state is the ring stage and the barrier phases.
+// With the run-time loop this replaced the issue cadence was 673 cycles per four MMAs; the pipe
+// itself needs 4 x 128.
 struct MmaPhases { uint32_t d_free = 0, a_kb = 0; };   // a_kb: the 4 K-block barriers flip together
 
-__device__ __forceinline__ void mma_tile(RingState& rs, MmaPhases& ph, uint8_t* smem,
-                                         Barriers* bars, bool sigma_only, bool dir_slice,
-                                         Timeline* tl = nullptr) {
+#ifdef NERFB200_TIMELINE
+#define NERFB200_TL_MARK(tl, role, tag) tl_mark(tl, role, tag)
+#else
+#define NERFB200_TL_MARK(tl, role, tag) ((void)0)
+#endif
+
+template <bool kSigmaOnly, bool kDirSlice>
+__device__ __forceinline__ void mma_tile_t(RingState& rs, MmaPhases& ph, uint8_t* smem, Barriers* bars,
+                                           Timeline* tl) {
+  static_assert(kPipelinedHandover && kAInTmem, "the issue loop implements the K-block hand-over with the TMEM operand");
   const uint32_t tmem = bars->tmem_base;
-  const uint32_t enc_base = smem_u32(smem + kSmemEnc);
-  const int n_layers = sigma_only ? kLayersSigma : kLayersFull;
+  const uint32_t d_tmem = tmem + kTmemD;
+  const uint32_t a_tmem = tmem + kTmemA;
+  const uint64_t enc_desc = make_desc_sw128(smem_u32(smem + kSmemEnc));
+  const uint64_t ring_desc = make_desc_sw128(smem_u32(smem + kSmemRing));
+  const uint32_t full0 = smem_u32(&bars->full[0]);
+  const uint32_t empty0 = smem_u32(&bars->empty[0]);
+  const uint32_t akb0 = smem_u32(&bars->a_kb[0]);
+  const uint32_t d_ready = smem_u32(&bars->d_ready);
+  const uint32_t idesc256 = make_idesc_f16(256), idesc128 = make_idesc_f16(128);
+  constexpr int n_layers = kSigmaOnly ? kLayersSigma : kLayersFull;
+#pragma unroll
   for (int l = 0; l < n_layers; ++l) {
-    if (kPipelinedHandover) {
-      // The first MMA of a layer overwrites the accumulator, so the previous epilogue must have
-      // drained it.  Layer 0: "tile start" (d_free, once per tile).  Later layers: a_kb[0] - every
-      // warp arrives on it only after its tcgen05.ld of the whole accumulator has completed.  This
-      // also covers layer 4, whose first slice (encoded input) needs no A columns at all.
-      if (l == 0) {
-        mbar_wait(smem_u32(&bars->d_free), ph.d_free, 3);
-        ph.d_free ^= 1;
-      } else {
-        mbar_wait(smem_u32(&bars->a_kb[0]), ph.a_kb, 6);
-      }
-    } else {
-      mbar_wait(smem_u32(&bars->a_ready), ph.d_free, 3);
+    // The first MMA of a layer overwrites the accumulator, so the previous epilogue must have
+    // drained it.  Layer 0: "tile start" (d_free, once per tile).  Later layers: a_kb[0] - every
+    // warp arrives on it only after its tcgen05.ld of the whole accumulator has completed.  This
+    // also covers layer 4, whose first slice (encoded input) needs no A columns at all.
+    if (l == 0) {
+      mbar_wait(smem_u32(&bars->d_free), ph.d_free, 3);
       ph.d_free ^= 1;
+    } else {
+      mbar_wait(akb0, ph.a_kb, 6);
     }
     tc_fence_after();
-    tl_mark(tl, 1, 100 + l);
-    const int n_slices = (l == 0) ? 1 : (l == 4) ? 5 : (l == 8 && dir_slice) ? 5 : 4;
-    const uint32_t idesc = (l == 8) ? make_idesc_f16(128) : make_idesc_f16(256);
-    for (int s = 0; s < n_slices; ++s) {
-      const bool from_enc = (l == 0) || (l == 4 && s == 0) || (l == 8 && s == 4);
-      const int kb = (l == 4) ? s - 1 : s;
-      const uint32_t b_addr = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
-      mbar_wait(smem_u32(&bars->full[rs.stage]), rs.phase, 4);
-      if (kPipelinedHandover && !from_enc && kb > 0) mbar_wait(smem_u32(&bars->a_kb[kb]), ph.a_kb, 6);
-      tc_fence_after();
-      const uint64_t bdesc = make_desc_sw128(b_addr);
-      if (from_enc) {
-        const uint64_t adesc = make_desc_sw128(enc_base);
+    NERFB200_TL_MARK(tl, 1, 100 + l);
+    const int n_slices = (l == 0) ? 1 : (l == 4) ? 5 : (l == 8 && kDirSlice) ? 5 : 4;
+    const uint32_t idesc = (l == 8) ? idesc128 : idesc256;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)   // +32 B per K=16 step inside the 128-byte swizzle row
-          umma_f16(tmem + kTmemD, adesc + 2 * j, bdesc + 2 * j, idesc, (s | j) != 0 ? 1u : 0u);
-      } else if (kAInTmem) {
+    for (int s = 0; s < 5; ++s) {
+      if (s < n_slices) {
+        const bool from_enc = (l == 0) || (l == 4 && s == 0) || (l == 8 && s == 4);
+        const int kb = (l == 4) ? s - 1 : s;
+        const uint32_t stage = rs.stage;
+        mbar_wait(full0 + 8u * stage, rs.phase, 4);
+        if (!from_enc && kb > 0) mbar_wait(akb0 + 8u * kb, ph.a_kb, 6);
+        tc_fence_after();
+        const uint64_t bdesc = ring_desc + static_cast<uint64_t>(stage * (kSliceBytes256 >> 4));
+        if (from_enc) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)   // A: 64 K-values per block = 32 columns, 8 per K=16 step
-          umma_f16_ts(tmem + kTmemD, tmem + kTmemA + kb * 32 + j * 8, bdesc + 2 * j, idesc,
-                      (s | j) != 0 ? 1u : 0u);
-      } else {
-        const uint64_t adesc = make_desc_sw128(smem_u32(smem + kSmemA) + kb * 16384);
+          for (int j = 0; j < 4; ++j)   // +32 B per K=16 step inside the 128-byte swizzle row
+            umma_f16(d_tmem, enc_desc + 2 * j, bdesc + 2 * j, idesc, (s | j) != 0 ? 1u : 0u);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          umma_f16(tmem + kTmemD, adesc + 2 * j, bdesc + 2 * j, idesc, (s | j) != 0 ? 1u : 0u);
+          for (int j = 0; j < 4; ++j)   // A: 64 K-values per block = 32 columns, 8 per K=16 step
+            umma_f16_ts(d_tmem, a_tmem + kb * 32 + j * 8, bdesc + 2 * j, idesc, (s | j) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8u * stage);
+        rs.advance();
+        NERFB200_TL_MARK(tl, 1, 500 + s);
       }
-      umma_commit(smem_u32(&bars->empty[rs.stage]));
-      rs.advance();
     }
-    umma_commit(smem_u32(&bars->d_ready));
+    umma_commit(d_ready);
     if (l != 0) ph.a_kb ^= 1;
-    tl_mark(tl, 1, 200 + l);
+    NERFB200_TL_MARK(tl, 1, 200 + l);
   }
+}
+
+__device__ __forceinline__ void mma_tile(RingState& rs, MmaPhases& ph, uint8_t* smem, Barriers* bars,
+                                         bool sigma_only, bool dir_slice, Timeline* tl = nullptr) {
+  if (sigma_only) mma_tile_t<true, false>(rs, ph, smem, bars, tl);
+  else if (dir_slice) mma_tile_t<false, true>(rs, ph, smem, bars, tl);
+  else mma_tile_t<false, false>(rs, ph, smem, bars, tl);
 }
 
 // --------------------------------------------------------------- epilogue
@@ -277,7 +322,7 @@ __device__ __forceinline__ void epi_signal_tile_start(EpiCtx& c) {
   tc_fence_before();
   __syncwarp();
   if (c.lane == 0) mbar_arrive(smem_u32(kPipelinedHandover ? &c.bars->d_free : &c.bars->a_ready));
-  tl_mark(c.tl, 0, 6);
+  NERFB200_TL_MARK(c.tl, 0, 6);
 }
 // Sequential hand-over: this warp's accumulator columns are drained and its A columns stored.
 __device__ __forceinline__ void epi_signal_a_ready(EpiCtx& c, bool smem_written) {
@@ -400,9 +445,9 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
   const uint32_t a_row = smem_u32(c.smem + kSmemA) + static_cast<uint32_t>(c.row) * 128u;
   const uint32_t a_tm = c.tmem_row + kTmemA + nb / 2;         // 2 fp16 per column
   const uint32_t d_src = c.tmem_row + kTmemD + nb;
-  tl_mark(c.tl, 0, 1);
+  NERFB200_TL_MARK(c.tl, 0, 1);
   epi_wait_d(c);
-  tl_mark(c.tl, 0, 2);
+  NERFB200_TL_MARK(c.tl, 0, 2);
   constexpr int kPairs = kColsPer / 64;                       // 64 columns = one K block of the next layer
   if (kPipelinedHandover) {
     // K-block interleaved: every warp owns kColsPer/4 columns of EACH 64-wide K block, so the
@@ -415,7 +460,7 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) tmem_ld16(c.tmem_row + kTmemD + kb * 64 + c.part * 16, r[kb]);
     tmem_ld_wait();
-    tl_mark(c.tl, 0, 3);
+    NERFB200_TL_MARK(c.tl, 0, 3);
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) {
       const int n0 = kb * 64 + c.part * 16;
@@ -449,6 +494,7 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
         tmem_st8(c.tmem_row + kTmemA + n0 / 2, h);
         if (kb == 3 && dir_row != nullptr) write_dir_row(c, dir_row);
         epi_signal_kb(c, kb, kb == 3 && dir_row != nullptr);
+        NERFB200_TL_MARK(c.tl, 0, 40 + kb);
       }
       if (kSave && c.save_act != nullptr && c.save_row >= 0) {
         uint4* dst = reinterpret_cast<uint4*>(c.save_act + (static_cast<long long>(l) * c.save_n + c.save_row) * 256 + n0);
@@ -461,7 +507,7 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
     tmem_ld32(d_src, r0);
     tmem_ld32(d_src + 32, r1);
     tmem_ld_wait();
-    tl_mark(c.tl, 0, 3);
+    NERFB200_TL_MARK(c.tl, 0, 3);
 #pragma unroll
     for (int pr = 0; pr < kPairs; ++pr) {
       epi_chunk<kRelu, kSigma, kStore>(r0, bias, nb + 64 * pr, kAInTmem ? a_tm + 32 * pr : a_row, wsig, sig_acc);
@@ -472,11 +518,11 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
         tmem_ld_wait();
       }
     }
-    tl_mark(c.tl, 0, 4);
+    NERFB200_TL_MARK(c.tl, 0, 4);
     if (dir_row != nullptr) write_dir_row(c, dir_row);
     if (kStore) epi_signal_a_ready(c, dir_row != nullptr);
   }
-  tl_mark(c.tl, 0, 5);
+  NERFB200_TL_MARK(c.tl, 0, 5);
 }
 
 // dir_encoding epilogue (N=128; this thread's 128/kColSplit columns) fused with the rgb head

@@ -265,6 +265,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
   extern __shared__ __align__(1024) uint8_t smem[];
   Scratch* sc = reinterpret_cast<Scratch*>(smem + kSmemScratch);
   Barriers* bars = &sc->bars;
+#ifdef NERFB200_TIMELINE
+  const long long t_entry = clock64();
+#endif
   if (!engine_setup(smem, bars)) {
     if (threadIdx.x == 0) atomicExch(p.status, 101);
     return;
@@ -324,6 +327,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
     c.save_act = nullptr; c.save_d = nullptr; c.save_n = 0; c.save_row = -1;
     Timeline tle{(blockIdx.x == 0 && threadIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
     c.tl = &tle;
+#ifdef NERFB200_TIMELINE
+    tl_val(c.tl, 0, 90, t_entry);
+#endif
+    NERFB200_TL_MARK(c.tl, 0, 91);
     const int t = threadIdx.x;   // 0..255
     uint8_t* enc = smem + kSmemEnc;
 
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
       const bool valid1 = rays_in_group(g) == 2;
       const int rid[2] = {ray0, valid1 ? ray0 + 1 : ray0};
       // ---- rays, direction embedding (models/rendering.py:179-186)
-      tl_mark(c.tl, 0, 30);
+      NERFB200_TL_MARK(c.tl, 0, 30);
       if (t < 16) sc->ray[t >> 3][t & 7] = __ldg(p.rays + static_cast<long long>(rid[t >> 3]) * p.ray_stride + (t & 7));
       epi_bar();
       if (t < 2) {
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
         sc->z[e] = z;
         sc->zc[r][i] = z;
       }
-      tl_mark(c.tl, 0, 31);
+      NERFB200_TL_MARK(c.tl, 0, 31);
       epi_bar();
 
       // ================= two passes: coarse, fine =================
@@ -394,13 +401,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
             for (int j = 0; j < 27; ++j) acc = fmaf(wv[j], sc->direnc[r][j], acc);
             sc->dirbias[r][n] = acc;
           }
-          tl_mark(c.tl, 0, 27);
+          NERFB200_TL_MARK(c.tl, 0, 27);
           epi_bar();
         }
         for (int tile = 0; tile < tiles; ++tile) {
           const int gr = tile * 128 + c.row;
           const int r = gr / S;
-          tl_mark(c.tl, 0, 10);
+          NERFB200_TL_MARK(c.tl, 0, 10);
           encode_row(enc, c.row, c.part, &sc->ray[r][0], &sc->ray[r][3], sc->z[gr]);
           const long long grow = (r == 0 || valid1) ? static_cast<long long>(rid[r]) * S + (gr - r * S) : -1;
           c.save_row = grow;
@@ -441,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
           epi_bar();
         }
         // ---- compositing: warp r renders ray r
-        tl_mark(c.tl, 0, 20);
+        NERFB200_TL_MARK(c.tl, 0, 20);
         if (warp < 2) {
           const int r = warp;
           const float* nz = nullptr;
@@ -451,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
                                          sc->rgb[1] + r * S, sc->rgb[2] + r * S, nz, p.noise_std,
                                          sc->dnorm[r], !sigma_only, sc->sigma + r * S);
           __syncwarp();
-          tl_mark(c.tl, 0, 22);
+          NERFB200_TL_MARK(c.tl, 0, 22);
           const bool wr = (r == 0) || valid1;
           if (wr) {
             const long long ri = rid[r];
@@ -477,13 +484,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
               }
             }
           }
-          tl_mark(c.tl, 0, 23);
+          NERFB200_TL_MARK(c.tl, 0, 23);
           // ---- hierarchical resampling, part 1 (models/rendering.py:28-33): pdf -> cdf
           if (pass == 0 && fine) pdf_to_cdf_ray(lane, Sc, sc->sigma + r * Sc, sc->cdf[r]);
-          tl_mark(c.tl, 0, 24);
+          NERFB200_TL_MARK(c.tl, 0, 24);
         }
         epi_bar();
-        tl_mark(c.tl, 0, 21);
+        NERFB200_TL_MARK(c.tl, 0, 21);
         if (pass == 0 && fine) {
           // ---- part 2 (:36-54): one u per thread -> inverse-CDF depth; u sorted first when random
           if (t < 2 * K) {
@@ -552,7 +559,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
               sc->z[r * Sf + rank] = v;
             }
           }
-          tl_mark(c.tl, 0, 25);
+          NERFB200_TL_MARK(c.tl, 0, 25);
           epi_bar();
           if (p.z_fine != nullptr) {
             for (int e = t; e < 2 * Sf; e += kEpiThreads) {
@@ -563,6 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
         }
       }
     }
+    NERFB200_TL_MARK(c.tl, 0, 99);
   }
   engine_teardown(bars);
 }

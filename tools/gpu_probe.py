@@ -8,6 +8,7 @@ import os
 import sys
 import time
 
+import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -199,7 +200,134 @@ def step_timeline():
     print("TIMELINE_DONE")
 
 
+def step_speed1():
+    ms = make_models()
+    emb = [nb.Embedding(3, 10), nb.Embedding(3, 4)]
+    n = int(os.environ.get("SPEED_N", "160000"))
+    rays = make_rays(n)
+    with torch.no_grad():
+        for _ in range(2):
+            nb.render_rays(ms, emb, rays, 64, False, 0, 0, 64, 32768, True, test_time=True)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            nb.render_rays(ms, emb, rays, 64, False, 0, 0, 64, 32768, True, test_time=True)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+    print(f"speed1 n={n} ctas={os.environ.get('NERFB200_MAX_CTAS', 'all')}: best {best:.3f} ms  {n * 192 / (best * 1e-3):.3e} ray-samples/s")
+
+
+def step_contention():
+    lib = _lib.load()
+    bgs = {0: "idle", 1: "ld", 2: "ld+cvt+st", 3: "st", 4: "per-kb ld/cvt/st", 5: "mbar poll", 6: "st+fence+arrive"}
+    vs = {0: "SS", 1: "TS in-place A", 2: "TS packed A"}
+    for n_ctas in (1,):
+        for v in vs:
+            for bg in bgs:
+                out = torch.zeros(n_ctas, 4, dtype=torch.long, device="cuda")
+                reps = 64
+                for _ in range(2):
+                    rc = lib.nerfb200_debug_mma_contention(out.data_ptr(), n_ctas, reps, bg, v, None)
+                torch.cuda.synchronize()
+                o = out.cpu().numpy().astype(float)
+                cyc = np.median(o[:, 0])
+                it = np.median(o[:, 1])
+                print(f"contention ctas={n_ctas:3d} {vs[v]:14s} bg={bgs[bg]:18s} rc={rc} cyc/MMA {cyc / (reps * 16):7.1f}  "
+                      f"bg iters {it:6.0f}  cyc/bg-iter {cyc / max(it, 1):8.1f}")
+    print("CONTENTION_DONE")
+
+
+def step_issue():
+    lib = _lib.load()
+    cases = [(0, 0, "back-to-back"), (1, 0, "commit/4"),
+             (2, 50, "spin 50 after every 4th"), (2, 100, "spin 100 after every 4th"), (2, 200, "spin 200 after every 4th"),
+             (2, 400, "spin 400 after every 4th"),
+             (3, 30, "spin 30 after every MMA"), (3, 60, "spin 60 after every MMA"), (3, 120, "spin 120 after every MMA"),
+             (4, 0, "2 waits+fence before every 4"), (8, 0, "1 wait+fence before every 4"),
+             (5, 0, "2 waits+fence after j=0"), (6, 0, "2 waits+fence after j=1"), (7, 0, "2 waits+fence after j=2")]
+    for mode, arg, nm in cases:
+        out = torch.zeros(1, 4, dtype=torch.long, device="cuda")
+        reps = 64
+        for _ in range(2):
+            rc = lib.nerfb200_debug_mma_contention(out.data_ptr(), 1, reps, -1 - arg, mode, None)
+        torch.cuda.synchronize()
+        o = out.cpu().numpy().astype(float)
+        print(f"issue mode {mode} {nm:30s} rc={rc} cyc/MMA {o[0, 0] / (reps * 16):7.1f}  cyc/slice {o[0, 0] / (reps * 4):7.1f}")
+    print("ISSUE_DONE")
+
+
+def step_tlsum():
+    """Timeline of CTA 0, summarised: per-tile phase durations (epilogue thread 0) and MMA-side waits."""
+    os.environ["NERFB200_FLAGS"] = str(int(os.environ.get("NERFB200_FLAGS", "0")) | 2)
+    lib = _lib.load()
+    ms = make_models()
+    emb = [nb.Embedding(3, 10), nb.Embedding(3, 4)]
+    n = int(os.environ.get("TL_N", "32768"))
+    rays = make_rays(n)
+    tt = bool(int(os.environ.get("TT", "1")))
+    perturb = float(os.environ.get("TL_PERTURB", "0"))
+    with torch.no_grad():
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            nb.render_rays(ms, emb, rays, 64, False, perturb, 0, 64, 32768, True, test_time=tt)
+            e1.record()
+            torch.cuda.synchronize()
+    print(f"kernel (events) {e0.elapsed_time(e1) * 1e3:.1f} us for n={n}")
+    buf = np.zeros((3, 512, 2), dtype=np.int64)
+    rc = lib.nerfb200_debug_timeline(buf.ctypes.data, buf.size)
+    epi = [(int(a), int(b)) for a, b in buf[0] if b != 0]
+    mma = [(int(a), int(b)) for a, b in buf[1] if b != 0]
+    print("rc", rc, "events", len(epi), len(mma))
+    t_entry = next((v for tg, v in epi if tg == 90), None)
+    t91 = next((v for tg, v in epi if tg == 91), None)
+    t99 = next((v for tg, v in epi if tg == 99), None)
+    if t_entry and t91:
+        print(f"setup (entry -> first group) {t91 - t_entry} cycles; entry -> end {t99 - t_entry if t99 else -1} cycles")
+    # generic: print consecutive deltas grouped by (tag -> next tag), aggregated
+    agg = {}
+    seq = [(tg, v) for tg, v in epi if tg != 90]
+    for (a, ta), (b, tb) in zip(seq, seq[1:]):
+        agg.setdefault((a, b), []).append(tb - ta)
+    print("EPI transitions (tag->tag: count, mean, min, max cycles)")
+    for k in sorted(agg):
+        v = agg[k]
+        print(f"  {k[0]:3d}->{k[1]:3d}: n={len(v):4d} mean {np.mean(v):8.0f} min {min(v):7d} max {max(v):7d}  total {sum(v):9d}")
+    # MMA side
+    lay = {}
+    cur = {}
+    for tg, v in mma:
+        if 100 <= tg < 200: cur[tg - 100] = v
+        elif 200 <= tg < 300 and (tg - 200) in cur: lay.setdefault(tg - 200, {}).setdefault("issue", []).append(v - cur[tg - 200])
+        elif 300 <= tg < 400: lay.setdefault(tg - 300, {}).setdefault("w_full", []).append(v)
+        elif 400 <= tg < 500: lay.setdefault(tg - 400, {}).setdefault("w_akb", []).append(v)
+    starts = [v for tg, v in mma if 100 <= tg < 200]
+    tags = [tg for tg, v in mma if 100 <= tg < 200]
+    per = {}
+    for (t0, v0), v1 in zip(zip(tags, starts), starts[1:]):
+        per.setdefault(t0 - 100, []).append(v1 - v0)
+    print("MMA per layer: start->next start mean | issue span | wait full | wait a_kb (cycles)")
+    for l in sorted(lay):
+        d = lay[l]
+        print(f"  L{l}: period {np.mean(per.get(l, [0])):7.0f} issue {np.mean(d.get('issue', [0])):7.0f} "
+              f"w_full {np.mean(d.get('w_full', [0])):7.0f} (max {max(d.get('w_full', [0]))}) w_akb {np.mean(d.get('w_akb', [0])):7.0f}")
+    if os.environ.get("TL_RAW"):
+        ev = [(v, "EPI", tg) for tg, v in epi if tg != 90] + [(v, "MMA", tg) for tg, v in mma if tg < 300 or tg >= 500]
+        ev.sort()
+        lo = int(os.environ.get("TL_RAW_LO", "150"))
+        t0 = ev[lo][0]
+        prev = {"EPI": t0, "MMA": t0}
+        for v, role, tg in ev[lo:lo + int(os.environ["TL_RAW"])]:
+            pad = "" if role == "EPI" else "                      "
+            print(f"{v - t0:8d} {pad}{role} {tg:4d} (+{v - prev[role]})")
+            prev[role] = v
+    print("TLSUM_DONE")
+
+
 if __name__ == "__main__":
     t0 = time.time()
-    {"gemm": step_gemm, "mlp": step_mlp, "render": step_render, "speed": step_speed, "timeline": step_timeline, "mmabench": step_mmabench, "cache": step_cache}[sys.argv[1]]()
+    {"gemm": step_gemm, "mlp": step_mlp, "render": step_render, "speed": step_speed, "timeline": step_timeline, "mmabench": step_mmabench, "speed1": step_speed1, "contention": step_contention, "issue": step_issue, "tlsum": step_tlsum, "cache": step_cache}[sys.argv[1]]()
     print(f"[{sys.argv[1]}] {time.time() - t0:.1f}s")
