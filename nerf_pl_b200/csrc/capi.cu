@@ -229,9 +229,9 @@ int nerfb200_render_rays(const nerfb200_render_args* a, void* stream) {
   }
   if (n_groups < ctas) ctas = n_groups;
   if (save)
-    render_rays_kernel<true><<<ctas, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
+    render_rays_kernel<true><<<ctas, kRenderThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
   else
-    render_rays_kernel<false><<<ctas, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
+    render_rays_kernel<false><<<ctas, kRenderThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
   g_launches++;
   CUDA_TRY(cudaGetLastError(), "render_rays launch");
   return 0;

@@ -53,8 +53,11 @@ constexpr bool kAInTmem = true;
 // B200: overlapping does not pay - the tensor core's TMEM (or smem) operand reads and
 // the epilogue's stores share one port, each slows the other by the overlap.
 constexpr bool kPipelinedHandover = true;
+// Ring depth: 3, 4 and 5 stages measure the same (the weights come from L2 and one layer of
+// look-ahead is enough), so the ring takes 96 KiB and the rest of shared memory holds the second
+// ENC tile and the per-group state of the render kernel's helper warps.
 #ifndef NERFB200_STAGES
-#define NERFB200_STAGES 5
+#define NERFB200_STAGES 3
 #endif
 constexpr int kStages = kAInTmem ? NERFB200_STAGES : 3;
 constexpr int kTmemCols = 512;
@@ -63,12 +66,15 @@ constexpr uint32_t kTmemD = 0, kTmemA = 256;
 constexpr uint32_t kSmemEnc = 0;                     // [128 x 64] fp16     16 KiB
 constexpr uint32_t kSmemA = 16384;                   // [4][128 x 64] fp16  64 KiB (only if !kAInTmem)
 constexpr uint32_t kSmemRing = kAInTmem ? 16384 : 81920;   // kStages x 32 KiB
-constexpr uint32_t kSmemConsts = kSmemRing + kStages * kSliceBytes256;    // 180224: fp32 biases + heads
+constexpr uint32_t kSmemEnc1 = kSmemRing + kStages * kSliceBytes256;      // second ENC tile (render kernel: double buffer)
+constexpr uint32_t kSmemConsts = kSmemEnc1 + 16384;                       // fp32 biases + heads of two networks
 constexpr uint32_t kConstFloats = kF32WDirPart;      // biases, sigma head, rgb head of one network
-constexpr uint32_t kSmemScratch = kSmemConsts + 32768;                    // 212992
-static_assert(2 * kConstFloats * 4 <= 32768, "constants of two networks must fit");
+constexpr uint32_t kConstRegion = 24576;
+constexpr uint32_t kSmemScratch = kSmemConsts + kConstRegion;
+static_assert(2 * kConstFloats * 4 <= kConstRegion, "constants of two networks must fit");
+static_assert(kSmemEnc1 % 1024 == 0 && kSmemConsts % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
 constexpr uint32_t kSmemTotal = 232448;              // 227 KiB (max opt-in)
-constexpr uint32_t kScratchBytes = kSmemTotal - kSmemScratch;       // 19456
+constexpr uint32_t kScratchBytes = kSmemTotal - kSmemScratch;
 
 constexpr int kLayersFull = 9;        // L1..L8, fused final.dir
 constexpr int kLayersSigma = 8;       // L1..L8
@@ -223,14 +229,16 @@ struct MmaPhases { uint32_t d_free = 0, a_kb = 0; };   // a_kb: the 4 K-block ba
 #define NERFB200_TL_MARK(tl, role, tag) ((void)0)
 #endif
 
+// enc_off: byte offset of this tile's ENC buffer; enc_bar != 0: additionally wait for that
+// mbarrier (parity enc_parity) before the first MMA ("ENC written by the helper warps").
 template <bool kSigmaOnly, bool kDirSlice>
 __device__ __forceinline__ void mma_tile_t(RingState& rs, MmaPhases& ph, uint8_t* smem, Barriers* bars,
-                                           Timeline* tl) {
+                                           Timeline* tl, uint32_t enc_off, uint32_t enc_bar, uint32_t enc_parity) {
   static_assert(kPipelinedHandover && kAInTmem, "the issue loop implements the K-block hand-over with the TMEM operand");
   const uint32_t tmem = bars->tmem_base;
   const uint32_t d_tmem = tmem + kTmemD;
   const uint32_t a_tmem = tmem + kTmemA;
-  const uint64_t enc_desc = make_desc_sw128(smem_u32(smem + kSmemEnc));
+  const uint64_t enc_desc = make_desc_sw128(smem_u32(smem + enc_off));
   const uint64_t ring_desc = make_desc_sw128(smem_u32(smem + kSmemRing));
   const uint32_t full0 = smem_u32(&bars->full[0]);
   const uint32_t empty0 = smem_u32(&bars->empty[0]);
@@ -247,6 +255,7 @@ __device__ __forceinline__ void mma_tile_t(RingState& rs, MmaPhases& ph, uint8_t
     if (l == 0) {
       mbar_wait(smem_u32(&bars->d_free), ph.d_free, 3);
       ph.d_free ^= 1;
+      if (enc_bar != 0) mbar_wait(enc_bar, enc_parity, 9);
     } else {
       mbar_wait(akb0, ph.a_kb, 6);
     }
@@ -285,10 +294,11 @@ __device__ __forceinline__ void mma_tile_t(RingState& rs, MmaPhases& ph, uint8_t
 }
 
 __device__ __forceinline__ void mma_tile(RingState& rs, MmaPhases& ph, uint8_t* smem, Barriers* bars,
-                                         bool sigma_only, bool dir_slice, Timeline* tl = nullptr) {
-  if (sigma_only) mma_tile_t<true, false>(rs, ph, smem, bars, tl);
-  else if (dir_slice) mma_tile_t<false, true>(rs, ph, smem, bars, tl);
-  else mma_tile_t<false, false>(rs, ph, smem, bars, tl);
+                                         bool sigma_only, bool dir_slice, Timeline* tl = nullptr,
+                                         uint32_t enc_off = kSmemEnc, uint32_t enc_bar = 0, uint32_t enc_parity = 0) {
+  if (sigma_only) mma_tile_t<true, false>(rs, ph, smem, bars, tl, enc_off, enc_bar, enc_parity);
+  else if (dir_slice) mma_tile_t<false, true>(rs, ph, smem, bars, tl, enc_off, enc_bar, enc_parity);
+  else mma_tile_t<false, false>(rs, ph, smem, bars, tl, enc_off, enc_bar, enc_parity);
 }
 
 // --------------------------------------------------------------- epilogue

@@ -260,14 +260,96 @@ __device__ __forceinline__ float inverse_cdf(int S, const float* zc, const float
   return __fadd_rn(b0, __fmul_rn(tt, __fsub_rn(b1, b0)));
 }
 
+// ---------------------------------------------------------------------------------------------
+// The render kernel.  Warp roles (kRenderThreads = 640, 96 registers per thread):
+//   0..15  MLP epilogue (csrc/mlp_engine.cuh) + sigma / rgb heads of every tile
+//   16     weight producer     17  tcgen05 issuer
+//   18, 19 helper warps: everything that is not the MLP - ray set-up, stratified depths, positional
+//          encoding of the NEXT tile into the other ENC buffer, alpha compositing, inverse-CDF
+//          resampling, merge, result stores - concurrently with the MLP of the current tile.
+// Tiles are issued in the order C(0), C(1), F(0), C(2), F(1), ...: the coarse tile of group g+1 and
+// the fine tiles of group g-1 run between the coarse tile of group g and its fine tiles, so the
+// dependent chain "coarse sigma -> weights -> cdf -> new depths -> encoding" is off the tensor
+// core's critical path.  Hand-over: enc_full[b] (helpers -> issuer + epilogue: ENC buffer b and
+// the group's direction bias are written), out_full[b] (epilogue -> helpers: sigma / rgb of the
+// 128 rows of the tile are in out_*[b]).  out_full of tile q-2 also tells the helpers that ENC
+// buffer (q & 1) is no longer read.
+constexpr int kHelperWarp0 = kMmaWarp + 1;       // 18
+constexpr int kHelperWarps = 2;                  // 20 warps x 96 registers fill the register file
+constexpr int kHelperThreads = kHelperWarps * 32;
+constexpr int kRenderThreads = (kHelperWarp0 + kHelperWarps) * 32;   // 640
+static_assert(kHelperWarps >= 2, "compositing uses one helper warp per ray of the group");
+constexpr int kGroupSlots = 3;                   // groups in flight: g-1 (fine), g (resampling), g+1 (coarse)
+
+struct alignas(16) GroupState {
+  float ray[2][8];
+  float dnorm[2];
+  float pad0[2];
+  float direnc[2][28];
+  alignas(16) float dirbias[2][2][kDirW];   // [pass][ray][n]: b_dir + W_dir[:,256:283] . dir_enc
+  float zc[2][kMaxSc];                      // coarse depths (kept for the merge)
+  float z[kMaxRows];                        // fine depths [ray][S_f] (merged, sorted)
+  float sigma[kMaxRows];                    // sigma of the current pass, overwritten in place by the weights
+  float rgb[3][kMaxRows];
+  float cdf[2][kMaxSc];
+  float znew[2][kMaxImp];                   // u (sorted) then the new depths
+};
+
+struct alignas(16) RenderScratch {
+  Barriers bars;
+  uint64_t enc_full[2];
+  uint64_t out_full[2];
+  float sig_part[kColSplit][128];           // [column group][row] partial sigma-head sums
+  float rgb_part[kColSplit][3][128];
+  float out_sigma[2][128];                  // [tile buffer][row]
+  float out_rgb[2][3][128];
+  GroupState gs[kGroupSlots];
+};
+static_assert(sizeof(RenderScratch) <= kScratchBytes, "render scratch does not fit");
+static_assert(sizeof(GroupState) % 16 == 0, "GroupState keeps float4 alignment");
+
+__device__ __forceinline__ void helper_bar() {
+  asm volatile("bar.sync 2, %0;" ::"n"(kHelperThreads) : "memory");
+}
+
+struct Tile { int q, g, pass, tile; bool last; };
+
+// Tile order of one CTA (see above); every role walks the same sequence.
+struct TileSeq {
+  int G, my_n, Sc, Sf;
+  bool fine;
+  int g = 0, phase = 0, t = 0, q = 0;
+  __device__ __forceinline__ TileSeq(int G_, int my_n_, int Sc_, int Sf_, bool fine_)
+      : G(G_), my_n(my_n_), Sc(Sc_), Sf(Sf_), fine(fine_) {}
+  __device__ __forceinline__ int nr(int gg) const { return min(2, my_n - 2 * gg); }
+  __device__ __forceinline__ static int tiles_of(int n_r, int S) { return (n_r * S + 127) >> 7; }
+  __device__ __forceinline__ bool next(Tile& o) {
+    while (g <= G) {
+      if (phase == 0) {
+        const int nt = (g < G) ? tiles_of(nr(g), Sc) : 0;
+        if (t < nt) { o = Tile{q, g, 0, t, t + 1 == nt}; ++t; ++q; return true; }
+        phase = 1; t = 0;
+      } else {
+        const int nt = (fine && g >= 1) ? tiles_of(nr(g - 1), Sf) : 0;
+        if (t < nt) { o = Tile{q, g - 1, 1, t, t + 1 == nt}; ++t; ++q; return true; }
+        phase = 0; t = 0; ++g;
+      }
+    }
+    return false;
+  }
+};
+
 template <bool kSave>
-__global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const RenderParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  Scratch* sc = reinterpret_cast<Scratch*>(smem + kSmemScratch);
+  RenderScratch* sc = reinterpret_cast<RenderScratch*>(smem + kSmemScratch);
   Barriers* bars = &sc->bars;
-#ifdef NERFB200_TIMELINE
-  const long long t_entry = clock64();
-#endif
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&sc->enc_full[b]), kHelperWarps);
+      mbar_init(smem_u32(&sc->out_full[b]), kEpiWarps);
+    }
+  }
   if (!engine_setup(smem, bars)) {
     if (threadIdx.x == 0) atomicExch(p.status, 101);
     return;
@@ -288,33 +370,28 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
   const int my_lo = static_cast<int>(blockIdx.x) * per_cta + min(static_cast<int>(blockIdx.x), rem_cta);
   const int my_n = per_cta + (static_cast<int>(blockIdx.x) < rem_cta ? 1 : 0);
   const int n_groups = (my_n + 1) >> 1;
-  auto rays_in_group = [&](int g) { return min(2, my_n - 2 * g); };
-  auto tiles_of = [](int n_r, int S) { return (n_r * S + 127) >> 7; };
+  TileSeq seq(n_groups, my_n, Sc, Sf, fine);
+  Tile tl;
 
-  if (warp == kProducerWarp) {
-    if (lane == 0) {
+  if (warp >= kEpiWarps && warp < kHelperWarp0) {
+    if (warp == kProducerWarp && lane == 0) {
       RingState rs;
-      for (int g = 0; g < n_groups; ++g) {
-        const int nr = rays_in_group(g);
-        for (int t = 0; t < tiles_of(nr, Sc); ++t)
-          produce_tile(rs, smem, bars, p.net_coarse, coarse_sigma_only, false);
-        if (fine)
-          for (int t = 0; t < tiles_of(nr, Sf); ++t) produce_tile(rs, smem, bars, p.net_fine, false, false);
-      }
-    }
-  } else if (warp == kMmaWarp) {
-    if (lane == 0) {
+      while (seq.next(tl))
+        produce_tile(rs, smem, bars, tl.pass ? p.net_fine : p.net_coarse, tl.pass == 0 && coarse_sigma_only, false);
+    } else if (warp == kMmaWarp && lane == 0) {
+      {
       RingState rs;
       MmaPhases ph;
       Timeline tlm{(blockIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
-      for (int g = 0; g < n_groups; ++g) {
-        const int nr = rays_in_group(g);
-        for (int t = 0; t < tiles_of(nr, Sc); ++t) mma_tile(rs, ph, smem, bars, coarse_sigma_only, false, &tlm);
-        if (fine)
-          for (int t = 0; t < tiles_of(nr, Sf); ++t) mma_tile(rs, ph, smem, bars, false, false, &tlm);
+      while (seq.next(tl)) {
+        const int b = tl.q & 1;
+        mma_tile(rs, ph, smem, bars, tl.pass == 0 && coarse_sigma_only, false, &tlm, b ? kSmemEnc1 : kSmemEnc,
+                 smem_u32(&sc->enc_full[b]), static_cast<uint32_t>(tl.q >> 1) & 1u);
+      }
       }
     }
-  } else {
+  } else if (warp < kEpiWarps) {
+    // ================================ MLP epilogue warps ================================
     EpiCtx c;
     c.smem = smem;
     c.bars = bars;
@@ -327,41 +404,242 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
     c.save_act = nullptr; c.save_d = nullptr; c.save_n = 0; c.save_row = -1;
     Timeline tle{(blockIdx.x == 0 && threadIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
     c.tl = &tle;
-#ifdef NERFB200_TIMELINE
-    tl_val(c.tl, 0, 90, t_entry);
-#endif
-    NERFB200_TL_MARK(c.tl, 0, 91);
-    const int t = threadIdx.x;   // 0..255
-    uint8_t* enc = smem + kSmemEnc;
-
-    for (int g = 0; g < n_groups; ++g) {
-      const int ray0 = my_lo + 2 * g;
-      const bool valid1 = rays_in_group(g) == 2;
-      const int rid[2] = {ray0, valid1 ? ray0 + 1 : ray0};
-      // ---- rays, direction embedding (models/rendering.py:179-186)
-      NERFB200_TL_MARK(c.tl, 0, 30);
-      if (t < 16) sc->ray[t >> 3][t & 7] = __ldg(p.rays + static_cast<long long>(rid[t >> 3]) * p.ray_stride + (t & 7));
+    while (seq.next(tl)) {
+      const int b = tl.q & 1;
+      const int pass = tl.pass;
+      const int S = pass ? Sf : Sc;
+      const bool valid1 = seq.nr(tl.g) == 2;
+      const int ray0 = my_lo + 2 * tl.g;
+      const bool sigma_only = (pass == 0) && coarse_sigma_only;
+      const uint8_t* blob = pass ? p.net_fine : p.net_coarse;
+      c.f32 = reinterpret_cast<const float*>(blob + kHalfRegionBytes);
+      c.cst = consts_ptr(smem, pass);
+      c.save_act = kSave ? (pass ? p.save_act_f : p.save_act_c) : nullptr;
+      c.save_d = kSave ? (pass ? p.save_d_f : p.save_d_c) : nullptr;
+      c.save_n = static_cast<long long>(p.n_rays) * S;
+      const GroupState& gs = sc->gs[tl.g % kGroupSlots];
+      const int gr = tl.tile * 128 + c.row;
+      const int r = gr / S;
+      const long long grow = (r == 0 || valid1) ? static_cast<long long>(ray0 + r) * S + (gr - r * S) : -1;
+      c.save_row = grow;
+      // ENC buffer b and the group's direction bias are ready
+      mbar_wait(smem_u32(&sc->enc_full[b]), static_cast<uint32_t>(tl.q >> 1) & 1u, 7);
+      float sig_part, rgb_part[3];
+      epi_run_tile<kSave>(c, sigma_only, gs.dirbias[pass][r], nullptr, sig_part, rgb_part);
+      sc->sig_part[c.part][c.row] = sig_part;
+      if (!sigma_only) {
+        sc->rgb_part[c.part][0][c.row] = rgb_part[0];
+        sc->rgb_part[c.part][1][c.row] = rgb_part[1];
+        sc->rgb_part[c.part][2][c.row] = rgb_part[2];
+      }
       epi_bar();
-      if (t < 2) {
-        const float* d = &sc->ray[t][3];
-        sc->dnorm[t] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
-      } else if (t >= 32 && t < 32 + 30) {
+      // combine the column groups' partial head sums: group 0 -> sigma, groups 1..3 -> r, g, b
+      if (c.part == 0) {
+        float sg = c.cst[kF32BSigma];
+#pragma unroll
+        for (int q = 0; q < kColSplit; ++q) sg += sc->sig_part[q][c.row];
+        sc->out_sigma[b][c.row] = sg;
+        if (kSave && grow >= 0) {
+          float* ss = pass ? p.save_sig_f : p.save_sig_c;
+          if (ss != nullptr) ss[grow] = sg;
+        }
+      } else if (!sigma_only) {
+        const int ch = c.part - 1;
+        float pre = c.cst[kF32BRgb + ch];
+#pragma unroll
+        for (int q = 0; q < kColSplit; ++q) pre += sc->rgb_part[q][ch][c.row];
+        const float col = sigmoid_ref(pre);
+        sc->out_rgb[b][ch][c.row] = col;
+        if (kSave && grow >= 0) {
+          float* sr = pass ? p.save_rgb_f : p.save_rgb_c;
+          if (sr != nullptr) sr[grow * 3 + ch] = col;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sc->out_full[b]));
+    }
+  } else if (warp >= kHelperWarp0) {
+    // ================================== helper warps ===================================
+    const int ht = threadIdx.x - kHelperWarp0 * 32;   // 0..127
+    const int hw = ht >> 5;
+    TileSeq cons_seq(n_groups, my_n, Sc, Sf, fine);
+    Tile tc;
+    int consumed = 0;           // tiles consumed so far (== q of the next tile to consume)
+    int cpos0 = 0, cpos1 = 0, cpos2 = 0;   // position of the (last) coarse tile of the group in slot 0 / 1 / 2
+
+    // ---- consume one finished tile: sigma / rgb rows -> group arrays; after the last tile of a
+    // pass: compositing (models/rendering.py:143-170), result stores, and after the coarse pass
+    // the hierarchical resampling (:28-54) and the merge (:229)
+    auto consume = [&](const Tile& tt) {
+      const int b = tt.q & 1;
+      const int pass = tt.pass;
+      const int S = pass ? Sf : Sc;
+      const bool valid1 = seq.nr(tt.g) == 2;
+      const int ray0 = my_lo + 2 * tt.g;
+      const int rid[2] = {ray0, valid1 ? ray0 + 1 : ray0};
+      const bool sigma_only = (pass == 0) && coarse_sigma_only;
+      GroupState& gs = sc->gs[tt.g % kGroupSlots];
+      mbar_wait(smem_u32(&sc->out_full[b]), static_cast<uint32_t>(tt.q >> 1) & 1u, 8);
+      for (int row = ht; row < 128; row += kHelperThreads) {
+        const int gr = tt.tile * 128 + row;
+        if (gr < 2 * S) {
+          gs.sigma[gr] = sc->out_sigma[b][row];
+          if (!sigma_only) {
+            gs.rgb[0][gr] = sc->out_rgb[b][0][row];
+            gs.rgb[1][gr] = sc->out_rgb[b][1][row];
+            gs.rgb[2][gr] = sc->out_rgb[b][2][row];
+          }
+        }
+      }
+      helper_bar();
+      if (!tt.last) return;
+      // ---- compositing: helper warp r renders ray r
+      if (hw < 2) {
+        const int r = hw;
+        const float* zr = pass ? (gs.z + r * S) : gs.zc[r];
+        const float* nz = nullptr;
+        if (p.noise_std > 0.f)
+          nz = (pass ? p.noise_fine : p.noise_coarse) + static_cast<long long>(rid[r]) * S;
+        const RayOut o = composite_ray(lane, S, zr, gs.sigma + r * S, gs.rgb[0] + r * S, gs.rgb[1] + r * S,
+                                       gs.rgb[2] + r * S, nz, p.noise_std, gs.dnorm[r], !sigma_only,
+                                       gs.sigma + r * S);
+        __syncwarp();
+        const bool wr = (r == 0) || valid1;
+        if (wr) {
+          const long long ri = rid[r];
+          float* wout = pass ? p.weights_fine : p.weights_coarse;
+          if (wout != nullptr)
+            for (int i = lane; i < S; i += 32) wout[ri * S + i] = gs.sigma[r * S + i];
+          if (lane == 0) {
+            float add = (p.white_back != 0) ? __fsub_rn(1.f, o.opac) : 0.f;
+            if (pass == 0) {
+              p.opacity_coarse[ri] = o.opac;
+              if (!sigma_only) {
+                p.rgb_coarse[3 * ri + 0] = o.r + add;
+                p.rgb_coarse[3 * ri + 1] = o.g + add;
+                p.rgb_coarse[3 * ri + 2] = o.b + add;
+                p.depth_coarse[ri] = o.depth;
+              }
+            } else {
+              p.opacity_fine[ri] = o.opac;
+              p.rgb_fine[3 * ri + 0] = o.r + add;
+              p.rgb_fine[3 * ri + 1] = o.g + add;
+              p.rgb_fine[3 * ri + 2] = o.b + add;
+              p.depth_fine[ri] = o.depth;
+            }
+          }
+        }
+        // ---- hierarchical resampling, part 1 (models/rendering.py:28-33): pdf -> cdf
+        if (pass == 0 && fine) pdf_to_cdf_ray(lane, Sc, gs.sigma + r * Sc, gs.cdf[r]);
+      }
+      helper_bar();
+      if (pass != 0 || !fine) return;
+      // ---- part 2 (:36-54): one u per thread -> inverse-CDF depth; u sorted first when random
+      for (int t = ht; t < 2 * K; t += kHelperThreads) {
+        const int r = t / K, j = t - r * K;
+        float uj;
+        int slot = j;
+        if (p.perturb > 0.f) {
+          const float* ur = p.u_rand + static_cast<long long>(rid[r]) * K;
+          uj = __ldg(ur + j);
+          slot = 0;
+#pragma unroll 8
+          for (int q = 0; q < K; ++q) {
+            const float uq = __ldg(ur + q);
+            slot += (uq < uj) || (uq == uj && q < j);
+          }
+        } else {
+          uj = linspace01(j, K);
+        }
+        gs.znew[r][slot] = inverse_cdf(Sc, gs.zc[r], gs.cdf[r], uj);
+      }
+      helper_bar();
+      // ---- merge: z_fine = sort(cat(z_coarse, z_new)) (:229) as a rank computation:
+      // position = number of elements that are smaller, ties broken by index in the
+      // concatenation (any tie order gives the same sorted VALUES, which is all torch.sort's
+      // output carries).  Both lists are sorted except for possible 1-ulp inversions from
+      // rounding, so every element first checks its predecessor; if no inversion exists
+      // anywhere (the common case) ranks come from two binary searches, otherwise from
+      // exhaustive counting.  Both paths give identical results on sorted input.
+      {
+        bool inv = false;
+        for (int e = ht; e < 2 * Sf; e += kHelperThreads) {
+          const int r = e / Sf, i = e - r * Sf;
+          if (i != 0 && i != Sc)
+            inv |= (i < Sc) ? (gs.zc[r][i] < gs.zc[r][i - 1]) : (gs.znew[r][i - Sc] < gs.znew[r][i - Sc - 1]);
+        }
+        int any_inv;
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+            "barrier.red.or.pred p, 2, %2, q;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(any_inv) : "r"(static_cast<int>(inv)), "n"(kHelperThreads) : "memory");
+        for (int e = ht; e < 2 * Sf; e += kHelperThreads) {
+          const int r = e / Sf, i = e - r * Sf;
+          const float* zc = gs.zc[r];
+          const float* zn = gs.znew[r];
+          const float v = (i < Sc) ? zc[i] : zn[i - Sc];
+          int rank;
+          if (!any_inv) {
+            // lower_bound in the other list for coarse elements (coarse first on ties),
+            // upper_bound for new elements
+            const float* other = (i < Sc) ? zn : zc;
+            int lo = 0, hi = (i < Sc) ? K : Sc;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              const float x = other[mid];
+              const bool right = (i < Sc) ? (x < v) : (x <= v);
+              if (right) lo = mid + 1; else hi = mid;
+            }
+            rank = lo + ((i < Sc) ? i : i - Sc);
+          } else {
+            rank = 0;
+#pragma unroll 8
+            for (int q = 0; q < Sc; ++q) rank += (zc[q] < v) || (zc[q] == v && q < i);
+#pragma unroll 8
+            for (int q = 0; q < K; ++q) rank += (zn[q] < v) || (zn[q] == v && (q + Sc) < i);
+          }
+          gs.z[r * Sf + rank] = v;
+        }
+      }
+      helper_bar();
+      if (p.z_fine != nullptr) {
+        for (int e = ht; e < 2 * Sf; e += kHelperThreads) {
+          const int r = e / Sf, i = e - r * Sf;
+          if (r == 0 || valid1) p.z_fine[static_cast<long long>(rid[r]) * Sf + i] = gs.z[e];
+        }
+      }
+    };
+
+    // ---- rays, direction embedding, stratified depths, direction bias of one group
+    auto setup_group = [&](int g) {
+      GroupState& gs = sc->gs[g % kGroupSlots];
+      const bool valid1 = seq.nr(g) == 2;
+      const int ray0 = my_lo + 2 * g;
+      const int rid[2] = {ray0, valid1 ? ray0 + 1 : ray0};
+      // models/rendering.py:179-186
+      if (ht < 16) gs.ray[ht >> 3][ht & 7] = __ldg(p.rays + static_cast<long long>(rid[ht >> 3]) * p.ray_stride + (ht & 7));
+      helper_bar();
+      if (ht < 2) {
+        const float* d = &gs.ray[ht][3];
+        gs.dnorm[ht] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+      } else if (ht >= 32 && ht < 32 + 30) {
+        static_assert(kHelperThreads >= 62, "direction embedding uses helper threads 32..61");
         // Embedding(3,4)(rays_d) (models/rendering.py:186): one (ray, coord, freq) per thread, accurate sincosf
-        const int q = t - 32, r = q / 15, cc = (q % 15) / 5, k = q % 5;     // k == 4: the raw value
-        const float dv = sc->ray[r][3 + cc];
+        const int q = ht - 32, r = q / 15, cc = (q % 15) / 5, k = q % 5;     // k == 4: the raw value
+        const float dv = gs.ray[r][3 + cc];
         if (k == 4) {
-          sc->direnc[r][cc] = dv;
+          gs.direnc[r][cc] = dv;
         } else {
           float sn, cs;
           sincosf(__fmul_rn(static_cast<float>(1 << k), dv), &sn, &cs);
-          sc->direnc[r][3 + 6 * k + cc] = sn;
-          sc->direnc[r][3 + 6 * k + 3 + cc] = cs;
+          gs.direnc[r][3 + 6 * k + cc] = sn;
+          gs.direnc[r][3 + 6 * k + 3 + cc] = cs;
         }
       }
       // ---- coarse depths (models/rendering.py:189-204)
-      for (int e = t; e < 2 * Sc; e += kEpiThreads) {
+      for (int e = ht; e < 2 * Sc; e += kHelperThreads) {
         const int r = e / Sc, i = e - r * Sc;
-        const float nr = sc->ray[r][6], fr = sc->ray[r][7];
+        const float nr = gs.ray[r][6], fr = gs.ray[r][7];
         float z = z_base(nr, fr, i, Sc, p.use_disp != 0);
         if (p.perturb > 0.f) {
           const float zl = (i > 0) ? z_base(nr, fr, i - 1, Sc, p.use_disp != 0) : z;
@@ -371,206 +649,64 @@ __global__ void __launch_bounds__(kThreads, 1) render_rays_kernel(const RenderPa
           const float pr = __fmul_rn(p.perturb, __ldg(p.perturb_rand + static_cast<long long>(rid[r]) * Sc + i));
           z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), pr));
         }
-        sc->z[e] = z;
-        sc->zc[r][i] = z;
+        gs.zc[r][i] = z;
       }
-      NERFB200_TL_MARK(c.tl, 0, 31);
-      epi_bar();
-
-      // ================= two passes: coarse, fine =================
+      helper_bar();
+      // ---- per-ray direction bias of both networks: b_dir + W_dir[:, 256:283] . dir_embedded (fp32)
       for (int pass = 0; pass < (fine ? 2 : 1); ++pass) {
-        const int S = pass ? Sf : Sc;
-        const int tiles = tiles_of(valid1 ? 2 : 1, S);
-        const bool sigma_only = (pass == 0) && coarse_sigma_only;
+        if (pass == 0 && coarse_sigma_only) continue;
         const uint8_t* blob = pass ? p.net_fine : p.net_coarse;
-        c.f32 = reinterpret_cast<const float*>(blob + kHalfRegionBytes);
-        c.cst = consts_ptr(smem, pass);
-        c.save_act = kSave ? (pass ? p.save_act_f : p.save_act_c) : nullptr;
-        c.save_d = kSave ? (pass ? p.save_d_f : p.save_d_c) : nullptr;
-        c.save_n = static_cast<long long>(p.n_rays) * S;
-        if (!sigma_only) {
-          // per-ray direction bias: b_dir + W_dir[:, 256:283] . dir_embedded   (fp32)
-          if (t < 256) {
-            const int r = t >> 7, n = t & 127;
-            const float* wd = c.f32 + kF32WDirPart + n;           // [j][n]: coalesced over n
-            float wv[27];
+        const float* f32 = reinterpret_cast<const float*>(blob + kHalfRegionBytes);
+        const float* cst = consts_ptr(smem, pass);
+        for (int e = ht; e < 2 * kDirW; e += kHelperThreads) {
+          const int r = e >> 7, n = e & 127;
+          const float* wd = f32 + kF32WDirPart + n;           // [j][n]: coalesced over n
+          float acc = cst[kF32Bias + 8 * 256 + n];
 #pragma unroll
-            for (int j = 0; j < 27; ++j) wv[j] = __ldg(wd + j * 128);
-            float acc = c.cst[kF32Bias + 8 * 256 + n];
-#pragma unroll
-            for (int j = 0; j < 27; ++j) acc = fmaf(wv[j], sc->direnc[r][j], acc);
-            sc->dirbias[r][n] = acc;
-          }
-          NERFB200_TL_MARK(c.tl, 0, 27);
-          epi_bar();
-        }
-        for (int tile = 0; tile < tiles; ++tile) {
-          const int gr = tile * 128 + c.row;
-          const int r = gr / S;
-          NERFB200_TL_MARK(c.tl, 0, 10);
-          encode_row(enc, c.row, c.part, &sc->ray[r][0], &sc->ray[r][3], sc->z[gr]);
-          const long long grow = (r == 0 || valid1) ? static_cast<long long>(rid[r]) * S + (gr - r * S) : -1;
-          c.save_row = grow;
-          float sig_part, rgb_part[3];
-          epi_run_tile<kSave>(c, sigma_only, sc->dirbias[r], nullptr, sig_part, rgb_part);
-          sc->sig_part[c.part][c.row] = sig_part;
-          if (!sigma_only) {
-            sc->rgb_part[c.part][0][c.row] = rgb_part[0];
-            sc->rgb_part[c.part][1][c.row] = rgb_part[1];
-            sc->rgb_part[c.part][2][c.row] = rgb_part[2];
-          }
-          epi_bar();
-          // combine the column groups' partial head sums: group 0 -> sigma, groups 1..3 -> r, g, b
-          if (c.part == 0) {
-            float sg = c.cst[kF32BSigma];
-#pragma unroll
-            for (int q = 0; q < kColSplit; ++q) sg += sc->sig_part[q][c.row];
-            sc->sigma[gr] = sg;
-            if (kSave && grow >= 0) {
-              float* ss = pass ? p.save_sig_f : p.save_sig_c;
-              if (ss != nullptr) ss[grow] = sg;
-            }
-          }
-          if (!sigma_only) {
-            for (int ch = c.part - (kColSplit == 4 ? 1 : 0); ch < 3 && ch >= 0; ch += (kColSplit == 4 ? 3 : 1)) {
-              if (kColSplit == 2 && c.part != 0) break;
-              float pre = c.cst[kF32BRgb + ch];
-#pragma unroll
-              for (int q = 0; q < kColSplit; ++q) pre += sc->rgb_part[q][ch][c.row];
-              const float col = sigmoid_ref(pre);
-              sc->rgb[ch][gr] = col;
-              if (kSave && grow >= 0) {
-                float* sr = pass ? p.save_rgb_f : p.save_rgb_c;
-                if (sr != nullptr) sr[grow * 3 + ch] = col;
-              }
-            }
-          }
-          epi_bar();
-        }
-        // ---- compositing: warp r renders ray r
-        NERFB200_TL_MARK(c.tl, 0, 20);
-        if (warp < 2) {
-          const int r = warp;
-          const float* nz = nullptr;
-          if (p.noise_std > 0.f)
-            nz = (pass ? p.noise_fine : p.noise_coarse) + static_cast<long long>(rid[r]) * S;
-          const RayOut o = composite_ray(lane, S, sc->z + r * S, sc->sigma + r * S, sc->rgb[0] + r * S,
-                                         sc->rgb[1] + r * S, sc->rgb[2] + r * S, nz, p.noise_std,
-                                         sc->dnorm[r], !sigma_only, sc->sigma + r * S);
-          __syncwarp();
-          NERFB200_TL_MARK(c.tl, 0, 22);
-          const bool wr = (r == 0) || valid1;
-          if (wr) {
-            const long long ri = rid[r];
-            float* wout = pass ? p.weights_fine : p.weights_coarse;
-            if (wout != nullptr)
-              for (int i = lane; i < S; i += 32) wout[ri * S + i] = sc->sigma[r * S + i];
-            if (lane == 0) {
-              float add = (p.white_back != 0) ? __fsub_rn(1.f, o.opac) : 0.f;
-              if (pass == 0) {
-                p.opacity_coarse[ri] = o.opac;
-                if (!sigma_only) {
-                  p.rgb_coarse[3 * ri + 0] = o.r + add;
-                  p.rgb_coarse[3 * ri + 1] = o.g + add;
-                  p.rgb_coarse[3 * ri + 2] = o.b + add;
-                  p.depth_coarse[ri] = o.depth;
-                }
-              } else {
-                p.opacity_fine[ri] = o.opac;
-                p.rgb_fine[3 * ri + 0] = o.r + add;
-                p.rgb_fine[3 * ri + 1] = o.g + add;
-                p.rgb_fine[3 * ri + 2] = o.b + add;
-                p.depth_fine[ri] = o.depth;
-              }
-            }
-          }
-          NERFB200_TL_MARK(c.tl, 0, 23);
-          // ---- hierarchical resampling, part 1 (models/rendering.py:28-33): pdf -> cdf
-          if (pass == 0 && fine) pdf_to_cdf_ray(lane, Sc, sc->sigma + r * Sc, sc->cdf[r]);
-          NERFB200_TL_MARK(c.tl, 0, 24);
-        }
-        epi_bar();
-        NERFB200_TL_MARK(c.tl, 0, 21);
-        if (pass == 0 && fine) {
-          // ---- part 2 (:36-54): one u per thread -> inverse-CDF depth; u sorted first when random
-          if (t < 2 * K) {
-            const int r = t / K, j = t - r * K;
-            float uj;
-            int slot = j;
-            if (p.perturb > 0.f) {
-              const float* ur = p.u_rand + static_cast<long long>(rid[r]) * K;
-              uj = __ldg(ur + j);
-              slot = 0;
-#pragma unroll 8
-              for (int q = 0; q < K; ++q) {
-                const float uq = __ldg(ur + q);
-                slot += (uq < uj) || (uq == uj && q < j);
-              }
-            } else {
-              uj = linspace01(j, K);
-            }
-            sc->znew[r][slot] = inverse_cdf(Sc, sc->zc[r], sc->cdf[r], uj);
-          }
-          epi_bar();
-          // ---- merge: z_fine = sort(cat(z_coarse, z_new)) (:229) as a rank computation:
-          // position = number of elements that are smaller, ties broken by index in the
-          // concatenation (any tie order gives the same sorted VALUES, which is all torch.sort's
-          // output carries).  Both lists are sorted except for possible 1-ulp inversions from
-          // rounding, so every element first checks its predecessor; if no inversion exists
-          // anywhere (the common case) ranks come from two binary searches, otherwise from
-          // exhaustive counting.  Both paths give identical results on sorted input.
-          {
-            bool inv = false;
-            for (int e = t; e < 2 * Sf; e += kEpiThreads) {
-              const int r = e / Sf, i = e - r * Sf;
-              if (i != 0 && i != Sc)
-                inv |= (i < Sc) ? (sc->zc[r][i] < sc->zc[r][i - 1]) : (sc->znew[r][i - Sc] < sc->znew[r][i - Sc - 1]);
-            }
-            int any_inv;
-            asm volatile(
-                "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
-                "barrier.red.or.pred p, 1, %2, q;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                : "=r"(any_inv) : "r"(static_cast<int>(inv)), "n"(kEpiThreads) : "memory");
-            for (int e = t; e < 2 * Sf; e += kEpiThreads) {
-              const int r = e / Sf, i = e - r * Sf;
-              const float* zc = sc->zc[r];
-              const float* zn = sc->znew[r];
-              const float v = (i < Sc) ? zc[i] : zn[i - Sc];
-              int rank;
-              if (!any_inv) {
-                // lower_bound in the other list for coarse elements (coarse first on ties),
-                // upper_bound for new elements
-                const float* other = (i < Sc) ? zn : zc;
-                int lo = 0, hi = (i < Sc) ? K : Sc;
-                while (lo < hi) {
-                  const int mid = (lo + hi) >> 1;
-                  const float x = other[mid];
-                  const bool right = (i < Sc) ? (x < v) : (x <= v);
-                  if (right) lo = mid + 1; else hi = mid;
-                }
-                rank = lo + ((i < Sc) ? i : i - Sc);
-              } else {
-                rank = 0;
-#pragma unroll 8
-                for (int q = 0; q < Sc; ++q) rank += (zc[q] < v) || (zc[q] == v && q < i);
-#pragma unroll 8
-                for (int q = 0; q < K; ++q) rank += (zn[q] < v) || (zn[q] == v && (q + Sc) < i);
-              }
-              sc->z[r * Sf + rank] = v;
-            }
-          }
-          NERFB200_TL_MARK(c.tl, 0, 25);
-          epi_bar();
-          if (p.z_fine != nullptr) {
-            for (int e = t; e < 2 * Sf; e += kEpiThreads) {
-              const int r = e / Sf, i = e - r * Sf;
-              if (r == 0 || valid1) p.z_fine[static_cast<long long>(rid[r]) * Sf + i] = sc->z[e];
-            }
-          }
+          for (int j = 0; j < 27; ++j) acc = fmaf(__ldg(wd + j * 128), gs.direnc[r][j], acc);
+          gs.dirbias[pass][r][n] = acc;
         }
       }
+    };
+
+    while (seq.next(tl)) {
+      int need = tl.q - 2;
+      if (tl.pass == 1 && tl.tile == 0) {
+        const int slot = tl.g % kGroupSlots;
+        need = max(need, slot == 0 ? cpos0 : (slot == 1 ? cpos1 : cpos2));
+      }
+      while (consumed <= need) {
+        cons_seq.next(tc);
+        consume(tc);
+        ++consumed;
+      }
+      // ---- prepare tile q: (new group: set-up) + positional encoding into ENC buffer q & 1
+      const int b = tl.q & 1;
+      GroupState& gs = sc->gs[tl.g % kGroupSlots];
+      if (tl.pass == 0) {
+        if (tl.tile == 0) setup_group(tl.g);
+        if (tl.last) {
+          const int slot = tl.g % kGroupSlots;
+          if (slot == 0) cpos0 = tl.q; else if (slot == 1) cpos1 = tl.q; else cpos2 = tl.q;
+        }
+      }
+      {
+        const int S = tl.pass ? Sf : Sc;
+        uint8_t* enc = smem + (b ? kSmemEnc1 : kSmemEnc);
+#pragma unroll 1
+        for (int row = ht; row < 128; row += kHelperThreads) {
+          const int gr = tl.tile * 128 + row;
+          const int r = gr / S;
+          const float zval = tl.pass ? gs.z[gr] : gs.zc[r][gr - r * S];
+#pragma unroll 1
+          for (int part = 0; part < kColSplit; ++part) encode_row(enc, row, part, &gs.ray[r][0], &gs.ray[r][3], zval);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sc->enc_full[b]));
     }
-    NERFB200_TL_MARK(c.tl, 0, 99);
+    while (cons_seq.next(tc)) consume(tc);
   }
   engine_teardown(bars);
 }
