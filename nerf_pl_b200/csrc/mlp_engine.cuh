@@ -253,9 +253,19 @@ __device__ __forceinline__ void mma_tile_t(RingState& rs, MmaPhases& ph, uint8_t
     // warp arrives on it only after its tcgen05.ld of the whole accumulator has completed.  This
     // also covers layer 4, whose first slice (encoded input) needs no A columns at all.
     if (l == 0) {
+#ifdef NERFB200_TIMELINE
+      const long long w0 = clock64();
+#endif
       mbar_wait(smem_u32(&bars->d_free), ph.d_free, 3);
       ph.d_free ^= 1;
+#ifdef NERFB200_TIMELINE
+      const long long w1 = clock64();
+#endif
       if (enc_bar != 0) mbar_wait(enc_bar, enc_parity, 9);
+#ifdef NERFB200_TIMELINE
+      tl_val(tl, 1, 600, w1 - w0);
+      tl_val(tl, 1, 601, clock64() - w1);
+#endif
     } else {
       mbar_wait(akb0, ph.a_kb, 6);
     }
@@ -320,6 +330,13 @@ struct EpiCtx {
   __half* save_d;                  // [save_n][128] fp16
   long long save_n;                // samples in the pass (rows per layer)
   long long save_row;              // this thread's global sample row, -1 = padding row
+  // Accumulator release.  false: d_free is signalled at tile start (the epilogue also wrote the
+  // ENC tile).  true (render kernel: ENC comes from the helper warps): d_free is signalled as soon
+  // as the LAST layer of a tile has been read out of tensor memory, so the next tile's first
+  // layer runs while this tile's heads are still being evaluated; `prime` = signal once at the
+  // start of the very first tile.
+  bool early = false;
+  bool prime = true;
 };
 
 __device__ __forceinline__ void epi_bar() {   // all 256 epilogue threads
@@ -333,6 +350,12 @@ __device__ __forceinline__ void epi_signal_tile_start(EpiCtx& c) {
   __syncwarp();
   if (c.lane == 0) mbar_arrive(smem_u32(kPipelinedHandover ? &c.bars->d_free : &c.bars->a_ready));
   NERFB200_TL_MARK(c.tl, 0, 6);
+}
+// This warp has read its share of the tile's last accumulator: the next tile may overwrite it.
+__device__ __forceinline__ void epi_release_accumulator(EpiCtx& c) {
+  tc_fence_before();
+  __syncwarp();
+  if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->d_free));
 }
 // Sequential hand-over: this warp's accumulator columns are drained and its A columns stored.
 __device__ __forceinline__ void epi_signal_a_ready(EpiCtx& c, bool smem_written) {
@@ -470,6 +493,7 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) tmem_ld16(c.tmem_row + kTmemD + kb * 64 + c.part * 16, r[kb]);
     tmem_ld_wait();
+    if (!kStore && c.early) epi_release_accumulator(c);
     NERFB200_TL_MARK(c.tl, 0, 3);
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) {
@@ -548,6 +572,7 @@ __device__ __forceinline__ void epi_dir(EpiCtx& c, const float* dbias, const flo
 #pragma unroll
   for (int u = 0; u < kChunks; ++u) tmem_ld32(c.tmem_row + kTmemD + n0 + 32 * u, r[u]);
   tmem_ld_wait();
+  if (c.early) epi_release_accumulator(c);
 #pragma unroll
   for (int u = 0; u < kChunks; ++u) {
 #pragma unroll
@@ -591,7 +616,8 @@ __device__ __forceinline__ void epi_run_tile(EpiCtx& c, bool sigma_only, const f
   sig_part = 0.f;
   rgb_part[0] = rgb_part[1] = rgb_part[2] = 0.f;
   float dummy = 0.f;
-  epi_signal_tile_start(c);
+  if (!c.early || c.prime) epi_signal_tile_start(c);
+  c.prime = false;
   for (int l = 0; l < 7; ++l) epi_hidden<true, false, true, kSave>(c, l, bias + l * 256, nullptr, dummy);
   if (sigma_only) {
     epi_hidden<true, true, false, kSave>(c, 7, bias + 7 * 256, wsig, sig_part);

@@ -309,13 +309,18 @@ def step_tlsum():
     per = {}
     for (t0, v0), v1 in zip(zip(tags, starts), starts[1:]):
         per.setdefault(t0 - 100, []).append(v1 - v0)
+    wd = [v for tg, v in mma if tg == 600]
+    we = [v for tg, v in mma if tg == 601]
+    if wd:
+        print(f"MMA tile start: wait d_free mean {np.mean(wd):.0f} max {max(wd)}; wait enc_full mean {np.mean(we):.0f} max {max(we)}  (n={len(wd)})")
+        print("  per tile (d_free, enc):", list(zip(wd, we))[:24])
     print("MMA per layer: start->next start mean | issue span | wait full | wait a_kb (cycles)")
     for l in sorted(lay):
         d = lay[l]
         print(f"  L{l}: period {np.mean(per.get(l, [0])):7.0f} issue {np.mean(d.get('issue', [0])):7.0f} "
               f"w_full {np.mean(d.get('w_full', [0])):7.0f} (max {max(d.get('w_full', [0]))}) w_akb {np.mean(d.get('w_akb', [0])):7.0f}")
     if os.environ.get("TL_RAW"):
-        ev = [(v, "EPI", tg) for tg, v in epi if tg != 90] + [(v, "MMA", tg) for tg, v in mma if tg < 300 or tg >= 500]
+        ev = [(v, "EPI", tg) for tg, v in epi if tg != 90] + [(v, "MMA", tg) for tg, v in mma if tg < 300 or 500 <= tg < 600]
         ev.sort()
         lo = int(os.environ.get("TL_RAW_LO", "150"))
         t0 = ev[lo][0]
