@@ -113,6 +113,19 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) of one bench-shaped render_rays launch from the committed ncu
+    --set full capture (profiles/*_ncu_traffic.json, written by tools/summarize_ncu.py); None if absent."""
+    import glob
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_ncu_traffic.json")))
+    if not files:
+        return None
+    try:
+        return float(json.load(open(files[-1]))["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -332,7 +345,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": BATCH * 8 * 4, "d2h_bytes_per_step": BATCH * 3 * 4},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                          "kernel": "render_rays_kernel", "kernel_ms": kern_ms,
                          "flop_per_launch": BATCH * FLOP_PER_RAY_TRAIN},
             "cpu_baseline": {"value": cpu_v, "unit": "ray-samples/s", "cores": cores, "kind": "port",

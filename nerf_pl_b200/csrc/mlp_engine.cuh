@@ -181,6 +181,11 @@ __device__ __forceinline__ void produce_tile(RingState& rs, uint8_t* smem, Barri
   for (int i = 0; i < n256; ++i) {
     mbar_wait(smem_u32(&bars->empty[rs.stage]), rs.phase ^ 1, 1);
     const uint32_t full = smem_u32(&bars->full[rs.stage]);
+#ifdef NERFB200_SANITIZE
+    // the previous copy into this stage has landed (implied by `empty`, which the tensor core
+    // signals after reading it; stated explicitly for racecheck, which cannot see tcgen05.commit)
+    mbar_wait(full, rs.phase ^ 1, 1);
+#endif
     const uint32_t dst = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
 #ifdef NERFB200_EXP_NOLOAD
     if (rs.filled >= static_cast<uint32_t>(kStages)) { mbar_arrive(full); rs.advance(); continue; }
@@ -197,6 +202,9 @@ __device__ __forceinline__ void produce_tile(RingState& rs, uint8_t* smem, Barri
     for (int i = 0; i < n128; ++i) {
       mbar_wait(smem_u32(&bars->empty[rs.stage]), rs.phase ^ 1, 2);
       const uint32_t full = smem_u32(&bars->full[rs.stage]);
+#ifdef NERFB200_SANITIZE
+      mbar_wait(full, rs.phase ^ 1, 2);
+#endif
       const uint32_t dst = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
 #ifdef NERFB200_EXP_NOLOAD
       if (rs.filled >= static_cast<uint32_t>(kStages)) { mbar_arrive(full); rs.advance(); continue; }

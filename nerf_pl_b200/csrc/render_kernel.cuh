@@ -279,6 +279,14 @@ constexpr int kHelperWarps = 2;                  // 20 warps x 96 registers fill
 constexpr int kHelperThreads = kHelperWarps * 32;
 constexpr int kRenderThreads = (kHelperWarp0 + kHelperWarps) * 32;   // 640
 static_assert(kHelperWarps >= 2, "compositing uses one helper warp per ray of the group");
+// Hand-over arrivals: one elected lane per warp after __syncwarp() (production), or every writing
+// thread itself (-DNERFB200_SANITIZE: compute-sanitizer's racecheck follows per-thread
+// arrive -> wait chains but not "other lanes' stores -> __syncwarp -> elected arrive").
+#ifdef NERFB200_SANITIZE
+constexpr bool kHandoffPerThread = true;
+#else
+constexpr bool kHandoffPerThread = false;
+#endif
 constexpr int kGroupSlots = 3;                   // groups in flight: g-1 (fine), g (resampling), g+1 (coarse)
 
 struct alignas(16) GroupState {
@@ -299,8 +307,9 @@ struct alignas(16) RenderScratch {
   Barriers bars;
   uint64_t enc_full[2];
   uint64_t out_full[2];
-  float sig_part[kColSplit][128];           // [column group][row] partial sigma-head sums
-  float rgb_part[kColSplit][3][128];
+  float sig_part[2][kColSplit][128];        // [tile buffer][column group][row] partial sigma-head sums
+  float rgb_part[2][kColSplit][3][128];     //   (double-buffered: the epi_bar of tile q+1 separates the reads of tile q
+                                            //    from the writes of tile q+2)
   float out_sigma[2][128];                  // [tile buffer][row]
   float out_rgb[2][3][128];
   GroupState gs[kGroupSlots];
@@ -346,8 +355,8 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
   Barriers* bars = &sc->bars;
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
-      mbar_init(smem_u32(&sc->enc_full[b]), kHelperWarps);
-      mbar_init(smem_u32(&sc->out_full[b]), kEpiWarps);
+      mbar_init(smem_u32(&sc->enc_full[b]), kHandoffPerThread ? kHelperThreads : kHelperWarps);
+      mbar_init(smem_u32(&sc->out_full[b]), kHandoffPerThread ? kEpiThreads : kEpiWarps);
     }
   }
   if (!engine_setup(smem, bars)) {
@@ -427,18 +436,18 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
       mbar_wait(smem_u32(&sc->enc_full[b]), static_cast<uint32_t>(tl.q >> 1) & 1u, 7);
       float sig_part, rgb_part[3];
       epi_run_tile<kSave>(c, sigma_only, gs.dirbias[pass][r], nullptr, sig_part, rgb_part);
-      sc->sig_part[c.part][c.row] = sig_part;
+      sc->sig_part[b][c.part][c.row] = sig_part;
       if (!sigma_only) {
-        sc->rgb_part[c.part][0][c.row] = rgb_part[0];
-        sc->rgb_part[c.part][1][c.row] = rgb_part[1];
-        sc->rgb_part[c.part][2][c.row] = rgb_part[2];
+        sc->rgb_part[b][c.part][0][c.row] = rgb_part[0];
+        sc->rgb_part[b][c.part][1][c.row] = rgb_part[1];
+        sc->rgb_part[b][c.part][2][c.row] = rgb_part[2];
       }
       epi_bar();
       // combine the column groups' partial head sums: group 0 -> sigma, groups 1..3 -> r, g, b
       if (c.part == 0) {
         float sg = c.cst[kF32BSigma];
 #pragma unroll
-        for (int q = 0; q < kColSplit; ++q) sg += sc->sig_part[q][c.row];
+        for (int q = 0; q < kColSplit; ++q) sg += sc->sig_part[b][q][c.row];
         sc->out_sigma[b][c.row] = sg;
         if (kSave && grow >= 0) {
           float* ss = pass ? p.save_sig_f : p.save_sig_c;
@@ -448,7 +457,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
         const int ch = c.part - 1;
         float pre = c.cst[kF32BRgb + ch];
 #pragma unroll
-        for (int q = 0; q < kColSplit; ++q) pre += sc->rgb_part[q][ch][c.row];
+        for (int q = 0; q < kColSplit; ++q) pre += sc->rgb_part[b][q][ch][c.row];
         const float col = sigmoid_ref(pre);
         sc->out_rgb[b][ch][c.row] = col;
         if (kSave && grow >= 0) {
@@ -456,8 +465,12 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
           if (sr != nullptr) sr[grow * 3 + ch] = col;
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&sc->out_full[b]));
+      if (kHandoffPerThread) {
+        mbar_arrive(smem_u32(&sc->out_full[b]));
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sc->out_full[b]));
+      }
     }
   } else if (warp >= kHelperWarp0) {
     // ================================== helper warps ===================================
@@ -704,8 +717,12 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
         }
       }
       fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&sc->enc_full[b]));
+      if (kHandoffPerThread) {
+        mbar_arrive(smem_u32(&sc->enc_full[b]));
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sc->enc_full[b]));
+      }
     }
     while (cons_seq.next(tc)) consume(tc);
   }

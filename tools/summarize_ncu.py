@@ -36,6 +36,32 @@ if os.path.exists(lp):
         out.append(f"\nrender_rays_kernel: {len(rr)} launches, mean {sum(rr) / len(rr) / 1e3:.1f} us "
                    f"(1024 rays x 192 samples each; excludes the 256 MiB L2-flush fill between bench steps).\n")
 
+# bench-shaped launch (1024 rays): DRAM traffic per launch for bench.py's roofline.traffic
+bp = os.path.join(ROOT, "gpurun_out", f"prof_{tag}_bench1024.ncu-rep")
+if os.path.exists(bp):
+    import json
+    raw = subprocess.run(["ncu", "-i", bp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    d = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
+
+    def to_bytes(key):
+        u, v = d[key]
+        f = float(v.replace(",", ""))
+        return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+    rd, wr = to_bytes("dram__bytes_read.sum"), to_bytes("dram__bytes_write.sum")
+    info = {"kernel": "render_rays_kernel", "launch": "1024 rays, 64+64, training-mode forward (bench.py workload), L2 cold",
+            "dram_bytes_read": rd, "dram_bytes_write": wr, "traffic_bytes_per_launch": rd + wr,
+            "gpu_time_us": float(d["gpu__time_duration.sum"][1].replace(",", "")) * {"us": 1, "ms": 1e3, "ns": 1e-3}.get(d["gpu__time_duration.sum"][0], 1),
+            "tensor_pipe_active_pct": float(d["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"][1]),
+            "source": f"profiles/{tag}_ncu_summary.md (ncu --set full --clock-control none, {os.path.basename(bp)})"}
+    json.dump(info, open(os.path.join(ROOT, "profiles", f"{tag}_ncu_traffic.json"), "w"), indent=1)
+    out.append(f"## Bench-shaped launch ({os.path.basename(bp)}: 1024 rays, L2 flushed before the launch)\n")
+    out.append("| metric | value |\n|---|---|")
+    for k, v in info.items():
+        out.append(f"| {k} | {v} |")
+    out.append("")
+
 rp = os.path.join(ROOT, "gpurun_out", f"prof_{tag}_render.ncu-rep")
 if os.path.exists(rp):
     raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
