@@ -207,7 +207,7 @@ def run_reference(args):
     ms = n_rays * SAMPLES_PER_RAY / v * 1e3
     sample = (f"{n_rays} rays of the 1024-ray batch per step (64+128 samples/ray), numpy/BLAS on {cores} threads "
               f"(fastest of 4..{os.cpu_count()} on this host)")
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "ray-samples/sec (coarse+fine)", "value": v, "unit": "ray-samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -353,12 +353,30 @@ def run_b200(args):
                                        f"{os.cpu_count()} host threads (fastest setting)"},
             "wall_s_timed_region": t_wall,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the process's original stdout; everything else that libraries
+    print on fd 1 (e.g. NCCL's version banner) has been redirected to stderr by main()."""
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
