@@ -221,7 +221,7 @@ def workload_config(n_gpus):
     return {"workload": "blender_lego_400x400 N_samples=64 N_importance=64 batch_size=1024/GPU, "
                         "render_rays training-mode forward (perturb=1, noise_std=0, white_back, coarse rgb)",
             "rays_per_step_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "samples_per_ray": SAMPLES_PER_RAY,
-            "parallelism": f"ray-sharded dp{n_gpus}, all_gather of rgb_fine" if n_gpus > 1 else "single GPU",
+            "parallelism": f"ray-sharded dp{n_gpus}, weights replicated, no data-path collective" if n_gpus > 1 else "single GPU",
             "l2": "flushed between timed steps (256 MiB write)"}
 
 
@@ -256,14 +256,10 @@ def run_b200(args):
     host_rays = [torch.from_numpy(blender_rays(BATCH, 100 * rank + i)).pin_memory() for i in range(n_batches)]
     dev_rays = [r.to(dev) for r in host_rays]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    gather = [torch.empty(BATCH, 3, device=dev) for _ in range(world)] if world > 1 else None
-
     def step(rays):
         out = nb.render_rays(models, emb, rays, N_SAMPLES, False, 1.0, 0.0, N_IMPORTANCE, 1024 * 32, True,
                              test_time=False)
-        if world > 1:
-            dist.all_gather(gather, out["rgb_fine"])
-        return out
+        return out       # rays are independent: no collective on the path
 
     def barrier():
         if world > 1:
