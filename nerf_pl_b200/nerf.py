@@ -26,11 +26,16 @@ _PARAM_ORDER = (
 def nerf_parameters(model: nn.Module) -> List[torch.Tensor]:
     """The 24 parameter tensors of a NeRF in state_dict order (works for this package's NeRF and,
     by duck typing, for the reference's own ``models.nerf.NeRF``)."""
+    # plain dict look-ups: nn.Module.__getattr__ and Sequential.__getitem__ are Python-level and
+    # this runs on every render_rays call (the packed-image cache key)
     out = []
+    mods = model._modules
     for name, idx in _PARAM_ORDER:
-        mod = getattr(model, name)
-        lin = mod[idx] if idx is not None else mod
-        out += [lin.weight, lin.bias]
+        mod = mods[name]
+        lin = mod._modules[str(idx)] if idx is not None else mod
+        ps = lin._parameters
+        out.append(ps["weight"])
+        out.append(ps["bias"])
     return out
 
 
@@ -54,7 +59,7 @@ class PackedWeights:
 
     def get(self, model: nn.Module) -> torch.Tensor:
         params = nerf_parameters(model)
-        key = tuple((p.data_ptr(), p._version, p.device) for p in params)
+        key = tuple([(p.data_ptr(), p._version) for p in params])   # data_ptr also changes with the device
         if self.blob is not None and key == self.key:
             return self.blob
         for p, shp in zip(params, _EXPECTED_SHAPES):

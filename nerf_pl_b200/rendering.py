@@ -202,13 +202,15 @@ def render_rays(models: List[torch.nn.Module],
 
     f32 = dict(dtype=torch.float32, device=dev)
     coarse_rgb = not test_time
+    # one allocation, contiguous (n,3) / (n,) views of it
+    flat = torch.empty(10 * n, **f32)
     out = {
-        "rgb_coarse": torch.empty(n, 3, **f32) if coarse_rgb else None,
-        "depth_coarse": torch.empty(n, **f32) if coarse_rgb else None,
-        "opacity_coarse": torch.empty(n, **f32),
-        "rgb_fine": torch.empty(n, 3, **f32) if K > 0 else None,
-        "depth_fine": torch.empty(n, **f32) if K > 0 else None,
-        "opacity_fine": torch.empty(n, **f32) if K > 0 else None,
+        "rgb_coarse": flat[0:3 * n].view(n, 3) if coarse_rgb else None,
+        "depth_coarse": flat[3 * n:4 * n] if coarse_rgb else None,
+        "opacity_coarse": flat[4 * n:5 * n],
+        "rgb_fine": flat[5 * n:8 * n].view(n, 3) if K > 0 else None,
+        "depth_fine": flat[8 * n:9 * n] if K > 0 else None,
+        "opacity_fine": flat[9 * n:10 * n] if K > 0 else None,
     }
     want_extras = extras or needs_graph
     z_fine = torch.empty(n, S_f, **f32) if (want_extras and K > 0) else None
@@ -229,8 +231,11 @@ def render_rays(models: List[torch.nn.Module],
         depth_fine=_ptr(out["depth_fine"]), opacity_fine=_ptr(out["opacity_fine"]),
         z_fine=_ptr(z_fine), weights_coarse=_ptr(w_c), weights_fine=_ptr(w_f),
         status=None, max_ctas=0)
-    with torch.cuda.device(dev):
+    if torch.cuda.current_device() == dev.index:
         _lib.check(lib.nerfb200_render_rays(ctypes.byref(args), _stream_ptr()), "nerfb200_render_rays")
+    else:
+        with torch.cuda.device(dev):
+            _lib.check(lib.nerfb200_render_rays(ctypes.byref(args), _stream_ptr()), "nerfb200_render_rays")
 
     if needs_graph:
         return _render_with_graph(models, embeddings, rays_c, S_c, K, bool(use_disp), perturb, noise_std,
