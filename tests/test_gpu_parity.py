@@ -196,6 +196,50 @@ def test_full_image_properties(models, emb, ws, dev):
         assert mx < tol_for(k)
 
 
+@pytest.mark.parametrize("K,test_time,perturb,use_disp,white_back", [
+    (128, False, 1.0, False, True),     # three fine tiles per group, training-mode coarse pass, rank-sorted u
+    (64, False, 1.0, True, False),      # disparity sampling
+    (0, False, 0.0, False, True),       # coarse only: every tile is a coarse tile
+    (64, True, 0.0, False, False),
+])
+def test_tile_pipeline_is_invisible(K, test_time, perturb, use_disp, white_back, models, emb, ws, dev):
+    """The render kernel pipelines tiles of different ray groups (C(g+1) before F(g), helper warps
+    working one tile ahead, double-buffered hand-over).  None of that may show: a launch in which
+    every CTA walks 7-8 groups (odd counts end in single-ray groups) must equal, bit for bit, the
+    same rays rendered in launches so small that every CTA has a single group - and the oracle."""
+    import bench
+    n = 148 * 14 + 3
+    rays_np = bench.blender_rays(n, 9)
+    rays = torch.from_numpy(rays_np).to(dev)
+    g = torch.Generator(device="cpu").manual_seed(4)
+    rnd = {}
+    if perturb > 0:
+        rnd["perturb_rand"] = torch.rand(n, 64, generator=g).to(dev)
+        if K > 0:
+            rnd["u_rand"] = torch.rand(n, K, generator=g).to(dev)
+
+    def run(lo, hi):
+        r = {k: v[lo:hi] for k, v in rnd.items()}
+        return nb.render_rays(models, emb, rays[lo:hi], 64, use_disp, perturb, 0.0, K, 32768, white_back,
+                              test_time=test_time, randoms=r, extras=True)
+    with torch.no_grad():
+        whole = run(0, n)
+        step = 290           # <= 2 rays per CTA: one group per CTA, nothing to pipeline
+        parts = [run(i, min(i + step, n)) for i in range(0, n, step)]
+    torch.cuda.synchronize()
+    for k in whole:
+        cat = torch.cat([p_[k] for p_ in parts], 0)
+        assert torch.isfinite(whole[k]).all()
+        assert torch.equal(cat, whole[k]), f"tile pipelining changed {k}"
+    idx = np.arange(0, n, 29)
+    rn = {k: v[torch.from_numpy(idx).to(dev)].cpu().numpy() for k, v in rnd.items()}
+    ref = orc.render_rays(ws, rays_np[idx], 64, use_disp, perturb, 0.0, K, white_back, test_time, randoms=rn)
+    for k, v in ref.items():
+        mx, p999, mean = cases.error_stats(whole[k][torch.from_numpy(idx).to(dev)].cpu().numpy(), v)
+        print(f"pipeline K={K} {k}: max {mx:.2e}")
+        assert mx < tol_for(k)
+
+
 def test_host_buffer_entry_matches_device_path(models, emb, dev):
     """nerfb200_render_rays_host (host pointers, copies inside) == device-pointer path, bitwise."""
     lib = _lib.load()
