@@ -127,7 +127,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const MlpParam
     c.part = warp >> 2;
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     c.d_phase = 0;
-    c.flags = 0;
     c.save_act = nullptr; c.save_d = nullptr; c.save_n = 0; c.save_row = -1;
     c.tl = nullptr;
     c.f32 = reinterpret_cast<const float*>(p.net + kHalfRegionBytes);
@@ -352,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_probe_kernel(const float* __
     }
   } else if (warp == kMmaWarp) {
     if (lane == 0) {
-      mbar_wait(smem_u32(kPipelinedHandover ? &bars->d_free : &bars->a_ready), 0, 12);
+      mbar_wait(smem_u32(&bars->d_free), 0, 12);
       tc_fence_after();
       mbar_wait(smem_u32(&bars->full[0]), 0, 13);
       tc_fence_after();
@@ -374,7 +373,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_probe_kernel(const float* __
     c.part = warp >> 2;
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     c.d_phase = 0;
-    c.flags = 0;
     c.save_act = nullptr; c.save_d = nullptr; c.save_n = 0; c.save_row = -1;
     c.tl = nullptr;
     if (mode == 0) {

@@ -12,14 +12,14 @@
 //                   rewritten by the epilogue once the layer's MMAs have retired
 //   warps 0..15 epilogue: warp w owns TMEM lanes 32(w&3).. and column group w>>2
 //   warp 16     weight producer: streams the packed 32 KiB K-slices (layout.h) through a
-//               5-stage ring with cp.async.bulk + mbarriers, up to 1.25 layers ahead
+//               3-stage ring with cp.async.bulk + mbarriers
 //   warp 17     MMA issuer (one thread): tcgen05.mma M=128, N=256|128, K=16; A from TMEM for
-//               hidden K blocks (139 cycles per K step measured, vs 129 from smem), from the
+//               hidden K blocks (128 cycles per K step when issued back to back), from the
 //               ENC shared-memory tile for the encoded-input slices
-//   smem also keeps the fp32 biases and head weights of both networks resident (25 KiB), so the
+//   smem also keeps the fp32 biases and head weights of both networks resident (24 KiB), so the
 //   epilogue reads them with broadcast LDS instead of L1/L2 loads
 //
-// Hand-over between layers (kPipelinedHandover): a tile has ONE accumulator, so its MMA and
+// Hand-over between layers: a tile has ONE accumulator, so its MMA and
 // epilogue cannot fully overlap, but the hand-over is pipelined at K-block granularity: every
 // epilogue warp first drains its 4 x 16 accumulator columns into registers (tcgen05.ld), then
 // converts the 16 columns belonging to K block 0, stores them (tcgen05.st) and arrives on
@@ -27,7 +27,7 @@
 // a_kb[0] completes (which also proves that every warp has drained the accumulator, so the first
 // MMA may overwrite it) while the warps are still converting blocks 1..3.
 // Measured alternatives are recorded in DESIGN.md section 4 (A in shared memory; N=128 split
-// accumulators; sequential hand-over).
+// accumulators; sequential hand-over; two tiles alternating on one accumulator).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -43,29 +43,18 @@ constexpr int kColsPer = 256 / kColSplit;     // accumulator columns per epilogu
 constexpr int kProducerWarp = kEpiWarps;
 constexpr int kMmaWarp = kEpiWarps + 1;
 constexpr int kThreads = (kEpiWarps + 2) * 32;   // 576
-// Where the hidden activations (the next layer's A operand) live:
-//   true : tensor memory (tcgen05.st, TS MMA 139 cyc/K-step; epilogue stores contend with the
-//          MMA's TMEM reads when the two overlap)
-//   false: shared memory (st.shared into the SWIZZLE_128B tile, SS MMA 129 cyc/K-step)
-constexpr bool kAInTmem = true;
-// Hand the accumulator / A operand over to the MMA issuer K block by K block while the epilogue
-// is still converting (true), or all at once when the epilogue is done (false).  Measured on
-// B200: overlapping does not pay - the tensor core's TMEM (or smem) operand reads and
-// the epilogue's stores share one port, each slows the other by the overlap.
-constexpr bool kPipelinedHandover = true;
 // Ring depth: 3, 4 and 5 stages measure the same (the weights come from L2 and one layer of
 // look-ahead is enough), so the ring takes 96 KiB and the rest of shared memory holds the second
 // ENC tile and the per-group state of the render kernel's helper warps.
 #ifndef NERFB200_STAGES
 #define NERFB200_STAGES 3
 #endif
-constexpr int kStages = kAInTmem ? NERFB200_STAGES : 3;
+constexpr int kStages = NERFB200_STAGES;
 constexpr int kTmemCols = 512;
 constexpr uint32_t kTmemD = 0, kTmemA = 256;
 
 constexpr uint32_t kSmemEnc = 0;                     // [128 x 64] fp16     16 KiB
-constexpr uint32_t kSmemA = 16384;                   // [4][128 x 64] fp16  64 KiB (only if !kAInTmem)
-constexpr uint32_t kSmemRing = kAInTmem ? 16384 : 81920;   // kStages x 32 KiB
+constexpr uint32_t kSmemRing = 16384;                // kStages x 32 KiB
 constexpr uint32_t kSmemEnc1 = kSmemRing + kStages * kSliceBytes256;      // second ENC tile (render kernel: double buffer)
 constexpr uint32_t kSmemConsts = kSmemEnc1 + 16384;                       // fp32 biases + heads of two networks
 constexpr uint32_t kConstFloats = kF32WDirPart;      // biases, sigma head, rgb head of one network
@@ -82,10 +71,10 @@ constexpr int kLayersSigma = 8;       // L1..L8
 struct Barriers {
   uint64_t full[kStages];
   uint64_t empty[kStages];
-  uint64_t a_ready;        // sequential hand-over: all epilogue warps -> MMA : "A written, D drained"
-                           //   (at tile start: "ENC tile written")
-  uint64_t d_free;         // pipelined hand-over: all epilogue warps -> MMA : "tile start: ENC written, D free"
-  uint64_t a_kb[4];        // pipelined hand-over: all warps -> MMA : "A columns of K block kb written"
+  uint64_t a_ready;        // not used by the engine (the microbenchmarks poll it as a barrier that never completes)
+  uint64_t d_free;         // all epilogue warps -> MMA : "the previous tile's accumulator is read out (and, when the
+                           //   epilogue writes the ENC tile itself, ENC is written)"
+  uint64_t a_kb[4];        // all epilogue warps -> MMA : "A columns of K block kb written"
                            //   (every warp has drained its accumulator columns before its first arrive)
   uint64_t d_ready;        // MMA -> epilogue : "accumulator complete"
   uint32_t tmem_base;
@@ -118,9 +107,6 @@ __device__ __forceinline__ void tl_val(Timeline* tl, int role, int tag, long lon
 
 struct RingState {
   uint32_t stage = 0, phase = 0;
-#ifdef NERFB200_EXP_NOLOAD
-  uint32_t filled = 0;      // timing experiment: only the first kStages slices are really fetched
-#endif
   __device__ __forceinline__ void advance() {
     if (++stage == kStages) { stage = 0; phase ^= 1; }
   }
@@ -187,10 +173,6 @@ __device__ __forceinline__ void produce_tile(RingState& rs, uint8_t* smem, Barri
     mbar_wait(full, rs.phase ^ 1, 1);
 #endif
     const uint32_t dst = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
-#ifdef NERFB200_EXP_NOLOAD
-    if (rs.filled >= static_cast<uint32_t>(kStages)) { mbar_arrive(full); rs.advance(); continue; }
-    ++rs.filled;
-#endif
     mbar_arrive_expect_tx(full, kSliceBytes256);
     const uint8_t* src = blob + static_cast<size_t>(i) * kSliceBytes256;
 #pragma unroll
@@ -206,10 +188,6 @@ __device__ __forceinline__ void produce_tile(RingState& rs, uint8_t* smem, Barri
       mbar_wait(full, rs.phase ^ 1, 2);
 #endif
       const uint32_t dst = smem_u32(smem + kSmemRing + rs.stage * kSliceBytes256);
-#ifdef NERFB200_EXP_NOLOAD
-      if (rs.filled >= static_cast<uint32_t>(kStages)) { mbar_arrive(full); rs.advance(); continue; }
-      ++rs.filled;
-#endif
       mbar_arrive_expect_tx(full, kSliceBytes128);
       const uint8_t* src = blob + kOffDir + static_cast<size_t>(i) * kSliceBytes128;
 #pragma unroll
@@ -242,7 +220,6 @@ struct MmaPhases { uint32_t d_free = 0, a_kb = 0; };   // a_kb: the 4 K-block ba
 template <bool kSigmaOnly, bool kDirSlice>
 __device__ __forceinline__ void mma_tile_t(RingState& rs, MmaPhases& ph, uint8_t* smem, Barriers* bars,
                                            Timeline* tl, uint32_t enc_off, uint32_t enc_bar, uint32_t enc_parity) {
-  static_assert(kPipelinedHandover && kAInTmem, "the issue loop implements the K-block hand-over with the TMEM operand");
   const uint32_t tmem = bars->tmem_base;
   const uint32_t d_tmem = tmem + kTmemD;
   const uint32_t a_tmem = tmem + kTmemA;
@@ -331,7 +308,6 @@ struct EpiCtx {
   int part;                        // 0..kColSplit-1 : which accumulator column group this warp drains
   int lane;
   Timeline* tl;                    // non-null only for the one traced thread
-  unsigned flags;                  // experiment switches (0 in production)
   // training mode ("save"): post-activation outputs of layers 1..8 and of the direction layer
   // are also written to HBM for the backward pass
   __half* save_act;                // [8][save_n][256] fp16 (null = off)
@@ -356,7 +332,7 @@ __device__ __forceinline__ void epi_signal_tile_start(EpiCtx& c) {
   fence_proxy_async();
   tc_fence_before();
   __syncwarp();
-  if (c.lane == 0) mbar_arrive(smem_u32(kPipelinedHandover ? &c.bars->d_free : &c.bars->a_ready));
+  if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->d_free));
   NERFB200_TL_MARK(c.tl, 0, 6);
 }
 // This warp has read its share of the tile's last accumulator: the next tile may overwrite it.
@@ -365,18 +341,10 @@ __device__ __forceinline__ void epi_release_accumulator(EpiCtx& c) {
   __syncwarp();
   if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->d_free));
 }
-// Sequential hand-over: this warp's accumulator columns are drained and its A columns stored.
-__device__ __forceinline__ void epi_signal_a_ready(EpiCtx& c, bool smem_written) {
-  if (smem_written || !kAInTmem) fence_proxy_async();
-  if (kAInTmem) tmem_st_wait();
-  tc_fence_before();
-  __syncwarp();
-  if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_ready));
-}
 // This warp's A columns of K block kb are stored in TMEM (and, optionally, ENC smem rewritten).
 __device__ __forceinline__ void epi_signal_kb(EpiCtx& c, int kb, bool smem_written) {
-  if (smem_written || !kAInTmem) fence_proxy_async();
-  if (kAInTmem) tmem_st_wait();
+  if (smem_written) fence_proxy_async();
+  tmem_st_wait();
   tc_fence_before();
   __syncwarp();
   if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_kb[kb]));
@@ -387,11 +355,6 @@ __device__ __forceinline__ void epi_wait_d(EpiCtx& c) {
   tc_fence_after();
 }
 
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z,
-                                             uint32_t w) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w)
-               : "memory");
-}
 __device__ __forceinline__ void add_f32x2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
   asm("{ .reg .b64 a, b, d; mov.b64 a, {%2,%3}; mov.b64 b, {%4,%5}; add.rn.f32x2 d, a, b; mov.b64 {%0,%1}, d; }"
       : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
@@ -405,61 +368,6 @@ __device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
-}
-
-// One 32-column chunk of a hidden-layer epilogue: v = act(acc + bias) -> 16 packed fp16x2
-// columns of the next layer's A operand in TMEM; optionally the sigma-head dot product.
-// bias / wsig point into shared memory (all lanes read the same address: broadcast LDS).
-template <bool kRelu, bool kSigma, bool kStore>
-__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* bias, int n0,
-                                          uint32_t a_dst, const float* wsig, float& sig_acc) {
-  uint32_t h[16];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int n = n0 + 8 * j;
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + n);
-    const float4 b1 = *reinterpret_cast<const float4*>(bias + n + 4);
-    float v[8];
-    add_f32x2(v[0], v[1], __uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]), b0.x, b0.y);
-    add_f32x2(v[2], v[3], __uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]), b0.z, b0.w);
-    add_f32x2(v[4], v[5], __uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]), b1.x, b1.y);
-    add_f32x2(v[6], v[7], __uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]), b1.z, b1.w);
-    if (kSigma) {
-      const float4 w0 = *reinterpret_cast<const float4*>(wsig + n);
-      const float4 w1 = *reinterpret_cast<const float4*>(wsig + n + 4);
-      sig_acc = fmaf(fmaxf(v[0], 0.f), w0.x, sig_acc);
-      sig_acc = fmaf(fmaxf(v[1], 0.f), w0.y, sig_acc);
-      sig_acc = fmaf(fmaxf(v[2], 0.f), w0.z, sig_acc);
-      sig_acc = fmaf(fmaxf(v[3], 0.f), w0.w, sig_acc);
-      sig_acc = fmaf(fmaxf(v[4], 0.f), w1.x, sig_acc);
-      sig_acc = fmaf(fmaxf(v[5], 0.f), w1.y, sig_acc);
-      sig_acc = fmaf(fmaxf(v[6], 0.f), w1.z, sig_acc);
-      sig_acc = fmaf(fmaxf(v[7], 0.f), w1.w, sig_acc);
-    }
-    if (kStore) {
-      if (kRelu) {
-        h[4 * j + 0] = cvt_f16x2_relu(v[0], v[1]); h[4 * j + 1] = cvt_f16x2_relu(v[2], v[3]);
-        h[4 * j + 2] = cvt_f16x2_relu(v[4], v[5]); h[4 * j + 3] = cvt_f16x2_relu(v[6], v[7]);
-      } else {
-        h[4 * j + 0] = cvt_f16x2(v[0], v[1]); h[4 * j + 1] = cvt_f16x2(v[2], v[3]);
-        h[4 * j + 2] = cvt_f16x2(v[4], v[5]); h[4 * j + 3] = cvt_f16x2(v[6], v[7]);
-      }
-    }
-  }
-  if (kStore) {
-    if (kAInTmem) {
-      tmem_st16(a_dst, h);
-    } else {
-      // a_dst = smem address of this row inside K block 0; n0 selects K block and 16-byte chunk
-      const uint32_t kb = static_cast<uint32_t>(n0) >> 6;
-      const uint32_t c0 = (static_cast<uint32_t>(n0) & 63u) >> 3;      // first of 4 chunks
-      const uint32_t rsw = (a_dst >> 7) & 7u;                          // row & 7 (tile is 1024-aligned)
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        st_shared_v4(a_dst + kb * 16384u + (((c0 + j) ^ rsw) << 4), h[4 * j], h[4 * j + 1], h[4 * j + 2],
-                     h[4 * j + 3]);
-    }
-  }
 }
 
 // NeRF.forward mode: the ENC tile is dead after layer 5; reuse it for this row's embedded direction
@@ -482,21 +390,14 @@ __device__ __forceinline__ void write_dir_row(EpiCtx& c, const float* __restrict
 template <bool kRelu, bool kSigma, bool kStore, bool kSave = false>
 __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, const float* wsig,
                                            float& sig_acc, const float* __restrict__ dir_row = nullptr) {
-  const int nb = c.part * kColsPer;
-  const uint32_t a_row = smem_u32(c.smem + kSmemA) + static_cast<uint32_t>(c.row) * 128u;
-  const uint32_t a_tm = c.tmem_row + kTmemA + nb / 2;         // 2 fp16 per column
-  const uint32_t d_src = c.tmem_row + kTmemD + nb;
   NERFB200_TL_MARK(c.tl, 0, 1);
   epi_wait_d(c);
   NERFB200_TL_MARK(c.tl, 0, 2);
-  constexpr int kPairs = kColsPer / 64;                       // 64 columns = one K block of the next layer
-  if (kPipelinedHandover) {
+  {
     // K-block interleaved: every warp owns kColsPer/4 columns of EACH 64-wide K block, so the
     // blocks complete one after the other and the MMA of the next layer can start on block 0
-    // while blocks 1..3 are still being converted.  Requires the TMEM A operand.
-    static_assert(kAInTmem || !kPipelinedHandover, "pipelined hand-over is implemented for the TMEM operand");
-    constexpr int kW16 = kColsPer / 4;                        // 16 columns per K block per thread
-    static_assert(kW16 == 16, "pipelined hand-over assumes 16 epilogue warps");
+    // while blocks 1..3 are still being converted.
+    static_assert(kColsPer / 4 == 16, "the hand-over assumes 16 epilogue warps (16 columns per K block per thread)");
     uint32_t r[4][16];
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) tmem_ld16(c.tmem_row + kTmemD + kb * 64 + c.part * 16, r[kb]);
@@ -544,25 +445,6 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
         dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
       }
     }
-  } else {
-    uint32_t r0[32], r1[32];
-    tmem_ld32(d_src, r0);
-    tmem_ld32(d_src + 32, r1);
-    tmem_ld_wait();
-    NERFB200_TL_MARK(c.tl, 0, 3);
-#pragma unroll
-    for (int pr = 0; pr < kPairs; ++pr) {
-      epi_chunk<kRelu, kSigma, kStore>(r0, bias, nb + 64 * pr, kAInTmem ? a_tm + 32 * pr : a_row, wsig, sig_acc);
-      if (pr + 1 < kPairs) tmem_ld32(d_src + 64 * (pr + 1), r0);
-      epi_chunk<kRelu, kSigma, kStore>(r1, bias, nb + 64 * pr + 32, kAInTmem ? a_tm + 32 * pr + 16 : a_row, wsig, sig_acc);
-      if (pr + 1 < kPairs) {
-        tmem_ld32(d_src + 64 * (pr + 1) + 32, r1);
-        tmem_ld_wait();
-      }
-    }
-    NERFB200_TL_MARK(c.tl, 0, 4);
-    if (dir_row != nullptr) write_dir_row(c, dir_row);
-    if (kStore) epi_signal_a_ready(c, dir_row != nullptr);
   }
   NERFB200_TL_MARK(c.tl, 0, 5);
 }

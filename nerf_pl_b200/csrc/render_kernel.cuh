@@ -409,7 +409,6 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
     c.part = warp >> 2;
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     c.d_phase = 0;
-    c.flags = p.flags;
     c.save_act = nullptr; c.save_d = nullptr; c.save_n = 0; c.save_row = -1;
     c.early = true;     // the accumulator is handed back as soon as a tile's last layer is read
     Timeline tle{(blockIdx.x == 0 && threadIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
