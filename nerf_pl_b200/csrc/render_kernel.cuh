@@ -1,6 +1,8 @@
 // Fused render_rays (models/rendering.py:58-244): stratified depths -> positional encoding
 // -> coarse MLP -> alpha compositing -> inverse-CDF resampling -> merge -> fine MLP ->
-// compositing, one persistent CTA per SM, two rays ("a group") at a time.  sigma / rgb never
+// compositing, one persistent CTA per SM.  A CTA walks its rays two at a time ("a group"); the
+// MLP tiles of neighbouring groups are interleaved so that everything that is not the MLP runs on
+// two helper warps concurrently with it (see the kernel's comment below).  sigma / rgb never
 // leave the SM; HBM traffic is 32 B in and <= 40 B out per ray.
 #pragma once
 #include "mlp_engine.cuh"
@@ -52,8 +54,10 @@ struct RenderParams {
   long long* timeline;          // experiment: device timeline buffer (flags & 2), else null
 };
 
+// Shared-memory scratch of the stand-alone kernels (aux_kernels.cuh: NeRF.forward, probes); the
+// render kernel has its own RenderScratch below.
 struct alignas(16) Scratch {
-  Barriers bars;                       //   96
+  Barriers bars;
   alignas(16) float dirbias[2][kDirW]; // 1024   per-ray b_dir + W_dir[:,256:283] . dir_enc
   float sig_part[kColSplit][128];      // [column group][row] partial sigma-head sums
   float rgb_part[kColSplit][3][128];   // partial rgb-head sums

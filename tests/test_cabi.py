@@ -88,3 +88,36 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src, fn
+
+
+def test_nerf_parameters_order_matches_state_dict():
+    """The packed-image cache reads the 24 parameters through Module._modules / _parameters
+    (hot path of every render_rays call); it must see the state_dict order, for this package's
+    NeRF and for a module built the way the reference builds its own (models/nerf.py:58-81)."""
+    import torch
+    from torch import nn
+
+    from nerf_pl_b200.nerf import NeRF, nerf_parameters
+
+    m = NeRF()
+    got = nerf_parameters(m)
+    want = [p for _, p in m.named_parameters()]
+    assert len(got) == 24 and all(a is b for a, b in zip(got, want))
+
+    class RefLike(nn.Module):            # attribute layout of the reference's NeRF
+        def __init__(self):
+            super().__init__()
+            for i in range(8):
+                n_in = 63 if i == 0 else (256 + 63 if i == 4 else 256)
+                setattr(self, f"xyz_encoding_{i + 1}", nn.Sequential(nn.Linear(n_in, 256), nn.ReLU(True)))
+            self.xyz_encoding_final = nn.Linear(256, 256)
+            self.dir_encoding = nn.Sequential(nn.Linear(256 + 27, 128), nn.ReLU(True))
+            self.sigma = nn.Linear(256, 1)
+            self.rgb = nn.Sequential(nn.Linear(128, 3), nn.Sigmoid())
+
+    r = RefLike()
+    got = nerf_parameters(r)
+    want = [p for _, p in r.named_parameters()]
+    assert len(got) == 24 and all(a is b for a, b in zip(got, want))
+    assert [tuple(p.shape) for p in got][:2] == [(256, 63), (256,)]
+    del torch
