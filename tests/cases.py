@@ -17,6 +17,8 @@ CASES = {
     "blender_disp": (64, "blender", 6, 64, 64, True, 0.0, 0.0, True, False),
     "blender_64_128": (64, "blender", 7, 64, 128, False, 0.0, 0.0, True, True),
     "odd_rays": (33, "blender", 8, 64, 64, False, 0.0, 0.0, False, False),
+    "ndc_perturb_128": (70, "ndc", 9, 64, 128, False, 1.0, 0.0, False, False),
+    "blender_disp_perturb": (50, "blender", 10, 64, 64, True, 1.0, 0.0, True, True),
 }
 W_SEEDS = (11, 12)
 RANDOM_KEYS = ("perturb_rand", "noise_coarse", "u_rand", "noise_fine")

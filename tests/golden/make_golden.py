@@ -2,6 +2,7 @@
 (kwea123/nerf_pl, /root/reference, read-only) on CPU in the build container.
 
     python tests/golden/make_golden.py            # writes tests/golden/*.npz
+    python tests/golden/make_golden.py NAME ...   # only the named render cases
 
 The reference's renderer imports `torchsearchsorted`, whose native extension does not build
 against torch 2.11; it is shimmed with torch.searchsorted, which the survey
@@ -62,6 +63,8 @@ CASES = {
     "blender_disp": (64, "blender", 6, 64, 64, True, 0.0, 0.0, True, False),
     "blender_64_128": (64, "blender", 7, 64, 128, False, 0.0, 0.0, True, True),
     "odd_rays": (33, "blender", 8, 64, 64, False, 0.0, 0.0, False, False),
+    "ndc_perturb_128": (70, "ndc", 9, 64, 128, False, 1.0, 0.0, False, False),
+    "blender_disp_perturb": (50, "blender", 10, 64, 64, True, 1.0, 0.0, True, True),
 }
 W_SEEDS = (11, 12)   # coarse, fine
 
@@ -72,7 +75,10 @@ def main():
     ws = [orc.make_weights(s) for s in W_SEEDS]
     models = [ref_model(NeRF, w) for w in ws]
     emb = [Embedding(3, 10), Embedding(3, 4)]
+    only = sys.argv[1:]
     for name, (n, kind, rseed, S, K, disp, perturb, noise, wb, tt) in CASES.items():
+        if only and name not in only:
+            continue
         rays = orc.make_rays(n, rseed, kind)
         store = {"rays": rays}
         torch.manual_seed(1000 + rseed)
@@ -95,6 +101,8 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"render_{name}.npz"), **store)
         print(name, {k: tuple(v.shape) for k, v in out.items()})
 
+    if only:
+        return
     # unit vectors: Embedding, NeRF.forward, sample_pdf
     rs = np.random.RandomState(21)
     x3 = rs.uniform(-6, 6, (64, 3)).astype(np.float32)
