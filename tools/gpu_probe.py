@@ -1,7 +1,8 @@
 """Bring-up probe for the tcgen05 engine (run on a B200 via gpurun; each step in its own process
 so a device trap in one step does not hide the others).
 
-    python tools/gpu_probe.py gemm | mlp | render | speed
+    python tools/gpu_probe.py gemm | mlp | render | speed | speed1 | mmabench | contention | issue | cache
+    python tools/gpu_probe.py timeline | tlsum        (needs a -DNERFB200_TIMELINE build: NERFB200_LIB=...)
 """
 import ctypes
 import os
