@@ -252,6 +252,11 @@ __device__ __forceinline__ void mma_tile_t(RingState& rs, MmaPhases& ph, uint8_t
       tl_val(tl, 1, 601, clock64() - w1);
 #endif
     } else {
+#ifdef NERFB200_EXP_HOIST_FULL
+      // experiment (not yet measured): the first weight slice is long in the ring; wait for it before
+      // a_kb[0] so that only one shared-memory round trip separates "signalled" from "first MMA"
+      mbar_wait(full0 + 8u * rs.stage, rs.phase, 4);
+#endif
       mbar_wait(akb0, ph.a_kb, 6);
     }
     tc_fence_after();
@@ -264,9 +269,17 @@ __device__ __forceinline__ void mma_tile_t(RingState& rs, MmaPhases& ph, uint8_t
         const bool from_enc = (l == 0) || (l == 4 && s == 0) || (l == 8 && s == 4);
         const int kb = (l == 4) ? s - 1 : s;
         const uint32_t stage = rs.stage;
+#ifdef NERFB200_EXP_HOIST_FULL
+        if (s > 0 || l == 0) mbar_wait(full0 + 8u * stage, rs.phase, 4);
+        if (!from_enc && kb > 0) {
+          mbar_wait(akb0 + 8u * kb, ph.a_kb, 6);
+          tc_fence_after();
+        }
+#else
         mbar_wait(full0 + 8u * stage, rs.phase, 4);
         if (!from_enc && kb > 0) mbar_wait(akb0 + 8u * kb, ph.a_kb, 6);
         tc_fence_after();
+#endif
         const uint64_t bdesc = ring_desc + static_cast<uint64_t>(stage * (kSliceBytes256 >> 4));
         if (from_enc) {
 #pragma unroll
