@@ -113,6 +113,28 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+_NERF_LAYERS = ([("xyz_encoding_1.0", 256, 63)] + [(f"xyz_encoding_{i}.0", 256, 256) for i in (2, 3, 4)]
+                + [("xyz_encoding_5.0", 256, 319)] + [(f"xyz_encoding_{i}.0", 256, 256) for i in (6, 7, 8)]
+                + [("xyz_encoding_final", 256, 256), ("dir_encoding.0", 128, 283), ("sigma", 1, 256), ("rgb.0", 3, 128)])
+
+
+def synthetic_weights(seed):
+    """Random-init NeRF state_dict (numpy): nn.Linear's default U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for the
+    reference architecture (models/nerf.py:58-81), with the sigma / rgb heads scaled so that
+    opacities and colours are not degenerate (there are no checkpoints to load).  bench.py's own
+    generator: the b200 arm does not touch oracle/."""
+    rs = np.random.RandomState(seed)
+    w = {}
+    for name, out_f, in_f in _NERF_LAYERS:
+        bound = 1.0 / np.sqrt(in_f)
+        w[name + ".weight"] = rs.uniform(-bound, bound, size=(out_f, in_f)).astype(np.float32)
+        w[name + ".bias"] = rs.uniform(-bound, bound, size=(out_f,)).astype(np.float32)
+    w["sigma.weight"] = (w["sigma.weight"] * np.float32(30.0)).astype(np.float32)
+    w["sigma.bias"] = (w["sigma.bias"] + np.float32(0.5)).astype(np.float32)
+    w["rgb.0.weight"] = (w["rgb.0.weight"] * np.float32(8.0)).astype(np.float32)
+    return w
+
+
 def ncu_traffic():
     """DRAM bytes (read + write) of one bench-shaped render_rays launch from the committed ncu
     --set full capture (profiles/*_ncu_traffic.json, written by tools/summarize_ncu.py); None if absent."""
@@ -150,7 +172,7 @@ def best_blas_threads():
         _BEST_THREADS = cores
         return cores
     from oracle import nerf_oracle as orc
-    ws = [orc.make_weights(11), orc.make_weights(12)]
+    ws = [synthetic_weights(11), synthetic_weights(12)]
     rays = blender_rays(128, 0)
     best, best_t = cores, float("inf")
     cands = sorted({c for c in (4, 8, 16, 32, 64, cores) if c <= cores})
@@ -178,8 +200,8 @@ def cpu_oracle_throughput(n_rays, reps, seed=0):
 
 
 def _cpu_oracle_throughput(n_rays, reps, seed=0):
-    from oracle import nerf_oracle as orc
-    ws = [orc.make_weights(11), orc.make_weights(12)]
+    from oracle import nerf_oracle as orc      # the cpu_baseline / reference leg: the oracle is what is timed
+    ws = [synthetic_weights(11), synthetic_weights(12)]
     rays = blender_rays(n_rays, seed)
     rs = np.random.RandomState(seed)
     rnd = {"perturb_rand": rs.rand(n_rays, N_SAMPLES).astype(np.float32),
@@ -231,7 +253,6 @@ def run_b200(args):
 
     import nerf_pl_b200 as nb
     from nerf_pl_b200 import _lib
-    from oracle import nerf_oracle as orc
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -245,7 +266,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
-    ws = [orc.make_weights(11), orc.make_weights(12)]     # weight *generator* only (random init)
+    ws = [synthetic_weights(11), synthetic_weights(12)]   # random init: there are no checkpoints
     models = []
     for w in ws:
         m = nb.NeRF()

@@ -121,3 +121,18 @@ def test_nerf_parameters_order_matches_state_dict():
     assert len(got) == 24 and all(a is b for a, b in zip(got, want))
     assert [tuple(p.shape) for p in got][:2] == [(256, 63), (256,)]
     del torch
+
+
+def test_bench_b200_arm_does_not_touch_oracle():
+    """Only bench.py's cpu_baseline / --impl reference legs may execute oracle/ (it is the thing
+    timed there); the measured arm builds its inputs with bench.py's own generators."""
+    import ast
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+    fns = {n.name: n for n in tree.body if isinstance(n, ast.FunctionDef)}
+    for name in ("run_b200", "synthetic_weights", "blender_rays", "main"):
+        src = ast.unparse(fns[name])
+        assert "oracle" not in src and "orc." not in src, name
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    assert all("oracle" not in ast.unparse(n) for n in top)

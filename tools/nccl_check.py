@@ -8,7 +8,6 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 import nerf_pl_b200 as nb  # noqa: E402
-from oracle import nerf_oracle as orc  # noqa: E402
 
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -17,7 +16,7 @@ dist.init_process_group("nccl", device_id=dev)
 models = []
 for s in (11, 12):
     m = nb.NeRF()
-    m.load_state_dict({k: torch.from_numpy(v) for k, v in orc.make_weights(s).items()})
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in bench.synthetic_weights(s).items()})
     models.append(m.to(dev).eval())
 emb = [nb.Embedding(3, 10), nb.Embedding(3, 4)]
 for n in (4001, 80000):

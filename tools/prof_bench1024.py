@@ -9,13 +9,12 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 import nerf_pl_b200 as nb  # noqa: E402
-from oracle import nerf_oracle as orc  # noqa: E402
 
 dev = torch.device("cuda:0")
 models = []
 for s in (11, 12):
     m = nb.NeRF()
-    m.load_state_dict({k: torch.from_numpy(v) for k, v in orc.make_weights(s).items()})
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in bench.synthetic_weights(s).items()})
     models.append(m.to(dev).eval())
 emb = [nb.Embedding(3, 10), nb.Embedding(3, 4)]
 n = 1024

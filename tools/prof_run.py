@@ -8,7 +8,6 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 import nerf_pl_b200 as nb  # noqa: E402
-from oracle import nerf_oracle as orc  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
@@ -17,7 +16,7 @@ dev = torch.device("cuda:0")
 models = []
 for s in (11, 12):
     m = nb.NeRF()
-    m.load_state_dict({k: torch.from_numpy(v) for k, v in orc.make_weights(s).items()})
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in bench.synthetic_weights(s).items()})
     models.append(m.to(dev).eval())
 emb = [nb.Embedding(3, 10), nb.Embedding(3, 4)]
 rays = torch.from_numpy(bench.blender_rays(n, 0)).to(dev)
