@@ -18,7 +18,6 @@ the reference itself (PyTorch + torchsearchsorted) cannot travel to the GPU box.
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

@@ -4,7 +4,6 @@ so a device trap in one step does not hide the others).
     python tools/gpu_probe.py gemm | mlp | render | speed | speed1 | mmabench | contention | issue | cache
     python tools/gpu_probe.py timeline | tlsum        (needs a -DNERFB200_TIMELINE build: NERFB200_LIB=...)
 """
-import ctypes
 import os
 import sys
 import time
