@@ -57,8 +57,12 @@ int nerfb200_pack_weights(const float* const params[24], void* packed, void* str
  * Optional outputs (NULL to skip): z_fine (n, N_samples+N_importance) merged sorted depths,
  *   weights_coarse (n,N_samples), weights_fine (n,N_samples+N_importance).
  * Supported shapes: N_samples = 64; N_importance in {0,64,128}.
- * `status` is a device int32 the kernel sets non-zero on a device-side fault (may be NULL,
- * then an internal one is used and checked with a synchronising copy). */
+ * `status` is a device int32 the kernel sets non-zero on a device-side fault.  It may be NULL:
+ * then a per-device internal word (mapped pinned host memory) is used; the library reads it
+ * without synchronising at the START of every later call on that device and returns
+ * NERFB200_EDEVICE once if an earlier kernel reported a fault (nerfb200_check_status() does the
+ * same check on demand, e.g. after a stream synchronise).  The *_host entry always checks the
+ * word of its own launch before returning. */
 typedef struct nerfb200_render_args {
   const float* rays;
   int64_t n_rays;
@@ -183,23 +187,10 @@ int nerfb200_to_uint8(const float* src, int64_t n, uint8_t* dst, void* stream);
  * Number of kernels this library has launched on the calling process so far (all entry
  * points).  bench.py reports the delta as `gpu_launches`. */
 int64_t nerfb200_launch_count(void);
-/* One K=64 weight slice of a packed image (csrc/layout.h) against a (128,64) fp32 A tile
- * through the tcgen05 engine: d (128, N), N = 256 for slices 0..33 and 128 for 34..38.
- * mode 0 stages A in shared memory (SS MMA), mode 1 in tensor memory (TS MMA).  Unit-test hook
- * for the operand layouts; not part of the reference API. */
-int nerfb200_debug_gemm(const float* a, const void* packed, int32_t slice, int32_t mode, float* d,
-                        void* stream);
-/* Raw tcgen05.mma issue-rate microbenchmark (timing only): out_dev (n_ctas, 8) int64 device
- * buffer; column v = SM cycles for reps x 16 MMAs of variant v (csrc/aux_kernels.cuh). */
-int nerfb200_debug_mma_bench(int64_t* out_dev, int32_t n_ctas, int32_t reps, void* stream);
-/* tcgen05.mma vs. concurrent tcgen05.ld/st microbenchmark (timing only): out_dev (n_ctas, 4)
- * int64; [0] = SM cycles of reps x 16 MMAs, [1] = background iterations meanwhile
- * (bg / variant codes: csrc/aux_kernels.cuh mma_contention_kernel). */
-int nerfb200_debug_mma_contention(int64_t* out_dev, int32_t n_ctas, int32_t reps, int32_t bg, int32_t variant,
-                                  void* stream);
-/* Experiment hook: with NERFB200_FLAGS bit 1 set, CTA 0 of the last render launch records
- * (tag, SM clock) pairs for its epilogue / MMA roles; this copies 3*512*2 int64 to host. */
-int nerfb200_debug_timeline(int64_t* host_out, int64_t n_values);
+/* Returns NERFB200_EDEVICE (and clears the flag) if a kernel launched by an earlier call on the
+ * current device reported a device-side fault through the internal status word; 0 otherwise.
+ * Does not synchronise: call it after synchronising the stream to cover the latest launch. */
+int nerfb200_check_status(void);
 /* Device properties the launcher uses: SM count of the current device (0 if none). */
 int nerfb200_sm_count(void);
 

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libnerf_pl_b200.so")
 if os.environ.get("NERFB200_LIB"):          # experiment builds (tools/build_variants.py); unset in production
     LIB_PATH = os.path.abspath(os.environ["NERFB200_LIB"])
 SOURCES = ["capi.cu"]
-HEADERS = ["ptx.cuh", "layout.h", "mlp_engine.cuh", "render_kernel.cuh", "aux_kernels.cuh"]
+HEADERS = ["ptx.cuh", "layout.h", "mlp_engine.cuh", "render_kernel.cuh", "aux_kernels.cuh", "diag_kernels.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -46,11 +46,16 @@ EXPORTS = [
     "nerfb200_generate_rays",
     "nerfb200_to_uint8",
     "nerfb200_launch_count",
+    "nerfb200_check_status",
+    "nerfb200_sm_count",
+]
+# include/nerf_pl_b200_diag.h: only in -DNERFB200_DIAG builds (tools/build_variants.py)
+DIAG_EXPORTS = [
     "nerfb200_debug_gemm",
+    "nerfb200_debug_gemm_mn",
     "nerfb200_debug_timeline",
     "nerfb200_debug_mma_bench",
     "nerfb200_debug_mma_contention",
-    "nerfb200_sm_count",
 ]
 
 
@@ -148,8 +153,6 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.nerfb200_composite.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                        c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p]
-    lib.nerfb200_debug_gemm.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
-    lib.nerfb200_debug_gemm.restype = c_int32
     lib.nerfb200_query_sigma.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
     lib.nerfb200_query_sigma.restype = c_int32
     lib.nerfb200_relu_backward.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]
@@ -161,12 +164,18 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.nerfb200_generate_rays.restype = c_int32
     lib.nerfb200_to_uint8.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
     lib.nerfb200_to_uint8.restype = c_int32
-    lib.nerfb200_debug_mma_bench.argtypes = [c_void_p, c_int32, c_int32, c_void_p]
-    lib.nerfb200_debug_mma_bench.restype = c_int32
-    lib.nerfb200_debug_mma_contention.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]
-    lib.nerfb200_debug_mma_contention.restype = c_int32
-    lib.nerfb200_debug_timeline.argtypes = [c_void_p, c_int64]
-    lib.nerfb200_debug_timeline.restype = c_int32
+    if hasattr(lib, "nerfb200_debug_gemm"):        # diagnostics build only
+        lib.nerfb200_debug_gemm.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
+        lib.nerfb200_debug_gemm.restype = c_int32
+        lib.nerfb200_debug_gemm_mn.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
+        lib.nerfb200_debug_gemm_mn.restype = c_int32
+        lib.nerfb200_debug_mma_bench.argtypes = [c_void_p, c_int32, c_int32, c_void_p]
+        lib.nerfb200_debug_mma_bench.restype = c_int32
+        lib.nerfb200_debug_mma_contention.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]
+        lib.nerfb200_debug_mma_contention.restype = c_int32
+        lib.nerfb200_debug_timeline.argtypes = [c_void_p, c_int64]
+        lib.nerfb200_debug_timeline.restype = c_int32
+    lib.nerfb200_check_status.restype = c_int32
     lib.nerfb200_launch_count.restype = c_int64
     lib.nerfb200_sm_count.restype = c_int32
     for name in ("nerfb200_pack_weights", "nerfb200_render_rays", "nerfb200_render_rays_host",

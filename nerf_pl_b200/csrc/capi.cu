@@ -7,6 +7,10 @@
 
 #include "../../include/nerf_pl_b200.h"
 #include "aux_kernels.cuh"
+#ifdef NERFB200_DIAG
+#include "../../include/nerf_pl_b200_diag.h"
+#include "diag_kernels.cuh"
+#endif
 
 using namespace nerfb200;
 
@@ -33,9 +37,26 @@ struct DeviceInfo {
   int sm_count = 0;
   int cc_major = 0;
   bool attrs_set = false;
-  int* status = nullptr;
+  bool diag_attrs_set = false;
+  int* status = nullptr;        // device view of the mapped status word below
+  volatile int* status_host = nullptr;   // pinned, mapped: the kernels write it, the host polls it without a sync
   long long* timeline = nullptr;
 };
+
+// Experiment switches are read ONCE per process (NERFB200_FLAGS: bit 1 = device timeline in
+// -DNERFB200_TIMELINE builds; NERFB200_MAX_CTAS: cap on the persistent grid).  Unset in production.
+struct EnvSwitches {
+  unsigned flags = 0;
+  int max_ctas = 0;
+  EnvSwitches() {
+    if (const char* f = std::getenv("NERFB200_FLAGS")) flags = static_cast<unsigned>(std::strtoul(f, nullptr, 0));
+    if (const char* mc = std::getenv("NERFB200_MAX_CTAS")) max_ctas = std::atoi(mc);
+  }
+};
+const EnvSwitches& env_switches() {
+  static const EnvSwitches e;
+  return e;
+}
 std::mutex g_mu;
 DeviceInfo g_dev[64];
 
@@ -57,18 +78,29 @@ int device_info(DeviceInfo** out) {
                                   static_cast<int>(kSmemTotal)), "smem attr render(save)");
     CUDA_TRY(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kSmemTotal)), "smem attr mlp");
-    CUDA_TRY(cudaFuncSetAttribute(gemm_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(kSmemTotal)), "smem attr probe");
-    CUDA_TRY(cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(kSmemTotal)), "smem attr bench");
-    CUDA_TRY(cudaFuncSetAttribute(mma_contention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(kSmemTotal)), "smem attr contention");
-    CUDA_TRY(cudaMalloc(&d.status, sizeof(int)), "status alloc");
-    CUDA_TRY(cudaMemset(d.status, 0, sizeof(int)), "status memset");
+    int* hs = nullptr;
+    CUDA_TRY(cudaHostAlloc(&hs, sizeof(int), cudaHostAllocMapped), "status alloc");
+    *hs = 0;
+    CUDA_TRY(cudaHostGetDevicePointer(&d.status, hs, 0), "status device pointer");
+    d.status_host = hs;
     d.attrs_set = true;
   }
   *out = &d;
   return 0;
+}
+
+// A kernel of an EARLIER call on this device reported a device-side fault (misaligned shared
+// memory, code 101) through the internal status word: surface it on this call and clear it.
+// (The word lives in mapped pinned host memory, so this is a plain host read, no synchronisation;
+// callers that want the fault of THIS call pass their own `status` word or call
+// nerfb200_check_status() after synchronising.)
+int check_sticky_status(DeviceInfo* d) {
+  if (d->status_host == nullptr) return 0;
+  const int st = *d->status_host;
+  if (st == 0) return 0;
+  *d->status_host = 0;
+  std::snprintf(g_err, sizeof(g_err), "an earlier nerf_pl_b200 kernel reported device status %d", st);
+  return NERFB200_EDEVICE;
 }
 
 int check_render_shapes(const nerfb200_render_args* a) {
@@ -170,6 +202,7 @@ int nerfb200_render_rays(const nerfb200_render_args* a, void* stream) {
   DeviceInfo* d = nullptr;
   rc = device_info(&d);
   if (rc) return rc;
+  if (!a->status && (rc = check_sticky_status(d)) != 0) return rc;
   RenderParams p;
   p.rays = a->rays;
   p.ray_stride = a->ray_stride;
@@ -208,25 +241,21 @@ int nerfb200_render_rays(const nerfb200_render_args* a, void* stream) {
   const bool save = p.save_act_c || p.save_act_f || p.save_d_c || p.save_d_f || p.save_sig_c || p.save_sig_f ||
                     p.save_rgb_c || p.save_rgb_f;
   if (save && a->test_time) return fail(NERFB200_EINVAL, "save_* buffers need test_time = 0%s");
-  {
-    const char* f = std::getenv("NERFB200_FLAGS");   // experiment switches; unset in production
-    p.flags = f ? static_cast<unsigned>(std::strtoul(f, nullptr, 0)) : 0u;
-    p.timeline = nullptr;
-    if (p.flags & 2u) {
-      if (!d->timeline) {
-        CUDA_TRY(cudaMalloc(&d->timeline, 3 * kTlMax * 2 * sizeof(long long)), "timeline alloc");
-      }
-      CUDA_TRY(cudaMemsetAsync(d->timeline, 0, 3 * kTlMax * 2 * sizeof(long long), static_cast<cudaStream_t>(stream)), "timeline memset");
-      p.timeline = d->timeline;
+  p.flags = env_switches().flags;
+  p.timeline = nullptr;
+#ifdef NERFB200_TIMELINE
+  if (p.flags & 2u) {
+    if (!d->timeline) {
+      CUDA_TRY(cudaMalloc(&d->timeline, 3 * kTlMax * 2 * sizeof(long long)), "timeline alloc");
     }
+    CUDA_TRY(cudaMemsetAsync(d->timeline, 0, 3 * kTlMax * 2 * sizeof(long long), static_cast<cudaStream_t>(stream)), "timeline memset");
+    p.timeline = d->timeline;
   }
+#endif
   const int n_groups = (p.n_rays + 1) / 2;     // two rays share the coarse tile
   int ctas = d->sm_count;
   if (a->max_ctas > 0 && a->max_ctas < ctas) ctas = a->max_ctas;
-  if (const char* mc = std::getenv("NERFB200_MAX_CTAS")) {   // experiment switch; unset in production
-    const int v = std::atoi(mc);
-    if (v > 0 && v < ctas) ctas = v;
-  }
+  if (env_switches().max_ctas > 0 && env_switches().max_ctas < ctas) ctas = env_switches().max_ctas;
   if (n_groups < ctas) ctas = n_groups;
   if (save)
     render_rays_kernel<true><<<ctas, kRenderThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
@@ -327,6 +356,7 @@ int nerfb200_nerf_forward(const float* x, int64_t n, int64_t x_stride, const voi
   DeviceInfo* d = nullptr;
   int rc = device_info(&d);
   if (rc) return rc;
+  if ((rc = check_sticky_status(d)) != 0) return rc;
   MlpParams p;
   p.raw_xyz = 0;
   p.x = x; p.x_stride = x_stride; p.n = n;
@@ -351,6 +381,7 @@ int nerfb200_query_sigma(const float* xyz, int64_t n, int64_t xyz_stride, const 
   DeviceInfo* d = nullptr;
   int rc = device_info(&d);
   if (rc) return rc;
+  if ((rc = check_sticky_status(d)) != 0) return rc;
   MlpParams p;
   p.raw_xyz = 1;
   p.x = xyz; p.x_stride = xyz_stride; p.n = n;
@@ -465,18 +496,6 @@ int nerfb200_composite(const float* sigmas, const float* rgbs, const float* z_va
   return 0;
 }
 
-int nerfb200_debug_timeline(int64_t* host_out, int64_t n_values) {
-  DeviceInfo* di = nullptr;
-  int rc = device_info(&di);
-  if (rc) return rc;
-  if (!di->timeline || !host_out) return fail(NERFB200_EINVAL, "debug_timeline: no timeline recorded%s");
-  const int64_t cap = 3 * kTlMax * 2;
-  CUDA_TRY(cudaDeviceSynchronize(), "timeline sync");
-  CUDA_TRY(cudaMemcpy(host_out, di->timeline, sizeof(long long) * (n_values < cap ? n_values : cap),
-                      cudaMemcpyDeviceToHost), "timeline copy");
-  return 0;
-}
-
 int nerfb200_generate_rays(int32_t H, int32_t W, float focal, const float c2w_host[12], float near, float far,
                            int32_t ndc, float* rays, void* stream) {
   if (H <= 0 || W <= 0 || !(focal > 0.f)) return fail(NERFB200_EINVAL, "generate_rays: bad H / W / focal%s");
@@ -506,11 +525,60 @@ int nerfb200_to_uint8(const float* src, int64_t n, uint8_t* dst, void* stream) {
   return 0;
 }
 
+int nerfb200_check_status(void) {
+  DeviceInfo* d = nullptr;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  return check_sticky_status(d);
+}
+
+#ifdef NERFB200_DIAG
+// ---------------------------------------------------------------------------- diagnostics build
+static int diag_attrs(DeviceInfo* di) {
+  if (di->diag_attrs_set) return 0;
+  CUDA_TRY(cudaFuncSetAttribute(gemm_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(kSmemTotal)), "smem attr probe");
+  CUDA_TRY(cudaFuncSetAttribute(gemm_mn_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(kSmemTotal)), "smem attr mn probe");
+  CUDA_TRY(cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(kSmemTotal)), "smem attr bench");
+  CUDA_TRY(cudaFuncSetAttribute(mma_contention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(kSmemTotal)), "smem attr contention");
+  di->diag_attrs_set = true;
+  return 0;
+}
+
+int nerfb200_debug_gemm_mn(const float* a, const float* b, int32_t lbo, int32_t sbo, float* d, void* stream) {
+  if (!a || !b || !d) return fail(NERFB200_EINVAL, "debug_gemm_mn: NULL argument%s");
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if ((rc = diag_attrs(di)) != 0) return rc;
+  gemm_mn_probe_kernel<<<1, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(
+      a, b, static_cast<uint32_t>(lbo), static_cast<uint32_t>(sbo), d, di->status);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "debug_gemm_mn launch");
+  return 0;
+}
+
+int nerfb200_debug_timeline(int64_t* host_out, int64_t n_values) {
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (!di->timeline || !host_out) return fail(NERFB200_EINVAL, "debug_timeline: no timeline recorded%s");
+  const int64_t cap = 3 * kTlMax * 2;
+  CUDA_TRY(cudaDeviceSynchronize(), "timeline sync");
+  CUDA_TRY(cudaMemcpy(host_out, di->timeline, sizeof(long long) * (n_values < cap ? n_values : cap),
+                      cudaMemcpyDeviceToHost), "timeline copy");
+  return 0;
+}
+
 int nerfb200_debug_mma_bench(int64_t* out_dev, int32_t n_ctas, int32_t reps, void* stream) {
   if (!out_dev || n_ctas < 1 || reps < 1) return fail(NERFB200_EINVAL, "debug_mma_bench: bad argument%s");
   DeviceInfo* di = nullptr;
   int rc = device_info(&di);
   if (rc) return rc;
+  if ((rc = diag_attrs(di)) != 0) return rc;
   mma_bench_kernel<<<n_ctas, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<long long*>(out_dev), reps, di->status);
   g_launches++;
@@ -524,6 +592,7 @@ int nerfb200_debug_mma_contention(int64_t* out_dev, int32_t n_ctas, int32_t reps
   DeviceInfo* di = nullptr;
   int rc = device_info(&di);
   if (rc) return rc;
+  if ((rc = diag_attrs(di)) != 0) return rc;
   if (bg < 0) {     // issue-pattern benchmark: variant = mode, -bg - 1 = arg
     const int arg = -bg - 1;
     long long* o = reinterpret_cast<long long*>(out_dev);
@@ -557,11 +626,14 @@ int nerfb200_debug_gemm(const float* a, const void* packed, int32_t slice, int32
   DeviceInfo* di = nullptr;
   int rc = device_info(&di);
   if (rc) return rc;
+  if ((rc = diag_attrs(di)) != 0) return rc;
   gemm_probe_kernel<<<1, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(
       a, static_cast<const uint8_t*>(packed), slice, mode, d, di->status);
   g_launches++;
   CUDA_TRY(cudaGetLastError(), "debug_gemm launch");
   return 0;
 }
+
+#endif  // NERFB200_DIAG
 
 }  // extern "C"

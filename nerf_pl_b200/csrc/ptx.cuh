@@ -12,6 +12,13 @@ namespace nerfb200 {
 // Checked by the host wrapper after launch errors (diagnostic only).
 __device__ int g_watchdog_code = 0;
 
+// Device-side fault report into the caller's status word (may live in mapped host memory).
+__device__ __forceinline__ void report_fault(int* status, int code) {
+  if (status == nullptr) return;
+  *reinterpret_cast<volatile int*>(status) = code;
+  __threadfence_system();
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -196,6 +203,24 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
          | (0u << 15) | (0u << 16)                  // A, B K-major
          | (static_cast<uint32_t>(n >> 3) << 17)    // N / 8
          | (static_cast<uint32_t>(128 >> 4) << 24); // M / 16
+}
+
+// MN-major shared-memory descriptor, SWIZZLE_128B, 16-bit elements (the canonical layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): one row per K index (= sample), 128 B =
+// 64 consecutive M/N elements per row, 16-byte chunk c of row r at chunk position c ^ (r & 7);
+// 8-row groups SBO bytes apart along K, 64-element blocks LBO bytes apart along M/N.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor with both operands MN-major (bits 15 / 16), fp16 in, fp32 out, M=128.
+__host__ __device__ constexpr uint32_t make_idesc_f16_mn(int n) {
+  return make_idesc_f16(n) | (1u << 15) | (1u << 16);
 }
 
 // Byte offset of element (row, k) inside a [rows x 64] fp16 SWIZZLE_128B block.

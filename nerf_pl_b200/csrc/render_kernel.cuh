@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
     }
   }
   if (!engine_setup(smem, bars)) {
-    if (threadIdx.x == 0) atomicExch(p.status, 101);
+    if (threadIdx.x == 0) report_fault(p.status, 101);
     return;
   }
   load_consts(smem, 0, p.net_coarse);

@@ -70,6 +70,23 @@ def step_gemm():
     print("GEMM_OK" if ok else "GEMM_FAIL")
 
 
+def step_gemm_mn():
+    """MN-major descriptor probe (the wgrad operand layout): sweep (LBO, SBO) candidates."""
+    lib = _lib.load()
+    torch.manual_seed(3)
+    a = torch.randn(64, 128, device="cuda")
+    b = torch.randn(64, 256, device="cuda")
+    ref = a.half().float().t() @ b.half().float()
+    for lbo, sbo in ((8192, 1024), (1024, 8192), (8192, 128), (128, 8192)):
+        d = torch.zeros(128, 256, device="cuda")
+        rc = lib.nerfb200_debug_gemm_mn(a.data_ptr(), b.data_ptr(), lbo, sbo, d.data_ptr(), None)
+        torch.cuda.synchronize()
+        err = (d - ref).abs().max().item()
+        print(f"gemm_mn lbo={lbo} sbo={sbo} rc={rc} max_abs_err={err:.3e} ref_absmax={ref.abs().max().item():.3f}"
+              + ("  <-- MATCH" if err < 2e-2 else ""))
+    print("GEMM_MN_DONE")
+
+
 def step_mlp():
     m = make_models()[0]
     torch.manual_seed(1)
@@ -337,5 +354,5 @@ def step_tlsum():
 
 if __name__ == "__main__":
     t0 = time.time()
-    {"gemm": step_gemm, "mlp": step_mlp, "render": step_render, "speed": step_speed, "timeline": step_timeline, "mmabench": step_mmabench, "speed1": step_speed1, "contention": step_contention, "issue": step_issue, "tlsum": step_tlsum, "cache": step_cache}[sys.argv[1]]()
+    {"gemm": step_gemm, "gemm_mn": step_gemm_mn, "mlp": step_mlp, "render": step_render, "speed": step_speed, "timeline": step_timeline, "mmabench": step_mmabench, "speed1": step_speed1, "contention": step_contention, "issue": step_issue, "tlsum": step_tlsum, "cache": step_cache}[sys.argv[1]]()
     print(f"[{sys.argv[1]}] {time.time() - t0:.1f}s")
