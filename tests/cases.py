@@ -39,3 +39,19 @@ def weights():
 def error_stats(a, b):
     d = np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)).ravel()
     return float(d.max()), float(np.percentile(d, 99.9)), float(d.mean())
+
+# Gradient goldens (mirrors tests/golden/make_golden.py GRAD_CASES):
+# name: (n_rays, kind, ray seed, N_importance, perturb, noise_std, white_back)
+GRAD_CASES = {
+    "grad_blender_noise0": (64, "blender", 31, 64, 1.0, 0.0, True),
+    "grad_ndc_noise1": (48, "ndc", 32, 64, 1.0, 1.0, False),
+}
+
+
+def load_grad_case(name):
+    """rays, target, randoms, reference loss, reference outputs, reference gradients ('coarse.<key>' / 'fine.<key>')."""
+    from oracle import nerf_oracle_grad as og
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    randoms = {k: z[k] for k in RANDOM_KEYS if k in z.files}
+    ref = {k[4:]: z[k] for k in z.files if k.startswith("out_")}
+    return z["rays"], z["target"], randoms, float(z["loss"]), ref, og.unpack_golden_grads(z)

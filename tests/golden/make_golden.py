@@ -68,6 +68,62 @@ CASES = {
 }
 W_SEEDS = (11, 12)   # coarse, fine
 
+# Gradient goldens: the reference's training step (train.py:103-117: results = render_rays(...);
+# loss = MSELoss(results, rgbs) (losses.py:9-14); loss.backward()) with autograd enabled.
+# name: (n_rays, ray kind, ray seed, N_importance, perturb, noise_std, white_back)
+GRAD_CASES = {
+    "grad_blender_noise0": (64, "blender", 31, 64, 1.0, 0.0, True),     # README Blender recipe (README.md:75-83)
+    "grad_ndc_noise1": (48, "ndc", 32, 64, 1.0, 1.0, False),            # README LLFF recipe (README.md:104-111)
+}
+
+
+def pack_grads(grads):
+    """48 fp32 gradient tensors -> per-tensor max-abs scale (fp32) + values / scale as fp16
+    (relative precision 5e-4, far below the 5e-2 test tolerance; keeps the fixture ~2.4 MB)."""
+    store = {}
+    for key, g in grads.items():
+        g = np.asarray(g, dtype=np.float32)
+        sc = np.float32(max(float(np.abs(g).max()), 1e-30))
+        store["gscale_" + key] = sc
+        store["g16_" + key] = (g / sc).astype(np.float16)
+    return store
+
+
+def make_grad_cases(NeRF, Embedding, render_rays, only):
+    for name, (n, kind, rseed, K, perturb, noise, wb) in GRAD_CASES.items():
+        if only and name not in only:
+            continue
+        S = 64
+        ws = [orc.make_weights(s) for s in W_SEEDS]
+        models = [ref_model(NeRF, w).train() for w in ws]
+        emb = [Embedding(3, 10), Embedding(3, 4)]
+        rays = orc.make_rays(n, rseed, kind)
+        target = np.random.RandomState(500 + rseed).uniform(0, 1, (n, 3)).astype(np.float32)
+        store = {"rays": rays, "target": target}
+        torch.manual_seed(2000 + rseed)
+        g = torch.get_rng_state()
+        store["perturb_rand"] = torch.rand(n, S).numpy()
+        store["noise_coarse"] = torch.randn(n, S).numpy()
+        store["u_rand"] = torch.rand(n, K).numpy()
+        store["noise_fine"] = torch.randn(n, S + K).numpy()
+        torch.set_rng_state(g)
+        out = render_rays(models, emb, torch.from_numpy(rays), S, False, perturb, noise, K, 1024 * 32, wb,
+                          test_time=False)
+        tgt = torch.from_numpy(target)
+        loss = torch.nn.functional.mse_loss(out["rgb_coarse"], tgt) + torch.nn.functional.mse_loss(out["rgb_fine"], tgt)
+        loss.backward()
+        store["loss"] = np.float32(loss.item())
+        for k, v in out.items():
+            store["out_" + k] = v.detach().numpy()
+        grads = {}
+        for tag, m in zip(("coarse", "fine"), models):
+            for key, prm in m.named_parameters():
+                grads[f"{tag}.{key}"] = prm.grad.numpy()
+        store.update(pack_grads(grads))
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **store)
+        gn = float(np.sqrt(sum(float((v.astype(np.float64) ** 2).sum()) for v in grads.values())))
+        print(name, "loss", float(loss.item()), "grad norm", gn)
+
 
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -76,6 +132,7 @@ def main():
     models = [ref_model(NeRF, w) for w in ws]
     emb = [Embedding(3, 10), Embedding(3, 4)]
     only = sys.argv[1:]
+    make_grad_cases(NeRF, Embedding, render_rays, only)
     for name, (n, kind, rseed, S, K, disp, perturb, noise, wb, tt) in CASES.items():
         if only and name not in only:
             continue

@@ -80,3 +80,23 @@ def test_ray_generation_matches_reference():
     np.testing.assert_allclose(orc.generate_rays(H, W, focal, g["c2w"], 2.0, 6.0, ndc=True), g["ndc"], atol=5e-6, rtol=1e-5)
     img = np.linspace(-0.2, 1.2, 97, dtype=np.float32)
     assert orc.to_uint8(img).dtype == np.uint8 and orc.to_uint8(img).max() == 255 and orc.to_uint8(img).min() == 0
+
+
+@pytest.mark.parametrize("name", list(cases.GRAD_CASES))
+def test_training_step_gradients_match_reference(name, ws):
+    """oracle/nerf_oracle_grad.py (hand-derived backward) against the 48 .grad tensors of the
+    unmodified reference's loss.backward() (train.py:103-117, losses.py:9-14)."""
+    from oracle import nerf_oracle_grad as og
+    n, kind, rseed, K, perturb, noise, wb = cases.GRAD_CASES[name]
+    rays, target, randoms, ref_loss, ref_out, ref_grads = cases.load_grad_case(name)
+    np.testing.assert_array_equal(rays, orc.make_rays(n, rseed, kind))
+    loss, out, grads = og.render_rays_loss_grad(ws, rays, target, 64, False, perturb, noise, K, wb, randoms)
+    assert abs(loss - ref_loss) < 1e-5 * max(1.0, abs(ref_loss))
+    for k in ("rgb_coarse", "rgb_fine"):
+        assert cases.error_stats(out[k], ref_out[k])[0] < TOL
+    assert set(grads) == set(ref_grads) and len(grads) == 48
+    rows, (rel, cos) = og.grad_compare(grads, ref_grads)
+    # the goldens are stored as per-tensor-scaled fp16 (5e-4 relative)
+    assert rel < 2e-3 and cos > 0.99999, (rel, cos)
+    for k, (r, c) in rows.items():
+        assert r < 1e-2 and c > 0.9999, (k, r, c)
