@@ -1,19 +1,31 @@
 """bench.py — ray-samples/s of the render_rays hot path on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    torchrun --nproc-per-node N ... bench.py --gpus N ...        (one rank per GPU, NCCL)
 
-Workload (BASELINE.json configs[1]): Blender-lego-shaped 400x400 pinhole rays, N_samples=64,
-N_importance=64, batch_size=1024 rays per GPU per step, training-mode forward
-(perturb=1, noise_std=0, white_back, coarse rgb computed) = 1024 x (64 + 128) = 196,608 MLP
-evaluations per GPU per step.  A "step" is one render_rays pass over one such batch.
-Synthetic rays / random-init (pseudo-trained) weights: no dataset or checkpoint on the box.
+Workload (BASELINE.json configs[1] at N=1; configs[4]'s training shape at N>1 = the same 1024 rays
+per GPU): Blender-lego-shaped 400x400 pinhole rays, N_samples=64, N_importance=64, batch_size=1024
+rays per GPU per step, perturb=1, noise_std=0, white_back, coarse rgb computed (test_time=False)
+= 1024 x (64 + 128) = 196,608 MLP evaluations per GPU per step.  Synthetic rays / random-init
+(pseudo-trained) weights: no dataset or checkpoint on the box.
 
-One JSON line on stdout (rank 0):  value = device-timed whole-job ray-samples/s with the batch
-resident in HBM; e2e = same through the public Python API with pinned HOST buffers (H2D of the
-rays and D2H of rgb_fine inside the timed region); roofline = the fused kernel against the
-measured dense tensor peak; cpu_baseline = the numpy oracle timed on the host cores.
-`--impl reference` times the reference algorithm's CPU restatement (oracle/) on the host cores —
-the reference itself (PyTorch + torchsearchsorted) cannot travel to the GPU box.
+One JSON line on stdout (rank 0):
+  value      device-timed whole-job ray-samples/s of the render_rays forward, batch resident in HBM.
+             A "step" = one render_rays pass over one batch (incl. drawing its random numbers); for
+             N>1 every step ends with ONE NCCL all-gather of the rendered batch (north_star).  The K
+             timed steps are captured in one CUDA graph (no host in the timed region) and bracketed
+             by two events; every step reads a different copy of the packed weights and a different
+             ray batch, 200+ MB in rotation (> the 126 MB L2), so no step finds its inputs in L2.
+  e2e        the same metric through the public Python API with pinned HOST buffers: H2D of the
+             rays, render_rays, D2H of all six result tensors, host sync every step.
+  train      config 2 as BASELINE.json labels it ("training"): forward with the fused loss +
+             hand-written sm_100a backward + Adam, ms per 1024-ray step.
+  roofline   the fused forward kernel against the measured dense tensor peak (algorithmic and
+             executed FLOPs, burst and sustained), cpu_baseline = the reference's own PyTorch path
+             timed on the host cores, parity = the timed batch's first rays checked against it.
+  image_800  configs[4] inference: one 800x800 view, contiguous ray shards + one all-gather.
+`--impl reference` times the unmodified reference (baseline/_ref, staged by tools/stage_reference.py)
+on the host cores; if it is absent, the numpy oracle port (oracle/) — `cpu_baseline.kind` says which.
 """
 import argparse
 import json
@@ -21,6 +33,7 @@ import os
 import sys
 import threading
 import time
+import types
 
 import numpy as np
 
@@ -30,23 +43,38 @@ sys.path.insert(0, ROOT)
 N_SAMPLES, N_IMPORTANCE = 64, 64
 BATCH = 1024
 SAMPLES_PER_RAY = N_SAMPLES + (N_SAMPLES + N_IMPORTANCE)          # 192
-FLOP_PER_RAY_TRAIN = 192 * 1186816                               # test_time=False  
+FLOP_PER_SAMPLE = 2 * 593408                                     # algorithmic
+FLOP_PER_RAY_TRAIN = 192 * FLOP_PER_SAMPLE                        # test_time=False
 IMG_W = IMG_H = 400
 CAMERA_ANGLE_X = 0.6911112070083618                              # lego transforms_*.json
+N_ROT = 96                                                       # weight / ray-batch copies in rotation
 
 
-def blender_rays(n, seed):
-    """n random rays of a 400x400 Blender-style pinhole camera on a radius-4 sphere looking at the
-    origin: unit directions, near=2, far=6 (reference datasets/ray_utils.py:5-43, blender.py:28-35)."""
+def executed_flop_per_sample():
+    """MACs the kernel's tensor core actually executes per MLP evaluation (csrc/layout.h): K padded to
+    64 / 320, xyz_encoding_final folded into dir_encoding (256x256 + 256x128 -> 256x128), the
+    direction part (27x128) and both heads (256 + 384) evaluated on the CUDA cores."""
+    macs = 64 * 256 + 3 * 256 * 256 + 320 * 256 + 3 * 256 * 256 + 256 * 128
+    return 2 * macs
+
+
+def blender_rays(n, seed, W=IMG_W, H=IMG_H, pixels=None):
+    """n rays of a Blender-style pinhole camera on a radius-4 sphere looking at the origin: unit
+    directions, near=2, far=6 (reference datasets/ray_utils.py:5-43, blender.py:28-35).
+    Random pixels, or all H*W pixels in row-major order with pixels='all'."""
     rs = np.random.RandomState(seed)
-    focal = 0.5 * IMG_W / np.tan(0.5 * CAMERA_ANGLE_X)
+    focal = 0.5 * W / np.tan(0.5 * CAMERA_ANGLE_X)
     th, ph = rs.uniform(0, 2 * np.pi), rs.uniform(np.pi / 6, np.pi / 3)
     cam = 4.0 * np.array([np.cos(th) * np.sin(ph), np.sin(th) * np.sin(ph), np.cos(ph)])
     fwd = -cam / np.linalg.norm(cam)
     right = np.cross(fwd, np.array([0.0, 0.0, 1.0])); right /= np.linalg.norm(right)
     up = np.cross(right, fwd)
-    px = rs.randint(0, IMG_W, n); py = rs.randint(0, IMG_H, n)
-    dc = np.stack([(px - IMG_W / 2) / focal, -(py - IMG_H / 2) / focal, -np.ones(n)], -1)
+    if pixels == "all":
+        py, px = np.divmod(np.arange(H * W), W)
+        n = H * W
+    else:
+        px = rs.randint(0, W, n); py = rs.randint(0, H, n)
+    dc = np.stack([(px - W / 2) / focal, -(py - H / 2) / focal, -np.ones(n)], -1)
     d = dc[:, :1] * right + dc[:, 1:2] * up - dc[:, 2:3] * fwd
     d /= np.linalg.norm(d, axis=-1, keepdims=True)
     o = np.broadcast_to(cam, (n, 3))
@@ -64,7 +92,6 @@ class ClockSampler:
         try:
             import pynvml
             pynvml.nvmlInit()
-            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES if it is a plain index list
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
             idx = self.gpu
             if vis:
@@ -90,7 +117,8 @@ class ClockSampler:
                     rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.rows.append((sm, rs))
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                self.rows.append((sm, rs, util))
             except Exception as e:      # noqa: BLE001
                 self.err = repr(e)
                 return
@@ -106,7 +134,7 @@ class ClockSampler:
                  "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
                  "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
                  "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
-        reasons = sorted(k for k, bit in names.items() if any(r & bit for _, r in self.rows))
+        reasons = sorted(k for k, bit in names.items() if any(r[1] & bit for r in self.rows))
         sm = [r[0] for r in self.rows]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.max_sm),
                 "reasons": reasons, "samples": len(sm)}
@@ -134,116 +162,212 @@ def synthetic_weights(seed):
     return w
 
 
-def ncu_traffic():
-    """DRAM bytes (read + write) of one bench-shaped render_rays launch from the committed ncu
-    --set full capture (profiles/*_ncu_traffic.json, written by tools/summarize_ncu.py); None if absent."""
+def ncu_profile():
+    """Numbers of the committed ncu --set full capture of the bench-shaped launch
+    (profiles/*_ncu_traffic.json, written by tools/summarize_ncu.py): DRAM bytes per launch and the
+    tensor-pipe active percentage; (None, None, None) if absent."""
     import glob
-    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_ncu_traffic.json")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_traffic.json")))
     if not files:
-        return None
+        return None, None, None
     try:
-        return float(json.load(open(files[-1]))["traffic_bytes_per_launch"])
+        j = json.load(open(files[-1]))
+        return float(j["traffic_bytes_per_launch"]), j.get("tensor_pipe_active_pct"), os.path.basename(files[-1])
     except Exception:
-        return None
+        return None, None, None
 
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         j = json.load(open(p))
-        return float(j["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst cuBLAS 8192^3)"
-    return 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+        return (float(j["bf16_tflops"]), float(j.get("bf16_tflops_sustained", j["bf16_tflops"])),
+                "measured (MEASURED_PEAKS.json: cuBLAS bf16 8192^3, burst / 4 s sustained)")
+    return 1590.0, 1400.0, "fallback (B200_PROFILING.md: 1.59 PFLOP/s burst, ~1.4 sustained)"
 
 
-_BEST_THREADS = None
+# ----------------------------------------------------------------------------- the reference on the host
+_REF = None
 
 
-def best_blas_threads():
-    """The numpy/BLAS thread count that renders fastest on this host (all cores is not always
-    best: on a 128-core box the 256-wide GEMMs oversubscribe).  Probed once, ~2 s."""
-    global _BEST_THREADS
-    if _BEST_THREADS is not None:
-        return _BEST_THREADS
-    cores = os.cpu_count() or 1
+def import_reference():
+    """The unmodified reference modules staged under baseline/_ref (tools/stage_reference.py), or None."""
+    global _REF
+    if _REF is not None:
+        return _REF or None
+    path = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(path, "models", "rendering.py")):
+        _REF = False
+        return None
+    import torch
+    shim = types.ModuleType("torchsearchsorted")       # SURVEY.md section 8c: bit-identical on the reference's test grid
+    shim.searchsorted = lambda a, v, out=None, side="left": torch.searchsorted(
+        a.contiguous(), v.contiguous(), right=(side == "right"))
+    sys.modules["torchsearchsorted"] = shim
+    sys.path.insert(0, path)
     try:
-        from threadpoolctl import threadpool_limits
-    except Exception:
-        _BEST_THREADS = cores
-        return cores
-    from oracle import nerf_oracle as orc
-    ws = [synthetic_weights(11), synthetic_weights(12)]
-    rays = blender_rays(128, 0)
-    best, best_t = cores, float("inf")
-    cands = sorted({c for c in (4, 8, 16, 32, 64, cores) if c <= cores})
-    for c in cands:
-        with threadpool_limits(limits=c):
-            orc.render_rays(ws, rays[:16], N_SAMPLES, False, 0.0, 0.0, N_IMPORTANCE, True, False)
+        from models.nerf import Embedding, NeRF
+        from models.rendering import render_rays
+        from losses import MSELoss
+    except Exception as e:      # noqa: BLE001
+        print("reference import failed:", repr(e), file=sys.stderr)
+        _REF = False
+        return None
+    _REF = {"Embedding": Embedding, "NeRF": NeRF, "render_rays": render_rays, "MSELoss": MSELoss}
+    return _REF
+
+
+class HostReference:
+    """The CPU arm: the reference's PyTorch path (kind 'reference') or the numpy oracle (kind 'port')."""
+
+    def __init__(self):
+        self.ref = import_reference()
+        self.kind = "reference" if self.ref else "port"
+        self.ws = [synthetic_weights(11), synthetic_weights(12)]
+        self.threads = None
+        if self.ref:
+            import torch
+            self.torch = torch
+            self.models = []
+            for w in self.ws:
+                m = self.ref["NeRF"]()
+                m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+                self.models.append(m)
+            self.emb = [self.ref["Embedding"](3, 10), self.ref["Embedding"](3, 4)]
+
+    def render(self, rays, randoms=None, seed=0):
+        """render_rays(perturb=1, noise_std=0, white_back, test_time=False) -> dict of numpy arrays.
+        With `randoms` (perturb_rand, u_rand) the draws are replayed exactly (oracle: passed in; torch:
+        the global generator is seeded so that rand() returns them — models/rendering.py:203, :39)."""
+        if self.ref:
+            torch = self.torch
+            if randoms is not None:
+                torch.manual_seed(seed)
+            with torch.no_grad():
+                out = self.ref["render_rays"](self.models, self.emb, torch.from_numpy(rays), N_SAMPLES, False, 1.0, 0.0,
+                                              N_IMPORTANCE, 1024 * 32, True, test_time=False)
+            return {k: v.numpy() for k, v in out.items()}
+        from oracle import nerf_oracle as orc
+        return orc.render_rays(self.ws, rays, N_SAMPLES, False, 1.0, 0.0, N_IMPORTANCE, True, False, randoms)
+
+    def replay_randoms(self, n, seed):
+        """The two uniform draws the reference makes for an n-ray batch after torch.manual_seed(seed)
+        (perturb_rand (n,64) at :203, then — noise_std = 0 still draws randn (n,64) at :152 — u (n,64) at :39)."""
+        if self.ref:
+            torch = self.torch
+            torch.manual_seed(seed)
+            pr = torch.rand(n, N_SAMPLES)
+            torch.randn(n, N_SAMPLES)
+            ur = torch.rand(n, N_IMPORTANCE)
+            return {"perturb_rand": pr.numpy(), "u_rand": ur.numpy()}
+        rs = np.random.RandomState(seed)
+        return {"perturb_rand": rs.rand(n, N_SAMPLES).astype(np.float32), "u_rand": rs.rand(n, N_IMPORTANCE).astype(np.float32)}
+
+    def pick_threads(self):
+        """Fastest thread count for this host on a 128-ray probe (all cores is not always best)."""
+        if self.threads is not None:
+            return self.threads
+        cores = os.cpu_count() or 1
+        cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
+        rays = blender_rays(128, 0)
+        best, best_t = cores, float("inf")
+        for c in cands:
+            self._set_threads(c)
+            self.render(rays[:16], self.replay_randoms(16, 1), 1)
             t0 = time.perf_counter()
-            orc.render_rays(ws, rays, N_SAMPLES, False, 0.0, 0.0, N_IMPORTANCE, True, False)
+            self.render(rays, self.replay_randoms(128, 1), 1)
             t = time.perf_counter() - t0
-        if t < best_t:
-            best, best_t = c, t
-    _BEST_THREADS = best
-    return best
+            if t < best_t:
+                best, best_t = c, t
+        self.threads = best
+        self._set_threads(best)
+        return best
+
+    def _set_threads(self, c):
+        if self.ref:
+            self.torch.set_num_threads(c)
+        else:
+            try:
+                from threadpoolctl import threadpool_limits
+                self._limit = threadpool_limits(limits=c)
+            except ImportError:
+                pass
+
+    def time_forward(self, n_rays, reps, seed=0):
+        self.pick_threads()
+        rays = blender_rays(n_rays, seed)
+        rnd = self.replay_randoms(n_rays, seed + 1)
+        self.render(rays[:32], self.replay_randoms(32, 2), 2)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            self.render(rays, rnd, seed + 1)
+            ts.append(time.perf_counter() - t0)
+        t = float(np.median(ts))
+        return n_rays * SAMPLES_PER_RAY / t, t
+
+    def time_train_step(self, n_rays, reps, seed=0):
+        """fwd + MSELoss + backward + Adam on the host (train.py:103-117), reference kind only."""
+        if not self.ref:
+            return None
+        torch = self.torch
+        self.pick_threads()
+        rays = torch.from_numpy(blender_rays(n_rays, seed))
+        tgt = torch.rand(n_rays, 3)
+        params = [p for m in self.models for p in m.parameters()]
+        opt = torch.optim.Adam(params, lr=5e-4)
+        lossf = self.ref["MSELoss"]()
+        ts = []
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            opt.zero_grad()
+            out = self.ref["render_rays"](self.models, self.emb, rays, N_SAMPLES, False, 1.0, 0.0, N_IMPORTANCE,
+                                          1024 * 32, True, test_time=False)
+            lossf(out, tgt).backward()
+            opt.step()
+            ts.append(time.perf_counter() - t0)
+        # restore the weights the other legs use
+        for m, w in zip(self.models, self.ws):
+            m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+        return float(np.median(ts[1:]))
 
 
-def cpu_oracle_throughput(n_rays, reps, seed=0):
-    """ray-samples/s of the oracle on the host cores over `reps` batches of n_rays (same workload),
-    with the BLAS thread count that is fastest on this host."""
-    try:
-        from threadpoolctl import threadpool_limits
-        with threadpool_limits(limits=best_blas_threads()):
-            return _cpu_oracle_throughput(n_rays, reps, seed)
-    except ImportError:
-        return _cpu_oracle_throughput(n_rays, reps, seed)
-
-
-def _cpu_oracle_throughput(n_rays, reps, seed=0):
-    from oracle import nerf_oracle as orc      # the cpu_baseline / reference leg: the oracle is what is timed
-    ws = [synthetic_weights(11), synthetic_weights(12)]
-    rays = blender_rays(n_rays, seed)
-    rs = np.random.RandomState(seed)
-    rnd = {"perturb_rand": rs.rand(n_rays, N_SAMPLES).astype(np.float32),
-           "u_rand": rs.rand(n_rays, N_IMPORTANCE).astype(np.float32)}
-    orc.render_rays(ws, rays[:32], N_SAMPLES, False, 1.0, 0.0, N_IMPORTANCE, True, False,
-                    {k: v[:32] for k, v in rnd.items()})       # warm BLAS threads
-    times = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        orc.render_rays(ws, rays, N_SAMPLES, False, 1.0, 0.0, N_IMPORTANCE, True, False, rnd)
-        times.append(time.perf_counter() - t0)
-    return n_rays * SAMPLES_PER_RAY / float(np.median(times)), float(np.median(times))
+def workload_config(n_gpus, graph):
+    return {"workload": "blender_lego_400x400 N_samples=64 N_importance=64 batch_size=1024/GPU (configs[1]; at N>1 "
+                        "configs[4]'s sharded batch), render_rays perturb=1 noise_std=0 white_back test_time=False",
+            "rays_per_step_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "samples_per_ray": SAMPLES_PER_RAY,
+            "parallelism": (f"ray-sharded dp{n_gpus}, weights replicated, one NCCL all-gather of the rendered batch "
+                            f"per step" if n_gpus > 1 else "single GPU"),
+            "timed_region": ("K steps in one CUDA graph, two events around the replay" if graph else
+                             "eager loop, two events around K steps"),
+            "l2": f"inputs larger than L2: {N_ROT} copies of the packed weights ({N_ROT * 2 * 1.09:.0f} MB read in rotation) "
+                  f"and {N_ROT} ray batches, one per step; no step re-reads what the previous steps cached"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = best_blas_threads()
-    n_rays = 256                      # bounded sample of the 1024-ray batch (same per-ray work)
-    for _ in range(max(args.warmup, 1)):
-        cpu_oracle_throughput(n_rays, 1)
-    vals = [cpu_oracle_throughput(n_rays, 1, seed=i)[0] for i in range(args.steps)]
+    host = HostReference()
+    cores = host.pick_threads()
+    n_rays = BATCH if host.kind == "reference" else 256
+    for _ in range(max(min(args.warmup, 2), 1)):
+        host.time_forward(n_rays, 1)
+    vals = [host.time_forward(n_rays, 1, seed=i)[0] for i in range(args.steps)]
     v = float(np.median(vals))
-    ms = n_rays * SAMPLES_PER_RAY / v * 1e3
-    sample = (f"{n_rays} rays of the 1024-ray batch per step (64+128 samples/ray), numpy/BLAS on {cores} threads "
-              f"(fastest of 4..{os.cpu_count()} on this host)")
+    ms = BATCH * SAMPLES_PER_RAY / v * 1e3
+    what = ("the unmodified reference (baseline/_ref: models/rendering.py render_rays + models/nerf.py, PyTorch fp32)"
+            if host.kind == "reference" else "numpy port of the reference (oracle/nerf_oracle.py)")
+    sample = (f"{n_rays} rays per step (64+128 samples/ray) through {what} on {cores} of {os.cpu_count()} host "
+              f"threads (fastest setting probed)")
     emit(({
         "impl": "reference", "metric": "ray-samples/sec (coarse+fine)", "value": v, "unit": "ray-samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": v, "unit": "ray-samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.gpus, False),
+        "cpu_baseline": {"value": v, "unit": "ray-samples/s", "cores": cores, "kind": host.kind, "sample": sample},
         "e2e": {"value": v, "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
-
-
-def workload_config(n_gpus):
-    return {"workload": "blender_lego_400x400 N_samples=64 N_importance=64 batch_size=1024/GPU, "
-                        "render_rays training-mode forward (perturb=1, noise_std=0, white_back, coarse rgb)",
-            "rays_per_step_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "samples_per_ray": SAMPLES_PER_RAY,
-            "parallelism": f"ray-sharded dp{n_gpus}, weights replicated, no data-path collective" if n_gpus > 1 else "single GPU",
-            "l2": "flushed between timed steps (256 MiB write)"}
 
 
 def run_b200(args):
@@ -252,6 +376,7 @@ def run_b200(args):
 
     import nerf_pl_b200 as nb
     from nerf_pl_b200 import _lib
+    from nerf_pl_b200.sharded import render_rays_sharded
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -259,114 +384,256 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION level
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    K = args.steps
 
     ws = [synthetic_weights(11), synthetic_weights(12)]   # random init: there are no checkpoints
-    models = []
-    for w in ws:
-        m = nb.NeRF()
-        m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
-        models.append(m.to(dev).eval())
+    sd = [{k: torch.from_numpy(v) for k, v in w.items()} for w in ws]
+
+    def make_models(train=False):
+        out = []
+        for s in sd:
+            m = nb.NeRF()
+            m.load_state_dict(s)
+            m = m.to(dev)
+            if not train:
+                m.eval().requires_grad_(False)     # inference configuration: packed once
+            out.append(m)
+        return out
+
     emb = [nb.Embedding(3, 10), nb.Embedding(3, 4)]
-    n_batches = 8
-    host_rays = [torch.from_numpy(blender_rays(BATCH, 100 * rank + i)).pin_memory() for i in range(n_batches)]
+    model_sets = [make_models() for _ in range(N_ROT)]           # identical weights at distinct addresses
+    host_rays = [torch.from_numpy(blender_rays(BATCH, 1000 * rank + i)).pin_memory() for i in range(N_ROT)]
     dev_rays = [r.to(dev) for r in host_rays]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    def step(rays):
-        out = nb.render_rays(models, emb, rays, N_SAMPLES, False, 1.0, 0.0, N_IMPORTANCE, 1024 * 32, True,
-                             test_time=False)
-        return out       # rays are independent: no collective on the path
+    gather_buf = torch.empty(world * BATCH, 10, device=dev) if world > 1 else None
+
+    def step(i, rays=None, randoms=None):
+        out = nb.render_rays(model_sets[i % N_ROT], emb, dev_rays[i % N_ROT] if rays is None else rays, N_SAMPLES, False,
+                             1.0, 0.0, N_IMPORTANCE, 1024 * 32, True, test_time=False, randoms=randoms,
+                             match_reference_rng=False)
+        if world > 1:      # north_star: the rendered batch is exchanged with ONE all-gather at the end
+            packed = out["rgb_coarse"].new_empty(BATCH, 10)
+            torch.cat((out["rgb_coarse"], out["depth_coarse"][:, None], out["opacity_coarse"][:, None],
+                       out["rgb_fine"], out["depth_fine"][:, None], out["opacity_fine"][:, None]), 1, out=packed)
+            dist.all_gather_into_tensor(gather_buf, packed)
+        return out
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.no_grad():
-        for i in range(args.warmup):
-            step(dev_rays[i % n_batches])
+    def timed_graph(fn, n_steps):
+        """Capture n_steps calls of fn(i) in one CUDA graph; returns (replay callable, True) or the
+        eager loop (callable, False) if capture is not possible on this box."""
+        try:
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn(0)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                for i in range(n_steps):
+                    fn(i)
+            return g.replay, True
+        except Exception as e:      # noqa: BLE001
+            print("CUDA graph capture unavailable, timing the eager loop:", repr(e), file=sys.stderr)
+            torch.cuda.synchronize()
+
+            def loop():
+                for i in range(n_steps):
+                    fn(i)
+            return loop, False
+
+    def time_region(run):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        # ---- device-timed steps (inputs resident in HBM); L2 flushed between steps, not timed
+        t0 = time.perf_counter()
+        e0.record()
+        run()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), time.perf_counter() - t0
+
+    with torch.no_grad():
+        for i in range(max(args.warmup, N_ROT)):        # also packs every weight copy once
+            step(i)
+        barrier()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        # ---- value: K steps, device-timed
+        run, graphed = timed_graph(lambda i: step(i), K)
+        for _ in range(2):
+            run()                                       # graph warm-up replays (not timed)
         l0 = lib.nerfb200_launch_count()
-        barrier()
-        t_wall0 = time.perf_counter()
-        for i in range(args.steps):
-            flush.fill_(i & 0xFF)
-            ev[i][0].record()
-            step(dev_rays[i % n_batches])
-            ev[i][1].record()
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
+        total_ms, t_wall = time_region(run)
         launches = lib.nerfb200_launch_count() - l0
-        step_ms = [a.elapsed_time(b) for a, b in ev]
-        total_ms = float(sum(step_ms))
+        if graphed:
+            launches = K                               # replayed nodes do not pass through the library's counter
 
-        # ---- kernel-only timing for the roofline (pre-drawn randoms: the only kernel between the
-        # events is the fused render kernel, on torch's current stream, which is the launch stream)
+        # ---- kernel-only (roofline): pre-drawn randoms, the render kernel is the only node of a step
         rnd = {"perturb_rand": torch.rand(BATCH, N_SAMPLES, device=dev),
                "u_rand": torch.rand(BATCH, N_IMPORTANCE, device=dev)}
-        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for i in range(args.steps):
-            flush.fill_(i & 0xFF)
-            kev[i][0].record()
-            nb.render_rays(models, emb, dev_rays[i % n_batches], N_SAMPLES, False, 1.0, 0.0, N_IMPORTANCE,
-                           1024 * 32, True, test_time=False, randoms=rnd)
-            kev[i][1].record()
-        torch.cuda.synchronize()
-        kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
 
-        # ---- end to end through the public API with HOST buffers
+        def kstep(i):
+            nb.render_rays(model_sets[i % N_ROT], emb, dev_rays[i % N_ROT], N_SAMPLES, False, 1.0, 0.0, N_IMPORTANCE,
+                           1024 * 32, True, test_time=False, randoms=rnd)
+        krun, _ = timed_graph(kstep, K)
+        krun()
+        kern_total, _ = time_region(krun)
+        kern_ms = kern_total / K
+        # sustained: >= 1 s of back-to-back launches (power-capped behaviour)
+        reps = max(1, int(1.2e3 / max(kern_total, 1e-3)))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            krun()
+        e1.record()
+        torch.cuda.synchronize()
+        kern_ms_sustained = e0.elapsed_time(e1) / (reps * K)
+
+        # ---- end to end through the public API with HOST buffers (all six result tensors come back)
+        host_out = torch.empty(BATCH, 10).pin_memory()
+        eev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         barrier()
-        eev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        host_out = torch.empty(BATCH, 3).pin_memory()
-        for i in range(args.steps):
-            flush.fill_(i & 0xFF)
+        for i in range(K):
             eev[i][0].record()
-            r = host_rays[i % n_batches].to(dev, non_blocking=True)
-            out = step(r)
-            host_out.copy_(out["rgb_fine"], non_blocking=True)
+            r = host_rays[i % N_ROT].to(dev, non_blocking=True)
+            out = step(i, rays=r)
+            flat = torch.cat((out["rgb_coarse"], out["depth_coarse"][:, None], out["opacity_coarse"][:, None],
+                              out["rgb_fine"], out["depth_fine"][:, None], out["opacity_fine"][:, None]), 1)
+            host_out.copy_(flat, non_blocking=True)
             eev[i][1].record()
             eev[i][1].synchronize()          # the result is read on the host every step
         barrier()
         e2e_ms = float(sum(a.elapsed_time(b) for a, b in eev))
         clocks = sampler.stop() if rank == 0 else None
 
+        # ---- configs[4] inference: one 800x800 view, contiguous shards + one all-gather (strong scaling)
+        img = None
+        try:
+            rays800 = torch.from_numpy(blender_rays(0, 7, 800, 800, pixels="all")).to(dev)
+            fn = lambda r: nb.render_rays(model_sets[0], emb, r, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 1024 * 32, True,
+                                          test_time=True, match_reference_rng=False)
+            render800 = (lambda: render_rays_sharded(fn, rays800)) if world > 1 else (lambda: fn(rays800))
+            render800()
+            t_img = min(time_region(render800)[0] for _ in range(2))
+            img = {"rays": 640000, "ms": t_img, "value": 640000 * SAMPLES_PER_RAY / (t_img * 1e-3), "unit": "ray-samples/s",
+                   "scaling": "strong", "all_gather_bytes": 640000 * 6 * 4 if world > 1 else 0,
+                   "note": "test_time=True, contiguous 640000/N-ray shards, ONE all_gather_into_tensor of the packed results"}
+            del rays800
+        except Exception as e:      # noqa: BLE001
+            img = {"error": repr(e)}
+
+    # ---- config 2 as a TRAINING step: fused forward+loss, sm_100a backward, Adam (train.py:103-117)
+    train = None
+    if not args.no_train:
+        try:
+            tm = make_models(train=True)
+            params = [p for m in tm for p in m.parameters()]
+            opt = torch.optim.Adam(params, lr=5e-4, fused=True)
+            tgt = [torch.rand(BATCH, 3, device=dev) for _ in range(4)]
+
+            def tstep(i):
+                opt.zero_grad(set_to_none=True)
+                out = nb.render_rays_loss(tm, emb, dev_rays[i % N_ROT], tgt[i % 4], N_SAMPLES, False, 1.0, 0.0, N_IMPORTANCE,
+                                          1024 * 32, True, match_reference_rng=False)
+                out["loss"].backward()
+                opt.step()
+                return out["loss"]
+            for i in range(max(args.warmup, 3)):
+                first = tstep(i)
+            barrier()
+            l0 = lib.nerfb200_launch_count()
+            n_t = max(K, 10)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(n_t):
+                last = tstep(i)
+            e1.record()
+            barrier()
+            t_ms = e0.elapsed_time(e1) / n_t
+            train = {"ms_per_step": t_ms, "value": BATCH * SAMPLES_PER_RAY / (t_ms * 1e-3), "unit": "ray-samples/s",
+                     "steps": n_t, "kernels_per_step": (lib.nerfb200_launch_count() - l0) / n_t,
+                     "includes": "pack of both weight images, fused forward + MSE loss, compositing/head/chain/wgrad/"
+                                 "reduce/unfold backward kernels, torch.optim.Adam(fused=True)",
+                     "loss_first": float(first), "loss_last": float(last),
+                     "l2": "a step streams ~3.4 GB of activations (> L2): no flush needed"}
+        except Exception as e:      # noqa: BLE001
+            train = {"error": repr(e)}
+
     # max over ranks
-    t = torch.tensor([total_ms, e2e_ms, kern_ms], device=dev)
+    t = torch.tensor([total_ms, e2e_ms, kern_ms, kern_ms_sustained, (img or {}).get("ms", 0.0)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, kern_ms = [float(x) for x in t.tolist()]
+    total_ms, e2e_ms, kern_ms, kern_ms_sustained, img_ms = [float(x) for x in t.tolist()]
     if rank == 0:
-        samples = BATCH * SAMPLES_PER_RAY * world * args.steps
+        if img and "ms" in img:
+            img["ms"] = img_ms
+            img["value"] = 640000 * SAMPLES_PER_RAY / (img_ms * 1e-3)
+        samples = BATCH * SAMPLES_PER_RAY * world * K
         value = samples / (total_ms * 1e-3)
-        peak, peak_src = measured_peaks()
-        ach = BATCH * FLOP_PER_RAY_TRAIN / (kern_ms * 1e-3) / 1e12
-        cpu_v, cpu_t = cpu_oracle_throughput(256, 3)
-        cores = best_blas_threads()
+        peak, peak_sus, peak_src = measured_peaks()
+        flop = BATCH * FLOP_PER_RAY_TRAIN
+        flop_x = BATCH * SAMPLES_PER_RAY * executed_flop_per_sample()
+        ach = flop / (kern_ms * 1e-3) / 1e12
+        traffic, pipe_pct, prof_file = ncu_profile()
+        # ---- parity + CPU baseline: the reference on the host cores
+        host = HostReference()
+        cores = host.pick_threads()
+        parity = None
+        try:
+            n_par = 128
+            rays_np = blender_rays(BATCH, 1000 * rank)[:n_par]          # = the first rays of timed batch 0
+            rnd_np = host.replay_randoms(n_par, 4321)
+            ref = host.render(rays_np, rnd_np, 4321)
+            with torch.no_grad():
+                got = nb.render_rays(model_sets[0], emb, torch.from_numpy(rays_np).to(dev), N_SAMPLES, False, 1.0, 0.0,
+                                     N_IMPORTANCE, 1024 * 32, True, test_time=False,
+                                     randoms={k: torch.from_numpy(v).to(dev) for k, v in rnd_np.items()})
+            dif = np.abs(got["rgb_fine"].cpu().numpy().astype(np.float64) - ref["rgb_fine"]).ravel()
+            mse = float((dif ** 2).mean())
+            parity = {"rgb_fine_max_abs": float(dif.max()), "rgb_fine_p99_9": float(np.percentile(dif, 99.9)),
+                      "psnr_db": float(-10 * np.log10(max(mse, 1e-30))), "n_rays": n_par, "against": host.kind,
+                      "rgb_coarse_max_abs": float(np.abs(got["rgb_coarse"].cpu().numpy() - ref["rgb_coarse"]).max()),
+                      "bar": "rgb_fine within 1e-3 abs (north_star)"}
+        except Exception as e:      # noqa: BLE001
+            parity = {"error": repr(e)}
+        n_cpu = BATCH if host.kind == "reference" else 256
+        cpu_v, cpu_t = host.time_forward(n_cpu, 3)
+        cpu_train = host.time_train_step(256, 2) if host.kind == "reference" else None
         line = {
             "metric": "ray-samples/sec (coarse+fine)", "value": value, "unit": "ray-samples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": total_ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate, "
-            "fp32 encoding/compositing)", "data": "synthetic", "config": workload_config(world),
+            "fp32 encoding/compositing)", "data": "synthetic", "config": workload_config(world, graphed),
             "clocks": clocks,
             "e2e": {"value": samples / (e2e_ms * 1e-3), "unit": "ray-samples/s",
-                    "h2d_bytes_per_step": BATCH * 8 * 4, "d2h_bytes_per_step": BATCH * 3 * 4},
+                    "h2d_bytes_per_step": BATCH * 8 * 4, "d2h_bytes_per_step": BATCH * 10 * 4},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                         "frac": ach / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
-                         "kernel": "render_rays_kernel", "kernel_ms": kern_ms,
-                         "flop_per_launch": BATCH * FLOP_PER_RAY_TRAIN},
-            "cpu_baseline": {"value": cpu_v, "unit": "ray-samples/s", "cores": cores, "kind": "port",
-                             "sample": f"256 rays of the same batch, 3 reps, median {cpu_t:.2f} s, numpy/BLAS on {cores} of "
-                                       f"{os.cpu_count()} host threads (fastest setting)"},
+                         "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "render_rays_kernel", "kernel_ms": kern_ms, "flop_per_launch": flop,
+                         "executed_flop_per_launch": flop_x, "frac_executed": flop_x / (kern_ms * 1e-3) / 1e12 / peak,
+                         "kernel_ms_sustained": kern_ms_sustained,
+                         "frac_sustained": flop / (kern_ms_sustained * 1e-3) / 1e12 / peak_sus,
+                         "peak_sustained": peak_sus,
+                         "tensor_pipe_active_pct": pipe_pct, "ncu_capture": prof_file},
+            "cpu_baseline": {"value": cpu_v, "unit": "ray-samples/s", "cores": cores, "kind": host.kind,
+                             "sample": f"{n_cpu} rays of the same workload, 3 reps, median {cpu_t:.2f} s, on {cores} of "
+                                       f"{os.cpu_count()} host threads (fastest setting probed)",
+                             "train_step_s_256_rays": cpu_train},
+            "parity": parity,
+            "train": train,
+            "image_800": img,
+            "collective": ("NCCL all_gather_into_tensor, %d B per rank per step" % (BATCH * 40)) if world > 1 else None,
             "wall_s_timed_region": t_wall,
         }
         emit(line)
@@ -395,9 +662,10 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

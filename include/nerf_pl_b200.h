@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define NERFB200_ABI_VERSION 1
+#define NERFB200_ABI_VERSION 2
 
 #define NERFB200_EINVAL (-1)      /* bad argument value / null pointer            */
 #define NERFB200_EUNSUPPORTED (-2) /* shape outside what the fused kernel supports */
@@ -35,7 +35,8 @@ const char* nerfb200_last_error(void);
  * state_dict order: xyz_encoding_{1..8}.0.{weight,bias}, xyz_encoding_final.{weight,bias},
  * dir_encoding.0.{weight,bias}, sigma.{weight,bias}, rgb.0.{weight,bias}; weights are
  * (out,in) row-major as torch stores them.  Produces the fp16/fp32 image the kernels stream
- * (nerfb200_packed_bytes() bytes, 1024-byte aligned). */
+ * (nerfb200_packed_bytes() bytes, 1024-byte aligned): the forward slices, the fp32 constants and
+ * the transposed 16-bit slices of the backward chain kernel. */
 size_t nerfb200_packed_bytes(void);
 int nerfb200_pack_weights(const float* const params[24], void* packed, void* stream);
 
@@ -91,23 +92,61 @@ typedef struct nerfb200_render_args {
   float* weights_fine;
   int32_t* status;
   int32_t max_ctas; /* 0 = one CTA per SM */
-  /* Training mode (all NULL = inference; requires test_time == 0): per-sample intermediates the
-   * backward pass needs, written by the same fused launch.  n_c = n_rays*N_samples,
-   * n_f = n_rays*(N_samples+N_importance); sample row = ray*S + index along the (sorted) ray.
-   *   save_act_*   fp16 (8, n, 256): outputs of xyz_encoding_1..8 (post-ReLU)
-   *   save_dir_*   fp16 (n, 128):    output of dir_encoding (post-ReLU)
-   *   save_sigma_* fp32 (n):         raw sigma          save_rgb_* fp32 (n, 3): sigmoid(rgb) */
-  void* save_act_coarse;
-  void* save_act_fine;
-  void* save_dir_coarse;
-  void* save_dir_fine;
-  float* save_sigma_coarse;
-  float* save_sigma_fine;
-  float* save_rgb_coarse;
-  float* save_rgb_fine;
+  /* Optional: the (stratified) coarse depths (n, N_samples) (models/rendering.py:189-204). */
+  float* z_coarse;
+  /* Training mode (NULL = inference; requires test_time == 0): a device workspace of
+   * nerfb200_train_workspace_bytes() bytes, initialised once with nerfb200_train_workspace_init().
+   * The same fused launch then also stores, per sample, what nerfb200_render_backward needs: the
+   * encoded input and the outputs of xyz_encoding_1..8 (fp16), the ReLU sign bits, the output of
+   * dir_encoding, raw sigma, rgb and the depths of both passes. */
+  void* train_workspace;
+  /* Fused loss epilogue (replaces losses.py:9-14 MSELoss.forward and metrics.py:4-13 psnr on the
+   * rendered batch; all NULL = off): target (n,3) -> loss_out[4] (device) = {mse(rgb_coarse),
+   * mse(rgb_fine) or 0, their sum (= MSELoss), psnr of the finest pass}.  Needs train_workspace
+   * (it holds the per-CTA partial sums; the reduction order is fixed, so the result is
+   * deterministic). */
+  const float* target;
+  float* loss_out;
 } nerfb200_render_args;
 
 int nerfb200_render_rays(const nerfb200_render_args* args, void* stream);
+
+/* ---- training step: backward of render_rays -------------------------------------------------
+ * Replaces: loss.backward() of train.py:103-117 through models/rendering.py:143-170 (quadrature)
+ * and models/nerf.py:100-124 (both MLPs); no gradient flows through the fine-depth sampling
+ * (models/rendering.py:225-227 .detach()) nor into the rays.
+ *
+ * Protocol: (1) nerfb200_render_rays(args with train_workspace set, test_time = 0);
+ * (2) nerfb200_render_backward with the SAME render args (rays, random inputs, flags, packed
+ * images, outputs) and either the upstream gradients of the result tensors (g_*, any may be
+ * NULL = zero) or `target` (the fused MSE seed dL/drgb = 2 (rgb - target) / (3 n) * *loss_grad for
+ * both passes, added to g_rgb_* if those are given).  Writes the gradients of the 24 parameter
+ * tensors of each network (state_dict order and shapes, fp32; `params_*` are the live fp32
+ * parameters).  grads_fine / params_fine are ignored when n_importance == 0.
+ * All kernels are hand-written sm_100a code on `stream`: compositing backward, rgb head,
+ * tcgen05 dgrad chain, tcgen05 split-K wgrad, partial reduction, unfolding of the packed
+ * final.dir layer. */
+size_t nerfb200_train_workspace_bytes(int64_t n_rays, int32_t n_samples, int32_t n_importance);
+/* One-time set-up of a workspace for (n_rays, n_samples, n_importance): zeroes the padding rows,
+ * counters and uploads the wgrad job table.  Synchronous with respect to `stream`. */
+int nerfb200_train_workspace_init(void* workspace, size_t bytes, int64_t n_rays, int32_t n_samples,
+                                  int32_t n_importance, void* stream);
+typedef struct nerfb200_backward_args {
+  const nerfb200_render_args* render;   /* as passed to the forward call */
+  const float* const* params_coarse;    /* 24 device pointers */
+  const float* const* params_fine;
+  const float* g_rgb_coarse;            /* (n,3) */
+  const float* g_depth_coarse;          /* (n)   */
+  const float* g_opacity_coarse;        /* (n)   */
+  const float* g_rgb_fine;
+  const float* g_depth_fine;
+  const float* g_opacity_fine;
+  const float* target;                  /* (n,3) or NULL */
+  const float* loss_grad;               /* device scalar or NULL (= 1) */
+  float* const* grads_coarse;           /* 24 device pointers, shapes of params_coarse */
+  float* const* grads_fine;
+} nerfb200_backward_args;
+int nerfb200_render_backward(const nerfb200_backward_args* args, void* stream);
 
 /* Same call with HOST buffers (pageable or pinned): copies rays (and the random inputs that
  * are non-NULL) to the device, renders, copies the requested outputs back, synchronises.
@@ -128,14 +167,6 @@ int nerfb200_nerf_forward(const float* x, int64_t n, int64_t x_stride, const voi
  * computed in the kernel, the direction does not enter sigma (models/nerf.py:112). */
 int nerfb200_query_sigma(const float* xyz, int64_t n, int64_t xyz_stride, const void* packed, float* sigma,
                          void* stream);
-
-/* ---- backward glue --------------------------------------------------------------------------
- * dpre = dh * (act > 0) for one ReLU layer of the hand-written MLP backward
- * (nerf_pl_b200/training.py; the derivative of models/nerf.py:68 nn.ReLU), fp16 (n_rows, n_cols),
- * written row-major (dpre, for the dgrad GEMM) and transposed (dpre_t (n_cols, n_rows), for the
- * wgrad GEMM) in one pass.  n_cols % 64 == 0, n_rows even. */
-int nerfb200_relu_backward(const void* dh, const void* act, int64_t n_rows, int32_t n_cols, void* dpre,
-                           void* dpre_t, void* stream);
 
 /* ---- loss / metric epilogue ("next" row) -------------------------------------------------
  * Replaces: losses.py:9-14 MSELoss.forward and metrics.py:4-13 psnr on the rendered batch.

@@ -34,8 +34,10 @@ int nerfb200_debug_timeline(int64_t* host_out, int64_t n_values);
 /* MN-major operand probe (the layout the wgrad kernel uses): d (128, 256) = a^T b for
  * a (64, 128), b (64, 256) fp32 inputs rounded to fp16, both staged in shared memory as
  * [64-feature block][64 rows = samples][128 B] SWIZZLE_128B images and read by tcgen05.mma with
- * MN-major descriptors (lbo / sbo in bytes). */
-int nerfb200_debug_gemm_mn(const float* a, const float* b, int32_t lbo, int32_t sbo, float* d, void* stream);
+ * MN-major descriptors (lbo / sbo in bytes).  fmt bit 0: A staged as bf16, bit 1: B as bf16
+ * (mixed formats = what the wgrad kernel issues: bf16 gradients x fp16 activations). */
+int nerfb200_debug_gemm_mn(const float* a, const float* b, int32_t lbo, int32_t sbo, int32_t fmt, float* d,
+                           void* stream);
 
 #ifdef __cplusplus
 }

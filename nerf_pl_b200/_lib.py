@@ -19,7 +19,8 @@ LIB_PATH = os.path.join(_HERE, "libnerf_pl_b200.so")
 if os.environ.get("NERFB200_LIB"):          # experiment builds (tools/build_variants.py); unset in production
     LIB_PATH = os.path.abspath(os.environ["NERFB200_LIB"])
 SOURCES = ["capi.cu"]
-HEADERS = ["ptx.cuh", "layout.h", "mlp_engine.cuh", "render_kernel.cuh", "aux_kernels.cuh", "diag_kernels.cuh"]
+HEADERS = ["ptx.cuh", "layout.h", "mlp_engine.cuh", "render_kernel.cuh", "aux_kernels.cuh", "bwd_kernels.cuh",
+           "diag_kernels.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -42,7 +43,9 @@ EXPORTS = [
     "nerfb200_composite",
     "nerfb200_query_sigma",
     "nerfb200_mse_psnr",
-    "nerfb200_relu_backward",
+    "nerfb200_train_workspace_bytes",
+    "nerfb200_train_workspace_init",
+    "nerfb200_render_backward",
     "nerfb200_generate_rays",
     "nerfb200_to_uint8",
     "nerfb200_launch_count",
@@ -90,14 +93,30 @@ class RenderArgs(ctypes.Structure):
         ("weights_fine", c_void_p),
         ("status", c_void_p),
         ("max_ctas", c_int32),
-        ("save_act_coarse", c_void_p),
-        ("save_act_fine", c_void_p),
-        ("save_dir_coarse", c_void_p),
-        ("save_dir_fine", c_void_p),
-        ("save_sigma_coarse", c_void_p),
-        ("save_sigma_fine", c_void_p),
-        ("save_rgb_coarse", c_void_p),
-        ("save_rgb_fine", c_void_p),
+        ("z_coarse", c_void_p),
+        ("train_workspace", c_void_p),
+        ("target", c_void_p),
+        ("loss_out", c_void_p),
+    ]
+
+
+class BackwardArgs(ctypes.Structure):
+    """Mirror of ``nerfb200_backward_args`` (include/nerf_pl_b200.h)."""
+
+    _fields_ = [
+        ("render", POINTER(RenderArgs)),
+        ("params_coarse", POINTER(c_void_p)),
+        ("params_fine", POINTER(c_void_p)),
+        ("g_rgb_coarse", c_void_p),
+        ("g_depth_coarse", c_void_p),
+        ("g_opacity_coarse", c_void_p),
+        ("g_rgb_fine", c_void_p),
+        ("g_depth_fine", c_void_p),
+        ("g_opacity_fine", c_void_p),
+        ("target", c_void_p),
+        ("loss_grad", c_void_p),
+        ("grads_coarse", POINTER(c_void_p)),
+        ("grads_fine", POINTER(c_void_p)),
     ]
 
 
@@ -155,8 +174,12 @@ def _declare(lib: ctypes.CDLL) -> None:
                                        c_void_p, c_void_p]
     lib.nerfb200_query_sigma.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
     lib.nerfb200_query_sigma.restype = c_int32
-    lib.nerfb200_relu_backward.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]
-    lib.nerfb200_relu_backward.restype = c_int32
+    lib.nerfb200_train_workspace_bytes.argtypes = [c_int64, c_int32, c_int32]
+    lib.nerfb200_train_workspace_bytes.restype = c_size_t
+    lib.nerfb200_train_workspace_init.argtypes = [c_void_p, c_size_t, c_int64, c_int32, c_int32, c_void_p]
+    lib.nerfb200_train_workspace_init.restype = c_int32
+    lib.nerfb200_render_backward.argtypes = [POINTER(BackwardArgs), c_void_p]
+    lib.nerfb200_render_backward.restype = c_int32
     lib.nerfb200_mse_psnr.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
     lib.nerfb200_mse_psnr.restype = c_int32
     lib.nerfb200_generate_rays.argtypes = [c_int32, c_int32, c_float, POINTER(c_float), c_float, c_float, c_int32,
@@ -167,7 +190,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     if hasattr(lib, "nerfb200_debug_gemm"):        # diagnostics build only
         lib.nerfb200_debug_gemm.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
         lib.nerfb200_debug_gemm.restype = c_int32
-        lib.nerfb200_debug_gemm_mn.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
+        lib.nerfb200_debug_gemm_mn.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
         lib.nerfb200_debug_gemm_mn.restype = c_int32
         lib.nerfb200_debug_mma_bench.argtypes = [c_void_p, c_int32, c_int32, c_void_p]
         lib.nerfb200_debug_mma_bench.restype = c_int32
@@ -195,7 +218,7 @@ def load() -> ctypes.CDLL:
                     "(nerf_pl_b200 has no CPU fallback)")
             lib = ctypes.CDLL(LIB_PATH)
             _declare(lib)
-            if lib.nerfb200_abi_version() != 1:
+            if lib.nerfb200_abi_version() != 2:
                 raise RuntimeError("libnerf_pl_b200.so ABI version mismatch")
             _lib = lib
     return _lib

@@ -3,6 +3,8 @@
 // fuses all of them; these entries exist so each row has its own parity test and so callers
 // that use the pieces directly (extract_color_mesh.py:127-140) have a drop-in.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "render_kernel.cuh"
 
 namespace nerfb200 {
@@ -11,6 +13,7 @@ namespace nerfb200 {
 struct PackParams {
   const float* p[kNumParams];   // device pointers, order in layout.h
   uint8_t* out;
+  int bwd_bf16;                 // element type of the backward region: 1 = bf16, 0 = fp16
 };
 
 // One thread per fp16 element of the slice region, then the fp32 tail.
@@ -57,7 +60,33 @@ __global__ void pack_weights_kernel(const PackParams pp) {
     return;
   }
   const long long f = idx - n_half;
-  if (f >= kF32Count) return;
+  if (f >= kF32Count) {
+    // ---- backward region (layout.h): transposed slices B[n][k] = W[k0 + k][n0 + n], 16-bit
+    const long long e = f - kF32Count;
+    if (e >= static_cast<long long>(kNumSlicesBwd) * 256 * 64) return;
+    const int slice = static_cast<int>(e / (256 * 64));
+    const int rem = static_cast<int>(e % (256 * 64));
+    const int n = rem / 64, k = rem % 64;
+    float v;
+    if (slice < 2) {
+      // W'[m][n] = sum_j W_dir[m][j] W_final[j][n], m = slice * 64 + k
+      const float* wd = pp.p[18] + static_cast<long long>(slice * 64 + k) * 283;
+      const float* wf = pp.p[16] + n;
+      float acc = 0.f;
+      for (int j = 0; j < 256; ++j) acc = fmaf(wd[j], wf[static_cast<long long>(j) * 256], acc);
+      v = acc;
+    } else {
+      const int step = (slice - 2) / 4, kb = (slice - 2) % 4;
+      const int L = 8 - step;                                   // xyz_encoding_L, L = 8 .. 2
+      const int ld = (L == 5) ? 319 : 256, n0 = (L == 5) ? 63 : 0;
+      v = pp.p[2 * (L - 1)][static_cast<long long>(kb * 64 + k) * ld + n0 + n];
+    }
+    uint16_t bits;
+    if (pp.bwd_bf16) bits = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    else bits = __half_as_ushort(__float2half_rn(v));
+    *reinterpret_cast<uint16_t*>(pp.out + kOffBwd + static_cast<uint32_t>(slice) * kSliceBytes256 + sw128_off(n, k)) = bits;
+    return;
+  }
   float* o = reinterpret_cast<float*>(pp.out + kHalfRegionBytes);
   float v = 0.f;
   const int i = static_cast<int>(f);

@@ -1,0 +1,769 @@
+// Backward of the render_rays training step (reference: train.py:103-117 loss.backward() through
+// models/rendering.py:143-170 and models/nerf.py:100-124), hand-written for sm_100a.
+//
+// The forward launch in "train" mode (render_kernel.cuh, kSave) leaves per sample in the training
+// workspace: the encoded input, the 8 hidden activations (fp16, tiled layout of layout.h), the ReLU
+// sign bits of the 8 hidden layers, the direction-layer output, raw sigma and rgb.  The backward is
+//
+//   composite_bwd_kernel  warp per ray: d(rgb, depth, opacity) [or the fused MSE seed] -> per-sample
+//                         d sigma, d rgb_pre                                   (CUDA cores)
+//   head_bwd_kernel       rgb head + ReLU of the direction layer: dd (tiled 16-bit), the rgb-head and
+//                         direction-part weight gradients                      (CUDA cores)
+//   chain_bwd_kernel      dgrad chain on the tcgen05 tile engine: per 128-sample tile
+//                         dd -> dh8 -> dpre8 -> ... -> dpre1, activations in TMEM exactly like the
+//                         forward, 30 transposed weight slices per tile; writes dpre_l (tiled)
+//   wgrad_kernel          split-K tcgen05 GEMMs gW_l = dpre_l^T h_{l-1}: one CTA per (layer, sample
+//                         range), both operands MN-major straight from the tiled arrays, fp32
+//                         accumulators in TMEM for the CTA's whole range; bias gradients as column
+//                         sums on the CUDA cores of the same tiles
+//   wgrad_reduce_kernel   fixed-order sum of the per-CTA partials into the .grad tensors
+//   unfold_kernel         chain rule through the pack-time folding W' = W_dir[:, :256] W_final
+//
+// Per-sample gradients are 16-bit: bf16 by default (fp32 range: no scaling, no overflow; 8-bit
+// mantissa is enough for gradients that are summed over ~1e5 samples), fp16 with a power-of-two
+// scale chosen on the device with -DNERFB200_BWD_FP16.  Weight gradients accumulate in fp32.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "render_kernel.cuh"
+
+namespace nerfb200 {
+
+#ifdef NERFB200_BWD_FP16
+constexpr bool kBwdBf16 = false;
+#else
+constexpr bool kBwdBf16 = true;
+#endif
+constexpr uint32_t kBwdFmt = kBwdBf16 ? 1u : 0u;      // instruction-descriptor format code: 0 = f16, 1 = bf16
+
+__device__ __forceinline__ uint32_t cvt_bwd_x2(float lo, float hi) {
+  uint32_t d;
+  if (kBwdBf16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint16_t cvt_bwd(float v) {
+  if (kBwdBf16) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  return __half_as_ushort(__float2half_rn(v));
+}
+__device__ __forceinline__ float2 bwd_x2_to_float2(uint32_t p) {
+  if (kBwdBf16) return make_float2(__uint_as_float(p << 16), __uint_as_float(p & 0xFFFF0000u));
+  return __half22float2(*reinterpret_cast<const __half2*>(&p));
+}
+
+// ------------------------------------------------------------------------- compositing backward
+// models/rendering.py:143-170 differentiated by hand (oracle/nerf_oracle_grad.py
+// volume_render_backward is the executable statement of the same formulas):
+//   w_i = alpha_i T_i,  T_i = prod_{j<i} (1 - alpha_j + 1e-10),  alpha_i = 1 - exp(-delta_i relu(s_i))
+//   dL/dw_i     = <g_rgb, c_i> + g_depth z_i + g_opac - [white_back] sum_ch g_rgb
+//   dL/dalpha_i = T_i dL/dw_i - (sum_{j>i} w_j dL/dw_j) / (1 - alpha_i + 1e-10)
+//   dL/dsigma_i = dL/dalpha_i delta_i exp(-delta_i relu(s_i)) [s_i > 0]
+//   dL/dc_i     = w_i g_rgb;  through the sigmoid: dL/dpre_i = dL/dc_i c_i (1 - c_i)
+// One warp per ray, each lane owns P = S / 32 consecutive samples.
+struct CompBwdParams {
+  int n_rays, S;
+  long long n_pad;
+  const float* z;
+  const float* sigma;
+  const float* rgb;
+  const float* rays;
+  long long ray_stride;
+  const float* noise;       // (n_rays, S) or null
+  float noise_std;
+  int white_back;
+  const float* g_rgb;       // (n_rays, 3) upstream gradient or null
+  const float* g_depth;     // (n_rays) or null
+  const float* g_opac;      // (n_rays) or null
+  const float* rgb_out;     // (n_rays, 3) rendered colour, used with `target`
+  const float* target;      // (n_rays, 3) or null: adds the MSE seed 2 (rgb_out - target) / (3 n_rays) * loss_grad
+  const float* loss_grad;   // device scalar dL/dloss or null (= 1)
+  float* dsigma;
+  float* dprergb;
+  unsigned* amax_bits;      // max |d sigma|, |d rgb_pre| as float bits (fp16 mode scale selection) or null
+};
+
+__global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdParams p) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const long long ray = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5);
+  const int S = p.S, P = S >> 5;
+  float amax = 0.f;
+  if (ray < p.n_rays) {
+    const float* rr = p.rays + ray * p.ray_stride;
+    const float dx = rr[3], dy = rr[4], dz = rr[5];
+    const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    float g[3] = {0.f, 0.f, 0.f};
+    if (p.g_rgb != nullptr) { g[0] = p.g_rgb[ray * 3]; g[1] = p.g_rgb[ray * 3 + 1]; g[2] = p.g_rgb[ray * 3 + 2]; }
+    if (p.target != nullptr) {
+      const float lg = (p.loss_grad != nullptr) ? *p.loss_grad : 1.f;
+      const float k = 2.f * lg / (3.f * static_cast<float>(p.n_rays));
+#pragma unroll
+      for (int c = 0; c < 3; ++c) g[c] += k * (p.rgb_out[ray * 3 + c] - p.target[ray * 3 + c]);
+    }
+    const float gd = (p.g_depth != nullptr) ? p.g_depth[ray] : 0.f;
+    float go = (p.g_opac != nullptr) ? p.g_opac[ray] : 0.f;
+    if (p.white_back) go -= g[0] + g[1] + g[2];
+    const float* z = p.z + ray * S;
+    const long long g0 = ray * S;
+    float alpha[6], tloc[6], om[6], dw[6], de[6], wgt[6];
+    bool pos[6];
+    float prod = 1.f;
+    for (int q = 0; q < P; ++q) {
+      const int i = lane * P + q;
+      float delta = (i < S - 1) ? __fsub_rn(z[i + 1], z[i]) : 1e10f;
+      delta = __fmul_rn(delta, dnorm);
+      float s = p.sigma[g0 + i];
+      if (p.noise != nullptr) s = __fadd_rn(s, __fmul_rn(p.noise[g0 + i], p.noise_std));
+      const float e = expf(-__fmul_rn(delta, fmaxf(s, 0.f)));
+      alpha[q] = __fsub_rn(1.f, e);
+      om[q] = __fadd_rn(__fsub_rn(1.f, alpha[q]), 1e-10f);
+      de[q] = delta * e;
+      pos[q] = s > 0.f;
+      tloc[q] = prod;
+      prod = __fmul_rn(prod, om[q]);
+      const float* c = p.rgb + (g0 + i) * 3;
+      dw[q] = g[0] * c[0] + g[1] * c[1] + g[2] * c[2] + gd * z[i] + go;
+    }
+    float incl = prod;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl *= v;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.f;
+    // suffix sums of a_i = w_i dL/dw_i (exclusive, from the far end)
+    float asum = 0.f;
+    for (int q = 0; q < P; ++q) {
+      tloc[q] *= excl;                     // T_i
+      wgt[q] = alpha[q] * tloc[q];         // w_i
+      asum += wgt[q] * dw[q];
+    }
+    float sincl = asum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float v = __shfl_down_sync(0xffffffffu, sincl, o);
+      if (lane + o < 32) sincl += v;
+    }
+    float after = __shfl_down_sync(0xffffffffu, sincl, 1);     // sum over lanes > this one
+    if (lane == 31) after = 0.f;
+    float run = after;
+    for (int q = P - 1; q >= 0; --q) {
+      const int i = lane * P + q;
+      const float dalpha = tloc[q] * dw[q] - run / om[q];
+      run += wgt[q] * dw[q];
+      const float ds = pos[q] ? dalpha * de[q] : 0.f;
+      p.dsigma[g0 + i] = ds;
+      amax = fmaxf(amax, fabsf(ds));
+      const float* c = p.rgb + (g0 + i) * 3;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float dp = wgt[q] * g[ch] * c[ch] * (1.f - c[ch]);
+        p.dprergb[(g0 + i) * 3 + ch] = dp;
+        amax = fmaxf(amax, fabsf(dp));
+      }
+    }
+  }
+  // padding rows carry no gradient
+  const long long n = static_cast<long long>(p.n_rays) * S;
+  if (blockIdx.x == gridDim.x - 1)
+    for (long long i = n + threadIdx.x; i < p.n_pad; i += blockDim.x) {
+      p.dsigma[i] = 0.f;
+      p.dprergb[3 * i] = 0.f; p.dprergb[3 * i + 1] = 0.f; p.dprergb[3 * i + 2] = 0.f;
+    }
+  if (p.amax_bits != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0 && amax > 0.f && amax < 3e38f) atomicMax(p.amax_bits, __float_as_uint(amax));
+  }
+}
+
+// scale[0] = 2^floor(log2(1024 / amax)) (fp16 mode) or 1 (bf16 mode); scale[1] = 1 / scale[0].
+__global__ void bwd_scale_kernel(unsigned* amax_bits, float* scale) {
+  float s = 1.f;
+  if (!kBwdBf16) {
+    const float amax = __uint_as_float(*amax_bits);
+    if (amax > 0.f) s = exp2f(floorf(log2f(1024.f / amax)));
+    s = fminf(fmaxf(s, 1e-30f), 1e30f);
+  }
+  scale[0] = s;
+  scale[1] = 1.f / s;
+  *amax_bits = 0u;
+}
+
+// ------------------------------------------------------------------------ rgb head / dir ReLU
+// models/nerf.py:119-120 backwards, per sample:  dd = (dpre_rgb W_rgb) * (d > 0)  -> tiled 16-bit
+// (A operand of the chain kernel's first step and of the W' wgrad), and the three small weight
+// gradients that contract over samples on the CUDA cores:
+//   gW_rgb[c][n] = sum_s dpre_rgb[s][c] d[s][n]     gb_rgb[c] = sum_s dpre_rgb[s][c]
+//   gW_dir[n][256 + j] = sum_rays (sum_{s in ray} dd[s][n]) dir_enc[ray][j]   (direction is constant per ray)
+// Block = 128 threads (thread n = column n of the direction layer), a contiguous range of rays per
+// block; per-block partials, summed in fixed order by wgrad_reduce_kernel.
+constexpr int kHeadPartRgbW = 0;            // [3][128]
+constexpr int kHeadPartRgbB = 384;          // [4]
+constexpr int kHeadPartDir = 388;           // [128][27]
+constexpr int kHeadPartFloats = 388 + 128 * 27;
+struct HeadBwdParams {
+  int n_rays, S;
+  long long n_pad;
+  const __half* d;
+  const float* dprergb;
+  const float* w_rgb;       // live fp32 (3,128)
+  const float* rays;
+  long long ray_stride;
+  const float* scale;
+  uint8_t* dd;
+  float* part;              // [gridDim.x][kHeadPartFloats]
+};
+
+__global__ void __launch_bounds__(128) head_bwd_kernel(const HeadBwdParams p) {
+  __shared__ float direnc[28];
+  const int n = threadIdx.x;
+  const int per = p.n_rays / static_cast<int>(gridDim.x), rem = p.n_rays % static_cast<int>(gridDim.x);
+  const int r0 = static_cast<int>(blockIdx.x) * per + min(static_cast<int>(blockIdx.x), rem);
+  const int r1 = r0 + per + (static_cast<int>(blockIdx.x) < rem ? 1 : 0);
+  const float w0 = p.w_rgb[n], w1 = p.w_rgb[128 + n], w2 = p.w_rgb[256 + n];
+  const float scale = p.scale[0];
+  float gw[3] = {0.f, 0.f, 0.f}, gb = 0.f;
+  float gdir[27];
+#pragma unroll
+  for (int j = 0; j < 27; ++j) gdir[j] = 0.f;
+  const int fb = n >> 6, k = n & 63;
+  for (int ray = r0; ray < r1; ++ray) {
+    __syncthreads();
+    if (n < 15) {     // Embedding(3,4)(rays_d) as the forward computes it (render_kernel.cuh setup_group)
+      const int cc = n / 5, kk = n % 5;
+      const float dv = p.rays[static_cast<long long>(ray) * p.ray_stride + 3 + cc];
+      if (kk == 4) {
+        direnc[cc] = dv;
+      } else {
+        float sn, cs;
+        sincosf(__fmul_rn(static_cast<float>(1 << kk), dv), &sn, &cs);
+        direnc[3 + 6 * kk + cc] = sn;
+        direnc[3 + 6 * kk + 3 + cc] = cs;
+      }
+    }
+    float raysum = 0.f;
+    const long long g0 = static_cast<long long>(ray) * p.S;
+    for (int i = 0; i < p.S; ++i) {
+      const long long g = g0 + i;
+      const float q0 = __ldg(p.dprergb + 3 * g), q1 = __ldg(p.dprergb + 3 * g + 1), q2 = __ldg(p.dprergb + 3 * g + 2);
+      const float dv = __half2float(p.d[g * 128 + n]);
+      gw[0] = fmaf(q0, dv, gw[0]); gw[1] = fmaf(q1, dv, gw[1]); gw[2] = fmaf(q2, dv, gw[2]);
+      if (n < 3) gb += (n == 0) ? q0 : (n == 1 ? q1 : q2);
+      const float val = (dv > 0.f) ? fmaf(q0, w0, fmaf(q1, w1, q2 * w2)) : 0.f;
+      raysum += val;
+      const unsigned long long off = tiled_block_off(static_cast<unsigned long long>(g >> 6), fb, 2) +
+                                     sw128_off(static_cast<uint32_t>(g & 63), k);
+      *reinterpret_cast<uint16_t*>(p.dd + off) = cvt_bwd(val * scale);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 27; ++j) gdir[j] = fmaf(raysum, direnc[j], gdir[j]);
+  }
+  float* out = p.part + static_cast<long long>(blockIdx.x) * kHeadPartFloats;
+  out[kHeadPartRgbW + n] = gw[0];
+  out[kHeadPartRgbW + 128 + n] = gw[1];
+  out[kHeadPartRgbW + 256 + n] = gw[2];
+  if (n < 4) out[kHeadPartRgbB + n] = (n < 3) ? gb : 0.f;
+#pragma unroll
+  for (int j = 0; j < 27; ++j) out[kHeadPartDir + n * 27 + j] = gdir[j];
+  // padding rows of dd are zero (they are operands of the chain and wgrad kernels)
+  if (blockIdx.x == gridDim.x - 1) {
+    const long long nn = static_cast<long long>(p.n_rays) * p.S;
+    for (long long g = nn; g < p.n_pad; ++g) {
+      const unsigned long long off = tiled_block_off(static_cast<unsigned long long>(g >> 6), fb, 2) +
+                                     sw128_off(static_cast<uint32_t>(g & 63), k);
+      *reinterpret_cast<uint16_t*>(p.dd + off) = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ dgrad chain
+// Per 128-sample tile, on the forward's tile engine (mlp_engine.cuh: same warp roles, same TMEM
+// map, same K-block hand-over between layers):
+//   step 0     D = dd[128 x 128] . W'           (A from shared memory: the dd tile, 2 K blocks)
+//              dh8 = D + dsigma (x) w_sigma ;  dpre8 = dh8 * relu'(h8)
+//   step s>=1  D = dpre_l[128 x 256] . W_l      (A from tensor memory, l = 8, 7, .., 2; for l = 5
+//              only the hidden columns 63..318 of W_5)        dpre_{l-1} = D * relu'(h_{l-1})
+// relu' comes from the sign bits the forward stored (64 per thread and layer, two registers).
+// Every dpre_l is also written to HBM (tiled 16-bit) for the wgrad kernel.  30 weight slices per
+// tile, 120 MMAs (N = 256, K = 16): the same tensor work as layers 2-8 of the forward.
+constexpr int kChainSteps = 8;
+constexpr uint32_t kChA0 = 0;                          // 2 x [2 K blocks][128 x 64] 16-bit = 2 x 32 KiB
+constexpr uint32_t kChA0Bytes = 32768;
+constexpr uint32_t kChRing = 2 * kChA0Bytes;           // kStages x 32 KiB
+constexpr uint32_t kChConsts = kChRing + kStages * kSliceBytes256;   // w_sigma of both networks (2 x 256 fp32)
+constexpr uint32_t kChScratch = kChConsts + 2048;
+constexpr uint32_t kChSmemTotal = kChScratch + 1024;
+
+struct ChainScratch {
+  Barriers bars;
+  uint64_t a0_full[2];
+  uint64_t a0_empty[2];
+};
+static_assert(sizeof(ChainScratch) <= 1024, "chain scratch");
+
+struct ChainParams {
+  PassBufs pass[2];
+  const uint8_t* net[2];      // packed images (backward region at kOffBwd, w_sigma in the fp32 region)
+  int n_pass;
+  long long tiles[2];         // 128-sample tiles per pass
+  const float* scale;
+  int* status;
+};
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+struct ChainEpi {
+  Barriers* bars;
+  uint32_t tmem_row;
+  uint32_t d_phase;
+  int row, part, lane;
+  uint8_t* dpre;          // this pass's dpre base
+  long long n_pad;
+  long long g;            // global sample row of this thread
+};
+
+// One step of the chain for this thread's 64 accumulator columns.
+//   kFirst: add the rank-1 sigma-head term;  kStore: hand the result to the next step (TMEM A operand)
+template <bool kFirst, bool kStore>
+__device__ __forceinline__ void epi_chain_step(ChainEpi& c, int out_idx, const uint2* __restrict__ mask, float dsig,
+                                               const float* wsig) {
+  // masks, off the critical path (fetched while the step's MMAs run): after << i the sign flag of
+  // pair i of K block kb sits in the top bit of byte 3 - kb (even elements in ylo, odd in yhi)
+  const uint2 mw = __ldg(mask + (static_cast<long long>(out_idx) * c.n_pad + c.g) * 4 + c.part);
+  uint32_t ylo[8], yhi[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { ylo[i] = mw.x << i; yhi[i] = mw.y << i; }
+  mbar_wait(smem_u32(&c.bars->d_ready), c.d_phase, 5);
+  c.d_phase ^= 1;
+  tc_fence_after();
+  uint32_t r[4][16];
+#pragma unroll
+  for (int kb = 0; kb < 4; ++kb) tmem_ld16(c.tmem_row + kTmemD + kb * 64 + c.part * 16, r[kb]);
+  tmem_ld_wait();
+  if (!kStore) {      // last step: the next tile may overwrite the accumulator
+    tc_fence_before();
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->d_free));
+  }
+  uint8_t* out = c.dpre + static_cast<long long>(out_idx) * c.n_pad * 512 + (c.g & 63) * 128;
+  const unsigned long long chunk = static_cast<unsigned long long>(c.g >> 6);
+  const uint32_t sw = static_cast<uint32_t>(c.g & 7);
+#pragma unroll
+  for (int kb = 0; kb < 4; ++kb) {
+    const int n0 = kb * 64 + c.part * 16;
+    // selector: bytes 0,1 <- sign of ylo byte (3 - kb), bytes 2,3 <- sign of yhi byte (3 - kb)
+    const uint32_t ln = 0x8u | (3u - kb), hn = 0x8u | (7u - kb);
+    const uint32_t sel = (hn << 12) | (hn << 8) | (ln << 4) | ln;
+    uint32_t h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = __uint_as_float(r[kb][2 * i]), b = __uint_as_float(r[kb][2 * i + 1]);
+      if (kFirst) {
+        const float2 ws = *reinterpret_cast<const float2*>(wsig + n0 + 2 * i);
+        a = fmaf(dsig, ws.x, a);
+        b = fmaf(dsig, ws.y, b);
+      }
+      h[i] = cvt_bwd_x2(a, b) & ~prmt(ylo[i], yhi[i], sel);
+    }
+    if (kStore) {
+      tmem_st8(c.tmem_row + kTmemA + n0 / 2, h);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_kb[kb]));
+    }
+    uint8_t* blk = out + tiled_block_off(chunk, kb, 4);
+    *reinterpret_cast<uint4*>(blk + (((2u * c.part) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(blk + (((2u * c.part + 1u) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) chain_bwd_kernel(const ChainParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  ChainScratch* sc = reinterpret_cast<ChainScratch*>(smem + kChScratch);
+  Barriers* bars = &sc->bars;
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&sc->a0_full[b]), 1);
+      mbar_init(smem_u32(&sc->a0_empty[b]), 1);
+    }
+  }
+  if (!engine_setup(smem, bars)) {
+    if (threadIdx.x == 0) report_fault(p.status, 101);
+    return;
+  }
+  float* wsig_s = reinterpret_cast<float*>(smem + kChConsts);
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    const int ps = i >> 8;
+    wsig_s[i] = (ps < p.n_pass) ? reinterpret_cast<const float*>(p.net[ps] + kHalfRegionBytes)[kF32WSigma + (i & 255)] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total = p.tiles[0] + (p.n_pass > 1 ? p.tiles[1] : 0);
+  const uint32_t idesc = make_idesc_f16(256) | (kBwdFmt << 7) | (kBwdFmt << 10);
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      RingState rs;
+      int it = 0;
+      for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int ps = (t >= p.tiles[0]) ? 1 : 0;
+        const long long tile = t - (ps ? p.tiles[0] : 0);
+        const int b = it & 1;
+        // the dd tile: rows 0..63 and 64..127 of column block kb are two 8 KiB blocks of the tiled array
+        mbar_wait(smem_u32(&sc->a0_empty[b]), ((it >> 1) & 1) ^ 1, 31);
+        const uint32_t full = smem_u32(&sc->a0_full[b]);
+        mbar_arrive_expect_tx(full, kChA0Bytes);
+        const uint32_t dst = smem_u32(smem + kChA0 + b * kChA0Bytes);
+        const uint8_t* dd = p.pass[ps].dd;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh)
+            bulk_g2s(dst + kb * 16384 + hh * 8192, dd + tiled_block_off(static_cast<unsigned long long>(tile * 2 + hh), kb, 2), 8192, full);
+        const uint8_t* w = p.net[ps] + kOffBwd;
+        for (int i = 0; i < kNumSlicesBwd; ++i) {
+          mbar_wait(smem_u32(&bars->empty[rs.stage]), rs.phase ^ 1, 1);
+          const uint32_t fl = smem_u32(&bars->full[rs.stage]);
+          const uint32_t d2 = smem_u32(smem + kChRing + rs.stage * kSliceBytes256);
+          mbar_arrive_expect_tx(fl, kSliceBytes256);
+          const uint8_t* src = w + static_cast<size_t>(i) * kSliceBytes256;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) bulk_g2s(d2 + cc * 8192, src + cc * 8192, 8192, fl);
+          rs.advance();
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      RingState rs;
+      uint32_t ph_dfree = 0, ph_akb = 0;
+      const uint32_t tmem = bars->tmem_base;
+      const uint32_t d_tmem = tmem + kTmemD, a_tmem = tmem + kTmemA;
+      const uint64_t ring_desc = make_desc_sw128(smem_u32(smem + kChRing));
+      const uint32_t full0 = smem_u32(&bars->full[0]), empty0 = smem_u32(&bars->empty[0]);
+      const uint32_t akb0 = smem_u32(&bars->a_kb[0]);
+      const uint32_t d_ready = smem_u32(&bars->d_ready);
+      int it = 0;
+      for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int b = it & 1;
+        const uint64_t a0_desc = make_desc_sw128(smem_u32(smem + kChA0 + b * kChA0Bytes));
+#pragma unroll
+        for (int s = 0; s < kChainSteps; ++s) {
+          if (s == 0) {
+            mbar_wait(smem_u32(&bars->d_free), ph_dfree, 3);
+            ph_dfree ^= 1;
+            mbar_wait(smem_u32(&sc->a0_full[b]), (it >> 1) & 1, 9);
+          } else {
+            mbar_wait(akb0, ph_akb, 6);      // also: every warp has drained the accumulator
+          }
+          tc_fence_after();
+          const int n_slices = (s == 0) ? 2 : 4;
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            if (kb < n_slices) {
+              const uint32_t stage = rs.stage;
+              mbar_wait(full0 + 8u * stage, rs.phase, 4);
+              if (s != 0 && kb > 0) mbar_wait(akb0 + 8u * kb, ph_akb, 6);
+              tc_fence_after();
+              const uint64_t bdesc = ring_desc + static_cast<uint64_t>(stage * (kSliceBytes256 >> 4));
+              if (s == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  umma_f16(d_tmem, a0_desc + static_cast<uint64_t>(kb * (16384 >> 4)) + 2 * j, bdesc + 2 * j, idesc,
+                           (kb | j) != 0 ? 1u : 0u);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  umma_f16_ts(d_tmem, a_tmem + kb * 32 + j * 8, bdesc + 2 * j, idesc, (kb | j) != 0 ? 1u : 0u);
+              }
+              umma_commit(empty0 + 8u * stage);
+              rs.advance();
+            }
+          }
+          if (s == 0) umma_commit(smem_u32(&sc->a0_empty[b]));
+          umma_commit(d_ready);
+          if (s != 0) ph_akb ^= 1;
+        }
+      }
+    }
+  } else {
+    ChainEpi c;
+    c.bars = bars;
+    c.lane = lane;
+    c.row = (warp & 3) * 32 + lane;
+    c.part = warp >> 2;
+    c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    c.d_phase = 0;
+    const float scale = p.scale[0];
+    // the accumulator is free at the start
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bars->d_free));
+    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+      const int ps = (t >= p.tiles[0]) ? 1 : 0;
+      const long long tile = t - (ps ? p.tiles[0] : 0);
+      const PassBufs& pb = p.pass[ps];
+      c.dpre = pb.dpre;
+      c.n_pad = pb.n_pad;
+      c.g = tile * 128 + c.row;
+      const float dsig = pb.dsigma[c.g] * scale;
+      const float* wsig = wsig_s + ps * 256;
+      epi_chain_step<true, true>(c, 7, pb.mask, dsig, wsig);
+#pragma unroll 1
+      for (int l = 6; l >= 1; --l) epi_chain_step<false, true>(c, l, pb.mask, 0.f, nullptr);
+      epi_chain_step<false, false>(c, 0, pb.mask, 0.f, nullptr);
+    }
+  }
+  engine_teardown(bars);
+}
+
+// ------------------------------------------------------------------------------------ wgrad
+// gW = A^T B over a range of 64-sample chunks:  A = a 16-bit gradient array (dpre_l or dd), B = an
+// fp16 activation array (h_{l-1} or the encoded input), both in the tiled layout, i.e. already the
+// MN-major SWIZZLE_128B operand image, so a chunk is staged with two plain bulk copies and the
+// tensor core contracts over the samples: per chunk and 128-row half of the output
+//   D_half[128 x N] += A[:, half]^T[128 x 64] . B[64 x N]      4 x tcgen05.mma (K = 16 samples)
+// The fp32 accumulators (2 halves x N <= 256 columns) stay in tensor memory for the CTA's whole
+// range and are written out once, as a partial that wgrad_reduce_kernel sums in a fixed order.
+// The kernel is HBM-bound by construction (128 FLOP per byte at N = 256): the point of the layout
+// is that it reads every byte exactly once, with no transposition pass and no staging through
+// registers.  Four more warps reduce the same shared-memory tiles on the CUDA cores: column sums of
+// A (the bias gradients) and, for the W' job, the dsigma-weighted column sums of B = h8 (the sigma
+// head's weight gradient).
+constexpr int kWgStages = 3;
+constexpr uint32_t kWgStageBytes = 65536;              // A chunk (<= 32 KiB) + B chunk (<= 32 KiB)
+constexpr uint32_t kWgScratch = kWgStages * kWgStageBytes;
+constexpr uint32_t kWgSmemTotal = kWgScratch + 1024;
+constexpr int kWgThreads = 6 * 32;                     // producer, issuer, 4 reduction / drain warps
+
+struct WgradJob {
+  const uint8_t* a;        // tiled (n_pad, 64 a_fb) 16-bit gradient array
+  const uint8_t* b;        // tiled (n_pad, 64 b_fb) fp16 activation array
+  int a_fb;                // column blocks of A: 4 (M = 256, two halves) or 2 (M = 128)
+  int b_fb;                // column blocks of B: N = 64 b_fb
+  int chunk0, chunk1;      // 64-sample chunks [chunk0, chunk1)
+  float* out;              // partial (64 a_fb, 64 b_fb) fp32 row-major
+  float* bias_out;         // partial column sums of A (64 a_fb) or null
+  const float* dsig;       // per-sample weights for the column sums of B (n_pad) or null
+  float* wsig_out;         // (64 b_fb + 1): weighted column sums of B, then sum of the weights
+};
+
+struct WgScratch {
+  uint64_t full[kWgStages];
+  uint64_t empty[kWgStages];
+  uint64_t d_ready;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradJob* __restrict__ jobs, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  WgScratch* sc = reinterpret_cast<WgScratch*>(smem + kWgScratch);
+  const WgradJob job = jobs[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) report_fault(status, 101);
+    return;
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgStages; ++i) {
+      mbar_init(smem_u32(&sc->full[i]), 1);
+      mbar_init(smem_u32(&sc->empty[i]), 5);        // tcgen05.commit + the four reduction warps
+    }
+    mbar_init(smem_u32(&sc->d_ready), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&sc->tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t a_bytes = job.a_fb * kTileBlockBytes, b_bytes = job.b_fb * kTileBlockBytes;
+  const int n_chunks = job.chunk1 - job.chunk0;
+  const int N = job.b_fb * 64, halves = job.a_fb >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int c = job.chunk0; c < job.chunk1; ++c) {
+        mbar_wait(smem_u32(&sc->empty[stage]), phase ^ 1, 51);
+        const uint32_t full = smem_u32(&sc->full[stage]);
+        const uint32_t dst = smem_u32(smem + stage * kWgStageBytes);
+        mbar_arrive_expect_tx(full, a_bytes + b_bytes);
+        const uint8_t* sa = job.a + static_cast<unsigned long long>(c) * a_bytes;
+        const uint8_t* sb = job.b + static_cast<unsigned long long>(c) * b_bytes;
+        for (uint32_t o = 0; o < a_bytes; o += 8192) bulk_g2s(dst + o, sa + o, 8192, full);
+        for (uint32_t o = 0; o < b_bytes; o += 8192) bulk_g2s(dst + 32768 + o, sb + o, 8192, full);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_chunks > 0) {
+      // A: bf16 / fp16 per build, B: fp16; both MN-major
+      const uint32_t idesc = make_idesc_f16_mn(N) | (kBwdFmt << 7);
+      uint32_t stage = 0, phase = 0;
+      for (int c = 0; c < n_chunks; ++c) {
+        mbar_wait(smem_u32(&sc->full[stage]), phase, 52);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + stage * kWgStageBytes);
+        for (int hh = 0; hh < halves; ++hh) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {        // 16 samples = two 8-row groups = 2048 B per K step
+            const uint64_t ad = make_desc_mn_sw128(base + hh * 16384 + j * 2048, 8192, 1024);
+            const uint64_t bd = make_desc_mn_sw128(base + 32768 + j * 2048, 8192, 1024);
+            umma_f16(sc->tmem_base + hh * 256, ad, bd, idesc, (c | j) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(smem_u32(&sc->empty[stage]));
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(smem_u32(&sc->d_ready));
+    }
+  } else {
+    // ---- reduction warps (threads 0..127 of this group): column pair 2t, 2t+1
+    const int t = threadIdx.x - 64;
+    const bool a_act = job.bias_out != nullptr && t < job.a_fb * 32;
+    const bool b_act = job.dsig != nullptr && t < job.b_fb * 32;
+    const uint32_t col_off = (t >> 5) * kTileBlockBytes + (t & 3) * 4;      // column block, word within the 16-byte chunk
+    const uint32_t chunk16 = (t & 31) >> 2;
+    float sa0 = 0.f, sa1 = 0.f, sb0 = 0.f, sb1 = 0.f, sw = 0.f;
+    uint32_t stage = 0, phase = 0;
+    for (int c = job.chunk0; c < job.chunk1; ++c) {
+      mbar_wait(smem_u32(&sc->full[stage]), phase, 53);
+      const uint8_t* base = smem + stage * kWgStageBytes;
+      if (a_act) {
+#pragma unroll 8
+        for (int r = 0; r < 64; ++r) {
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(base + col_off + r * 128 + ((chunk16 ^ (r & 7)) << 4));
+          const float2 f = bwd_x2_to_float2(v);
+          sa0 += f.x; sa1 += f.y;
+        }
+      }
+      if (b_act) {
+        const float* ds = job.dsig + static_cast<long long>(c) * 64;
+#pragma unroll 8
+        for (int r = 0; r < 64; ++r) {
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(base + 32768 + col_off + r * 128 + ((chunk16 ^ (r & 7)) << 4));
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+          const float w = __ldg(ds + r);
+          sb0 = fmaf(w, f.x, sb0); sb1 = fmaf(w, f.y, sb1);
+          sw += w;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sc->empty[stage]));
+      if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+    }
+    if (a_act) { job.bias_out[2 * t] = sa0; job.bias_out[2 * t + 1] = sa1; }
+    if (b_act) {
+      job.wsig_out[2 * t] = sb0; job.wsig_out[2 * t + 1] = sb1;
+      if (t == 0) job.wsig_out[N] = sw;
+    }
+    // ---- drain the accumulators: thread = output row (TMEM lane) of each half
+    const int m = (warp & 3) * 32 + lane;
+    if (n_chunks > 0) {
+      mbar_wait(smem_u32(&sc->d_ready), 0, 54);
+      tc_fence_after();
+    }
+    const uint32_t trow = sc->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    for (int hh = 0; hh < halves; ++hh) {
+      float* orow = job.out + static_cast<long long>(hh * 128 + m) * N;
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t r[32];
+        if (n_chunks > 0) {
+          tmem_ld32(trow + hh * 256 + c0, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<uint4*>(orow + c0 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(sc->tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------- partial sums -> gradients
+// out[r][out_col0 + c] = mul * sum_s part[s * split_stride + r * part_ld + c]   (fixed order)
+struct ReduceItem {
+  const float* part;
+  long long split_stride;
+  float* out;
+  const float* mul;        // device scalar or null (= 1)
+  int n_split, rows, cols, part_ld, out_ld, out_col0;
+};
+constexpr int kMaxReduceItems = 64;
+struct ReduceTable {
+  int n;
+  ReduceItem it[kMaxReduceItems];
+};
+
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ ReduceTable tab) {
+  const ReduceItem& it = tab.it[blockIdx.y];
+  const int total = it.rows * it.cols;
+  const float mul = (it.mul != nullptr) ? *it.mul : 1.f;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx / it.cols, c = idx - r * it.cols;
+    const float* src = it.part + static_cast<long long>(r) * it.part_ld + c;
+    float acc = 0.f;
+    for (int s = 0; s < it.n_split; ++s) acc += src[s * it.split_stride];
+    it.out[static_cast<long long>(r) * it.out_ld + it.out_col0 + c] = acc * mul;
+  }
+}
+
+// Chain rule through the pack-time folding (layout.h): W' = Wd[:, :256] Wf, b' = Wd[:, :256] bf + bd
+//   gWd[:, :256] = gW' Wf^T + gb' (x) bf     gWf = Wd[:, :256]^T gW'     gbf = Wd[:, :256]^T gb'     gbd = gb'
+struct UnfoldParams {
+  const float* gWp[2];     // (128, 256) gradient of the folded matrix
+  const float* gbp[2];     // (128)
+  const float* Wf[2];      // live xyz_encoding_final.weight (256,256)
+  const float* bf[2];      // (256)
+  const float* Wd[2];      // live dir_encoding.0.weight (128,283)
+  float* gWd[2];           // (128,283): columns 0..255 written here
+  float* gbd[2];           // (128)
+  float* gWf[2];           // (256,256)
+  float* gbf[2];           // (256)
+};
+__global__ void __launch_bounds__(256) unfold_kernel(const UnfoldParams p) {
+  const int ps = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < 128 * 256) {                              // gWd[m][j] = sum_n gW'[m][n] Wf[j][n] + gb'[m] bf[j]
+    const int m = idx >> 8, j = idx & 255;
+    const float* a = p.gWp[ps] + m * 256;
+    const float* w = p.Wf[ps] + j * 256;
+    float acc = p.gbp[ps][m] * p.bf[ps][j];
+    for (int n = 0; n < 256; ++n) acc = fmaf(a[n], w[n], acc);
+    p.gWd[ps][m * 283 + j] = acc;
+    if (j == 0) p.gbd[ps][m] = p.gbp[ps][m];
+  } else if (idx < 128 * 256 + 256 * 256) {           // gWf[j][n] = sum_m Wd[m][j] gW'[m][n]
+    const int q = idx - 128 * 256;
+    const int j = q >> 8, n = q & 255;
+    float acc = 0.f;
+    for (int m = 0; m < 128; ++m) acc = fmaf(p.Wd[ps][m * 283 + j], p.gWp[ps][m * 256 + n], acc);
+    p.gWf[ps][j * 256 + n] = acc;
+  } else if (idx < 128 * 256 + 256 * 256 + 256) {     // gbf[j] = sum_m Wd[m][j] gb'[m]
+    const int j = idx - (128 * 256 + 256 * 256);
+    float acc = 0.f;
+    for (int m = 0; m < 128; ++m) acc = fmaf(p.Wd[ps][m * 283 + j], p.gbp[ps][m], acc);
+    p.gbf[ps][j] = acc;
+  }
+}
+
+}  // namespace nerfb200

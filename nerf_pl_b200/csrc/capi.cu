@@ -4,9 +4,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "../../include/nerf_pl_b200.h"
 #include "aux_kernels.cuh"
+#include "bwd_kernels.cuh"
 #ifdef NERFB200_DIAG
 #include "../../include/nerf_pl_b200_diag.h"
 #include "diag_kernels.cuh"
@@ -78,6 +80,10 @@ int device_info(DeviceInfo** out) {
                                   static_cast<int>(kSmemTotal)), "smem attr render(save)");
     CUDA_TRY(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kSmemTotal)), "smem attr mlp");
+    CUDA_TRY(cudaFuncSetAttribute(chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kChSmemTotal)), "smem attr chain");
+    CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kWgSmemTotal)), "smem attr wgrad");
     int* hs = nullptr;
     CUDA_TRY(cudaHostAlloc(&hs, sizeof(int), cudaHostAllocMapped), "status alloc");
     *hs = 0;
@@ -137,6 +143,140 @@ int check_render_shapes(const nerfb200_render_args* a) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------ training workspace layout
+// One device buffer per (n_rays, N_samples, N_importance); the layout is a pure function of those
+// numbers and the SM count, recomputed on every call (no state kept in the library).
+struct WgJobPlan { int ps, kind, split, n_split; };
+enum { kJ1 = 0, kJ2, kJ3, kJ4, kJ5a, kJ5b, kJ6, kJ7, kJ8, kJ9, kNumJobKinds };
+constexpr int kWgSlotFloats = 256 * 256 + 256 + 264;     // partial of one job: out, bias, wsig
+constexpr int kMaxWgJobs = 1024;
+struct TrainLayout {
+  PassBufs pass[2];
+  int n_pass, n_rays;
+  WgradJob* jobs_dev;
+  int n_jobs;
+  int n_split[2][kNumJobKinds];
+  int first_job[2][kNumJobKinds];
+  float* wg_part;                 // [n_jobs][kWgSlotFloats]
+  int head_grid[2];
+  float* head_part[2];            // [head_grid][kHeadPartFloats]
+  float* gWp[2];                  // (128,256)
+  float* gbp[2];                  // (128)
+  float* scale;                   // {scale, 1/scale}
+  unsigned* amax;
+  float* loss_part;               // [max CTAs][2]
+  unsigned* loss_counter;
+  size_t bytes;
+};
+
+void job_shape(int kind, int* a_fb, int* b_fb) {
+  *a_fb = (kind == kJ9) ? 2 : 4;
+  *b_fb = (kind == kJ1 || kind == kJ5a) ? 1 : 4;
+}
+
+void make_train_layout(TrainLayout* L, uint8_t* base, int64_t n_rays, int n_samples, int n_importance, int sm_count) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> uint8_t* {
+    uint8_t* ptr = base ? base + off : nullptr;
+    off += (bytes + 1023) & ~static_cast<size_t>(1023);
+    return ptr;
+  };
+  L->n_pass = n_importance > 0 ? 2 : 1;
+  L->n_rays = static_cast<int>(n_rays);
+  std::memset(L->pass, 0, sizeof(L->pass));
+  for (int ps = 0; ps < L->n_pass; ++ps) {
+    PassBufs& b = L->pass[ps];
+    b.S = ps ? n_samples + n_importance : n_samples;
+    b.n = n_rays * b.S;
+    b.n_pad = (b.n + 127) / 128 * 128;
+    const size_t np = static_cast<size_t>(b.n_pad);
+    b.enc = take(np * 128);
+    b.act = take(np * 512 * 8);
+    b.mask = reinterpret_cast<uint2*>(take(np * 32 * 8));
+    b.d = reinterpret_cast<__half*>(take(np * 256));
+    b.sigma = reinterpret_cast<float*>(take(np * 4));
+    b.rgb = reinterpret_cast<float*>(take(np * 12));
+    b.z = reinterpret_cast<float*>(take(static_cast<size_t>(b.n) * 4));
+    b.dsigma = reinterpret_cast<float*>(take(np * 4));
+    b.dprergb = reinterpret_cast<float*>(take(np * 12));
+    b.dd = take(np * 256);
+    b.dpre = take(np * 512 * 8);
+  }
+  // wgrad jobs: splits proportional to the bytes each (pass, layer) streams, ~2 CTAs per SM in total
+  double work[2][kNumJobKinds], total = 0;
+  for (int ps = 0; ps < L->n_pass; ++ps)
+    for (int k = 0; k < kNumJobKinds; ++k) {
+      int a_fb, b_fb;
+      job_shape(k, &a_fb, &b_fb);
+      work[ps][k] = static_cast<double>(L->pass[ps].n_pad / 64) * (a_fb + b_fb);
+      total += work[ps][k];
+    }
+  const int target = 2 * (sm_count > 0 ? sm_count : 148);
+  L->n_jobs = 0;
+  for (int ps = 0; ps < L->n_pass; ++ps)
+    for (int k = 0; k < kNumJobKinds; ++k) {
+      const long long chunks = L->pass[ps].n_pad / 64;
+      int ns = static_cast<int>(work[ps][k] / total * target + 0.5);
+      if (ns < 1) ns = 1;
+      if (ns > chunks) ns = static_cast<int>(chunks);
+      if (L->n_jobs + ns > kMaxWgJobs) ns = kMaxWgJobs - L->n_jobs;
+      L->n_split[ps][k] = ns;
+      L->first_job[ps][k] = L->n_jobs;
+      L->n_jobs += ns;
+    }
+  L->jobs_dev = reinterpret_cast<WgradJob*>(take(sizeof(WgradJob) * kMaxWgJobs));
+  L->wg_part = reinterpret_cast<float*>(take(static_cast<size_t>(L->n_jobs) * kWgSlotFloats * 4));
+  for (int ps = 0; ps < 2; ++ps) {
+    L->head_grid[ps] = static_cast<int>(n_rays < 2 * 148 ? (n_rays > 0 ? n_rays : 1) : 2 * 148);
+    L->head_part[ps] = reinterpret_cast<float*>(take(static_cast<size_t>(L->head_grid[ps]) * kHeadPartFloats * 4));
+    L->gWp[ps] = reinterpret_cast<float*>(take(128 * 256 * 4));
+    L->gbp[ps] = reinterpret_cast<float*>(take(128 * 4));
+  }
+  L->scale = reinterpret_cast<float*>(take(16));
+  L->amax = reinterpret_cast<unsigned*>(take(16));
+  L->loss_part = reinterpret_cast<float*>(take(1024 * 2 * 4));
+  L->loss_counter = reinterpret_cast<unsigned*>(take(16));
+  L->bytes = off;
+}
+
+// Host image of the wgrad job table of a layout.
+void build_wgrad_jobs(const TrainLayout& L, WgradJob* jobs) {
+  for (int ps = 0; ps < L.n_pass; ++ps) {
+    const PassBufs& b = L.pass[ps];
+    const size_t lay = static_cast<size_t>(b.n_pad) * 512;
+    const long long chunks = b.n_pad / 64;
+    for (int k = 0; k < kNumJobKinds; ++k) {
+      int a_fb, b_fb;
+      job_shape(k, &a_fb, &b_fb);
+      const uint8_t* A; const uint8_t* B;
+      switch (k) {
+        case kJ1: A = b.dpre; B = b.enc; break;
+        case kJ5a: A = b.dpre + 4 * lay; B = b.enc; break;
+        case kJ5b: A = b.dpre + 4 * lay; B = b.act + 3 * lay; break;
+        case kJ9: A = b.dd; B = b.act + 7 * lay; break;
+        default: {
+          const int l = (k <= kJ4) ? k + 1 : k;            // kJ2..kJ4 -> layers 2..4, kJ6..kJ8 -> layers 6..8
+          A = b.dpre + static_cast<size_t>(l - 1) * lay;
+          B = b.act + static_cast<size_t>(l - 2) * lay;
+        }
+      }
+      const int ns = L.n_split[ps][k];
+      for (int sp = 0; sp < ns; ++sp) {
+        WgradJob& j = jobs[L.first_job[ps][k] + sp];
+        float* slot = L.wg_part + static_cast<size_t>(L.first_job[ps][k] + sp) * kWgSlotFloats;
+        j.a = A; j.b = B; j.a_fb = a_fb; j.b_fb = b_fb;
+        j.chunk0 = static_cast<int>(chunks * sp / ns);
+        j.chunk1 = static_cast<int>(chunks * (sp + 1) / ns);
+        j.out = slot;
+        j.bias_out = (k == kJ5b) ? nullptr : slot + 256 * 256;
+        j.dsig = (k == kJ9) ? b.dsigma : nullptr;
+        j.wsig_out = (k == kJ9) ? slot + 256 * 256 + 256 : nullptr;
+      }
+    }
+  }
+}
+
 // grow-only device arena for the *_host entry
 struct Arena {
   uint8_t* base = nullptr;
@@ -185,7 +325,8 @@ int nerfb200_pack_weights(const float* const params[24], void* packed, void* str
     pp.p[i] = params[i];
   }
   pp.out = static_cast<uint8_t*>(packed);
-  const long long total = kHalfRegionBytes / 2 + kF32Count;
+  pp.bwd_bf16 = kBwdBf16 ? 1 : 0;
+  const long long total = kHalfRegionBytes / 2 + kF32Count + static_cast<long long>(kNumSlicesBwd) * 256 * 64;
   const int threads = 256;
   const int blocks = static_cast<int>((total + threads - 1) / threads);
   pack_weights_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(pp);
@@ -230,17 +371,33 @@ int nerfb200_render_rays(const nerfb200_render_args* a, void* stream) {
   p.weights_coarse = a->weights_coarse;
   p.weights_fine = a->weights_fine;
   p.status = a->status ? a->status : d->status;
-  p.save_act_c = static_cast<__half*>(a->save_act_coarse);
-  p.save_act_f = static_cast<__half*>(a->save_act_fine);
-  p.save_d_c = static_cast<__half*>(a->save_dir_coarse);
-  p.save_d_f = static_cast<__half*>(a->save_dir_fine);
-  p.save_sig_c = a->save_sigma_coarse;
-  p.save_sig_f = a->save_sigma_fine;
-  p.save_rgb_c = a->save_rgb_coarse;
-  p.save_rgb_f = a->save_rgb_fine;
-  const bool save = p.save_act_c || p.save_act_f || p.save_d_c || p.save_d_f || p.save_sig_c || p.save_sig_f ||
-                    p.save_rgb_c || p.save_rgb_f;
-  if (save && a->test_time) return fail(NERFB200_EINVAL, "save_* buffers need test_time = 0%s");
+  p.z_coarse = a->z_coarse;
+  p.train = 0;
+  p.target = nullptr; p.loss_part = nullptr; p.loss_out = nullptr; p.loss_counter = nullptr;
+  std::memset(p.tr, 0, sizeof(p.tr));
+  const bool save = a->train_workspace != nullptr;
+  if (save && a->test_time) return fail(NERFB200_EINVAL, "train_workspace needs test_time = 0%s");
+  if ((a->target != nullptr) != (a->loss_out != nullptr)) return fail(NERFB200_EINVAL, "target and loss_out go together%s");
+  if (a->target && !save) return fail(NERFB200_EINVAL, "the fused loss epilogue needs train_workspace%s");
+  if (save) {
+    TrainLayout L;
+    make_train_layout(&L, static_cast<uint8_t*>(a->train_workspace), a->n_rays, a->n_samples, a->n_importance, d->sm_count);
+    p.train = 1;
+    p.tr[0] = L.pass[0];
+    p.tr[1] = L.pass[1];
+    if (!p.z_coarse) p.z_coarse = L.pass[0].z;
+    else return fail(NERFB200_EINVAL, "z_coarse is owned by the workspace in training mode%s");
+    if (a->n_importance > 0) {
+      if (p.z_fine) return fail(NERFB200_EINVAL, "z_fine is owned by the workspace in training mode%s");
+      p.z_fine = L.pass[1].z;
+    }
+    if (a->target) {
+      p.target = a->target;
+      p.loss_out = a->loss_out;
+      p.loss_part = L.loss_part;
+      p.loss_counter = L.loss_counter;
+    }
+  }
   p.flags = env_switches().flags;
   p.timeline = nullptr;
 #ifdef NERFB200_TIMELINE
@@ -285,9 +442,8 @@ int nerfb200_render_rays_host(const nerfb200_render_args* h, void* stream_v) {
   ar.off = 0;
   nerfb200_render_args a = *h;
   a.ray_stride = 8;
-  if (h->save_act_coarse || h->save_act_fine || h->save_dir_coarse || h->save_dir_fine || h->save_sigma_coarse ||
-      h->save_sigma_fine || h->save_rgb_coarse || h->save_rgb_fine)
-    return fail(NERFB200_EINVAL, "render_rays_host: save_* buffers are device-only%s");
+  if (h->train_workspace || h->target || h->z_coarse)
+    return fail(NERFB200_EINVAL, "render_rays_host: train_workspace / target / z_coarse are device-only%s");
   auto up = [&](const float* src, size_t count, size_t src_stride, size_t width) -> const float* {
     if (!src) return nullptr;
     float* dst = static_cast<float*>(ar.take(count * fl));
@@ -394,21 +550,6 @@ int nerfb200_query_sigma(const float* xyz, int64_t n, int64_t xyz_stride, const 
   mlp_forward_kernel<<<ctas, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
   g_launches++;
   CUDA_TRY(cudaGetLastError(), "query_sigma launch");
-  return 0;
-}
-
-int nerfb200_relu_backward(const void* dh, const void* act, int64_t n_rows, int32_t n_cols, void* dpre,
-                           void* dpre_t, void* stream) {
-  if (n_rows < 0 || n_cols <= 0 || (n_cols % 64) != 0) return fail(NERFB200_EINVAL, "relu_backward: n_cols must be a multiple of 64%s");
-  if (n_rows == 0) return 0;
-  if ((n_rows & 1) != 0) return fail(NERFB200_EINVAL, "relu_backward: n_rows must be even%s");
-  if (!dh || !act || !dpre || !dpre_t) return fail(NERFB200_EINVAL, "relu_backward: NULL argument%s");
-  dim3 grid(static_cast<unsigned>((n_rows + 63) / 64), static_cast<unsigned>(n_cols / 64));
-  relu_bwd_transpose_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(dh), static_cast<const __half*>(act), n_rows, n_cols, static_cast<__half*>(dpre),
-      static_cast<__half*>(dpre_t));
-  g_launches++;
-  CUDA_TRY(cudaGetLastError(), "relu_backward launch");
   return 0;
 }
 
@@ -525,6 +666,156 @@ int nerfb200_to_uint8(const float* src, int64_t n, uint8_t* dst, void* stream) {
   return 0;
 }
 
+size_t nerfb200_train_workspace_bytes(int64_t n_rays, int32_t n_samples, int32_t n_importance) {
+  if (n_rays <= 0 || n_samples <= 0 || n_importance < 0) return 0;
+  TrainLayout L;
+  make_train_layout(&L, nullptr, n_rays, n_samples, n_importance, nerfb200_sm_count());
+  return L.bytes;
+}
+
+int nerfb200_train_workspace_init(void* workspace, size_t bytes, int64_t n_rays, int32_t n_samples,
+                                  int32_t n_importance, void* stream_v) {
+  if (!workspace || n_rays <= 0) return fail(NERFB200_EINVAL, "train_workspace_init: bad argument%s");
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(NERFB200_EINVAL, "train workspace must be 1024-byte aligned%s");
+  DeviceInfo* d = nullptr;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  TrainLayout L;
+  make_train_layout(&L, static_cast<uint8_t*>(workspace), n_rays, n_samples, n_importance, d->sm_count);
+  if (bytes < L.bytes) return fail(NERFB200_EINVAL, "train workspace too small%s");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  // padding rows of the operand arrays must be zero (never written afterwards), counters zero
+  CUDA_TRY(cudaMemsetAsync(workspace, 0, L.bytes, stream), "workspace memset");
+  std::vector<WgradJob> jobs(kMaxWgJobs);
+  std::memset(jobs.data(), 0, sizeof(WgradJob) * kMaxWgJobs);
+  build_wgrad_jobs(L, jobs.data());
+  CUDA_TRY(cudaMemcpyAsync(L.jobs_dev, jobs.data(), sizeof(WgradJob) * kMaxWgJobs, cudaMemcpyHostToDevice, stream),
+           "job table upload");
+  CUDA_TRY(cudaStreamSynchronize(stream), "workspace init sync");
+  return 0;
+}
+
+int nerfb200_render_backward(const nerfb200_backward_args* b, void* stream_v) {
+  if (!b || !b->render) return fail(NERFB200_EINVAL, "render_backward: NULL argument%s");
+  const nerfb200_render_args* a = b->render;
+  int rc = check_render_shapes(a);
+  if (rc) return rc;
+  if (a->n_rays == 0) return 0;
+  if (!a->train_workspace || a->test_time) return fail(NERFB200_EINVAL, "render_backward needs the forward's train_workspace, test_time = 0%s");
+  const bool fine = a->n_importance > 0;
+  if (!b->params_coarse || !b->grads_coarse || (fine && (!b->params_fine || !b->grads_fine)))
+    return fail(NERFB200_EINVAL, "render_backward: params / grads tables are NULL%s");
+  for (int i = 0; i < kNumParams; ++i)
+    if (!b->params_coarse[i] || !b->grads_coarse[i] || (fine && (!b->params_fine[i] || !b->grads_fine[i])))
+      return fail(NERFB200_EINVAL, "render_backward: NULL parameter / gradient tensor%s");
+  DeviceInfo* d = nullptr;
+  rc = device_info(&d);
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  TrainLayout L;
+  make_train_layout(&L, static_cast<uint8_t*>(a->train_workspace), a->n_rays, a->n_samples, a->n_importance, d->sm_count);
+  const float* const* params[2] = {b->params_coarse, b->params_fine};
+  float* const* grads[2] = {b->grads_coarse, b->grads_fine};
+  const float* g_rgb[2] = {b->g_rgb_coarse, b->g_rgb_fine};
+  const float* g_depth[2] = {b->g_depth_coarse, b->g_depth_fine};
+  const float* g_opac[2] = {b->g_opacity_coarse, b->g_opacity_fine};
+  const float* rgb_out[2] = {a->rgb_coarse, a->rgb_fine};
+  const float* noise[2] = {a->noise_coarse, a->noise_fine};
+
+  // 1. compositing backward -> per-sample d sigma / d rgb_pre
+  for (int ps = 0; ps < L.n_pass; ++ps) {
+    CompBwdParams cp;
+    cp.n_rays = L.n_rays; cp.S = L.pass[ps].S; cp.n_pad = L.pass[ps].n_pad;
+    cp.z = L.pass[ps].z; cp.sigma = L.pass[ps].sigma; cp.rgb = L.pass[ps].rgb;
+    cp.rays = a->rays; cp.ray_stride = a->ray_stride;
+    cp.noise = a->noise_std > 0.f ? noise[ps] : nullptr;
+    cp.noise_std = a->noise_std; cp.white_back = a->white_back;
+    cp.g_rgb = g_rgb[ps]; cp.g_depth = g_depth[ps]; cp.g_opac = g_opac[ps];
+    cp.rgb_out = rgb_out[ps]; cp.target = b->target; cp.loss_grad = b->loss_grad;
+    cp.dsigma = L.pass[ps].dsigma; cp.dprergb = L.pass[ps].dprergb;
+    cp.amax_bits = kBwdBf16 ? nullptr : L.amax;
+    composite_bwd_kernel<<<(L.n_rays + 3) / 4, 128, 0, stream>>>(cp);
+    g_launches++;
+  }
+  bwd_scale_kernel<<<1, 1, 0, stream>>>(L.amax, L.scale);
+  g_launches++;
+  // 2. rgb head, ReLU of the direction layer
+  for (int ps = 0; ps < L.n_pass; ++ps) {
+    HeadBwdParams hp;
+    hp.n_rays = L.n_rays; hp.S = L.pass[ps].S; hp.n_pad = L.pass[ps].n_pad;
+    hp.d = L.pass[ps].d; hp.dprergb = L.pass[ps].dprergb; hp.w_rgb = params[ps][22];
+    hp.rays = a->rays; hp.ray_stride = a->ray_stride; hp.scale = L.scale;
+    hp.dd = L.pass[ps].dd; hp.part = L.head_part[ps];
+    head_bwd_kernel<<<L.head_grid[ps], 128, 0, stream>>>(hp);
+    g_launches++;
+  }
+  // 3. dgrad chain (tcgen05)
+  {
+    ChainParams cp;
+    cp.n_pass = L.n_pass;
+    cp.pass[0] = L.pass[0]; cp.pass[1] = L.pass[1];
+    cp.net[0] = static_cast<const uint8_t*>(a->packed_coarse);
+    cp.net[1] = static_cast<const uint8_t*>(a->packed_fine);
+    cp.tiles[0] = L.pass[0].n_pad / 128;
+    cp.tiles[1] = fine ? L.pass[1].n_pad / 128 : 0;
+    cp.scale = L.scale;
+    cp.status = d->status;
+    const long long total = cp.tiles[0] + cp.tiles[1];
+    const int ctas = static_cast<int>(total < d->sm_count ? total : d->sm_count);
+    chain_bwd_kernel<<<ctas, kThreads, kChSmemTotal, stream>>>(cp);
+    g_launches++;
+  }
+  // 4. split-K wgrad (tcgen05)
+  wgrad_kernel<<<L.n_jobs, kWgThreads, kWgSmemTotal, stream>>>(L.jobs_dev, d->status);
+  g_launches++;
+  // 5. partial sums -> gradient tensors (fixed order), 6. unfold W'
+  ReduceTable tab;
+  tab.n = 0;
+  auto add = [&](const float* part, long long stride, int n_split, float* out, const float* mul, int rows, int cols,
+                 int part_ld, int out_ld, int out_col0) {
+    ReduceItem& it = tab.it[tab.n++];
+    it.part = part; it.split_stride = stride; it.n_split = n_split; it.out = out; it.mul = mul;
+    it.rows = rows; it.cols = cols; it.part_ld = part_ld; it.out_ld = out_ld; it.out_col0 = out_col0;
+  };
+  const float* inv = L.scale + 1;
+  for (int ps = 0; ps < L.n_pass; ++ps) {
+    auto slot = [&](int kind) { return L.wg_part + static_cast<size_t>(L.first_job[ps][kind]) * kWgSlotFloats; };
+    auto ns = [&](int kind) { return L.n_split[ps][kind]; };
+    float* const* g = grads[ps];
+    add(slot(kJ1), kWgSlotFloats, ns(kJ1), g[0], inv, 256, 63, 64, 63, 0);
+    add(slot(kJ1) + 65536, kWgSlotFloats, ns(kJ1), g[1], inv, 1, 256, 256, 256, 0);
+    const int hidden[6] = {kJ2, kJ3, kJ4, kJ6, kJ7, kJ8};
+    const int layer[6] = {2, 3, 4, 6, 7, 8};
+    for (int i = 0; i < 6; ++i) {
+      add(slot(hidden[i]), kWgSlotFloats, ns(hidden[i]), g[2 * (layer[i] - 1)], inv, 256, 256, 256, 256, 0);
+      add(slot(hidden[i]) + 65536, kWgSlotFloats, ns(hidden[i]), g[2 * (layer[i] - 1) + 1], inv, 1, 256, 256, 256, 0);
+    }
+    add(slot(kJ5a), kWgSlotFloats, ns(kJ5a), g[8], inv, 256, 63, 64, 319, 0);
+    add(slot(kJ5b), kWgSlotFloats, ns(kJ5b), g[8], inv, 256, 256, 256, 319, 63);
+    add(slot(kJ5a) + 65536, kWgSlotFloats, ns(kJ5a), g[9], inv, 1, 256, 256, 256, 0);
+    add(slot(kJ9), kWgSlotFloats, ns(kJ9), L.gWp[ps], inv, 128, 256, 256, 256, 0);
+    add(slot(kJ9) + 65536, kWgSlotFloats, ns(kJ9), L.gbp[ps], inv, 1, 128, 128, 128, 0);
+    add(slot(kJ9) + 65536 + 256, kWgSlotFloats, ns(kJ9), g[20], nullptr, 1, 256, 256, 256, 0);
+    add(slot(kJ9) + 65536 + 256 + 256, kWgSlotFloats, ns(kJ9), g[21], nullptr, 1, 1, 1, 1, 0);
+    add(L.head_part[ps] + kHeadPartRgbW, kHeadPartFloats, L.head_grid[ps], g[22], nullptr, 1, 384, 384, 384, 0);
+    add(L.head_part[ps] + kHeadPartRgbB, kHeadPartFloats, L.head_grid[ps], g[23], nullptr, 1, 3, 3, 3, 0);
+    add(L.head_part[ps] + kHeadPartDir, kHeadPartFloats, L.head_grid[ps], g[18], nullptr, 128, 27, 27, 283, 256);
+  }
+  wgrad_reduce_kernel<<<dim3(16, tab.n), 256, 0, stream>>>(tab);
+  g_launches++;
+  UnfoldParams up;
+  for (int ps = 0; ps < 2; ++ps) {
+    const int q = ps < L.n_pass ? ps : 0;
+    up.gWp[ps] = L.gWp[q]; up.gbp[ps] = L.gbp[q];
+    up.Wf[ps] = params[q][16]; up.bf[ps] = params[q][17]; up.Wd[ps] = params[q][18];
+    up.gWd[ps] = grads[q][18]; up.gbd[ps] = grads[q][19]; up.gWf[ps] = grads[q][16]; up.gbf[ps] = grads[q][17];
+  }
+  unfold_kernel<<<dim3((128 * 256 + 256 * 256 + 256 + 255) / 256, L.n_pass), 256, 0, stream>>>(up);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "render_backward launches");
+  return 0;
+}
+
 int nerfb200_check_status(void) {
   DeviceInfo* d = nullptr;
   int rc = device_info(&d);
@@ -548,14 +839,14 @@ static int diag_attrs(DeviceInfo* di) {
   return 0;
 }
 
-int nerfb200_debug_gemm_mn(const float* a, const float* b, int32_t lbo, int32_t sbo, float* d, void* stream) {
+int nerfb200_debug_gemm_mn(const float* a, const float* b, int32_t lbo, int32_t sbo, int32_t fmt, float* d, void* stream) {
   if (!a || !b || !d) return fail(NERFB200_EINVAL, "debug_gemm_mn: NULL argument%s");
   DeviceInfo* di = nullptr;
   int rc = device_info(&di);
   if (rc) return rc;
   if ((rc = diag_attrs(di)) != 0) return rc;
   gemm_mn_probe_kernel<<<1, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(
-      a, b, static_cast<uint32_t>(lbo), static_cast<uint32_t>(sbo), d, di->status);
+      a, b, static_cast<uint32_t>(lbo), static_cast<uint32_t>(sbo), static_cast<uint32_t>(fmt), d, di->status);
   g_launches++;
   CUDA_TRY(cudaGetLastError(), "debug_gemm_mn launch");
   return 0;

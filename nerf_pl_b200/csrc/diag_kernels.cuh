@@ -2,6 +2,8 @@
 // NOT part of the product library: compiled only with -DNERFB200_DIAG (tools/build_variants.py
 // diag=-DNERFB200_DIAG); the entry points are declared in include/nerf_pl_b200_diag.h.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "aux_kernels.cuh"
 
 namespace nerfb200 {
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_probe_kernel(const float* __
 // [64-feature block][64 rows][128 B] SWIZZLE_128B images (block stride 8 KiB), read MN-major.
 __global__ void __launch_bounds__(kThreads, 1) gemm_mn_probe_kernel(const float* __restrict__ a,
                                                                     const float* __restrict__ b, uint32_t lbo,
-                                                                    uint32_t sbo, float* __restrict__ d, int* status) {
+                                                                    uint32_t sbo, uint32_t fmt, float* __restrict__ d, int* status) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Scratch* sc = reinterpret_cast<Scratch*>(smem + kSmemScratch);
   Barriers* bars = &sc->bars;
@@ -104,11 +106,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_mn_probe_kernel(const float*
   if (warp < kEpiWarps) {
     for (int i = threadIdx.x; i < 64 * 128; i += kEpiThreads) {
       const int s = i / 128, m = i % 128;
-      *reinterpret_cast<__half*>(sa + (m >> 6) * 8192 + sw128_off(s, m & 63)) = __float2half_rn(a[i]);
+      uint8_t* dst = sa + (m >> 6) * 8192 + sw128_off(s, m & 63);
+      if (fmt & 1u) *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(a[i]);     // A as bf16
+      else *reinterpret_cast<__half*>(dst) = __float2half_rn(a[i]);
     }
     for (int i = threadIdx.x; i < 64 * 256; i += kEpiThreads) {
       const int s = i / 256, n = i % 256;
-      *reinterpret_cast<__half*>(sb + (n >> 6) * 8192 + sw128_off(s, n & 63)) = __float2half_rn(b[i]);
+      uint8_t* dst = sb + (n >> 6) * 8192 + sw128_off(s, n & 63);
+      if (fmt & 2u) *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(b[i]);     // B as bf16
+      else *reinterpret_cast<__half*>(dst) = __float2half_rn(b[i]);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -127,7 +133,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_mn_probe_kernel(const float*
   } else if (warp == kMmaWarp && (threadIdx.x & 31) == 0) {
     mbar_wait(smem_u32(&bars->d_free), 0, 42);
     tc_fence_after();
-    const uint32_t idesc = make_idesc_f16_mn(256);
+    // operand formats: idesc bits [7,10) = A, [10,13) = B; 0 = f16, 1 = bf16 (mixed = the wgrad's bf16 x f16)
+    const uint32_t idesc = make_idesc_f16_mn(256) | ((fmt & 1u) << 7) | (((fmt >> 1) & 1u) << 10);
     for (int j = 0; j < 4; ++j) {      // 16 samples = two 8-row groups = 2048 B per K step
       const uint64_t ad = make_desc_mn_sw128(smem_u32(sa) + j * 2048, lbo, sbo);
       const uint64_t bd = make_desc_mn_sw128(smem_u32(sb) + j * 2048, lbo, sbo);

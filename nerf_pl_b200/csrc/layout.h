@@ -46,7 +46,36 @@ constexpr int kF32WRgb = kF32BSigma + 4;         // [3][128]
 constexpr int kF32BRgb = kF32WRgb + 3 * 128;     // [4]  (3 used)
 constexpr int kF32WDirPart = kF32BRgb + 4;       // [28][128] transposed: [j][n] = W_dir[n][256+j] (27 used)
 constexpr int kF32Count = kF32WDirPart + 28 * 128;
-constexpr uint32_t kPackedBytes = kHalfRegionBytes + kF32Count * 4;
+constexpr uint32_t kFwdBytes = kHalfRegionBytes + kF32Count * 4;
+
+// [backward region]  the transposed ("dgrad") slices the backward chain kernel streams, 16-bit
+// (bf16 by default, csrc/bwd_kernels.cuh), in consumption order.  A slice is a [256 x 64] K-major
+// SWIZZLE_128B block with B[n][k] = W[k0 + k][n0 + n]: n = INPUT feature of the layer (the output
+// column of the dgrad GEMM), k = OUTPUT feature (its contraction index).
+//       slice 0..1     W'        (128 x 256, the folded final.dir matrix above)  k blocks 0..1
+//       slice 2..5     xyz_encoding_8 W      6..9 _7      10..13 _6
+//       slice 14..17   xyz_encoding_5 W[:, 63:319]  (only the hidden part carries gradient on)
+//       slice 18..21   xyz_encoding_4        22..25 _3    26..29 _2
+// xyz_encoding_1 has no dgrad (its input is the encoding).
+constexpr int kNumSlicesBwd = 30;
+constexpr uint32_t kOffBwd = (kFwdBytes + 1023u) & ~1023u;
+constexpr uint32_t kPackedBytes = kOffBwd + kNumSlicesBwd * kSliceBytes256;
+
+// ---- activation / gradient arrays of the training path ("tiled" layout, 16-bit) ----------------
+// A (rows, C) array, C a multiple of 64, is stored as 8 KiB blocks [64 rows x 64 columns]; block
+// (chunk c = row / 64, column block fb = col / 64) starts at ((c * (C / 64)) + fb) * 8192 bytes and
+// is a [64 x 128 B] SWIZZLE_128B image: element (rr, k) at rr * 128 + (((k >> 3) ^ (rr & 7)) << 4) +
+// (k & 7) * 2.  This is at the same time
+//   * the MN-major UMMA operand image (one 128-byte row per sample = K index, 64 features per
+//     row; LBO = 8192 between column blocks, SBO = 1024 between 8-sample groups), which the wgrad
+//     kernel reads with plain bulk copies (contraction over samples), and
+//   * the K-major UMMA operand image of a [64 rows x 64 K] block, which the backward chain kernel
+//     uses for its first A operand (contraction over features).
+constexpr uint32_t kTileBlockBytes = 8192;
+__host__ __device__ __forceinline__ constexpr unsigned long long tiled_block_off(unsigned long long chunk, uint32_t fb,
+                                                                                uint32_t n_fb) {
+  return (chunk * n_fb + fb) * static_cast<unsigned long long>(kTileBlockBytes);
+}
 
 // Parameter order of the 24 tensors handed to the pack routine
 // (state_dict order of models/nerf.py NeRF):

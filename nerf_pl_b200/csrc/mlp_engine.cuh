@@ -368,9 +368,10 @@ struct EpiCtx {
   Timeline* tl;                    // non-null only for the one traced thread
   // training mode ("save"): post-activation outputs of layers 1..8 and of the direction layer
   // are also written to HBM for the backward pass
-  __half* save_act;                // [8][save_n][256] fp16 (null = off)
-  __half* save_d;                  // [save_n][128] fp16
-  long long save_n;                // samples in the pass (rows per layer)
+  uint8_t* save_act;               // 8 x tiled (save_n, 256) fp16 (layout.h), null = off
+  uint2* save_mask;                // [8][save_n][4]: sign bits of this thread's 64 pre-activations per layer
+  __half* save_d;                  // [save_n][128] fp16 row-major
+  long long save_n;                // padded rows per layer
   long long save_row;              // this thread's global sample row, -1 = padding row
   // Accumulator release.  false: d_free is signalled at tile start (the epilogue also wrote the
   // ENC tile).  true (render kernel: ENC comes from the helper warps): d_free is signalled as soon
@@ -468,6 +469,7 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
     // while blocks 1..3 are still being converted.
     static_assert(kColsPer / 4 == 16, "the hand-over assumes 16 epilogue warps (16 columns per K block per thread)");
     uint32_t r[4][16];
+    uint32_t sgn_lo = 0, sgn_hi = 0;   // kSave: sign bits of the even / odd pre-activations, first in = top bit
 #ifdef NERFB200_EXP_PINGPONG
     const uint32_t d_base = c.tmem_row + ((l & 1) ? 256u : 0u);   // odd layers accumulate in the upper half
 #pragma unroll
@@ -500,6 +502,15 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
           sig_acc = fmaf(fmaxf(v[4], 0.f), w1.x, sig_acc); sig_acc = fmaf(fmaxf(v[5], 0.f), w1.y, sig_acc);
           sig_acc = fmaf(fmaxf(v[6], 0.f), w1.z, sig_acc); sig_acc = fmaf(fmaxf(v[7], 0.f), w1.w, sig_acc);
         }
+        if (kSave) {
+          // backward ReLU masks (bwd_kernels.cuh epi_chain_step): pair i of K block kb ends up at bit
+          // 31 - (8 kb + i) of sgn_lo (even element) / sgn_hi (odd element); one SHF per value
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            sgn_lo = __funnelshift_l(__float_as_uint(v[2 * i]), sgn_lo, 1);
+            sgn_hi = __funnelshift_l(__float_as_uint(v[2 * i + 1]), sgn_hi, 1);
+          }
+        }
         if (kRelu) {
           h[4 * j + 0] = cvt_f16x2_relu(v[0], v[1]); h[4 * j + 1] = cvt_f16x2_relu(v[2], v[3]);
           h[4 * j + 2] = cvt_f16x2_relu(v[4], v[5]); h[4 * j + 3] = cvt_f16x2_relu(v[6], v[7]);
@@ -519,11 +530,16 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
         NERFB200_TL_MARK(c.tl, 0, 40 + kb);
       }
       if (kSave && c.save_act != nullptr && c.save_row >= 0) {
-        uint4* dst = reinterpret_cast<uint4*>(c.save_act + (static_cast<long long>(l) * c.save_n + c.save_row) * 256 + n0);
-        dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
-        dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
+        // tiled layout: column block kb of chunk (row / 64), 16-byte chunks 2 part, 2 part + 1 of the row
+        uint8_t* blk = c.save_act + static_cast<long long>(l) * c.save_n * 512 +
+                       tiled_block_off(static_cast<unsigned long long>(c.save_row >> 6), kb, 4) + (c.save_row & 63) * 128;
+        const uint32_t sw = static_cast<uint32_t>(c.save_row & 7);
+        *reinterpret_cast<uint4*>(blk + (((2u * c.part) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(blk + (((2u * c.part + 1u) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
       }
     }
+    if (kSave && c.save_mask != nullptr && c.save_row >= 0)
+      c.save_mask[(static_cast<long long>(l) * c.save_n + c.save_row) * 4 + c.part] = make_uint2(sgn_lo, sgn_hi);
   }
   NERFB200_TL_MARK(c.tl, 0, 5);
 }

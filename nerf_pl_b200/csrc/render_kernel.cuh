@@ -14,6 +14,27 @@ constexpr int kMaxImp = 128;    // max importance samples / ray
 constexpr int kMaxSf = 192;     // max fine samples / ray (N_samples + N_importance)
 constexpr int kMaxRows = 2 * kMaxSf;
 
+// Everything one render pass (coarse or fine) leaves behind in the training workspace / what the
+// backward launches produce there (csrc/bwd_kernels.cuh).  "tiled": the layout of layout.h.
+struct PassBufs {
+  long long n;            // samples in the pass = n_rays * S
+  long long n_pad;        // rounded up to 128
+  int S;
+  // written by the forward launch
+  uint8_t* enc;           // tiled (n_pad, 64) fp16: encoded xyz, column 63 zero
+  uint8_t* act;           // 8 x tiled (n_pad, 256) fp16: outputs of xyz_encoding_1..8 (layer l at l * n_pad * 512)
+  uint2* mask;            // [8][n_pad][4]: ReLU sign bits of the 64 columns thread (row, column group) owns
+  __half* d;              // (n_pad, 128) fp16 row-major: output of dir_encoding
+  float* sigma;           // (n_pad) raw sigma
+  float* rgb;             // (n_pad, 3) sigmoid(rgb)
+  float* z;               // (n_rays, S) depths of the pass
+  // written by the backward launches
+  float* dsigma;          // (n_pad)    dL / d sigma
+  float* dprergb;         // (n_pad, 3) dL / d (rgb before the sigmoid)
+  uint8_t* dd;            // tiled (n_pad, 128) 16-bit: dL / d (dir_encoding pre-activation) (scaled)
+  uint8_t* dpre;          // 8 x tiled (n_pad, 256) 16-bit: dL / d (xyz_encoding_l pre-activation) (scaled)
+};
+
 struct RenderParams {
   const float* rays;            // (n_rays, ray_stride) : o(3) d(3) near far
   long long ray_stride;         // in floats
@@ -41,15 +62,16 @@ struct RenderParams {
   float* weights_coarse;        // (n_rays, S_c) optional
   float* weights_fine;          // (n_rays, S_f) optional
   int* status;                  // device int: nonzero on device-detected error
-  // training mode: per-sample intermediates for the backward pass (all null = inference)
-  __half* save_act_c;           // [8][n_rays*S_c][256] fp16: coarse h1..h8
-  __half* save_act_f;           // [8][n_rays*S_f][256]
-  __half* save_d_c;             // [n_rays*S_c][128] fp16: direction-layer activation
-  __half* save_d_f;             // [n_rays*S_f][128]
-  float* save_sig_c;            // [n_rays*S_c] raw sigma
-  float* save_sig_f;            // [n_rays*S_f]
-  float* save_rgb_c;            // [n_rays*S_c][3] sigmoid(rgb)
-  float* save_rgb_f;            // [n_rays*S_f][3]
+  // training mode (train != 0, requires test_time == 0): the per-sample intermediates the backward
+  // needs are written into the training workspace (PassBufs of the coarse / fine pass)
+  int train;
+  PassBufs tr[2];
+  float* z_coarse;              // (n_rays, S_c) optional: the (stratified) coarse depths
+  // fused loss epilogue (losses.py:9-14, metrics.py:4-13), all null = off
+  const float* target;          // (n_rays, 3)
+  float* loss_part;             // [gridDim.x][2] per-CTA sums of squared errors (coarse, fine)
+  float* loss_out;              // [4]: mse_coarse, mse_fine, mse_coarse + mse_fine, psnr of the finest pass
+  unsigned* loss_counter;       // zero-initialised ticket counter (reset by the kernel)
   unsigned flags;               // experiment switches (NERFB200_FLAGS), 0 in production
   long long* timeline;          // experiment: device timeline buffer (flags & 2), else null
 };
@@ -413,7 +435,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
     c.part = warp >> 2;
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     c.d_phase = 0;
-    c.save_act = nullptr; c.save_d = nullptr; c.save_n = 0; c.save_row = -1;
+    c.save_act = nullptr; c.save_mask = nullptr; c.save_d = nullptr; c.save_n = 0; c.save_row = -1;
     c.early = true;     // the accumulator is handed back as soon as a tile's last layer is read
     Timeline tle{(blockIdx.x == 0 && threadIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
     c.tl = &tle;
@@ -427,9 +449,10 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
       const uint8_t* blob = pass ? p.net_fine : p.net_coarse;
       c.f32 = reinterpret_cast<const float*>(blob + kHalfRegionBytes);
       c.cst = consts_ptr(smem, pass);
-      c.save_act = kSave ? (pass ? p.save_act_f : p.save_act_c) : nullptr;
-      c.save_d = kSave ? (pass ? p.save_d_f : p.save_d_c) : nullptr;
-      c.save_n = static_cast<long long>(p.n_rays) * S;
+      c.save_act = kSave ? p.tr[pass].act : nullptr;
+      c.save_mask = kSave ? p.tr[pass].mask : nullptr;
+      c.save_d = kSave ? p.tr[pass].d : nullptr;
+      c.save_n = kSave ? p.tr[pass].n_pad : 0;
       const GroupState& gs = sc->gs[tl.g % kGroupSlots];
       const int gr = tl.tile * 128 + c.row;
       const int r = gr / S;
@@ -437,6 +460,15 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
       c.save_row = grow;
       // ENC buffer b and the group's direction bias are ready
       mbar_wait(smem_u32(&sc->enc_full[b]), static_cast<uint32_t>(tl.q >> 1) & 1u, 7);
+      if (kSave && grow >= 0) {
+        // the encoded-input tile is the B operand of the wgrad of layers 1 and 5: copy this thread's
+        // 32 bytes of its row; the shared-memory image is already the tiled layout (row & 7 == grow & 7)
+        const uint8_t* src = smem + (b ? kSmemEnc1 : kSmemEnc) + c.row * 128 + c.part * 32;
+        uint8_t* dst = p.tr[pass].enc + tiled_block_off(static_cast<unsigned long long>(grow >> 6), 0, 1) +
+                       (grow & 63) * 128 + c.part * 32;
+        reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(src)[0];
+        reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(src)[1];
+      }
       float sig_part, rgb_part[3];
       epi_run_tile<kSave>(c, sigma_only, gs.dirbias[pass][r], nullptr, sig_part, rgb_part);
       sc->sig_part[b][c.part][c.row] = sig_part;
@@ -453,8 +485,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
         for (int q = 0; q < kColSplit; ++q) sg += sc->sig_part[b][q][c.row];
         sc->out_sigma[b][c.row] = sg;
         if (kSave && grow >= 0) {
-          float* ss = pass ? p.save_sig_f : p.save_sig_c;
-          if (ss != nullptr) ss[grow] = sg;
+          p.tr[pass].sigma[grow] = sg;
         }
       } else if (!sigma_only) {
         const int ch = c.part - 1;
@@ -464,8 +495,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
         const float col = sigmoid_ref(pre);
         sc->out_rgb[b][ch][c.row] = col;
         if (kSave && grow >= 0) {
-          float* sr = pass ? p.save_rgb_f : p.save_rgb_c;
-          if (sr != nullptr) sr[grow * 3 + ch] = col;
+          p.tr[pass].rgb[grow * 3 + ch] = col;
         }
       }
       if (kHandoffPerThread) {
@@ -481,6 +511,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
     const int hw = ht >> 5;
     TileSeq cons_seq(n_groups, my_n, Sc, Sf, fine);
     Tile tc;
+    float loss_c = 0.f, loss_f = 0.f;   // lane 0 of each helper warp: squared error of its rays (coarse, fine)
     int consumed = 0;           // tiles consumed so far (== q of the next tile to consume)
     int cpos0 = 0, cpos1 = 0, cpos2 = 0;   // position of the (last) coarse tile of the group in slot 0 / 1 / 2
 
@@ -543,6 +574,12 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
               p.rgb_fine[3 * ri + 1] = o.g + add;
               p.rgb_fine[3 * ri + 2] = o.b + add;
               p.depth_fine[ri] = o.depth;
+            }
+            if (p.target != nullptr && !sigma_only) {      // losses.py:9-14: squared error of this ray
+              const float e0 = (o.r + add) - __ldg(p.target + 3 * ri), e1 = (o.g + add) - __ldg(p.target + 3 * ri + 1),
+                          e2 = (o.b + add) - __ldg(p.target + 3 * ri + 2);
+              const float se = e0 * e0 + e1 * e1 + e2 * e2;
+              if (pass == 0) loss_c += se; else loss_f += se;
             }
           }
         }
@@ -667,6 +704,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
           z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), pr));
         }
         gs.zc[r][i] = z;
+        if (p.z_coarse != nullptr && (r == 0 || valid1)) p.z_coarse[static_cast<long long>(rid[r]) * Sc + i] = z;
       }
       helper_bar();
       // ---- per-ray direction bias of both networks: b_dir + W_dir[:, 256:283] . dir_embedded (fp32)
@@ -728,6 +766,35 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
       }
     }
     while (cons_seq.next(tc)) consume(tc);
+    // ---- fused loss epilogue: per-CTA partial sums, the last CTA to finish reduces them in a fixed
+    // order (deterministic) and writes MSELoss / psnr (losses.py:9-14, metrics.py:4-13)
+    if (p.target != nullptr) {
+      float* lsum = &sc->sig_part[0][0][0];       // the epilogue warps are done with it
+      helper_bar();
+      if (lane == 0 && hw < 2) { lsum[2 * hw] = loss_c; lsum[2 * hw + 1] = loss_f; }
+      helper_bar();
+      if (ht == 0) {
+        p.loss_part[2 * blockIdx.x] = lsum[0] + lsum[2];
+        p.loss_part[2 * blockIdx.x + 1] = lsum[1] + lsum[3];
+        __threadfence();
+        const unsigned ticket = atomicAdd(p.loss_counter, 1u);
+        if (ticket == gridDim.x - 1) {
+          __threadfence();
+          double sc_ = 0.0, sf_ = 0.0;
+          for (unsigned i = 0; i < gridDim.x; ++i) {
+            sc_ += static_cast<double>(*reinterpret_cast<volatile float*>(p.loss_part + 2 * i));
+            sf_ += static_cast<double>(*reinterpret_cast<volatile float*>(p.loss_part + 2 * i + 1));
+          }
+          const double ne = 3.0 * static_cast<double>(p.n_rays);
+          const float mc = static_cast<float>(sc_ / ne), mf = static_cast<float>(sf_ / ne);
+          p.loss_out[0] = mc;
+          p.loss_out[1] = fine ? mf : 0.f;
+          p.loss_out[2] = fine ? mc + mf : mc;
+          p.loss_out[3] = -10.f * log10f(fine ? mf : mc);
+          *p.loss_counter = 0u;
+        }
+      }
+    }
   }
   engine_teardown(bars);
 }

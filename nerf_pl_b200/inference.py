@@ -63,8 +63,9 @@ def batched_inference(models: Sequence[torch.nn.Module], embeddings: Sequence[to
     del chunk
 
     def fn(r):
+        # eval never consumes the reference's noise draws: do not materialise them for a whole image
         return render_rays(list(models), list(embeddings), r, N_samples, use_disp, 0, 0, N_importance,
-                           1024 * 32, white_back, test_time=True)
+                           1024 * 32, white_back, test_time=True, match_reference_rng=False)
 
     return render_rays_sharded(fn, rays) if sharded else fn(rays)
 

@@ -50,8 +50,15 @@ def _stream_ptr() -> ctypes.c_void_p:
 
 
 class PackedWeights:
-    """Device-resident packed image of one NeRF (csrc/layout.h), refreshed when a parameter
-    changes (optimizer step / load_state_dict bump ``Tensor._version``)."""
+    """Device-resident packed image of one NeRF (csrc/layout.h).
+
+    Refresh policy: while any parameter requires grad the image is re-packed on EVERY use — weights
+    under training change between calls in ways no cheap key sees (the reference's own RAdam / Ranger
+    update through ``p.data.copy_`` (utils/optimizers.py:88,163,242), which does not bump
+    ``Tensor._version``); one 2.4 MB pack kernel per call is negligible next to a training step.
+    Frozen networks (``requires_grad_(False)``, the inference configuration) are re-packed when a
+    parameter's storage or ``_version`` changes (``load_state_dict``, ``.to(device)``, in-place
+    ops); call ``invalidate_packed(model)`` after editing frozen weights through ``.data``."""
 
     def __init__(self) -> None:
         self.blob = None
@@ -59,9 +66,16 @@ class PackedWeights:
 
     def get(self, model: nn.Module) -> torch.Tensor:
         params = nerf_parameters(model)
-        key = tuple([(p.data_ptr(), p._version) for p in params])   # data_ptr also changes with the device
-        if self.blob is not None and key == self.key:
-            return self.blob
+        trainable = False
+        for p in params:
+            if p.requires_grad:
+                trainable = True
+                break
+        key = None
+        if not trainable:
+            key = tuple([(p.data_ptr(), p._version) for p in params])   # data_ptr also changes with the device
+            if self.blob is not None and key == self.key:
+                return self.blob
         for p, shp in zip(params, _EXPECTED_SHAPES):
             if tuple(p.shape) != shp:
                 raise ValueError(
@@ -72,7 +86,11 @@ class PackedWeights:
         lib = _lib.load()
         dev = params[0].device
         if self.blob is None or self.blob.device != dev:
-            self.blob = torch.empty(lib.nerfb200_packed_bytes(), dtype=torch.uint8, device=dev)
+            # the library wants 1024-byte alignment; torch's caching allocator guarantees 512
+            raw = torch.empty(lib.nerfb200_packed_bytes() + 1024, dtype=torch.uint8, device=dev)
+            off = (-raw.data_ptr()) % 1024
+            self.raw = raw
+            self.blob = raw[off:off + lib.nerfb200_packed_bytes()]
         keep = [p.detach().contiguous() for p in params]
         arr = (ctypes.c_void_p * 24)(*[ctypes.c_void_p(t.data_ptr()) for t in keep])
         with torch.cuda.device(dev):
@@ -80,6 +98,15 @@ class PackedWeights:
                        "nerfb200_pack_weights")
         self.key = key
         return self.blob
+
+
+def invalidate_packed(model: nn.Module) -> None:
+    """Force the next use of ``model`` to re-pack its weights (after editing frozen weights via ``.data``)."""
+    cache = model.__dict__.get("_nerfb200_packed")
+    if cache is not None:
+        cache.key = None
+        if cache.blob is not None:
+            cache.key = ()
 
 
 def packed_weights(model: nn.Module) -> torch.Tensor:

@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from .nerf import _stream_ptr, nerf_forward_torch, packed_weights
 
-__all__ = ["render_rays", "sample_pdf", "searchsorted", "volume_render"]
+__all__ = ["render_rays", "render_rays_loss", "sample_pdf", "searchsorted", "volume_render"]
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -170,6 +170,8 @@ def render_rays(models: List[torch.nn.Module],
     evaluation instead (the gradient reference used by the tests).
     """
     del chunk
+    if autograd_impl not in ("fused", "torch"):
+        raise ValueError("autograd_impl must be 'fused' or 'torch'")
     if rays.dim() != 2 or rays.shape[1] != 8:
         raise ValueError("rays must be (N_rays, 8)")
     if not rays.is_cuda:
@@ -196,7 +198,9 @@ def render_rays(models: List[torch.nn.Module],
     keep = [t.to(torch.float32).contiguous() if t is not None else None for t in (pr, nc, ur, nf)]
     pr, nc, ur, nf = keep
 
-    if needs_graph and autograd_impl == "fused" and not test_time and not extras and n > 0:
+    if needs_graph and extras:
+        raise ValueError("extras=True is an inference-only option (no gradient graph is built for the extra tensors)")
+    if needs_graph and autograd_impl == "fused" and not test_time and n > 0:
         from .training import render_rays_train
         return render_rays_train(models, rays_c, S_c, use_disp, perturb, noise_std, K, white_back, pr, nc, ur, nf)
 
@@ -212,8 +216,7 @@ def render_rays(models: List[torch.nn.Module],
         "depth_fine": flat[8 * n:9 * n] if K > 0 else None,
         "opacity_fine": flat[9 * n:10 * n] if K > 0 else None,
     }
-    want_extras = extras or needs_graph
-    z_fine = torch.empty(n, S_f, **f32) if (want_extras and K > 0) else None
+    z_fine = torch.empty(n, S_f, **f32) if ((extras or needs_graph) and K > 0) else None
     w_c = torch.empty(n, S_c, **f32) if extras else None
     w_f = torch.empty(n, S_f, **f32) if (extras and K > 0) else None
 
@@ -250,12 +253,56 @@ def render_rays(models: List[torch.nn.Module],
     return result
 
 
+def render_rays_loss(models: List[torch.nn.Module],
+                     embeddings: List[torch.nn.Module],
+                     rays: torch.Tensor,
+                     rgbs: torch.Tensor,
+                     N_samples: int = 64,
+                     use_disp: bool = False,
+                     perturb: float = 0,
+                     noise_std: float = 1,
+                     N_importance: int = 0,
+                     chunk: int = 1024 * 32,
+                     white_back: bool = False,
+                     *,
+                     randoms: Optional[Dict[str, torch.Tensor]] = None,
+                     match_reference_rng: bool = True) -> Dict[str, torch.Tensor]:
+    """One training-step forward with the loss fused into the render launch: the reference's
+    ``results = render_rays(...)`` (train.py:55-64), ``loss = MSELoss(results, rgbs)``
+    (losses.py:9-14) and ``psnr(results['rgb_fine'], rgbs)`` (metrics.py:12-13, train.py:107-112) as
+    ONE kernel.  Returns the render_rays result dict plus ``loss`` (differentiable scalar),
+    ``psnr``, ``mse_coarse``, ``mse_fine``; ``loss.backward()`` runs the fused sm_100a backward with
+    the gradient seed 2 (rgb - rgbs) / (3 N) formed inside the compositing-backward kernel."""
+    del chunk
+    if rays.dim() != 2 or rays.shape[1] != 8:
+        raise ValueError("rays must be (N_rays, 8)")
+    if not rays.is_cuda:
+        raise RuntimeError("nerf_pl_b200.render_rays_loss runs on CUDA tensors only (no CPU fallback)")
+    _check_embeddings(embeddings)
+    if N_importance > 0 and len(models) < 2:
+        raise ValueError("N_importance > 0 needs a fine model (models[1])")
+    n, S_c, K = rays.shape[0], int(N_samples), int(N_importance)
+    if n == 0:
+        raise ValueError("empty ray batch")
+    rays_c = rays.detach().to(torch.float32).contiguous()
+    if randoms is None:
+        pr, nc, ur, nf = _draw_randoms(n, S_c, K, float(perturb), float(noise_std), rays.device, match_reference_rng)
+    else:
+        pr, nc = randoms.get("perturb_rand"), randoms.get("noise_coarse")
+        ur, nf = randoms.get("u_rand"), randoms.get("noise_fine")
+    pr, nc, ur, nf = [t.to(torch.float32).contiguous() if t is not None else None for t in (pr, nc, ur, nf)]
+    from .training import render_rays_train
+    return render_rays_train(models, rays_c, S_c, use_disp, float(perturb), float(noise_std), K, white_back,
+                             pr, nc, ur, nf, target=rgbs)
+
+
 # ---------------------------------------------------------------------------------------------
 # Autograd path (training): the fused kernel has produced the detached fine depths
 # (models/rendering.py:225-229: no gradient flows through sampling); the differentiable part
 # - embedding, MLP, quadrature at those depths - is evaluated with torch ops so that
-# .backward() fills the parameters' .grad exactly as in the reference.
-# TODO(round 2): replace with the fused tcgen05 backward (dgrad/wgrad) behind the same Function.
+# .backward() fills the parameters' .grad exactly as in the reference.  This is the
+# ``autograd_impl="torch"`` path: plain torch autograd, kept as an independent check of the fused
+# backward (nerf_pl_b200/training.py) in the GPU tests; the product's training path never uses it.
 def _coarse_depths(rays: torch.Tensor, S: int, use_disp: bool, perturb: float, pr) -> torch.Tensor:
     near, far = rays[:, 6:7], rays[:, 7:8]
     t = torch.linspace(0, 1, S, device=rays.device)

@@ -25,17 +25,41 @@ def lib():
 def test_header_symbols_exported(lib):
     hdr = open(os.path.join(ROOT, "include", "nerf_pl_b200.h")).read()
     declared = set(re.findall(r"\b(nerfb200_[a-z_0-9]+)\s*\(", hdr))
-    declared.discard("nerfb200_render_args")
+    declared -= {"nerfb200_render_args", "nerfb200_backward_args"}
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
+    # the diagnostics (include/nerf_pl_b200_diag.h) are NOT in the product library
+    diag = open(os.path.join(ROOT, "include", "nerf_pl_b200_diag.h")).read()
+    diag_decl = set(re.findall(r"\b(nerfb200_[a-z_0-9]+)\s*\(", diag))
+    assert diag_decl == set(_lib.DIAG_EXPORTS), diag_decl ^ set(_lib.DIAG_EXPORTS)
+    if not os.environ.get("NERFB200_LIB"):
+        for name in diag_decl:
+            assert not hasattr(lib, name), name
 
 
 def test_abi_basics(lib):
-    assert lib.nerfb200_abi_version() == 1
-    # layout.h: 30 x 32 KiB + 5 x 16 KiB fp16 slices + fp32 tail
-    assert lib.nerfb200_packed_bytes() == 30 * 32768 + 5 * 16384 + 4 * (9 * 256 + 256 + 4 + 384 + 4 + 28 * 128)
+    assert lib.nerfb200_abi_version() == 2
+    # layout.h: 30 x 32 KiB + 5 x 16 KiB fp16 slices + fp32 tail, rounded to 1 KiB, + 30 backward slices
+    fwd = 30 * 32768 + 5 * 16384 + 4 * (9 * 256 + 256 + 4 + 384 + 4 + 28 * 128)
+    assert lib.nerfb200_packed_bytes() == (fwd + 1023) // 1024 * 1024 + 30 * 32768
     assert lib.nerfb200_launch_count() >= 0
+    # the Python mirrors of the argument structs have the C sizes (x86-64 / aarch64 LP64 layout)
+    assert ctypes.sizeof(_lib.RenderArgs) == 8 * 5 + 4 * 2 + 4 + 4 * 2 + 4 * 2 + 4 + 8 * 14 + 8 + 8 * 4
+    assert ctypes.sizeof(_lib.BackwardArgs) == 8 * 13
+
+
+def test_training_workspace_layout(lib):
+    """Workspace size is a pure function of the shape: monotone in n_rays, ~9 KiB per ray-sample."""
+    b1 = lib.nerfb200_train_workspace_bytes(1024, 64, 64)
+    b2 = lib.nerfb200_train_workspace_bytes(2048, 64, 64)
+    assert 0 < b1 < b2
+    per_sample = (b2 - b1) / (1024 * 192)
+    assert 8000 < per_sample < 11000
+    assert lib.nerfb200_train_workspace_bytes(0, 64, 64) == 0
+    a = _lib.RenderArgs(n_rays=4, n_samples=64, n_importance=0)
+    b = _lib.BackwardArgs(render=ctypes.pointer(a))
+    assert lib.nerfb200_render_backward(ctypes.byref(b), None) == -1      # NULL rays / tables
 
 
 def test_argument_validation_without_gpu(lib):
@@ -156,5 +180,7 @@ def test_bench_reference_arm_prints_one_json_line():
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
               "scaling", "config", "cpu_baseline", "e2e"):
         assert k in d, k
-    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    staged = os.path.exists(os.path.join(root, "baseline", "_ref", "models", "rendering.py"))
+    assert d["impl"] == "reference" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0

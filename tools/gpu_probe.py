@@ -76,14 +76,17 @@ def step_gemm_mn():
     torch.manual_seed(3)
     a = torch.randn(64, 128, device="cuda")
     b = torch.randn(64, 256, device="cuda")
-    ref = a.half().float().t() @ b.half().float()
-    for lbo, sbo in ((8192, 1024), (1024, 8192), (8192, 128), (128, 8192)):
-        d = torch.zeros(128, 256, device="cuda")
-        rc = lib.nerfb200_debug_gemm_mn(a.data_ptr(), b.data_ptr(), lbo, sbo, d.data_ptr(), None)
-        torch.cuda.synchronize()
-        err = (d - ref).abs().max().item()
-        print(f"gemm_mn lbo={lbo} sbo={sbo} rc={rc} max_abs_err={err:.3e} ref_absmax={ref.abs().max().item():.3f}"
-              + ("  <-- MATCH" if err < 2e-2 else ""))
+    for fmt in (0, 1, 2, 3):
+        ah = a.bfloat16().float() if fmt & 1 else a.half().float()
+        bh = b.bfloat16().float() if fmt & 2 else b.half().float()
+        ref = ah.t() @ bh
+        for lbo, sbo in ((8192, 1024), (1024, 8192)) if fmt == 0 else ((8192, 1024),):
+            d = torch.zeros(128, 256, device="cuda")
+            rc = lib.nerfb200_debug_gemm_mn(a.data_ptr(), b.data_ptr(), lbo, sbo, fmt, d.data_ptr(), None)
+            torch.cuda.synchronize()
+            err = (d - ref).abs().max().item()
+            print(f"gemm_mn fmt={fmt} lbo={lbo} sbo={sbo} rc={rc} max_abs_err={err:.3e} ref_absmax={ref.abs().max().item():.3f}"
+                  + ("  <-- MATCH" if err < 2e-3 else ""))
     print("GEMM_MN_DONE")
 
 
