@@ -57,7 +57,8 @@ int nerfb200_pack_weights(const float* const params[24], void* packed, void* str
  *   opacity_coarse (n); rgb_fine (n,3), depth_fine (n), opacity_fine (n) iff N_importance > 0
  * Optional outputs (NULL to skip): z_fine (n, N_samples+N_importance) merged sorted depths,
  *   weights_coarse (n,N_samples), weights_fine (n,N_samples+N_importance).
- * Supported shapes: N_samples = 64; N_importance in {0,64,128}.
+ * Supported shapes: N_samples in {32, 64, 128}; N_importance a multiple of 32 (0 = coarse only);
+ * N_samples + N_importance <= 192 (the reference defaults 64 + 128 and the README recipes 64 + 64 included).
  * `status` is a device int32 the kernel sets non-zero on a device-side fault.  It may be NULL:
  * then a per-device internal word (mapped pinned host memory) is used; the library reads it
  * without synchronising at the START of every later call on that device and returns

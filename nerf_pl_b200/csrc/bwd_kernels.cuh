@@ -19,9 +19,14 @@
 //   wgrad_reduce_kernel   fixed-order sum of the per-CTA partials into the .grad tensors
 //   unfold_kernel         chain rule through the pack-time folding W' = W_dir[:, :256] W_final
 //
-// Per-sample gradients are 16-bit: bf16 by default (fp32 range: no scaling, no overflow; 8-bit
-// mantissa is enough for gradients that are summed over ~1e5 samples), fp16 with a power-of-two
-// scale chosen on the device with -DNERFB200_BWD_FP16.  Weight gradients accumulate in fp32.
+// Per-sample gradients are fp16 with ONE power-of-two scale per step, chosen on the device from the
+// largest |d sigma|, |d rgb_pre| so that it maps to 256 (bwd_scale_kernel; 8 bits of headroom to the
+// fp16 maximum for growth through the layers, 32 bits of range below), conversions saturate instead
+// of producing inf, and the weight gradients accumulate in fp32 and are un-scaled by the reduction.
+// fp16 rather than bf16 because the wgrad GEMM contracts the gradients with the forward's fp16
+// activations and tcgen05.mma kind::f16 does not take mixed bf16 x fp16 operands (measured: illegal
+// instruction, tools/gpu_probe.py gemm_mn); -DNERFB200_BWD_BF16 builds the all-bf16 variant for
+// experiments (it needs bf16 activations from the forward and is not wired up).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -29,22 +34,22 @@
 
 namespace nerfb200 {
 
-#ifdef NERFB200_BWD_FP16
-constexpr bool kBwdBf16 = false;
-#else
+#ifdef NERFB200_BWD_BF16
 constexpr bool kBwdBf16 = true;
+#else
+constexpr bool kBwdBf16 = false;
 #endif
 constexpr uint32_t kBwdFmt = kBwdBf16 ? 1u : 0u;      // instruction-descriptor format code: 0 = f16, 1 = bf16
 
 __device__ __forceinline__ uint32_t cvt_bwd_x2(float lo, float hi) {
   uint32_t d;
   if (kBwdBf16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
 __device__ __forceinline__ uint16_t cvt_bwd(float v) {
   if (kBwdBf16) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
-  return __half_as_ushort(__float2half_rn(v));
+  return static_cast<uint16_t>(cvt_bwd_x2(v, 0.f) & 0xFFFFu);
 }
 __device__ __forceinline__ float2 bwd_x2_to_float2(uint32_t p) {
   if (kBwdBf16) return make_float2(__uint_as_float(p << 16), __uint_as_float(p & 0xFFFF0000u));
@@ -178,12 +183,12 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdParams 
   }
 }
 
-// scale[0] = 2^floor(log2(1024 / amax)) (fp16 mode) or 1 (bf16 mode); scale[1] = 1 / scale[0].
+// scale[0] = 2^floor(log2(256 / amax)) (fp16 mode) or 1 (bf16 mode); scale[1] = 1 / scale[0].
 __global__ void bwd_scale_kernel(unsigned* amax_bits, float* scale) {
   float s = 1.f;
   if (!kBwdBf16) {
     const float amax = __uint_as_float(*amax_bits);
-    if (amax > 0.f) s = exp2f(floorf(log2f(1024.f / amax)));
+    if (amax > 0.f) s = exp2f(floorf(log2f(256.f / amax)));
     s = fminf(fmaxf(s, 1e-30f), 1e30f);
   }
   scale[0] = s;

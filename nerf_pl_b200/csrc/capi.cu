@@ -112,10 +112,10 @@ int check_sticky_status(DeviceInfo* d) {
 int check_render_shapes(const nerfb200_render_args* a) {
   if (a == nullptr) return fail(NERFB200_EINVAL, "args is NULL%s");
   if (a->n_rays < 0) return fail(NERFB200_EINVAL, "n_rays < 0%s");
-  if (a->n_samples != 64)
-    return fail(NERFB200_EUNSUPPORTED, "N_samples must be 64%s");
-  if (a->n_importance != 0 && a->n_importance != 64 && a->n_importance != 128)
-    return fail(NERFB200_EUNSUPPORTED, "N_importance must be 0, 64 or 128%s");
+  if (a->n_samples != 32 && a->n_samples != 64 && a->n_samples != 128)
+    return fail(NERFB200_EUNSUPPORTED, "N_samples must be 32, 64 or 128%s");
+  if (a->n_importance < 0 || (a->n_importance % 32) != 0)
+    return fail(NERFB200_EUNSUPPORTED, "N_importance must be a multiple of 32%s");
   if (a->n_samples + a->n_importance > kMaxSf)
     return fail(NERFB200_EUNSUPPORTED, "N_samples + N_importance must be <= 192%s");
   if (a->n_rays == 0) return 0;

@@ -52,17 +52,6 @@ constexpr int kThreads = (kEpiWarps + 2) * 32;   // 576
 constexpr int kStages = NERFB200_STAGES;
 constexpr int kTmemCols = 512;
 constexpr uint32_t kTmemD = 0, kTmemA = 256;
-// Experiment for the next round (not yet measured, off by default): the
-// accumulator alternates between columns 0-255 (even layers) and 256-511 (odd layers) and every
-// warp writes its fp16 A columns in place over the accumulator columns it has just read (8 of its
-// 16 columns of a K block = exactly one K=16 MMA step).  The next layer then accumulates into the
-// other half, so its first MMA no longer has to wait until all 16 warps have drained the
-// accumulator: K block 0 is handed over per MMA step (a_k0[j], the 4 warps of column group j).
-#ifdef NERFB200_EXP_PINGPONG
-constexpr bool kPingPong = true;
-#else
-constexpr bool kPingPong = false;
-#endif
 
 constexpr uint32_t kSmemEnc = 0;                     // [128 x 64] fp16     16 KiB
 constexpr uint32_t kSmemRing = 16384;                // kStages x 32 KiB
@@ -88,9 +77,6 @@ struct Barriers {
   uint64_t a_kb[4];        // all epilogue warps -> MMA : "A columns of K block kb written"
                            //   (every warp has drained its accumulator columns before its first arrive)
   uint64_t d_ready;        // MMA -> epilogue : "accumulator complete"
-#ifdef NERFB200_EXP_PINGPONG
-  uint64_t a_k0[4];        // column group j (4 warps) -> MMA : "A columns of K block 0, step j written"
-#endif
   uint32_t tmem_base;
   uint32_t pad[1];
 };
@@ -139,9 +125,6 @@ __device__ __forceinline__ bool engine_setup(uint8_t* smem, Barriers* bars) {
     mbar_init(smem_u32(&bars->a_ready), kEpiWarps);
     mbar_init(smem_u32(&bars->d_free), kEpiWarps);
     for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&bars->a_kb[k]), kEpiWarps);   // all warps work on one K block at a time
-#ifdef NERFB200_EXP_PINGPONG
-    for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&bars->a_k0[k]), 4);
-#endif
     mbar_init(smem_u32(&bars->d_ready), 1);
     fence_mbar_init();
   }
@@ -238,10 +221,8 @@ template <bool kSigmaOnly, bool kDirSlice>
 __device__ __forceinline__ void mma_tile_t(RingState& rs, MmaPhases& ph, uint8_t* smem, Barriers* bars,
                                            Timeline* tl, uint32_t enc_off, uint32_t enc_bar, uint32_t enc_parity) {
   const uint32_t tmem = bars->tmem_base;
-#ifndef NERFB200_EXP_PINGPONG
   const uint32_t d_tmem = tmem + kTmemD;
   const uint32_t a_tmem = tmem + kTmemA;
-#endif
   const uint64_t enc_desc = make_desc_sw128(smem_u32(smem + enc_off));
   const uint64_t ring_desc = make_desc_sw128(smem_u32(smem + kSmemRing));
   const uint32_t full0 = smem_u32(&bars->full[0]);
@@ -270,57 +251,22 @@ __device__ __forceinline__ void mma_tile_t(RingState& rs, MmaPhases& ph, uint8_t
       tl_val(tl, 1, 600, w1 - w0);
       tl_val(tl, 1, 601, clock64() - w1);
 #endif
-#ifndef NERFB200_EXP_PINGPONG
     } else {
-#ifdef NERFB200_EXP_HOIST_FULL
-      // experiment (not yet measured): the first weight slice is long in the ring; wait for it before
-      // a_kb[0] so that only one shared-memory round trip separates "signalled" from "first MMA"
-      mbar_wait(full0 + 8u * rs.stage, rs.phase, 4);
-#endif
       mbar_wait(akb0, ph.a_kb, 6);
-#endif
     }
     tc_fence_after();
     NERFB200_TL_MARK(tl, 1, 100 + l);
     const int n_slices = (l == 0) ? 1 : (l == 4) ? 5 : (l == 8 && kDirSlice) ? 5 : 4;
     const uint32_t idesc = (l == 8) ? idesc128 : idesc256;
-#ifdef NERFB200_EXP_PINGPONG
-    // accumulator / A operand columns of this layer
-    const uint32_t d_tmem = tmem + ((l & 1) ? 256u : 0u);
-    const uint32_t a_tmem = tmem + (((l - 1) & 1) ? 256u : 0u);
-#endif
 #pragma unroll
     for (int s = 0; s < 5; ++s) {
       if (s < n_slices) {
         const bool from_enc = (l == 0) || (l == 4 && s == 0) || (l == 8 && s == 4);
         const int kb = (l == 4) ? s - 1 : s;
         const uint32_t stage = rs.stage;
-#ifdef NERFB200_EXP_HOIST_FULL
-        if (s > 0 || l == 0) mbar_wait(full0 + 8u * stage, rs.phase, 4);
-        if (!from_enc && kb > 0) {
-          mbar_wait(akb0 + 8u * kb, ph.a_kb, 6);
-          tc_fence_after();
-        }
-#else
         mbar_wait(full0 + 8u * stage, rs.phase, 4);
         if (!from_enc && kb > 0) mbar_wait(akb0 + 8u * kb, ph.a_kb, 6);
         tc_fence_after();
-#endif
-#ifdef NERFB200_EXP_PINGPONG
-        if (!from_enc && kb == 0) {
-          const uint32_t ak0 = smem_u32(&bars->a_k0[0]);
-          const uint64_t bdesc0 = ring_desc + static_cast<uint64_t>(stage * (kSliceBytes256 >> 4));
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {   // hand-over per MMA step
-            mbar_wait(ak0 + 8u * j, ph.a_kb, 6);
-            tc_fence_after();
-            umma_f16_ts(d_tmem, a_tmem + j * 16, bdesc0 + 2 * j, idesc, (s | j) != 0 ? 1u : 0u);
-          }
-          umma_commit(empty0 + 8u * stage);
-          rs.advance();
-          continue;
-        }
-#endif
         const uint64_t bdesc = ring_desc + static_cast<uint64_t>(stage * (kSliceBytes256 >> 4));
         if (from_enc) {
 #pragma unroll
@@ -329,11 +275,7 @@ __device__ __forceinline__ void mma_tile_t(RingState& rs, MmaPhases& ph, uint8_t
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)   // A: 64 K-values per block = 32 columns, 8 per K=16 step
-#ifdef NERFB200_EXP_PINGPONG
-            umma_f16_ts(d_tmem, a_tmem + kb * 64 + j * 16, bdesc + 2 * j, idesc, (s | j) != 0 ? 1u : 0u);
-#else
             umma_f16_ts(d_tmem, a_tmem + kb * 32 + j * 8, bdesc + 2 * j, idesc, (s | j) != 0 ? 1u : 0u);
-#endif
         }
         umma_commit(empty0 + 8u * stage);
         rs.advance();
@@ -406,12 +348,6 @@ __device__ __forceinline__ void epi_signal_kb(EpiCtx& c, int kb, bool smem_writt
   tmem_st_wait();
   tc_fence_before();
   __syncwarp();
-#ifdef NERFB200_EXP_PINGPONG
-  if (kb == 0) {      // K block 0 is handed over per MMA step: this warp's columns are step c.part
-    if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_k0[c.part]));
-    return;
-  }
-#endif
   if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_kb[kb]));
 }
 __device__ __forceinline__ void epi_wait_d(EpiCtx& c) {
@@ -470,16 +406,19 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
     static_assert(kColsPer / 4 == 16, "the hand-over assumes 16 epilogue warps (16 columns per K block per thread)");
     uint32_t r[4][16];
     uint32_t sgn_lo = 0, sgn_hi = 0;   // kSave: sign bits of the even / odd pre-activations, first in = top bit
-#ifdef NERFB200_EXP_PINGPONG
-    const uint32_t d_base = c.tmem_row + ((l & 1) ? 256u : 0u);   // odd layers accumulate in the upper half
+    // K block 0 is on the critical path "accumulator complete -> first MMA of the next layer": its 16
+    // columns are fetched alone, the other three loads are in flight while it is converted and stored
+#ifdef NERFB200_EXP_SPLIT_LD
+    tmem_ld16(c.tmem_row + kTmemD + c.part * 16, r[0]);
+    tmem_ld_wait();
 #pragma unroll
-    for (int kb = 0; kb < 4; ++kb) tmem_ld16(d_base + kb * 64 + c.part * 16, r[kb]);
+    for (int kb = 1; kb < 4; ++kb) tmem_ld16(c.tmem_row + kTmemD + kb * 64 + c.part * 16, r[kb]);
 #else
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) tmem_ld16(c.tmem_row + kTmemD + kb * 64 + c.part * 16, r[kb]);
-#endif
     tmem_ld_wait();
     if (!kStore && c.early) epi_release_accumulator(c);
+#endif
     NERFB200_TL_MARK(c.tl, 0, 3);
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) {
@@ -519,12 +458,15 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
           h[4 * j + 2] = cvt_f16x2(v[4], v[5]); h[4 * j + 3] = cvt_f16x2(v[6], v[7]);
         }
       }
-      if (kStore) {
-#ifdef NERFB200_EXP_PINGPONG
-        tmem_st8(d_base + n0, h);      // in place: the first 8 of this warp's 16 columns
-#else
-        tmem_st8(c.tmem_row + kTmemA + n0 / 2, h);
+      if (kStore) tmem_st8(c.tmem_row + kTmemA + n0 / 2, h);
+#ifdef NERFB200_EXP_SPLIT_LD
+      if (kb == 0) {      // every column of the accumulator is in registers from here on
+        tmem_ld_wait();
+        reg_fence16(r[1]); reg_fence16(r[2]); reg_fence16(r[3]);
+        if (!kStore && c.early) epi_release_accumulator(c);
+      }
 #endif
+      if (kStore) {
         if (kb == 3 && dir_row != nullptr) write_dir_row(c, dir_row);
         epi_signal_kb(c, kb, kb == 3 && dir_row != nullptr);
         NERFB200_TL_MARK(c.tl, 0, 40 + kb);

@@ -9,7 +9,7 @@
 
 namespace nerfb200 {
 
-constexpr int kMaxSc = 64;      // max coarse samples / ray
+constexpr int kMaxSc = 128;     // max coarse samples / ray
 constexpr int kMaxImp = 128;    // max importance samples / ray
 constexpr int kMaxSf = 192;     // max fine samples / ray (N_samples + N_importance)
 constexpr int kMaxRows = 2 * kMaxSf;
@@ -455,8 +455,8 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
       c.save_n = kSave ? p.tr[pass].n_pad : 0;
       const GroupState& gs = sc->gs[tl.g % kGroupSlots];
       const int gr = tl.tile * 128 + c.row;
-      const int r = gr / S;
-      const long long grow = (r == 0 || valid1) ? static_cast<long long>(ray0 + r) * S + (gr - r * S) : -1;
+      const int r = (gr >= S) ? 1 : 0;       // rows past the group's 2 S samples (S < 64 k) are padding
+      const long long grow = (gr < 2 * S && (r == 0 || valid1)) ? static_cast<long long>(ray0 + r) * S + (gr - r * S) : -1;
       c.save_row = grow;
       // ENC buffer b and the group's direction bias are ready
       mbar_wait(smem_u32(&sc->enc_full[b]), static_cast<uint32_t>(tl.q >> 1) & 1u, 7);
@@ -751,8 +751,8 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
 #pragma unroll 1
         for (int row = ht; row < 128; row += kHelperThreads) {
           const int gr = tl.tile * 128 + row;
-          const int r = gr / S;
-          const float zval = tl.pass ? gs.z[gr] : gs.zc[r][gr - r * S];
+          const int r = (gr >= S) ? 1 : 0;   // padding rows encode whatever is there; their results are dropped
+          const float zval = tl.pass ? gs.z[gr] : gs.zc[r][min(gr - r * S, kMaxSc - 1)];
 #pragma unroll 1
           for (int part = 0; part < kColSplit; ++part) encode_row(enc, row, part, &gs.ray[r][0], &gs.ray[r][3], zval);
         }

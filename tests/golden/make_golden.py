@@ -65,6 +65,8 @@ CASES = {
     "odd_rays": (33, "blender", 8, 64, 64, False, 0.0, 0.0, False, False),
     "ndc_perturb_128": (70, "ndc", 9, 64, 128, False, 1.0, 0.0, False, False),
     "blender_disp_perturb": (50, "blender", 10, 64, 64, True, 1.0, 0.0, True, True),
+    # configs[3] (LLFF fern recipe, README.md:104-111): NDC rays, perturb 1, noise_std 1, white_back False
+    "ndc_train_noise1": (80, "ndc", 13, 64, 64, False, 1.0, 1.0, False, False),
 }
 W_SEEDS = (11, 12)   # coarse, fine
 

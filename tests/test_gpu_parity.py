@@ -196,6 +196,71 @@ def test_full_image_properties(models, emb, ws, dev):
         assert mx < tol_for(k)
 
 
+def test_llff_view_with_noise_properties(models, emb, ws, dev):
+    """BASELINE.json configs[3]: one LLFF-fern-shaped view, 504x378 = 190,512 NDC rays (near 0, far 1,
+    non-unit directions; datasets/llff.py:236-241), the README recipe's perturb=1 / noise_std=1,
+    white_back=False, training-mode forward.  Size-independent properties (bit-exact determinism and
+    chunk invariance with the same random tensors, ranges, weights sum) + a 256-ray subset against
+    the oracle on the same random draws."""
+    H, W, focal = 378, 504, 407.0
+    c2w = np.array([[1, 0, 0, 0.05], [0, 1, 0, -0.02], [0, 0, 1, 0.1]], np.float32)
+    rays = nb.generate_rays(H, W, focal, c2w, 0.0, 1.0, ndc=True, device=dev)
+    n = H * W
+    assert rays.shape == (n, 8) and n == 190512
+    g = torch.Generator(device=dev).manual_seed(11)
+    rnd = {"perturb_rand": torch.rand(n, 64, device=dev, generator=g), "noise_coarse": torch.randn(n, 64, device=dev, generator=g),
+           "u_rand": torch.rand(n, 64, device=dev, generator=g), "noise_fine": torch.randn(n, 128, device=dev, generator=g)}
+    with torch.no_grad():
+        a = nb.render_rays(models, emb, rays, 64, False, 1.0, 1.0, 64, 32768, False, randoms=rnd, extras=True)
+        b = nb.render_rays(models, emb, rays, 64, False, 1.0, 1.0, 64, 32768, False, randoms=rnd, extras=True)
+        lo, hi = 70001, 70001 + 4097
+        part = nb.render_rays(models, emb, rays[lo:hi], 64, False, 1.0, 1.0, 64, 32768, False,
+                              randoms={k: v[lo:hi] for k, v in rnd.items()}, extras=True)
+    torch.cuda.synchronize()
+    for k in a:
+        assert torch.isfinite(a[k]).all(), k
+        assert torch.equal(a[k], b[k]), f"non-deterministic {k}"
+        assert torch.equal(a[k][lo:hi], part[k]), f"chunking changed {k}"
+    z = a["z_vals_fine"]
+    assert bool((z[:, 1:] >= z[:, :-1]).all()) and float(z.min()) >= -1e-6 and float(z.max()) <= 1 + 1e-6
+    for k in ("opacity_coarse", "opacity_fine"):
+        assert float(a[k].min()) >= 0.0 and float(a[k].max()) <= 1.0 + 1e-5
+    assert torch.allclose(a["weights_fine"].sum(1), a["opacity_fine"], atol=1e-5)
+    idx = np.random.RandomState(1).choice(n, 256, replace=False)
+    ti = torch.from_numpy(idx).to(dev)
+    ref = orc.render_rays(ws, rays[ti].cpu().numpy(), 64, False, 1.0, 1.0, 64, False, False,
+                          {k: v[ti].cpu().numpy() for k, v in rnd.items()})
+    for k, v in ref.items():
+        mx, p999, mean = cases.error_stats(a[k][ti].cpu().numpy(), v)
+        print(f"llff subset {k}: max {mx:.2e} p99.9 {p999:.2e} mean {mean:.2e}")
+        # NDC depths are in [0,1]; under noise a sign flip of sigma+noise at the far plane moves depth/opacity
+        # by the remaining transmittance (DESIGN.md section 5): bound the bulk, and rgb by the north-star bar
+        if k.startswith("rgb"):
+            assert p999 < 1e-3 and mx < 5e-3, (k, mx, p999)
+        else:
+            assert mean < 1e-3, (k, mean)
+
+
+def test_800x800_view(models, emb, ws, dev):
+    """BASELINE.json configs[4]'s image: 640,000 rays in one launch (the single-GPU leg of the sharded
+    render), test_time=True: finite, deterministic, oracle-checked subset."""
+    import bench
+    rays_np = bench.blender_rays(0, 7, 800, 800, pixels="all")
+    rays = torch.from_numpy(rays_np).to(dev)
+    with torch.no_grad():
+        a = nb.render_rays(models, emb, rays, 64, False, 0, 0, 64, 32768, True, test_time=True, match_reference_rng=False)
+        b = nb.render_rays(models, emb, rays, 64, False, 0, 0, 64, 32768, True, test_time=True, match_reference_rng=False)
+    torch.cuda.synchronize()
+    assert a["rgb_fine"].shape == (640000, 3)
+    for k in a:
+        assert torch.isfinite(a[k]).all() and torch.equal(a[k], b[k]), k
+    idx = np.random.RandomState(2).choice(640000, 256, replace=False)
+    ref = orc.render_rays(ws, rays_np[idx], 64, False, 0.0, 0.0, 64, True, True)
+    for k, v in ref.items():
+        mx, _, _ = cases.error_stats(a[k][torch.from_numpy(idx).to(dev)].cpu().numpy(), v)
+        assert mx < tol_for(k), (k, mx)
+
+
 @pytest.mark.parametrize("K,test_time,perturb,use_disp,white_back", [
     (128, False, 1.0, False, True),     # three fine tiles per group, training-mode coarse pass, rank-sorted u
     (64, False, 1.0, True, False),      # disparity sampling
@@ -303,6 +368,30 @@ def test_unsupported_shapes_fail_loudly(models, emb, dev):
     assert out["rgb_coarse"].shape == (0, 3)
 
 
+@pytest.mark.parametrize("S,K,test_time,perturb", [(32, 0, False, 0.0), (32, 32, False, 1.0), (64, 32, True, 0.0),
+                                                   (64, 96, False, 1.0), (128, 64, True, 0.0), (32, 160, False, 1.0),
+                                                   (128, 0, False, 1.0)])
+def test_general_sample_counts(S, K, test_time, perturb, models, emb, ws, dev):
+    """N_samples in {32, 64, 128}, N_importance any multiple of 32 with N_samples + N_importance <= 192
+    (opt.py:19-22 lets the user choose them) against the oracle on the same inputs; odd ray count."""
+    n = 75
+    rays = orc.make_rays(n, 50 + S + K)
+    rs = np.random.RandomState(S * 7 + K)
+    randoms = {}
+    if perturb > 0:
+        randoms = {"perturb_rand": rs.rand(n, S).astype(np.float32)}
+        if K > 0:
+            randoms["u_rand"] = rs.rand(n, K).astype(np.float32)
+    ref = orc.render_rays(ws, rays, S, False, perturb, 0.0, K, True, test_time, randoms)
+    with torch.no_grad():
+        out = nb.render_rays(models, emb, torch.from_numpy(rays).to(dev), S, False, perturb, 0.0, K, 32768, True,
+                             test_time=test_time, randoms=to_dev(randoms, dev))
+    assert set(out) == set(ref)
+    for k in ref:
+        mx, p999, mean = cases.error_stats(out[k].cpu().numpy(), ref[k])
+        assert mx < tol_for(k), f"S={S} K={K} {k}: max {mx:.3e} p99.9 {p999:.3e}"
+
+
 def test_ray_generation_and_image_driver(models, emb, ws, dev):
     """on-GPU rays (vs reference ray_utils golden), one-launch image render,
     uint8 conversion (eval.py:58-86, 119-128)."""
@@ -385,9 +474,12 @@ def test_training_step_gradients_vs_reference_golden(name, fused_loss, ws, emb, 
         loss = ((out["rgb_coarse"] - t) ** 2).mean() + ((out["rgb_fine"] - t) ** 2).mean()
     loss.backward()
     torch.cuda.synchronize()
-    assert abs(float(loss) - ref_loss) < 1e-3 * ref_loss, (float(loss), ref_loss)
+    assert abs(float(loss.detach()) - ref_loss) < 1e-3 * ref_loss, (float(loss.detach()), ref_loss)
     for k in ("rgb_coarse", "rgb_fine"):
-        assert cases.error_stats(out[k].detach().cpu().numpy(), ref_out[k])[0] < 1e-3, k
+        # under sigma noise a sign flip of sigma+noise at the far plane (delta = 1e10) moves single rays by
+        # their remaining transmittance: bound the bulk there
+        mx, p999, mean = cases.error_stats(out[k].detach().cpu().numpy(), ref_out[k])
+        assert (mx < 1e-3) if noise == 0 else (mx < 5e-3 and mean < 1e-4), (k, mx, mean)
     grads = _named_grads(m)
     assert set(grads) == set(ref_grads)
     rows, (rel, cos) = og.grad_compare(grads, ref_grads)
@@ -516,3 +608,18 @@ def test_fused_training_gradients_match_torch_autograd(ws, emb, dev):
         worst = max(worst, rel)
         assert rel < 5e-2 and cos > 0.998, f"{name}: rel {rel:.3e} cos {cos:.5f}"
     print(f"worst relative gradient error {worst:.3e}")
+
+
+def test_sharded_render_over_nccl_equals_single_gpu():
+    """SURVEY section 8e on real hardware: 2 ranks (one process per GPU, torchrun, NCCL), contiguous
+    ray shards + ONE all-gather == the single-GPU render, bit-exactly (tools/nccl_check.py).
+    Needs 2 GPUs on the box; skipped otherwise (the gloo twin runs on CPU in test_sharded_gloo.py)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", "tools/nccl_check.py"],
+                       cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.count("NCCL_CHECK_OK") == 2, r.stdout[-2000:] + r.stderr[-2000:]
