@@ -117,8 +117,7 @@ class ClockSampler:
                     rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
-                self.rows.append((sm, rs, util))
+                self.rows.append((sm, rs))
             except Exception as e:      # noqa: BLE001
                 self.err = repr(e)
                 return

@@ -48,6 +48,7 @@ __global__ void pack_weights_kernel(const PackParams pp) {
       const float* wd = pp.p[18] + static_cast<long long>(n) * 283;
       const float* wf = pp.p[16] + koff + k;
       float acc = 0.f;
+#pragma unroll 16
       for (int m = 0; m < 256; ++m) acc = fmaf(wd[m], wf[static_cast<long long>(m) * 256], acc);
       v = acc;
     } else if (k < kvalid) {
@@ -73,6 +74,7 @@ __global__ void pack_weights_kernel(const PackParams pp) {
       const float* wd = pp.p[18] + static_cast<long long>(slice * 64 + k) * 283;
       const float* wf = pp.p[16] + n;
       float acc = 0.f;
+#pragma unroll 16
       for (int j = 0; j < 256; ++j) acc = fmaf(wd[j], wf[static_cast<long long>(j) * 256], acc);
       v = acc;
     } else {

@@ -19,10 +19,15 @@
 //   wgrad_reduce_kernel   fixed-order sum of the per-CTA partials into the .grad tensors
 //   unfold_kernel         chain rule through the pack-time folding W' = W_dir[:, :256] W_final
 //
-// Per-sample gradients are fp16 with ONE power-of-two scale per step, chosen on the device from the
-// largest |d sigma|, |d rgb_pre| so that it maps to 256 (bwd_scale_kernel; 8 bits of headroom to the
-// fp16 maximum for growth through the layers, 32 bits of range below), conversions saturate instead
-// of producing inf, and the weight gradients accumulate in fp32 and are un-scaled by the reduction.
+// Per-sample gradients are fp16 with a power-of-two scale PER LAYER, chosen on the device in the
+// same step (no state carried between steps, deterministic): level 0 (dd) from a bound on its
+// largest element, |d rgb_pre|_max * max_n sum_c |W_rgb[c][n]|; levels 1..8 (dpre_8..dpre_1) from
+// the largest elements a PROBE pass of the chain kernel sees on one tile per SM (no stores), each
+// mapped to 64 (10 bits of headroom to the fp16 maximum, 20 bits of normal range below; gradients
+// shrink or grow by orders of magnitude through 8 layers, one global scale costs precision in the
+// deep layers: measured 4e-2 relative error at layer 1 vs 4e-3 with per-layer scales).
+// Conversions saturate instead of producing inf; the weight gradients accumulate in fp32 and are
+// un-scaled per layer by the reduction.
 // fp16 rather than bf16 because the wgrad GEMM contracts the gradients with the forward's fp16
 // activations and tcgen05.mma kind::f16 does not take mixed bf16 x fp16 operands (measured: illegal
 // instruction, tools/gpu_probe.py gemm_mn); -DNERFB200_BWD_BF16 builds the all-bf16 variant for
@@ -84,7 +89,7 @@ struct CompBwdParams {
   const float* loss_grad;   // device scalar dL/dloss or null (= 1)
   float* dsigma;
   float* dprergb;
-  unsigned* amax_bits;      // max |d sigma|, |d rgb_pre| as float bits (fp16 mode scale selection) or null
+  unsigned* amax_bits;      // [2]: max |d sigma|, max |d rgb_pre| as float bits (scale selection) or null
 };
 
 __global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdParams p) {
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdParams 
   const int wpb = blockDim.x >> 5;
   const long long ray = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5);
   const int S = p.S, P = S >> 5;
-  float amax = 0.f;
+  float amax = 0.f, amax_rgb = 0.f;
   if (ray < p.n_rays) {
     const float* rr = p.rays + ray * p.ray_stride;
     const float dx = rr[3], dy = rr[4], dz = rr[5];
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdParams 
       for (int ch = 0; ch < 3; ++ch) {
         const float dp = wgt[q] * g[ch] * c[ch] * (1.f - c[ch]);
         p.dprergb[(g0 + i) * 3 + ch] = dp;
-        amax = fmaxf(amax, fabsf(dp));
+        amax_rgb = fmaxf(amax_rgb, fabsf(dp));
       }
     }
   }
@@ -178,110 +183,215 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdParams 
     }
   if (p.amax_bits != nullptr) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    for (int o = 16; o > 0; o >>= 1) {
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      amax_rgb = fmaxf(amax_rgb, __shfl_xor_sync(0xffffffffu, amax_rgb, o));
+    }
     if (lane == 0 && amax > 0.f && amax < 3e38f) atomicMax(p.amax_bits, __float_as_uint(amax));
+    if (lane == 0 && amax_rgb > 0.f && amax_rgb < 3e38f) atomicMax(p.amax_bits + 1, __float_as_uint(amax_rgb));
   }
 }
 
-// scale[0] = 2^floor(log2(256 / amax)) (fp16 mode) or 1 (bf16 mode); scale[1] = 1 / scale[0].
-__global__ void bwd_scale_kernel(unsigned* amax_bits, float* scale) {
-  float s = 1.f;
-  if (!kBwdBf16) {
-    const float amax = __uint_as_float(*amax_bits);
-    if (amax > 0.f) s = exp2f(floorf(log2f(256.f / amax)));
-    s = fminf(fmaxf(s, 1e-30f), 1e30f);
+// Per-pass, per-level scales (see the header comment).  Level v: 0 = dd, v = 1..8 = dpre_{9-v}.
+//   phase 0 (before head_bwd / the probe): every level gets the level-0 scale
+//            2^floor(log2(64 / max(|d rgb_pre|_max wmax_rgb, |d sigma|_max wmax_sigma)))
+//   phase 1 (after the probe pass): levels 1..8 from the probe's per-level maxima (true, un-scaled
+//            values), clamped to [2^-12, 2^40] x level 0; a level the probe saw nothing in keeps its
+//            predecessor's scale.  Resets the statistics for the next step.
+constexpr int kLevels = 9;
+struct ScaleParams {
+  int n_pass, phase;
+  unsigned* amax;            // [2 passes][2]: |d sigma|, |d rgb_pre| maxima (float bits)
+  unsigned* lamax;           // [2 passes][kLevels] probe maxima (float bits)
+  float* lscale;             // [2][kLevels]
+  float* linv;               // [2][kLevels]
+  const float* w_rgb[2];     // live fp32 (3,128)
+  const float* w_sigma[2];   // live fp32 (256)
+};
+__global__ void __launch_bounds__(128) bwd_scale_kernel(const ScaleParams p) {
+  __shared__ float red[2][128];
+  const int t = threadIdx.x;
+  for (int ps = 0; ps < p.n_pass; ++ps) {
+    if (p.phase == 0) {
+      float wr = fabsf(p.w_rgb[ps][t]) + fabsf(p.w_rgb[ps][128 + t]) + fabsf(p.w_rgb[ps][256 + t]);
+      float wsg = fmaxf(fabsf(p.w_sigma[ps][t]), fabsf(p.w_sigma[ps][128 + t]));
+      red[0][t] = wr; red[1][t] = wsg;
+      __syncthreads();
+      for (int o = 64; o > 0; o >>= 1) {
+        if (t < o) { red[0][t] = fmaxf(red[0][t], red[0][t + o]); red[1][t] = fmaxf(red[1][t], red[1][t + o]); }
+        __syncthreads();
+      }
+      if (t < kLevels) {
+        float s = 1.f;
+        if (!kBwdBf16) {
+          const float bound = fmaxf(__uint_as_float(p.amax[2 * ps + 1]) * red[0][0], __uint_as_float(p.amax[2 * ps]) * red[1][0]);
+          if (bound > 0.f) s = exp2f(floorf(log2f(64.f / bound)));
+          s = fminf(fmaxf(s, 1e-30f), 1e30f);
+        }
+        p.lscale[ps * kLevels + t] = s;
+        p.linv[ps * kLevels + t] = 1.f / s;
+        p.lamax[ps * kLevels + t] = 0u;
+      }
+      __syncthreads();
+      if (t < 2) p.amax[2 * ps + t] = 0u;
+    } else if (t == 0 && !kBwdBf16) {
+      const float s0 = p.lscale[ps * kLevels];
+      float prev = s0;
+      for (int v = 1; v < kLevels; ++v) {
+        const float am = __uint_as_float(p.lamax[ps * kLevels + v]);
+        float s = prev;
+        if (am > 0.f) s = exp2f(floorf(log2f(64.f / am)));
+        s = fminf(fmaxf(s, s0 * 2.44140625e-4f), s0 * 1.0995116e12f);
+        p.lscale[ps * kLevels + v] = s;
+        p.linv[ps * kLevels + v] = 1.f / s;
+        p.lamax[ps * kLevels + v] = 0u;
+        prev = s;
+      }
+    }
   }
-  scale[0] = s;
-  scale[1] = 1.f / s;
-  *amax_bits = 0u;
 }
 
 // ------------------------------------------------------------------------ rgb head / dir ReLU
-// models/nerf.py:119-120 backwards, per sample:  dd = (dpre_rgb W_rgb) * (d > 0)  -> tiled 16-bit
-// (A operand of the chain kernel's first step and of the W' wgrad), and the three small weight
-// gradients that contract over samples on the CUDA cores:
+// models/nerf.py:119-120 backwards, per sample:  dd = (dpre_rgb W_rgb) * (d > 0)  -> tiled fp16 (the
+// A operand of the chain kernel's first step and of the W' wgrad), plus the small weight gradients
+// that contract over samples on the CUDA cores:
 //   gW_rgb[c][n] = sum_s dpre_rgb[s][c] d[s][n]     gb_rgb[c] = sum_s dpre_rgb[s][c]
-//   gW_dir[n][256 + j] = sum_rays (sum_{s in ray} dd[s][n]) dir_enc[ray][j]   (direction is constant per ray)
-// Block = 128 threads (thread n = column n of the direction layer), a contiguous range of rays per
-// block; per-block partials, summed in fixed order by wgrad_reduce_kernel.
+//   raysum[ray][n] = sum_{s in ray} dd[s][n]        (the direction is constant along a ray: the direction
+//   part of gW_dir is sum_rays raysum[ray] (x) dir_enc[ray], dir_grad_kernel below)
+// A streaming kernel (0.5 KB per sample): one warp per ray and pass, lane = 4 adjacent columns, 8-byte
+// loads / stores of the tiled arrays, the sample loop unrolled so that 8 rows are in flight per warp.
+// Per-block partials of gW_rgb / gb_rgb, summed in fixed order by wgrad_reduce_kernel.
+constexpr int kHeadWarps = 8;
 constexpr int kHeadPartRgbW = 0;            // [3][128]
 constexpr int kHeadPartRgbB = 384;          // [4]
-constexpr int kHeadPartDir = 388;           // [128][27]
-constexpr int kHeadPartFloats = 388 + 128 * 27;
+constexpr int kHeadPartFloats = 388;
 struct HeadBwdParams {
-  int n_rays, S;
-  long long n_pad;
-  const __half* d;
-  const float* dprergb;
-  const float* w_rgb;       // live fp32 (3,128)
+  int n_rays, n_pass;
+  PassBufs pass[2];
+  const float* w_rgb[2];    // live fp32 (3,128)
+  const float* lscale;      // [2][kLevels]: level 0 of each pass scales dd
   const float* rays;
   long long ray_stride;
-  const float* scale;
-  uint8_t* dd;
-  float* part;              // [gridDim.x][kHeadPartFloats]
+  float* raysum[2];         // (n_rays, 128)
+  float* direnc;            // (n_rays, 28): Embedding(3,4)(rays_d), as the forward computes it
+  float* part[2];           // [gridDim.x][kHeadPartFloats] per pass (blocks of the other pass write zeros)
 };
 
-__global__ void __launch_bounds__(128) head_bwd_kernel(const HeadBwdParams p) {
-  __shared__ float direnc[28];
-  const int n = threadIdx.x;
-  const int per = p.n_rays / static_cast<int>(gridDim.x), rem = p.n_rays % static_cast<int>(gridDim.x);
-  const int r0 = static_cast<int>(blockIdx.x) * per + min(static_cast<int>(blockIdx.x), rem);
-  const int r1 = r0 + per + (static_cast<int>(blockIdx.x) < rem ? 1 : 0);
-  const float w0 = p.w_rgb[n], w1 = p.w_rgb[128 + n], w2 = p.w_rgb[256 + n];
-  const float scale = p.scale[0];
-  float gw[3] = {0.f, 0.f, 0.f}, gb = 0.f;
-  float gdir[27];
+__global__ void __launch_bounds__(kHeadWarps * 32) head_bwd_kernel(const HeadBwdParams p) {
+  __shared__ float red[kHeadWarps][kHeadPartFloats];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long unit = static_cast<long long>(blockIdx.x) * kHeadWarps + warp;     // (pass, ray)
+  const int ps = unit >= p.n_rays ? 1 : 0;
+  const long long ray = unit - (ps ? p.n_rays : 0);
+  const bool active = ray < p.n_rays && ps < p.n_pass;
+  float gw[3][4], gb[3] = {0.f, 0.f, 0.f}, rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int j = 0; j < 27; ++j) gdir[j] = 0.f;
-  const int fb = n >> 6, k = n & 63;
-  for (int ray = r0; ray < r1; ++ray) {
-    __syncthreads();
-    if (n < 15) {     // Embedding(3,4)(rays_d) as the forward computes it (render_kernel.cuh setup_group)
-      const int cc = n / 5, kk = n % 5;
-      const float dv = p.rays[static_cast<long long>(ray) * p.ray_stride + 3 + cc];
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gw[c][i] = 0.f;
+  if (active) {
+    const PassBufs& pb = p.pass[ps];
+    const int S = pb.S;
+    const float scale = p.lscale[ps * kLevels];
+    float w[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[c][i] = p.w_rgb[ps][c * 128 + 4 * lane + i];
+    if (ps == 0 && lane < 15) {     // Embedding(3,4)(rays_d) exactly as render_kernel.cuh setup_group
+      const int cc = lane / 5, kk = lane % 5;
+      const float dv = p.rays[ray * p.ray_stride + 3 + cc];
+      float* de = p.direnc + ray * 28;
       if (kk == 4) {
-        direnc[cc] = dv;
+        de[cc] = dv;
       } else {
         float sn, cs;
         sincosf(__fmul_rn(static_cast<float>(1 << kk), dv), &sn, &cs);
-        direnc[3 + 6 * kk + cc] = sn;
-        direnc[3 + 6 * kk + 3 + cc] = cs;
+        de[3 + 6 * kk + cc] = sn;
+        de[3 + 6 * kk + 3 + cc] = cs;
       }
     }
-    float raysum = 0.f;
-    const long long g0 = static_cast<long long>(ray) * p.S;
-    for (int i = 0; i < p.S; ++i) {
+    // lane's 4 columns: column block lane / 16, 16-byte chunk (lane % 16) / 2, half (lane & 1)
+    const uint32_t fb = lane >> 4, ch = (lane & 15) >> 1, hf = (lane & 1) * 8;
+    const long long g0 = ray * S;
+#pragma unroll 8
+    for (int i = 0; i < S; ++i) {
       const long long g = g0 + i;
-      const float q0 = __ldg(p.dprergb + 3 * g), q1 = __ldg(p.dprergb + 3 * g + 1), q2 = __ldg(p.dprergb + 3 * g + 2);
-      const float dv = __half2float(p.d[g * 128 + n]);
-      gw[0] = fmaf(q0, dv, gw[0]); gw[1] = fmaf(q1, dv, gw[1]); gw[2] = fmaf(q2, dv, gw[2]);
-      if (n < 3) gb += (n == 0) ? q0 : (n == 1 ? q1 : q2);
-      const float val = (dv > 0.f) ? fmaf(q0, w0, fmaf(q1, w1, q2 * w2)) : 0.f;
-      raysum += val;
-      const unsigned long long off = tiled_block_off(static_cast<unsigned long long>(g >> 6), fb, 2) +
-                                     sw128_off(static_cast<uint32_t>(g & 63), k);
-      *reinterpret_cast<uint16_t*>(p.dd + off) = cvt_bwd(val * scale);
+      const unsigned long long off = tiled_block_off(static_cast<unsigned long long>(g >> 6), fb, 2) + (g & 63) * 128 +
+                                     ((ch ^ static_cast<uint32_t>(g & 7)) << 4) + hf;
+      const uint2 dv2 = __ldg(reinterpret_cast<const uint2*>(pb.d + off));
+      const float q0 = __ldg(pb.dprergb + 3 * g), q1 = __ldg(pb.dprergb + 3 * g + 1), q2 = __ldg(pb.dprergb + 3 * g + 2);
+      const float2 d01 = __half22float2(*reinterpret_cast<const __half2*>(&dv2.x));
+      const float2 d23 = __half22float2(*reinterpret_cast<const __half2*>(&dv2.y));
+      const float dv[4] = {d01.x, d01.y, d23.x, d23.y};
+      float val[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        gw[0][k] = fmaf(q0, dv[k], gw[0][k]);
+        gw[1][k] = fmaf(q1, dv[k], gw[1][k]);
+        gw[2][k] = fmaf(q2, dv[k], gw[2][k]);
+        val[k] = (dv[k] > 0.f) ? fmaf(q0, w[0][k], fmaf(q1, w[1][k], q2 * w[2][k])) : 0.f;
+        rs[k] += val[k];
+      }
+      gb[0] += q0; gb[1] += q1; gb[2] += q2;
+      *reinterpret_cast<uint2*>(pb.dd + off) = make_uint2(cvt_bwd_x2(val[0] * scale, val[1] * scale),
+                                                          cvt_bwd_x2(val[2] * scale, val[3] * scale));
     }
+    *reinterpret_cast<float4*>(p.raysum[ps] + ray * 128 + 4 * lane) = make_float4(rs[0], rs[1], rs[2], rs[3]);
+  }
+  // per-block partial of gW_rgb / gb_rgb: warps in fixed order
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[warp][c * 128 + 4 * lane + k] = gw[c][k];
+  if (lane < 4) red[warp][kHeadPartRgbB + lane] = (lane < 3) ? gb[lane] : 0.f;
+  __syncthreads();
+  // a block's warps all belong to one pass unless it straddles the boundary: sum per pass
+  for (int q = 0; q < p.n_pass; ++q) {
+    float* out = p.part[q] + static_cast<long long>(blockIdx.x) * kHeadPartFloats;
+    for (int i = threadIdx.x; i < kHeadPartFloats; i += blockDim.x) {
+      float acc = 0.f;
+      for (int wv = 0; wv < kHeadWarps; ++wv) {
+        const long long u = static_cast<long long>(blockIdx.x) * kHeadWarps + wv;
+        if ((u >= p.n_rays ? 1 : 0) == q) acc += red[wv][i];
+      }
+      out[i] = acc;
+    }
+  }
+}
+
+// gW_dir[n][256 + j] = sum_rays raysum[ray][n] dir_enc[ray][j]: block = 128 threads (n), blockIdx.x = ray slice,
+// blockIdx.y = pass; per-slice partials [slice][n][27], summed by wgrad_reduce_kernel.
+constexpr int kDirSlices = 16;
+struct DirGradParams {
+  int n_rays;
+  const float* raysum[2];
+  const float* direnc;
+  float* part[2];           // [kDirSlices][128][27]
+};
+__global__ void __launch_bounds__(128) dir_grad_kernel(const DirGradParams p) {
+  __shared__ float de[64][28];
+  const int ps = blockIdx.y, n = threadIdx.x;
+  const int per = (p.n_rays + kDirSlices - 1) / kDirSlices;
+  const int r0 = blockIdx.x * per, r1 = min(r0 + per, p.n_rays);
+  float acc[27];
+#pragma unroll
+  for (int j = 0; j < 27; ++j) acc[j] = 0.f;
+  for (int base = r0; base < r1; base += 64) {
+    const int cnt = min(64, r1 - base);
     __syncthreads();
+    for (int i = n; i < cnt * 28; i += 128) de[i / 28][i % 28] = p.direnc[static_cast<long long>(base) * 28 + i];
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < cnt; ++r) {
+      const float v = p.raysum[ps][static_cast<long long>(base + r) * 128 + n];
 #pragma unroll
-    for (int j = 0; j < 27; ++j) gdir[j] = fmaf(raysum, direnc[j], gdir[j]);
-  }
-  float* out = p.part + static_cast<long long>(blockIdx.x) * kHeadPartFloats;
-  out[kHeadPartRgbW + n] = gw[0];
-  out[kHeadPartRgbW + 128 + n] = gw[1];
-  out[kHeadPartRgbW + 256 + n] = gw[2];
-  if (n < 4) out[kHeadPartRgbB + n] = (n < 3) ? gb : 0.f;
-#pragma unroll
-  for (int j = 0; j < 27; ++j) out[kHeadPartDir + n * 27 + j] = gdir[j];
-  // padding rows of dd are zero (they are operands of the chain and wgrad kernels)
-  if (blockIdx.x == gridDim.x - 1) {
-    const long long nn = static_cast<long long>(p.n_rays) * p.S;
-    for (long long g = nn; g < p.n_pad; ++g) {
-      const unsigned long long off = tiled_block_off(static_cast<unsigned long long>(g >> 6), fb, 2) +
-                                     sw128_off(static_cast<uint32_t>(g & 63), k);
-      *reinterpret_cast<uint16_t*>(p.dd + off) = 0;
+      for (int j = 0; j < 27; ++j) acc[j] = fmaf(v, de[r][j], acc[j]);
     }
   }
+  float* out = p.part[ps] + (static_cast<long long>(blockIdx.x) * 128 + n) * 27;
+#pragma unroll
+  for (int j = 0; j < 27; ++j) out[j] = acc[j];
 }
 
 // ------------------------------------------------------------------------------ dgrad chain
@@ -299,7 +409,8 @@ constexpr uint32_t kChA0 = 0;                          // 2 x [2 K blocks][128 x
 constexpr uint32_t kChA0Bytes = 32768;
 constexpr uint32_t kChRing = 2 * kChA0Bytes;           // kStages x 32 KiB
 constexpr uint32_t kChConsts = kChRing + kStages * kSliceBytes256;   // w_sigma of both networks (2 x 256 fp32)
-constexpr uint32_t kChScratch = kChConsts + 2048;
+constexpr uint32_t kChStage = kChConsts + 2048;                      // 4 row groups x 4 KiB staging blocks
+constexpr uint32_t kChScratch = kChStage + kStageBytes;
 constexpr uint32_t kChSmemTotal = kChScratch + 1024;
 
 struct ChainScratch {
@@ -313,8 +424,9 @@ struct ChainParams {
   PassBufs pass[2];
   const uint8_t* net[2];      // packed images (backward region at kOffBwd, w_sigma in the fp32 region)
   int n_pass;
-  long long tiles[2];         // 128-sample tiles per pass
-  const float* scale;
+  long long tiles[2];         // 128-sample tiles per pass (probe mode: the first tiles only)
+  const float* lscale;        // [2][kLevels] per-level scales (bwd_scale_kernel)
+  unsigned* lamax;            // probe mode: [2][kLevels] maxima of the un-scaled values per level
   int* status;
 };
 
@@ -332,19 +444,24 @@ struct ChainEpi {
   uint8_t* dpre;          // this pass's dpre base
   long long n_pad;
   long long g;            // global sample row of this thread
+  long long g0;           // global sample row of this thread's 32-row group
+  uint8_t* stage;         // the row group's staging block
 };
 
 // One step of the chain for this thread's 64 accumulator columns.
 //   kFirst: add the rank-1 sigma-head term;  kStore: hand the result to the next step (TMEM A operand)
-template <bool kFirst, bool kStore>
-__device__ __forceinline__ void epi_chain_step(ChainEpi& c, int out_idx, const uint2* __restrict__ mask, float dsig,
-                                               const float* wsig) {
+//   ratio = scale of the produced level / scale of the consumed level (a power of two)
+//   kProbe: no HBM stores; returns the largest |value| (in units of the produced level's scale)
+template <bool kFirst, bool kStore, bool kProbe>
+__device__ __forceinline__ float epi_chain_step(ChainEpi& c, int out_idx, const uint2* __restrict__ mask, float dsig,
+                                                const float* wsig, float ratio) {
   // masks, off the critical path (fetched while the step's MMAs run): after << i the sign flag of
   // pair i of K block kb sits in the top bit of byte 3 - kb (even elements in ylo, odd in yhi)
   const uint2 mw = __ldg(mask + (static_cast<long long>(out_idx) * c.n_pad + c.g) * 4 + c.part);
   uint32_t ylo[8], yhi[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { ylo[i] = mw.x << i; yhi[i] = mw.y << i; }
+  float vmax = 0.f;
   mbar_wait(smem_u32(&c.bars->d_ready), c.d_phase, 5);
   c.d_phase ^= 1;
   tc_fence_after();
@@ -357,9 +474,8 @@ __device__ __forceinline__ void epi_chain_step(ChainEpi& c, int out_idx, const u
     __syncwarp();
     if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->d_free));
   }
-  uint8_t* out = c.dpre + static_cast<long long>(out_idx) * c.n_pad * 512 + (c.g & 63) * 128;
-  const unsigned long long chunk = static_cast<unsigned long long>(c.g >> 6);
-  const uint32_t sw = static_cast<uint32_t>(c.g & 7);
+  uint8_t* out = c.dpre + static_cast<long long>(out_idx) * c.n_pad * 512 + (c.g0 & 63) * 128;
+  const unsigned long long chunk = static_cast<unsigned long long>(c.g0 >> 6);
 #pragma unroll
   for (int kb = 0; kb < 4; ++kb) {
     const int n0 = kb * 64 + c.part * 16;
@@ -375,7 +491,14 @@ __device__ __forceinline__ void epi_chain_step(ChainEpi& c, int out_idx, const u
         a = fmaf(dsig, ws.x, a);
         b = fmaf(dsig, ws.y, b);
       }
-      h[i] = cvt_bwd_x2(a, b) & ~prmt(ylo[i], yhi[i], sel);
+      a *= ratio;
+      b *= ratio;
+      const uint32_t keep = ~prmt(ylo[i], yhi[i], sel);
+      h[i] = cvt_bwd_x2(a, b) & keep;
+      if (kProbe) {
+        if (keep & 0xFFFFu) vmax = fmaxf(vmax, fabsf(a));
+        if (keep >> 16) vmax = fmaxf(vmax, fabsf(b));
+      }
     }
     if (kStore) {
       tmem_st8(c.tmem_row + kTmemA + n0 / 2, h);
@@ -384,12 +507,14 @@ __device__ __forceinline__ void epi_chain_step(ChainEpi& c, int out_idx, const u
       __syncwarp();
       if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_kb[kb]));
     }
-    uint8_t* blk = out + tiled_block_off(chunk, kb, 4);
-    *reinterpret_cast<uint4*>(blk + (((2u * c.part) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(blk + (((2u * c.part + 1u) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+    if (!kProbe)      // line-coalesced: staged per 32-row group, one 4 KiB bulk store (mlp_engine.cuh stage_store)
+      stage_store(c.stage, c.row >> 5, c.lane, c.part, make_uint4(h[0], h[1], h[2], h[3]),
+                  make_uint4(h[4], h[5], h[6], h[7]), 2u * c.part, out + tiled_block_off(chunk, kb, 4));
   }
+  return vmax;
 }
 
+template <bool kProbe>
 __global__ void __launch_bounds__(kThreads, 1) chain_bwd_kernel(const ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   ChainScratch* sc = reinterpret_cast<ChainScratch*>(smem + kChScratch);
@@ -507,11 +632,14 @@ __global__ void __launch_bounds__(kThreads, 1) chain_bwd_kernel(const ChainParam
     c.part = warp >> 2;
     c.tmem_row = bars->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     c.d_phase = 0;
-    const float scale = p.scale[0];
+    c.stage = smem + kChStage + (warp & 3) * 4096;
     // the accumulator is free at the start
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&bars->d_free));
+    float amx[2][8];      // probe mode only: per pass and level, in un-scaled units
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { amx[0][i] = 0.f; amx[1][i] = 0.f; }
     for (long long t = blockIdx.x; t < total; t += gridDim.x) {
       const int ps = (t >= p.tiles[0]) ? 1 : 0;
       const long long tile = t - (ps ? p.tiles[0] : 0);
@@ -519,12 +647,37 @@ __global__ void __launch_bounds__(kThreads, 1) chain_bwd_kernel(const ChainParam
       c.dpre = pb.dpre;
       c.n_pad = pb.n_pad;
       c.g = tile * 128 + c.row;
-      const float dsig = pb.dsigma[c.g] * scale;
+      c.g0 = tile * 128 + (c.row & ~31);
+      const float* ls = p.lscale + ps * kLevels;
+      float sc_in = ls[0];
+      const float dsig = pb.dsigma[c.g] * sc_in;
       const float* wsig = wsig_s + ps * 256;
-      epi_chain_step<true, true>(c, 7, pb.mask, dsig, wsig);
+      float sc_out = ls[1];
+      float m = epi_chain_step<true, true, kProbe>(c, 7, pb.mask, dsig, wsig, sc_out / sc_in);
+      if (kProbe) amx[ps][0] = fmaxf(amx[ps][0], m / sc_out);
 #pragma unroll 1
-      for (int l = 6; l >= 1; --l) epi_chain_step<false, true>(c, l, pb.mask, 0.f, nullptr);
-      epi_chain_step<false, false>(c, 0, pb.mask, 0.f, nullptr);
+      for (int s = 1; s < 7; ++s) {
+        sc_in = sc_out;
+        sc_out = ls[s + 1];
+        m = epi_chain_step<false, true, kProbe>(c, 7 - s, pb.mask, 0.f, nullptr, sc_out / sc_in);
+        if (kProbe) amx[ps][s] = fmaxf(amx[ps][s], m / sc_out);
+      }
+      sc_in = sc_out;
+      sc_out = ls[8];
+      m = epi_chain_step<false, false, kProbe>(c, 0, pb.mask, 0.f, nullptr, sc_out / sc_in);
+      if (kProbe) amx[ps][7] = fmaxf(amx[ps][7], m / sc_out);
+    }
+    if (!kProbe) bulk_wait_all();
+    if (kProbe) {
+#pragma unroll
+      for (int ps = 0; ps < 2; ++ps)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float v = amx[ps][i];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+          if (lane == 0 && v > 0.f && v < 3e38f) atomicMax(p.lamax + ps * kLevels + 1 + i, __float_as_uint(v));
+        }
     }
   }
   engine_teardown(bars);
@@ -728,6 +881,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant
     const int r = idx / it.cols, c = idx - r * it.cols;
     const float* src = it.part + static_cast<long long>(r) * it.part_ld + c;
     float acc = 0.f;
+#pragma unroll 4
     for (int s = 0; s < it.n_split; ++s) acc += src[s * it.split_stride];
     it.out[static_cast<long long>(r) * it.out_ld + it.out_col0 + c] = acc * mul;
   }
@@ -748,23 +902,33 @@ struct UnfoldParams {
 };
 __global__ void __launch_bounds__(256) unfold_kernel(const UnfoldParams p) {
   const int ps = blockIdx.y;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < 128 * 256) {                              // gWd[m][j] = sum_n gW'[m][n] Wf[j][n] + gb'[m] bf[j]
-    const int m = idx >> 8, j = idx & 255;
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);       // global warp index
+  if (gw < 128 * 256) {
+    // gWd[m][j] = sum_n gW'[m][n] Wf[j][n] + gb'[m] bf[j]: one warp per output, both rows read coalesced
+    const int m = gw >> 8, j = gw & 255;
     const float* a = p.gWp[ps] + m * 256;
     const float* w = p.Wf[ps] + j * 256;
-    float acc = p.gbp[ps][m] * p.bf[ps][j];
-    for (int n = 0; n < 256; ++n) acc = fmaf(a[n], w[n], acc);
-    p.gWd[ps][m * 283 + j] = acc;
-    if (j == 0) p.gbd[ps][m] = p.gbp[ps][m];
-  } else if (idx < 128 * 256 + 256 * 256) {           // gWf[j][n] = sum_m Wd[m][j] gW'[m][n]
-    const int q = idx - 128 * 256;
-    const int j = q >> 8, n = q & 255;
     float acc = 0.f;
+#pragma unroll
+    for (int n = lane; n < 256; n += 32) acc = fmaf(a[n], w[n], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      p.gWd[ps][m * 283 + j] = acc + p.gbp[ps][m] * p.bf[ps][j];
+      if (j == 0) p.gbd[ps][m] = p.gbp[ps][m];
+    }
+    return;
+  }
+  const int idx = (gw - 128 * 256) * 32 + lane;
+  if (idx < 256 * 256) {                              // gWf[j][n] = sum_m Wd[m][j] gW'[m][n]: coalesced over n
+    const int j = idx >> 8, n = idx & 255;
+    float acc = 0.f;
+#pragma unroll 8
     for (int m = 0; m < 128; ++m) acc = fmaf(p.Wd[ps][m * 283 + j], p.gWp[ps][m * 256 + n], acc);
     p.gWf[ps][j * 256 + n] = acc;
-  } else if (idx < 128 * 256 + 256 * 256 + 256) {     // gbf[j] = sum_m Wd[m][j] gb'[m]
-    const int j = idx - (128 * 256 + 256 * 256);
+  } else if (idx < 256 * 256 + 256) {                 // gbf[j] = sum_m Wd[m][j] gb'[m]
+    const int j = idx - 256 * 256;
     float acc = 0.f;
     for (int m = 0; m < 128; ++m) acc = fmaf(p.Wd[ps][m * 283 + j], p.gbp[ps][m], acc);
     p.gbf[ps][j] = acc;

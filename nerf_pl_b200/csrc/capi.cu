@@ -80,8 +80,10 @@ int device_info(DeviceInfo** out) {
                                   static_cast<int>(kSmemTotal)), "smem attr render(save)");
     CUDA_TRY(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kSmemTotal)), "smem attr mlp");
-    CUDA_TRY(cudaFuncSetAttribute(chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(chain_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kChSmemTotal)), "smem attr chain");
+    CUDA_TRY(cudaFuncSetAttribute(chain_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kChSmemTotal)), "smem attr chain (probe)");
     CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kWgSmemTotal)), "smem attr wgrad");
     int* hs = nullptr;
@@ -159,12 +161,17 @@ struct TrainLayout {
   int n_split[2][kNumJobKinds];
   int first_job[2][kNumJobKinds];
   float* wg_part;                 // [n_jobs][kWgSlotFloats]
-  int head_grid[2];
-  float* head_part[2];            // [head_grid][kHeadPartFloats]
+  int head_grid;                  // blocks of head_bwd_kernel (both passes in one launch)
+  float* head_part[2];            // [head_grid][kHeadPartFloats] per pass
+  float* raysum[2];               // (n_rays, 128) per-ray sums of dd
+  float* direnc;                  // (n_rays, 28) embedded directions
+  float* dir_part[2];             // [kDirSlices][128][27]
   float* gWp[2];                  // (128,256)
   float* gbp[2];                  // (128)
-  float* scale;                   // {scale, 1/scale}
-  unsigned* amax;
+  float* lscale;                  // [2][kLevels] per-pass, per-level gradient scales
+  float* linv;                    // [2][kLevels] their inverses
+  unsigned* lamax;                // [2][kLevels] probe statistics
+  unsigned* amax;                 // [2][2] max |d sigma|, |d rgb_pre| per pass
   float* loss_part;               // [max CTAs][2]
   unsigned* loss_counter;
   size_t bytes;
@@ -194,7 +201,7 @@ void make_train_layout(TrainLayout* L, uint8_t* base, int64_t n_rays, int n_samp
     b.enc = take(np * 128);
     b.act = take(np * 512 * 8);
     b.mask = reinterpret_cast<uint2*>(take(np * 32 * 8));
-    b.d = reinterpret_cast<__half*>(take(np * 256));
+    b.d = take(np * 256);
     b.sigma = reinterpret_cast<float*>(take(np * 4));
     b.rgb = reinterpret_cast<float*>(take(np * 12));
     b.z = reinterpret_cast<float*>(take(static_cast<size_t>(b.n) * 4));
@@ -227,13 +234,18 @@ void make_train_layout(TrainLayout* L, uint8_t* base, int64_t n_rays, int n_samp
     }
   L->jobs_dev = reinterpret_cast<WgradJob*>(take(sizeof(WgradJob) * kMaxWgJobs));
   L->wg_part = reinterpret_cast<float*>(take(static_cast<size_t>(L->n_jobs) * kWgSlotFloats * 4));
+  L->head_grid = static_cast<int>((L->n_pass * n_rays + kHeadWarps - 1) / kHeadWarps);
+  L->direnc = reinterpret_cast<float*>(take(static_cast<size_t>(n_rays) * 28 * 4));
   for (int ps = 0; ps < 2; ++ps) {
-    L->head_grid[ps] = static_cast<int>(n_rays < 2 * 148 ? (n_rays > 0 ? n_rays : 1) : 2 * 148);
-    L->head_part[ps] = reinterpret_cast<float*>(take(static_cast<size_t>(L->head_grid[ps]) * kHeadPartFloats * 4));
+    L->head_part[ps] = reinterpret_cast<float*>(take(static_cast<size_t>(L->head_grid) * kHeadPartFloats * 4));
+    L->raysum[ps] = reinterpret_cast<float*>(take(static_cast<size_t>(n_rays) * 128 * 4));
+    L->dir_part[ps] = reinterpret_cast<float*>(take(static_cast<size_t>(kDirSlices) * 128 * 27 * 4));
     L->gWp[ps] = reinterpret_cast<float*>(take(128 * 256 * 4));
     L->gbp[ps] = reinterpret_cast<float*>(take(128 * 4));
   }
-  L->scale = reinterpret_cast<float*>(take(16));
+  L->lscale = reinterpret_cast<float*>(take(2 * kLevels * 4));
+  L->linv = reinterpret_cast<float*>(take(2 * kLevels * 4));
+  L->lamax = reinterpret_cast<unsigned*>(take(2 * kLevels * 4));
   L->amax = reinterpret_cast<unsigned*>(take(16));
   L->loss_part = reinterpret_cast<float*>(take(1024 * 2 * 4));
   L->loss_counter = reinterpret_cast<unsigned*>(take(16));
@@ -733,36 +745,68 @@ int nerfb200_render_backward(const nerfb200_backward_args* b, void* stream_v) {
     cp.g_rgb = g_rgb[ps]; cp.g_depth = g_depth[ps]; cp.g_opac = g_opac[ps];
     cp.rgb_out = rgb_out[ps]; cp.target = b->target; cp.loss_grad = b->loss_grad;
     cp.dsigma = L.pass[ps].dsigma; cp.dprergb = L.pass[ps].dprergb;
-    cp.amax_bits = kBwdBf16 ? nullptr : L.amax;
+    cp.amax_bits = L.amax + 2 * ps;
     composite_bwd_kernel<<<(L.n_rays + 3) / 4, 128, 0, stream>>>(cp);
     g_launches++;
   }
-  bwd_scale_kernel<<<1, 1, 0, stream>>>(L.amax, L.scale);
+  ScaleParams sp;
+  sp.n_pass = L.n_pass; sp.phase = 0;
+  sp.amax = L.amax; sp.lamax = L.lamax; sp.lscale = L.lscale; sp.linv = L.linv;
+  for (int ps = 0; ps < 2; ++ps) {
+    const int q = ps < L.n_pass ? ps : 0;
+    sp.w_rgb[ps] = params[q][22];
+    sp.w_sigma[ps] = params[q][20];
+  }
+  bwd_scale_kernel<<<1, 128, 0, stream>>>(sp);
   g_launches++;
-  // 2. rgb head, ReLU of the direction layer
-  for (int ps = 0; ps < L.n_pass; ++ps) {
+  // 2. rgb head, ReLU of the direction layer (both passes in one launch), direction part of gW_dir
+  {
     HeadBwdParams hp;
-    hp.n_rays = L.n_rays; hp.S = L.pass[ps].S; hp.n_pad = L.pass[ps].n_pad;
-    hp.d = L.pass[ps].d; hp.dprergb = L.pass[ps].dprergb; hp.w_rgb = params[ps][22];
-    hp.rays = a->rays; hp.ray_stride = a->ray_stride; hp.scale = L.scale;
-    hp.dd = L.pass[ps].dd; hp.part = L.head_part[ps];
-    head_bwd_kernel<<<L.head_grid[ps], 128, 0, stream>>>(hp);
+    hp.n_rays = L.n_rays; hp.n_pass = L.n_pass;
+    hp.pass[0] = L.pass[0]; hp.pass[1] = L.pass[1];
+    hp.w_rgb[0] = params[0][22]; hp.w_rgb[1] = fine ? params[1][22] : params[0][22];
+    hp.lscale = L.lscale;
+    hp.rays = a->rays; hp.ray_stride = a->ray_stride;
+    hp.raysum[0] = L.raysum[0]; hp.raysum[1] = L.raysum[1];
+    hp.direnc = L.direnc;
+    hp.part[0] = L.head_part[0]; hp.part[1] = L.head_part[1];
+    head_bwd_kernel<<<L.head_grid, kHeadWarps * 32, 0, stream>>>(hp);
+    g_launches++;
+    DirGradParams dp;
+    dp.n_rays = L.n_rays;
+    dp.raysum[0] = L.raysum[0]; dp.raysum[1] = L.raysum[1];
+    dp.direnc = L.direnc;
+    dp.part[0] = L.dir_part[0]; dp.part[1] = L.dir_part[1];
+    dir_grad_kernel<<<dim3(kDirSlices, L.n_pass), 128, 0, stream>>>(dp);
     g_launches++;
   }
-  // 3. dgrad chain (tcgen05)
+  // 3. dgrad chain (tcgen05): a probe pass over one tile per SM picks the per-layer scales, then the real pass
   {
     ChainParams cp;
     cp.n_pass = L.n_pass;
     cp.pass[0] = L.pass[0]; cp.pass[1] = L.pass[1];
     cp.net[0] = static_cast<const uint8_t*>(a->packed_coarse);
     cp.net[1] = static_cast<const uint8_t*>(a->packed_fine);
-    cp.tiles[0] = L.pass[0].n_pad / 128;
-    cp.tiles[1] = fine ? L.pass[1].n_pad / 128 : 0;
-    cp.scale = L.scale;
+    cp.lscale = L.lscale;
+    cp.lamax = L.lamax;
     cp.status = d->status;
-    const long long total = cp.tiles[0] + cp.tiles[1];
+    const long long t0 = L.pass[0].n_pad / 128, t1 = fine ? L.pass[1].n_pad / 128 : 0;
+    if (!kBwdBf16) {
+      const long long half = (d->sm_count + 1) / 2;
+      cp.tiles[0] = fine ? (t0 < half ? t0 : half) : (t0 < d->sm_count ? t0 : d->sm_count);
+      cp.tiles[1] = fine ? (t1 < half ? t1 : half) : 0;
+      const int pc = static_cast<int>(cp.tiles[0] + cp.tiles[1]);
+      chain_bwd_kernel<true><<<pc, kThreads, kChSmemTotal, stream>>>(cp);
+      g_launches++;
+      sp.phase = 1;
+      bwd_scale_kernel<<<1, 128, 0, stream>>>(sp);
+      g_launches++;
+    }
+    cp.tiles[0] = t0;
+    cp.tiles[1] = t1;
+    const long long total = t0 + t1;
     const int ctas = static_cast<int>(total < d->sm_count ? total : d->sm_count);
-    chain_bwd_kernel<<<ctas, kThreads, kChSmemTotal, stream>>>(cp);
+    chain_bwd_kernel<false><<<ctas, kThreads, kChSmemTotal, stream>>>(cp);
     g_launches++;
   }
   // 4. split-K wgrad (tcgen05)
@@ -777,29 +821,30 @@ int nerfb200_render_backward(const nerfb200_backward_args* b, void* stream_v) {
     it.part = part; it.split_stride = stride; it.n_split = n_split; it.out = out; it.mul = mul;
     it.rows = rows; it.cols = cols; it.part_ld = part_ld; it.out_ld = out_ld; it.out_col0 = out_col0;
   };
-  const float* inv = L.scale + 1;
   for (int ps = 0; ps < L.n_pass; ++ps) {
+    const float* linv = L.linv + ps * kLevels;       // level v: 0 = dd, v = 1..8 = dpre_{9-v}
     auto slot = [&](int kind) { return L.wg_part + static_cast<size_t>(L.first_job[ps][kind]) * kWgSlotFloats; };
     auto ns = [&](int kind) { return L.n_split[ps][kind]; };
     float* const* g = grads[ps];
-    add(slot(kJ1), kWgSlotFloats, ns(kJ1), g[0], inv, 256, 63, 64, 63, 0);
-    add(slot(kJ1) + 65536, kWgSlotFloats, ns(kJ1), g[1], inv, 1, 256, 256, 256, 0);
+    add(slot(kJ1), kWgSlotFloats, ns(kJ1), g[0], linv + 8, 256, 63, 64, 63, 0);
+    add(slot(kJ1) + 65536, kWgSlotFloats, ns(kJ1), g[1], linv + 8, 1, 256, 256, 256, 0);
     const int hidden[6] = {kJ2, kJ3, kJ4, kJ6, kJ7, kJ8};
     const int layer[6] = {2, 3, 4, 6, 7, 8};
     for (int i = 0; i < 6; ++i) {
+      const float* inv = linv + (9 - layer[i]);
       add(slot(hidden[i]), kWgSlotFloats, ns(hidden[i]), g[2 * (layer[i] - 1)], inv, 256, 256, 256, 256, 0);
       add(slot(hidden[i]) + 65536, kWgSlotFloats, ns(hidden[i]), g[2 * (layer[i] - 1) + 1], inv, 1, 256, 256, 256, 0);
     }
-    add(slot(kJ5a), kWgSlotFloats, ns(kJ5a), g[8], inv, 256, 63, 64, 319, 0);
-    add(slot(kJ5b), kWgSlotFloats, ns(kJ5b), g[8], inv, 256, 256, 256, 319, 63);
-    add(slot(kJ5a) + 65536, kWgSlotFloats, ns(kJ5a), g[9], inv, 1, 256, 256, 256, 0);
-    add(slot(kJ9), kWgSlotFloats, ns(kJ9), L.gWp[ps], inv, 128, 256, 256, 256, 0);
-    add(slot(kJ9) + 65536, kWgSlotFloats, ns(kJ9), L.gbp[ps], inv, 1, 128, 128, 128, 0);
+    add(slot(kJ5a), kWgSlotFloats, ns(kJ5a), g[8], linv + 4, 256, 63, 64, 319, 0);
+    add(slot(kJ5b), kWgSlotFloats, ns(kJ5b), g[8], linv + 4, 256, 256, 256, 319, 63);
+    add(slot(kJ5a) + 65536, kWgSlotFloats, ns(kJ5a), g[9], linv + 4, 1, 256, 256, 256, 0);
+    add(slot(kJ9), kWgSlotFloats, ns(kJ9), L.gWp[ps], linv, 128, 256, 256, 256, 0);
+    add(slot(kJ9) + 65536, kWgSlotFloats, ns(kJ9), L.gbp[ps], linv, 1, 128, 128, 128, 0);
     add(slot(kJ9) + 65536 + 256, kWgSlotFloats, ns(kJ9), g[20], nullptr, 1, 256, 256, 256, 0);
     add(slot(kJ9) + 65536 + 256 + 256, kWgSlotFloats, ns(kJ9), g[21], nullptr, 1, 1, 1, 1, 0);
-    add(L.head_part[ps] + kHeadPartRgbW, kHeadPartFloats, L.head_grid[ps], g[22], nullptr, 1, 384, 384, 384, 0);
-    add(L.head_part[ps] + kHeadPartRgbB, kHeadPartFloats, L.head_grid[ps], g[23], nullptr, 1, 3, 3, 3, 0);
-    add(L.head_part[ps] + kHeadPartDir, kHeadPartFloats, L.head_grid[ps], g[18], nullptr, 128, 27, 27, 283, 256);
+    add(L.head_part[ps] + kHeadPartRgbW, kHeadPartFloats, L.head_grid, g[22], nullptr, 1, 384, 384, 384, 0);
+    add(L.head_part[ps] + kHeadPartRgbB, kHeadPartFloats, L.head_grid, g[23], nullptr, 1, 3, 3, 3, 0);
+    add(L.dir_part[ps], 128 * 27, kDirSlices, g[18], nullptr, 128, 27, 27, 283, 256);
   }
   wgrad_reduce_kernel<<<dim3(16, tab.n), 256, 0, stream>>>(tab);
   g_launches++;
@@ -810,7 +855,8 @@ int nerfb200_render_backward(const nerfb200_backward_args* b, void* stream_v) {
     up.Wf[ps] = params[q][16]; up.bf[ps] = params[q][17]; up.Wd[ps] = params[q][18];
     up.gWd[ps] = grads[q][18]; up.gbd[ps] = grads[q][19]; up.gWf[ps] = grads[q][16]; up.gbf[ps] = grads[q][17];
   }
-  unfold_kernel<<<dim3((128 * 256 + 256 * 256 + 256 + 255) / 256, L.n_pass), 256, 0, stream>>>(up);
+  // warps: one per gWd output (128 x 256), then one thread per gWf / gbf output
+  unfold_kernel<<<dim3((128 * 256 + (256 * 256 + 256 + 31) / 32 + 7) / 8, L.n_pass), 256, 0, stream>>>(up);
   g_launches++;
   CUDA_TRY(cudaGetLastError(), "render_backward launches");
   return 0;

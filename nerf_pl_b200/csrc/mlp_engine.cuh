@@ -312,9 +312,11 @@ struct EpiCtx {
   // are also written to HBM for the backward pass
   uint8_t* save_act;               // 8 x tiled (save_n, 256) fp16 (layout.h), null = off
   uint2* save_mask;                // [8][save_n][4]: sign bits of this thread's 64 pre-activations per layer
-  __half* save_d;                  // [save_n][128] fp16 row-major
+  uint8_t* save_d;                 // tiled (save_n, 128) fp16: output of dir_encoding
   long long save_n;                // padded rows per layer
   long long save_row;              // this thread's global sample row, -1 = padding row
+  long long save_g0;               // global sample row of this thread's 32-row group (lane 0), -1 = padding group
+  uint8_t* stage;                  // this row group's 4 KiB staging block in shared memory (training mode)
   // Accumulator release.  false: d_free is signalled at tile start (the epilogue also wrote the
   // ENC tile).  true (render kernel: ENC comes from the helper warps): d_free is signalled as soon
   // as the LAST layer of a tile has been read out of tensor memory, so the next tile's first
@@ -354,6 +356,32 @@ __device__ __forceinline__ void epi_wait_d(EpiCtx& c) {
   mbar_wait(smem_u32(&c.bars->d_ready), c.d_phase, 5);
   c.d_phase ^= 1;
   tc_fence_after();
+}
+
+// ---- line-coalesced stores of an epilogue result (training mode / backward chain) -------------
+// The four warps that own the same 32 tile rows (column groups 0..3) assemble one [32 rows x 128 B]
+// block of the tiled layout (layout.h) in shared memory - each thread two 16-byte chunks of its
+// row, already at their swizzled positions - and one of them hands the 4 KiB block to the TMA store
+// engine.  Two named barriers per call: "the previous store has left the staging block" and "the
+// block is complete".  stage: this row group's 4 KiB staging block; gdst: the block's place in HBM
+// (null = rows are padding, nothing is stored).
+constexpr int kStageBar0 = 3;          // named barriers 3..6: row groups 0..3 (128 threads each)
+constexpr uint32_t kStageBytes = 4 * 4096;
+__device__ __forceinline__ void stage_store(uint8_t* stage, int rg, int lane, int part, uint4 c0, uint4 c1,
+                                            uint32_t chunk0, uint8_t* gdst) {
+  const bool issuer = (part == 0) && (lane == 0);
+  if (issuer) bulk_wait_read();
+  named_bar_sync(kStageBar0 + rg, 128);
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);         // == global row & 7 (row groups are 32-aligned)
+  uint8_t* row = stage + lane * 128;
+  *reinterpret_cast<uint4*>(row + ((chunk0 ^ sw) << 4)) = c0;
+  *reinterpret_cast<uint4*>(row + (((chunk0 + 1u) ^ sw) << 4)) = c1;
+  fence_proxy_async();
+  named_bar_sync(kStageBar0 + rg, 128);
+  if (issuer && gdst != nullptr) {
+    bulk_s2g(gdst, smem_u32(stage), 4096);
+    bulk_commit();
+  }
 }
 
 __device__ __forceinline__ void add_f32x2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
@@ -471,13 +499,14 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
         epi_signal_kb(c, kb, kb == 3 && dir_row != nullptr);
         NERFB200_TL_MARK(c.tl, 0, 40 + kb);
       }
-      if (kSave && c.save_act != nullptr && c.save_row >= 0) {
-        // tiled layout: column block kb of chunk (row / 64), 16-byte chunks 2 part, 2 part + 1 of the row
-        uint8_t* blk = c.save_act + static_cast<long long>(l) * c.save_n * 512 +
-                       tiled_block_off(static_cast<unsigned long long>(c.save_row >> 6), kb, 4) + (c.save_row & 63) * 128;
-        const uint32_t sw = static_cast<uint32_t>(c.save_row & 7);
-        *reinterpret_cast<uint4*>(blk + (((2u * c.part) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(blk + (((2u * c.part + 1u) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+      if (kSave && c.save_act != nullptr) {
+        // tiled layout: this row group's 32 rows of column block kb are 4 KiB contiguous in HBM
+        uint8_t* gdst = nullptr;
+        if (c.save_g0 >= 0)
+          gdst = c.save_act + static_cast<long long>(l) * c.save_n * 512 +
+                 tiled_block_off(static_cast<unsigned long long>(c.save_g0 >> 6), kb, 4) + (c.save_g0 & 63) * 128;
+        stage_store(c.stage, (c.row >> 5), c.lane, c.part, make_uint4(h[0], h[1], h[2], h[3]),
+                    make_uint4(h[4], h[5], h[6], h[7]), 2u * c.part, gdst);
       }
     }
     if (kSave && c.save_mask != nullptr && c.save_row >= 0)
@@ -496,6 +525,7 @@ __device__ __forceinline__ void epi_dir(EpiCtx& c, const float* dbias, const flo
   constexpr int kChunks = kCols / 32;
   const int n0 = c.part * kCols;
   uint32_t r[kChunks][32];
+  uint32_t dsave[kSave ? 16 * kChunks : 1];
 #pragma unroll
   for (int u = 0; u < kChunks; ++u) tmem_ld32(c.tmem_row + kTmemD + n0 + 32 * u, r[u]);
   tmem_ld_wait();
@@ -519,9 +549,39 @@ __device__ __forceinline__ void epi_dir(EpiCtx& c, const float* dbias, const flo
       rgb_acc[1] = fmaf(v2, wg.z, rgb_acc[1]); rgb_acc[1] = fmaf(v3, wg.w, rgb_acc[1]);
       rgb_acc[2] = fmaf(v0, wb.x, rgb_acc[2]); rgb_acc[2] = fmaf(v1, wb.y, rgb_acc[2]);
       rgb_acc[2] = fmaf(v2, wb.z, rgb_acc[2]); rgb_acc[2] = fmaf(v3, wb.w, rgb_acc[2]);
-      if (kSave && c.save_d != nullptr && c.save_row >= 0) {
-        uint2* dst = reinterpret_cast<uint2*>(c.save_d + c.save_row * 128 + n);
-        *dst = make_uint2(cvt_f16x2(v0, v1), cvt_f16x2(v2, v3));
+      if (kSave) {
+        dsave[u * 16 + 2 * j] = cvt_f16x2(v0, v1);
+        dsave[u * 16 + 2 * j + 1] = cvt_f16x2(v2, v3);
+      }
+    }
+  }
+  if (kSave && c.save_d != nullptr) {
+    // output of dir_encoding, tiled (save_n, 128): this thread's 32 columns are 4 chunks of column
+    // block part / 2; one staging round per column block
+    static_assert(kChunks == 1, "the dir-layer save assumes 16 epilogue warps (32 columns per thread)");
+#pragma unroll
+    for (int fb = 0; fb < 2; ++fb) {
+      uint8_t* gdst = nullptr;
+      if (c.save_g0 >= 0)
+        gdst = c.save_d + tiled_block_off(static_cast<unsigned long long>(c.save_g0 >> 6), fb, 2) +
+               (c.save_g0 & 63) * 128;
+      const bool mine = (c.part >> 1) == fb;
+      const bool issuer = (c.part == 0) && (c.lane == 0);
+      if (issuer) bulk_wait_read();
+      named_bar_sync(kStageBar0 + (c.row >> 5), 128);
+      if (mine) {
+        const uint32_t sw = static_cast<uint32_t>(c.lane & 7);
+        uint8_t* row = c.stage + c.lane * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(row + ((((c.part & 1) * 4u + q) ^ sw) << 4)) =
+              make_uint4(dsave[4 * q], dsave[4 * q + 1], dsave[4 * q + 2], dsave[4 * q + 3]);
+      }
+      fence_proxy_async();
+      named_bar_sync(kStageBar0 + (c.row >> 5), 128);
+      if (issuer && gdst != nullptr) {
+        bulk_s2g(gdst, smem_u32(c.stage), 4096);
+        bulk_commit();
       }
     }
   }

@@ -24,7 +24,7 @@ struct PassBufs {
   uint8_t* enc;           // tiled (n_pad, 64) fp16: encoded xyz, column 63 zero
   uint8_t* act;           // 8 x tiled (n_pad, 256) fp16: outputs of xyz_encoding_1..8 (layer l at l * n_pad * 512)
   uint2* mask;            // [8][n_pad][4]: ReLU sign bits of the 64 columns thread (row, column group) owns
-  __half* d;              // (n_pad, 128) fp16 row-major: output of dir_encoding
+  uint8_t* d;             // tiled (n_pad, 128) fp16: output of dir_encoding
   float* sigma;           // (n_pad) raw sigma
   float* rgb;             // (n_pad, 3) sigmoid(rgb)
   float* z;               // (n_rays, S) depths of the pass
@@ -329,7 +329,8 @@ struct alignas(16) GroupState {
   float znew[2][kMaxImp];                   // u (sorted) then the new depths
 };
 
-struct alignas(16) RenderScratch {
+struct alignas(128) RenderScratch {
+  alignas(128) uint8_t stage[4][4096];      // training mode: per row group, one [32 rows x 128 B] block on its way to HBM
   Barriers bars;
   uint64_t enc_full[2];
   uint64_t out_full[2];
@@ -453,21 +454,22 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
       c.save_mask = kSave ? p.tr[pass].mask : nullptr;
       c.save_d = kSave ? p.tr[pass].d : nullptr;
       c.save_n = kSave ? p.tr[pass].n_pad : 0;
+      c.stage = sc->stage[c.row >> 5];
       const GroupState& gs = sc->gs[tl.g % kGroupSlots];
       const int gr = tl.tile * 128 + c.row;
       const int r = (gr >= S) ? 1 : 0;       // rows past the group's 2 S samples (S < 64 k) are padding
       const long long grow = (gr < 2 * S && (r == 0 || valid1)) ? static_cast<long long>(ray0 + r) * S + (gr - r * S) : -1;
       c.save_row = grow;
+      c.save_g0 = __shfl_sync(0xffffffffu, grow, 0);      // rows come in whole rays of S = 32 k samples: a 32-row group is all valid or all padding
       // ENC buffer b and the group's direction bias are ready
       mbar_wait(smem_u32(&sc->enc_full[b]), static_cast<uint32_t>(tl.q >> 1) & 1u, 7);
-      if (kSave && grow >= 0) {
-        // the encoded-input tile is the B operand of the wgrad of layers 1 and 5: copy this thread's
-        // 32 bytes of its row; the shared-memory image is already the tiled layout (row & 7 == grow & 7)
-        const uint8_t* src = smem + (b ? kSmemEnc1 : kSmemEnc) + c.row * 128 + c.part * 32;
-        uint8_t* dst = p.tr[pass].enc + tiled_block_off(static_cast<unsigned long long>(grow >> 6), 0, 1) +
-                       (grow & 63) * 128 + c.part * 32;
-        reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(src)[0];
-        reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(src)[1];
+      if (kSave && c.part == 0 && lane == 0 && c.save_g0 >= 0) {
+        // the encoded-input tile is the B operand of the wgrad of layers 1 and 5: the shared-memory image IS the
+        // tiled layout (row & 7 == global row & 7), so this row group's 32 rows go out as one 4 KiB bulk store
+        uint8_t* dst = p.tr[pass].enc + tiled_block_off(static_cast<unsigned long long>(c.save_g0 >> 6), 0, 1) +
+                       (c.save_g0 & 63) * 128;
+        bulk_s2g(dst, smem_u32(smem + (b ? kSmemEnc1 : kSmemEnc) + (c.row >> 5) * 4096), 4096);
+        bulk_commit();
       }
       float sig_part, rgb_part[3];
       epi_run_tile<kSave>(c, sigma_only, gs.dirbias[pass][r], nullptr, sig_part, rgb_part);
@@ -505,6 +507,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
         if (lane == 0) mbar_arrive(smem_u32(&sc->out_full[b]));
       }
     }
+    if (kSave) bulk_wait_all();      // this thread's bulk stores (if any) have left shared memory and landed
   } else if (warp >= kHelperWarp0) {
     // ================================== helper warps ===================================
     const int ht = threadIdx.x - kHelperWarp0 * 32;   // 0..127

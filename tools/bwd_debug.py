@@ -68,8 +68,13 @@ def decode_masks(m, n_pad):
 
 
 def stat(name, got, ref, scale=1.0):
-    got = np.asarray(got, np.float64) / scale
+    got = np.asarray(got, np.float64)
     ref = np.asarray(ref, np.float64)
+    if scale is None:       # per-layer power-of-two scale chosen on the device: recover it from the data
+        big = np.abs(ref) > 0.1 * np.abs(ref).max()
+        scale = 2.0 ** np.round(np.log2(np.median(np.abs(got[big]) / np.abs(ref[big]))))
+        name = f"{name} (scale 2^{int(np.log2(scale))})"
+    got = got / scale
     err = np.abs(got - ref)
     den = np.linalg.norm(ref) + 1e-30
     print(f"{name:28s} rel_l2 {np.linalg.norm(got - ref) / den:.3e}  max_abs {err.max():.3e}  ref_absmax {np.abs(ref).max():.3e}"
@@ -129,7 +134,7 @@ def main():
             neg = decode_masks(masks[l], npad)[:nn]
             agree = (neg == (tape[f"h{l + 1}"] <= 0)).mean()
             print(f"[{tag}] mask{l + 1} agreement with (h <= 0): {agree:.5f}")
-        dd_row = np.frombuffer(raw, np.float16, nn * 128, P["d"]).reshape(nn, 128)
+        dd_row = untile(raw[P["d"]:P["d"] + npad * 256], npad, 128)[:nn]
         stat(f"[{tag}] d", dd_row, tape["d"])
         # compositing backward on the oracle's tape
         diff = (res[f"rgb_{tag}"] - target).astype(np.float64)
@@ -147,8 +152,6 @@ def main():
     for P in L:
         amax_all = max(amax_all, np.abs(np.frombuffer(raw, np.float32, P["n"], P["dsigma"])).max(),
                        np.abs(np.frombuffer(raw, np.float32, P["n"] * 3, P["dprergb"])).max())
-    scale = 2.0 ** np.floor(np.log2(256.0 / amax_all))
-    print("expected scale", scale)
     for ps, (tag, w) in enumerate(zip(("coarse", "fine"), ws)):
         P = L[ps]
         S, nn, npad = P["S"], P["n"], P["n_pad"]
@@ -160,13 +163,13 @@ def main():
         dpre_rgb = np.frombuffer(raw, np.float32, nn * 3, P["dprergb"]).reshape(nn, 3).astype(np.float64)
         dd = (dpre_rgb @ w["rgb.0.weight"]) * (tape["d"] > 0)
         got = untile(raw[P["dd"]:P["dd"] + npad * 256], npad, 128)[:nn]
-        stat(f"[{tag}] dd", got, dd, scale)
+        stat(f"[{tag}] dd", got, dd, None)
         Wp = w["dir_encoding.0.weight"][:, :256].astype(np.float64) @ w["xyz_encoding_final.weight"].astype(np.float64)
         dh = dd @ Wp + dsig[:, None] * w["sigma.weight"].astype(np.float64)
         for l in range(7, -1, -1):
             dp = dh * (tape[f"h{l + 1}"] > 0)
             got = untile(raw[P["dpre"] + l * npad * 512:P["dpre"] + (l + 1) * npad * 512], npad, 256)[:nn]
-            stat(f"[{tag}] dpre{l + 1}", got, dp, scale)
+            stat(f"[{tag}] dpre{l + 1}", got, dp, None)
             if l > 0:
                 W = w[f"xyz_encoding_{l + 1}.0.weight"].astype(np.float64)
                 dh = dp @ (W[:, 63:] if l == 4 else W)

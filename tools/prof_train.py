@@ -71,6 +71,19 @@ if mode == "time":
                     torch.cuda.current_stream().synchronize()
             torch.cuda.synchronize()
             print(f"e2e loop sync_each={sync_each}: {(time.perf_counter() - t0) / 200 * 1e6:.1f} us per step")
+        # the same with a ClockSampler thread polling NVML (what bench.py does while it times)
+        cs = bench.ClockSampler(0)
+        cs.start()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(200):
+            r = pin.to(dev, non_blocking=True)
+            out = nb.render_rays(models, emb, r, 64, False, 1.0, 0.0, 64, 32768, True, match_reference_rng=False)
+            flat = torch.cat((out["rgb_coarse"], out["depth_coarse"][:, None], out["opacity_coarse"][:, None],
+                              out["rgb_fine"], out["depth_fine"][:, None], out["opacity_fine"][:, None]), 1)
+            hout.copy_(flat, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        print(f"e2e loop with NVML sampler thread: {(time.perf_counter() - t0) / 200 * 1e6:.1f} us per step", cs.stop())
 else:
     for _ in range(steps):
         step()

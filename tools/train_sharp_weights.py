@@ -1,13 +1,18 @@
-"""Produce TRAINED ("sharp") NeRF weights for parity tests by running the UNMODIFIED reference's own
-training step (models/rendering.py render_rays + losses.py MSELoss + torch.optim.Adam, train.py:103-117)
-on CPU against a procedural scene.  Random-init weights exercise the fp16 MLP and the final.dir folding
-least; trained weights have larger norms and use the high positional frequencies.
+"""Train NeRF weights on a procedural scene with THIS repository's fused training step (forward + loss +
+hand-written sm_100a backward, torch Adam) and save them for parity tests (run on a B200 via gpurun).
 
-    python tools/train_sharp_weights.py [steps]     # writes tests/golden/sharp_weights.npz (+ loss curve)
+    python tools/train_sharp_weights.py [steps] [out.npz]
+
+Two purposes: (1) random-init weights exercise the fp16 MLP and the final.dir folding least — trained
+weights have larger norms and use the high positional frequencies; tests/golden/make_golden.py runs
+the UNMODIFIED reference on the saved weights and the GPU tests hold the kernels to those outputs;
+(2) evidence that the loss goes down through the fused backward (the curve is stored with the weights).
 
 The scene is analytic (no dataset on the box): three soft spheres with a position-dependent
 high-frequency colour pattern, white background; ground-truth pixel colours come from a 512-sample
-quadrature of the analytic field along each ray.  Deterministic: seeds below.
+quadrature of the analytic field along each ray.  The recipe is the reference's Blender one
+(README.md:75-83: 64+64 samples, perturb 1, noise_std 0, batch 1024, Adam lr 5e-4; train.py:103-117).
+Deterministic seeds below.
 """
 import os
 import sys
@@ -16,66 +21,72 @@ import time
 import numpy as np
 import torch
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(HERE)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import bench  # noqa: E402
-from make_golden import import_reference  # noqa: E402
+import nerf_pl_b200 as nb  # noqa: E402
 
-CENTERS = np.array([[0.0, 0.0, 0.0], [0.9, 0.3, -0.2], [-0.6, -0.7, 0.4]], np.float32)
-RADII = np.array([0.8, 0.45, 0.55], np.float32)
-
-
-def scene(x):
-    """density (.., ) and colour (.., 3) of the analytic field at points x (.., 3)."""
-    d = np.linalg.norm(x[..., None, :] - CENTERS, axis=-1)                      # (.., 3 spheres)
-    sig = (40.0 / (1.0 + np.exp((d - RADII) * 30.0))).sum(-1)
-    col = 0.5 + 0.5 * np.stack([np.sin(9.0 * x[..., 0] + 2.0 * x[..., 1]), np.sin(7.0 * x[..., 1] - 3.0 * x[..., 2]),
-                                np.cos(8.0 * x[..., 2] + x[..., 0])], -1)
-    return sig.astype(np.float32), col.astype(np.float32)
+CENTERS = torch.tensor([[0.0, 0.0, 0.0], [0.9, 0.3, -0.2], [-0.6, -0.7, 0.4]])
+RADII = torch.tensor([0.8, 0.45, 0.55])
 
 
 def ground_truth(rays, n=512):
+    """White-background colour of the analytic scene along each ray (n-sample quadrature on [2, 6])."""
+    dev = rays.device
     o, d = rays[:, :3], rays[:, 3:6]
-    z = np.linspace(2.0, 6.0, n, dtype=np.float32)
+    z = torch.linspace(2.0, 6.0, n, device=dev)
     x = o[:, None, :] + d[:, None, :] * z[None, :, None]
-    sig, col = scene(x)
-    delta = np.full(n, z[1] - z[0], np.float32)
-    alpha = 1 - np.exp(-sig * delta)
-    T = np.cumprod(np.concatenate([np.ones_like(alpha[:, :1]), 1 - alpha + 1e-10], -1), -1)[:, :-1]
+    dist = (x[:, :, None, :] - CENTERS.to(dev)).norm(dim=-1)
+    sig = (40.0 / (1.0 + torch.exp((dist - RADII.to(dev)) * 30.0))).sum(-1)
+    col = 0.5 + 0.5 * torch.stack([torch.sin(9.0 * x[..., 0] + 2.0 * x[..., 1]), torch.sin(7.0 * x[..., 1] - 3.0 * x[..., 2]),
+                                   torch.cos(8.0 * x[..., 2] + x[..., 0])], -1)
+    alpha = 1 - torch.exp(-sig * (z[1] - z[0]))
+    T = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1 - alpha + 1e-10], -1), -1)[:, :-1]
     w = alpha * T
-    return ((w[..., None] * col).sum(1) + 1 - w.sum(1, keepdims=True)).astype(np.float32)
+    return (w[..., None] * col).sum(1) + 1 - w.sum(1, keepdim=True)
 
 
 def main():
-    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 400
-    torch.set_num_threads(os.cpu_count() or 1)
-    Embedding, NeRF, render_rays, _ = import_reference()
+    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
+    out_path = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "sharp_weights.npz")
+    dev = torch.device("cuda:0")
     torch.manual_seed(1234)
-    models = [NeRF(), NeRF()]
-    emb = [Embedding(3, 10), Embedding(3, 4)]
-    opt = torch.optim.Adam([p for m in models for p in m.parameters()], lr=5e-4, eps=1e-8)     # opt.py:47-58 defaults
+    models = [nb.NeRF().to(dev), nb.NeRF().to(dev)]
+    emb = [nb.Embedding(3, 10), nb.Embedding(3, 4)]
+    opt = torch.optim.Adam([p for m in models for p in m.parameters()], lr=5e-4, eps=1e-8, fused=True)
+    n_views = 64
+    views = [torch.from_numpy(bench.blender_rays(16384, 7000 + v)).to(dev) for v in range(n_views)]
+    targets = [ground_truth(v) for v in views]
+    gen = torch.Generator(device=dev).manual_seed(99)
     curve = []
     t0 = time.time()
     for it in range(steps):
-        rays = bench.blender_rays(1024, 5000 + it)
-        tgt = torch.from_numpy(ground_truth(rays))
-        out = render_rays(models, emb, torch.from_numpy(rays), 64, False, 1.0, 0.0, 64, 1024 * 32, True, test_time=False)
-        loss = torch.nn.functional.mse_loss(out["rgb_coarse"], tgt) + torch.nn.functional.mse_loss(out["rgb_fine"], tgt)
-        opt.zero_grad()
-        loss.backward()
+        v = it % n_views
+        idx = torch.randint(0, views[v].shape[0], (1024,), device=dev, generator=gen)
+        out = nb.render_rays_loss(models, emb, views[v][idx], targets[v][idx], 64, False, 1.0, 0.0, 64, 32768, True,
+                                  match_reference_rng=False)
+        opt.zero_grad(set_to_none=True)
+        out["loss"].backward()
         opt.step()
-        curve.append(float(loss))
-        if it % 20 == 0:
-            psnr = -10 * np.log10(float(torch.nn.functional.mse_loss(out["rgb_fine"], tgt)))
-            print(f"step {it:4d} loss {float(loss):.5f} psnr_fine {psnr:.2f} dB  ({time.time() - t0:.0f} s)", flush=True)
-    store = {"loss_curve": np.array(curve, np.float32), "steps": steps}
+        if it % 50 == 0 or it == steps - 1:
+            curve.append((it, float(out["loss"].detach()), float(out["psnr"])))
+            if it % 500 == 0 or it == steps - 1:
+                print(f"step {it:5d} loss {curve[-1][1]:.5f} psnr_fine {curve[-1][2]:.2f} dB ({time.time() - t0:.1f} s)", flush=True)
+    torch.cuda.synchronize()
+    print(f"{steps} steps in {time.time() - t0:.1f} s")
+    # held-out view through the inference path
+    with torch.no_grad():
+        hv = torch.from_numpy(bench.blender_rays(16384, 9999)).to(dev)
+        res = nb.render_rays(models, emb, hv, 64, False, 0, 0, 64, 32768, True, test_time=True)
+        mse = float(((res["rgb_fine"] - ground_truth(hv)) ** 2).mean())
+    print(f"held-out view psnr {-10 * np.log10(mse):.2f} dB")
+    store = {"loss_curve": np.array(curve, np.float32), "steps": steps, "heldout_psnr": np.float32(-10 * np.log10(mse))}
     for tag, m in zip(("coarse", "fine"), models):
-        for k, v in m.state_dict().items():
-            store[f"{tag}.{k}"] = v.numpy()
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "sharp_weights.npz"), **store)
-    print("saved; final loss", curve[-1])
+        for k, p in m.state_dict().items():
+            store[f"{tag}.{k}"] = p.detach().cpu().numpy()
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    np.savez_compressed(out_path, **store)
+    print("saved", out_path)
 
 
 if __name__ == "__main__":
