@@ -149,8 +149,17 @@ typedef struct nerfb200_backward_args {
 } nerfb200_backward_args;
 int nerfb200_render_backward(const nerfb200_backward_args* args, void* stream);
 
+/* ---- optimiser step ("next" row: the caller of the backward) ---------------------------------
+ * Replaces: torch.optim.Adam.step() as the reference configures it (utils/__init__.py:16-18:
+ * Adam(lr, eps, weight_decay), betas (0.9, 0.999), no amsgrad; train.py:77-82) for up to 64 fp32
+ * tensors in one launch.  `step` is the 1-based count of this update (bias correction). */
+int nerfb200_adam_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                       float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int64_t step, void* stream);
+
 /* Same call with HOST buffers (pageable or pinned): copies rays (and the random inputs that
- * are non-NULL) to the device, renders, copies the requested outputs back, synchronises.
+ * are non-NULL and not already device memory - they may be drawn on the device by the caller) to
+ * the device, renders, copies the requested outputs back, synchronises.
  * The packed weight images stay device-resident.  This is the end-to-end entry the
  * reference's eval.py loop (eval.py:117-123 `.cuda()` ... `.cpu()`) maps to. */
 int nerfb200_render_rays_host(const nerfb200_render_args* host_args, void* stream);

@@ -46,6 +46,7 @@ EXPORTS = [
     "nerfb200_train_workspace_bytes",
     "nerfb200_train_workspace_init",
     "nerfb200_render_backward",
+    "nerfb200_adam_step",
     "nerfb200_generate_rays",
     "nerfb200_to_uint8",
     "nerfb200_launch_count",
@@ -180,6 +181,9 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.nerfb200_train_workspace_init.restype = c_int32
     lib.nerfb200_render_backward.argtypes = [POINTER(BackwardArgs), c_void_p]
     lib.nerfb200_render_backward.restype = c_int32
+    lib.nerfb200_adam_step.argtypes = [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                       POINTER(c_int64), c_float, c_float, c_float, c_float, c_float, c_int64, c_void_p]
+    lib.nerfb200_adam_step.restype = c_int32
     lib.nerfb200_mse_psnr.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
     lib.nerfb200_mse_psnr.restype = c_int32
     lib.nerfb200_generate_rays.argtypes = [c_int32, c_int32, c_float, POINTER(c_float), c_float, c_float, c_int32,

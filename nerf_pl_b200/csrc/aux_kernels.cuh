@@ -67,7 +67,7 @@ __global__ void pack_weights_kernel(const PackParams pp) {
     if (e >= static_cast<long long>(kNumSlicesBwd) * 256 * 64) return;
     const int slice = static_cast<int>(e / (256 * 64));
     const int rem = static_cast<int>(e % (256 * 64));
-    const int n = rem / 64, k = rem % 64;
+    const int k = rem / 256, n = rem % 256;       // n fastest: the reads below are coalesced over n
     float v;
     if (slice < 2) {
       // W'[m][n] = sum_j W_dir[m][j] W_final[j][n], m = slice * 64 + k

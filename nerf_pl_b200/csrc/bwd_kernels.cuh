@@ -476,13 +476,14 @@ __device__ __forceinline__ float epi_chain_step(ChainEpi& c, int out_idx, const 
   }
   uint8_t* out = c.dpre + static_cast<long long>(out_idx) * c.n_pad * 512 + (c.g0 & 63) * 128;
   const unsigned long long chunk = static_cast<unsigned long long>(c.g0 >> 6);
+  uint32_t hs[4][8];
 #pragma unroll
   for (int kb = 0; kb < 4; ++kb) {
     const int n0 = kb * 64 + c.part * 16;
     // selector: bytes 0,1 <- sign of ylo byte (3 - kb), bytes 2,3 <- sign of yhi byte (3 - kb)
     const uint32_t ln = 0x8u | (3u - kb), hn = 0x8u | (7u - kb);
     const uint32_t sel = (hn << 12) | (hn << 8) | (ln << 4) | ln;
-    uint32_t h[8];
+    uint32_t (&h)[8] = hs[kb];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float a = __uint_as_float(r[kb][2 * i]), b = __uint_as_float(r[kb][2 * i + 1]);
@@ -507,9 +508,14 @@ __device__ __forceinline__ float epi_chain_step(ChainEpi& c, int out_idx, const 
       __syncwarp();
       if (c.lane == 0) mbar_arrive(smem_u32(&c.bars->a_kb[kb]));
     }
-    if (!kProbe)      // line-coalesced: staged per 32-row group, one 4 KiB bulk store (mlp_engine.cuh stage_store)
-      stage_store(c.stage, c.row >> 5, c.lane, c.part, make_uint4(h[0], h[1], h[2], h[3]),
-                  make_uint4(h[4], h[5], h[6], h[7]), 2u * c.part, out + tiled_block_off(chunk, kb, 4));
+  }
+  // the HBM copy for the wgrad kernel goes out after the hand-over, behind the next step's MMAs:
+  // line-coalesced, staged per 32-row group, one 4 KiB bulk store each (mlp_engine.cuh stage_store)
+  if (!kProbe) {
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb)
+      stage_store(c.stage, c.row >> 5, c.lane, c.part, make_uint4(hs[kb][0], hs[kb][1], hs[kb][2], hs[kb][3]),
+                  make_uint4(hs[kb][4], hs[kb][5], hs[kb][6], hs[kb][7]), 2u * c.part, out + tiled_block_off(chunk, kb, 4));
   }
   return vmax;
 }
@@ -702,13 +708,14 @@ constexpr uint32_t kWgScratch = kWgStages * kWgStageBytes;
 constexpr uint32_t kWgSmemTotal = kWgScratch + 1024;
 constexpr int kWgThreads = 6 * 32;                     // producer, issuer, 4 reduction / drain warps
 
-struct WgradJob {
+struct WgradJob {          // one piece: a (pass, layer) GEMM over a contiguous range of 64-sample chunks
   const uint8_t* a;        // tiled (n_pad, 64 a_fb) 16-bit gradient array
   const uint8_t* b;        // tiled (n_pad, 64 b_fb) fp16 activation array
   int a_fb;                // column blocks of A: 4 (M = 256, two halves) or 2 (M = 128)
   int b_fb;                // column blocks of B: N = 64 b_fb
-  int chunk0, chunk1;      // 64-sample chunks [chunk0, chunk1)
-  float* out;              // partial (64 a_fb, 64 b_fb) fp32 row-major
+  int chunk0, chunk1;      // 64-sample chunks chunk0, chunk0 + chunk_step, ... < chunk1
+  int chunk_step;          // > 1: the CTAs of one GEMM interleave their chunks (they read one moving window of HBM)
+  float* out;              // partial, TRANSPOSED: element (m, n) at out[n * 64 a_fb + m] (coalesced drain)
   float* bias_out;         // partial column sums of A (64 a_fb) or null
   const float* dsig;       // per-sample weights for the column sums of B (n_pad) or null
   float* wsig_out;         // (64 b_fb + 1): weighted column sums of B, then sum of the weights
@@ -717,14 +724,19 @@ struct WgradJob {
 struct WgScratch {
   uint64_t full[kWgStages];
   uint64_t empty[kWgStages];
-  uint64_t d_ready;
+  uint64_t d_ready;        // issuer -> drain warps: the piece's accumulators are complete
+  uint64_t acc_free;       // drain warps -> issuer: the accumulators have been read out
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradJob* __restrict__ jobs, int* status) {
+// Persistent: CTA b works through pieces [cta_first[b], cta_first[b + 1]) - the host cuts the
+// concatenation of all (pass, layer) GEMMs into one equal-byte share per SM (capi.cu plan_wgrad), so
+// there is exactly one wave and every SM streams the same number of bytes.
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradJob* __restrict__ jobs,
+                                                               const int* __restrict__ cta_first, uint32_t copy_bytes,
+                                                               uint32_t exp_flags, int* status) {
   extern __shared__ __align__(1024) uint8_t smem[];
   WgScratch* sc = reinterpret_cast<WgScratch*>(smem + kWgScratch);
-  const WgradJob job = jobs[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) report_fault(status, 101);
@@ -736,6 +748,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradJob* __
       mbar_init(smem_u32(&sc->empty[i]), 5);        // tcgen05.commit + the four reduction warps
     }
     mbar_init(smem_u32(&sc->d_ready), 1);
+    mbar_init(smem_u32(&sc->acc_free), 4);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -745,108 +758,134 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradJob* __
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t a_bytes = job.a_fb * kTileBlockBytes, b_bytes = job.b_fb * kTileBlockBytes;
-  const int n_chunks = job.chunk1 - job.chunk0;
-  const int N = job.b_fb * 64, halves = job.a_fb >> 1;
+  const int p0 = cta_first[blockIdx.x], p1 = cta_first[blockIdx.x + 1];
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int c = job.chunk0; c < job.chunk1; ++c) {
-        mbar_wait(smem_u32(&sc->empty[stage]), phase ^ 1, 51);
-        const uint32_t full = smem_u32(&sc->full[stage]);
-        const uint32_t dst = smem_u32(smem + stage * kWgStageBytes);
-        mbar_arrive_expect_tx(full, a_bytes + b_bytes);
-        const uint8_t* sa = job.a + static_cast<unsigned long long>(c) * a_bytes;
-        const uint8_t* sb = job.b + static_cast<unsigned long long>(c) * b_bytes;
-        for (uint32_t o = 0; o < a_bytes; o += 8192) bulk_g2s(dst + o, sa + o, 8192, full);
-        for (uint32_t o = 0; o < b_bytes; o += 8192) bulk_g2s(dst + 32768 + o, sb + o, 8192, full);
-        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      for (int pi = p0; pi < p1; ++pi) {
+        const WgradJob job = jobs[pi];
+        const uint32_t a_bytes = job.a_fb * kTileBlockBytes, b_bytes = job.b_fb * kTileBlockBytes;
+        for (int c = job.chunk0; c < job.chunk1; c += job.chunk_step) {
+          mbar_wait(smem_u32(&sc->empty[stage]), phase ^ 1, 51);
+          const uint32_t full = smem_u32(&sc->full[stage]);
+          const uint32_t dst = smem_u32(smem + stage * kWgStageBytes);
+          mbar_arrive_expect_tx(full, a_bytes + b_bytes);
+          const uint8_t* sa = job.a + static_cast<unsigned long long>(c) * a_bytes;
+          const uint8_t* sb = job.b + static_cast<unsigned long long>(c) * b_bytes;
+          for (uint32_t o = 0; o < a_bytes; o += copy_bytes) bulk_g2s(dst + o, sa + o, min(copy_bytes, a_bytes - o), full);
+          for (uint32_t o = 0; o < b_bytes; o += copy_bytes) bulk_g2s(dst + 32768 + o, sb + o, min(copy_bytes, b_bytes - o), full);
+          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_chunks > 0) {
-      // A: bf16 / fp16 per build, B: fp16; both MN-major
-      const uint32_t idesc = make_idesc_f16_mn(N) | (kBwdFmt << 7);
-      uint32_t stage = 0, phase = 0;
-      for (int c = 0; c < n_chunks; ++c) {
-        mbar_wait(smem_u32(&sc->full[stage]), phase, 52);
-        tc_fence_after();
-        const uint32_t base = smem_u32(smem + stage * kWgStageBytes);
-        for (int hh = 0; hh < halves; ++hh) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {        // 16 samples = two 8-row groups = 2048 B per K step
-            const uint64_t ad = make_desc_mn_sw128(base + hh * 16384 + j * 2048, 8192, 1024);
-            const uint64_t bd = make_desc_mn_sw128(base + 32768 + j * 2048, 8192, 1024);
-            umma_f16(sc->tmem_base + hh * 256, ad, bd, idesc, (c | j) != 0 ? 1u : 0u);
-          }
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, free_phase = 0;
+      bool first = true;
+      for (int pi = p0; pi < p1; ++pi) {
+        const WgradJob job = jobs[pi];
+        const int n_chunks = (job.chunk1 - job.chunk0 + job.chunk_step - 1) / job.chunk_step;
+        if (n_chunks <= 0) continue;
+        const int N = job.b_fb * 64, halves = job.a_fb >> 1;
+        // A: fp16 (bf16 in the experiment build), B: fp16; both MN-major
+        const uint32_t idesc = make_idesc_f16_mn(N) | (kBwdFmt << 7);
+        if (!first) {       // the previous piece's accumulators have been drained
+          mbar_wait(smem_u32(&sc->acc_free), free_phase, 55);
+          free_phase ^= 1;
+          tc_fence_after();
         }
-        umma_commit(smem_u32(&sc->empty[stage]));
-        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        first = false;
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_wait(smem_u32(&sc->full[stage]), phase, 52);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + stage * kWgStageBytes);
+          for (int hh = 0; hh < halves && !(exp_flags & 1u); ++hh) {      // exp bit 0: no MMAs (timing experiment)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {        // 16 samples = two 8-row groups = 2048 B per K step
+              const uint64_t ad = make_desc_mn_sw128(base + hh * 16384 + j * 2048, 8192, 1024);
+              const uint64_t bd = make_desc_mn_sw128(base + 32768 + j * 2048, 8192, 1024);
+              umma_f16(sc->tmem_base + hh * 256, ad, bd, idesc, (c | j) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(smem_u32(&sc->empty[stage]));
+          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&sc->d_ready));
       }
-      umma_commit(smem_u32(&sc->d_ready));
     }
   } else {
-    // ---- reduction warps (threads 0..127 of this group): column pair 2t, 2t+1
+    // ---- reduction / drain warps (threads 0..127 of this group): column pair 2t, 2t+1
     const int t = threadIdx.x - 64;
-    const bool a_act = job.bias_out != nullptr && t < job.a_fb * 32;
-    const bool b_act = job.dsig != nullptr && t < job.b_fb * 32;
     const uint32_t col_off = (t >> 5) * kTileBlockBytes + (t & 3) * 4;      // column block, word within the 16-byte chunk
     const uint32_t chunk16 = (t & 31) >> 2;
-    float sa0 = 0.f, sa1 = 0.f, sb0 = 0.f, sb1 = 0.f, sw = 0.f;
-    uint32_t stage = 0, phase = 0;
-    for (int c = job.chunk0; c < job.chunk1; ++c) {
-      mbar_wait(smem_u32(&sc->full[stage]), phase, 53);
-      const uint8_t* base = smem + stage * kWgStageBytes;
-      if (a_act) {
-#pragma unroll 8
-        for (int r = 0; r < 64; ++r) {
-          const uint32_t v = *reinterpret_cast<const uint32_t*>(base + col_off + r * 128 + ((chunk16 ^ (r & 7)) << 4));
-          const float2 f = bwd_x2_to_float2(v);
-          sa0 += f.x; sa1 += f.y;
-        }
-      }
-      if (b_act) {
-        const float* ds = job.dsig + static_cast<long long>(c) * 64;
-#pragma unroll 8
-        for (int r = 0; r < 64; ++r) {
-          const uint32_t v = *reinterpret_cast<const uint32_t*>(base + 32768 + col_off + r * 128 + ((chunk16 ^ (r & 7)) << 4));
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
-          const float w = __ldg(ds + r);
-          sb0 = fmaf(w, f.x, sb0); sb1 = fmaf(w, f.y, sb1);
-          sw += w;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&sc->empty[stage]));
-      if (++stage == kWgStages) { stage = 0; phase ^= 1; }
-    }
-    if (a_act) { job.bias_out[2 * t] = sa0; job.bias_out[2 * t + 1] = sa1; }
-    if (b_act) {
-      job.wsig_out[2 * t] = sb0; job.wsig_out[2 * t + 1] = sb1;
-      if (t == 0) job.wsig_out[N] = sw;
-    }
-    // ---- drain the accumulators: thread = output row (TMEM lane) of each half
     const int m = (warp & 3) * 32 + lane;
-    if (n_chunks > 0) {
-      mbar_wait(smem_u32(&sc->d_ready), 0, 54);
-      tc_fence_after();
-    }
     const uint32_t trow = sc->tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    for (int hh = 0; hh < halves; ++hh) {
-      float* orow = job.out + static_cast<long long>(hh * 128 + m) * N;
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t r[32];
-        if (n_chunks > 0) {
-          tmem_ld32(trow + hh * 256 + c0, r);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = 0u;
+    uint32_t stage = 0, phase = 0, ready_phase = 0;
+    for (int pi = p0; pi < p1; ++pi) {
+      const WgradJob job = jobs[pi];
+      const int n_chunks = (job.chunk1 - job.chunk0 + job.chunk_step - 1) / job.chunk_step;
+      const int N = job.b_fb * 64, halves = job.a_fb >> 1, M = job.a_fb * 64;
+      const bool a_act = job.bias_out != nullptr && t < job.a_fb * 32 && !(exp_flags & 2u);   // exp bit 1: no reductions
+      const bool b_act = job.dsig != nullptr && t < job.b_fb * 32 && !(exp_flags & 2u);
+      float sa0 = 0.f, sa1 = 0.f, sb0 = 0.f, sb1 = 0.f, sw = 0.f;
+      for (int c = job.chunk0; c < job.chunk1; c += job.chunk_step) {
+        mbar_wait(smem_u32(&sc->full[stage]), phase, 53);
+        const uint8_t* base = smem + stage * kWgStageBytes;
+        if (a_act) {
+#pragma unroll 8
+          for (int r = 0; r < 64; ++r) {
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(base + col_off + r * 128 + ((chunk16 ^ (r & 7)) << 4));
+            const float2 f = bwd_x2_to_float2(v);
+            sa0 += f.x; sa1 += f.y;
+          }
         }
+        if (b_act) {
+          const float* ds = job.dsig + static_cast<long long>(c) * 64;
+#pragma unroll 8
+          for (int r = 0; r < 64; ++r) {
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(base + 32768 + col_off + r * 128 + ((chunk16 ^ (r & 7)) << 4));
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+            const float w = __ldg(ds + r);
+            sb0 = fmaf(w, f.x, sb0); sb1 = fmaf(w, f.y, sb1);
+            sw += w;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sc->empty[stage]));
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+      if (a_act) { job.bias_out[2 * t] = sa0; job.bias_out[2 * t + 1] = sa1; }
+      if (b_act) {
+        job.wsig_out[2 * t] = sb0; job.wsig_out[2 * t + 1] = sb1;
+        if (t == 0) job.wsig_out[N] = sw;
+      }
+      // ---- drain the accumulators: thread = output row m (TMEM lane) of each half; the partial is stored
+      // transposed (element (m, n) at n * M + m) so that a warp writes 32 consecutive floats per column
+      if (n_chunks > 0) {
+        mbar_wait(smem_u32(&sc->d_ready), ready_phase, 54);
+        ready_phase ^= 1;
+        tc_fence_after();
+      }
+      for (int hh = 0; hh < halves; ++hh) {
+        float* ocol = job.out + hh * 128 + m;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t r[32];
+          if (n_chunks > 0) {
+            tmem_ld32(trow + hh * 256 + c0, r);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<uint4*>(orow + c0 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+            for (int i = 0; i < 32; ++i) r[i] = 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ocol[static_cast<long long>(c0 + i) * M] = __uint_as_float(r[i]);
+        }
+      }
+      if (n_chunks > 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sc->acc_free));
       }
     }
   }
@@ -866,6 +905,7 @@ struct ReduceItem {
   float* out;
   const float* mul;        // device scalar or null (= 1)
   int n_split, rows, cols, part_ld, out_ld, out_col0;
+  int transposed;          // partial element (r, c) at part[c * part_ld + r] (wgrad drains) instead of part[r * part_ld + c]
 };
 constexpr int kMaxReduceItems = 64;
 struct ReduceTable {
@@ -878,10 +918,16 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant
   const int total = it.rows * it.cols;
   const float mul = (it.mul != nullptr) ? *it.mul : 1.f;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int r = idx / it.cols, c = idx - r * it.cols;
-    const float* src = it.part + static_cast<long long>(r) * it.part_ld + c;
+    int r, c;
+    const float* src;
+    if (it.transposed) {       // r fastest: coalesced reads of the transposed partials
+      c = idx / it.rows; r = idx - c * it.rows;
+      src = it.part + static_cast<long long>(c) * it.part_ld + r;
+    } else {
+      r = idx / it.cols; c = idx - r * it.cols;
+      src = it.part + static_cast<long long>(r) * it.part_ld + c;
+    }
     float acc = 0.f;
-#pragma unroll 4
     for (int s = 0; s < it.n_split; ++s) acc += src[s * it.split_stride];
     it.out[static_cast<long long>(r) * it.out_ld + it.out_col0 + c] = acc * mul;
   }
@@ -932,6 +978,48 @@ __global__ void __launch_bounds__(256) unfold_kernel(const UnfoldParams p) {
     float acc = 0.f;
     for (int m = 0; m < 128; ++m) acc = fmaf(p.Wd[ps][m * 283 + j], p.gbp[ps][m], acc);
     p.gbf[ps][j] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------- Adam
+// torch.optim.Adam's update (the reference's default optimiser, utils/__init__.py:16-18:
+// Adam(lr, eps, weight_decay), betas (0.9, 0.999), no amsgrad) for all parameter tensors of the two
+// networks in ONE launch: torch's fused implementation costs two 80 us multi-tensor kernels for
+// these 48 small tensors, a fifth of the remaining step.  Same arithmetic as torch (fp32):
+//   g = grad + weight_decay * p;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2
+//   p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+constexpr int kAdamMaxTensors = 64;
+struct AdamParams {
+  int n_tensors;
+  float* p[kAdamMaxTensors];
+  const float* g[kAdamMaxTensors];
+  float* m[kAdamMaxTensors];
+  float* v[kAdamMaxTensors];
+  int block0[kAdamMaxTensors + 1];     // first block of each tensor (1024 elements per block)
+  int numel[kAdamMaxTensors];
+  float lr, beta1, beta2, eps, weight_decay, bias1, bias2_sqrt;     // bias1 = 1 - b1^t, bias2_sqrt = sqrt(1 - b2^t)
+};
+__global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamParams a) {
+  int lo = 0, hi = a.n_tensors;
+  while (hi - lo > 1) {        // the tensor this block belongs to
+    const int mid = (lo + hi) >> 1;
+    if (a.block0[mid] <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid;
+  }
+  const int t = lo;
+  const int base = (static_cast<int>(blockIdx.x) - a.block0[t]) * 1024;
+  const float step = a.lr / a.bias1;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = base + q * 256 + threadIdx.x;
+    if (i < a.numel[t]) {
+      const float pv = a.p[t][i];
+      const float g = a.g[t][i] + a.weight_decay * pv;
+      const float m = a.beta1 * a.m[t][i] + (1.f - a.beta1) * g;
+      const float v = a.beta2 * a.v[t][i] + (1.f - a.beta2) * g * g;
+      a.m[t][i] = m;
+      a.v[t][i] = v;
+      a.p[t][i] = pv - step * m / (sqrtf(v) / a.bias2_sqrt + a.eps);
+    }
   }
 }
 

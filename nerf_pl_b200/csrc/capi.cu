@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -50,7 +51,13 @@ struct DeviceInfo {
 struct EnvSwitches {
   unsigned flags = 0;
   int max_ctas = 0;
+  int wg_plan = 1;        // wgrad plan: 0 = contiguous equal-byte shares, 1 = whole CTAs per GEMM, chunks interleaved
+  int wg_copy = 32768;    // bytes per bulk copy of a wgrad operand chunk
+  unsigned wg_exp = 0;    // wgrad timing experiments: bit 0 = no MMAs, bit 1 = no CUDA-core reductions
   EnvSwitches() {
+    if (const char* v = std::getenv("NERFB200_WG_EXP")) wg_exp = static_cast<unsigned>(std::atoi(v));
+    if (const char* v = std::getenv("NERFB200_WG_PLAN")) wg_plan = std::atoi(v);
+    if (const char* v = std::getenv("NERFB200_WG_COPY")) wg_copy = std::atoi(v);
     if (const char* f = std::getenv("NERFB200_FLAGS")) flags = static_cast<unsigned>(std::strtoul(f, nullptr, 0));
     if (const char* mc = std::getenv("NERFB200_MAX_CTAS")) max_ctas = std::atoi(mc);
   }
@@ -153,12 +160,14 @@ struct WgJobPlan { int ps, kind, split, n_split; };
 enum { kJ1 = 0, kJ2, kJ3, kJ4, kJ5a, kJ5b, kJ6, kJ7, kJ8, kJ9, kNumJobKinds };
 constexpr int kWgSlotFloats = 256 * 256 + 256 + 264;     // partial of one job: out, bias, wsig
 constexpr int kMaxWgJobs = 1024;
+constexpr int kMaxWgCtas = 512;
 struct TrainLayout {
   PassBufs pass[2];
   int n_pass, n_rays;
-  WgradJob* jobs_dev;
-  int n_jobs;
-  int n_split[2][kNumJobKinds];
+  WgradJob* jobs_dev;             // pieces, in (pass, layer, chunk) order
+  int* cta_first_dev;             // [n_cta + 1]: CTA b works on pieces [cta_first[b], cta_first[b + 1])
+  int n_jobs, n_cta;
+  int n_split[2][kNumJobKinds];   // pieces of each (pass, layer)
   int first_job[2][kNumJobKinds];
   float* wg_part;                 // [n_jobs][kWgSlotFloats]
   int head_grid;                  // blocks of head_bwd_kernel (both passes in one launch)
@@ -176,6 +185,9 @@ struct TrainLayout {
   unsigned* loss_counter;
   size_t bytes;
 };
+
+struct TrainLayout;
+void plan_wgrad(TrainLayout* L, int n_cta, WgradJob* jobs, int* cta_first);
 
 void job_shape(int kind, int* a_fb, int* b_fb) {
   *a_fb = (kind == kJ9) ? 2 : 4;
@@ -210,29 +222,11 @@ void make_train_layout(TrainLayout* L, uint8_t* base, int64_t n_rays, int n_samp
     b.dd = take(np * 256);
     b.dpre = take(np * 512 * 8);
   }
-  // wgrad jobs: splits proportional to the bytes each (pass, layer) streams, ~2 CTAs per SM in total
-  double work[2][kNumJobKinds], total = 0;
-  for (int ps = 0; ps < L->n_pass; ++ps)
-    for (int k = 0; k < kNumJobKinds; ++k) {
-      int a_fb, b_fb;
-      job_shape(k, &a_fb, &b_fb);
-      work[ps][k] = static_cast<double>(L->pass[ps].n_pad / 64) * (a_fb + b_fb);
-      total += work[ps][k];
-    }
-  const int target = 2 * (sm_count > 0 ? sm_count : 148);
-  L->n_jobs = 0;
-  for (int ps = 0; ps < L->n_pass; ++ps)
-    for (int k = 0; k < kNumJobKinds; ++k) {
-      const long long chunks = L->pass[ps].n_pad / 64;
-      int ns = static_cast<int>(work[ps][k] / total * target + 0.5);
-      if (ns < 1) ns = 1;
-      if (ns > chunks) ns = static_cast<int>(chunks);
-      if (L->n_jobs + ns > kMaxWgJobs) ns = kMaxWgJobs - L->n_jobs;
-      L->n_split[ps][k] = ns;
-      L->first_job[ps][k] = L->n_jobs;
-      L->n_jobs += ns;
-    }
+  // wgrad plan: the concatenation of all (pass, layer) GEMMs, measured in 8 KiB blocks streamed, is cut
+  // into one equal share per SM; a share boundary inside a GEMM splits it into two pieces
+  plan_wgrad(L, sm_count > 0 ? sm_count : 148, nullptr, nullptr);
   L->jobs_dev = reinterpret_cast<WgradJob*>(take(sizeof(WgradJob) * kMaxWgJobs));
+  L->cta_first_dev = reinterpret_cast<int*>(take(sizeof(int) * (kMaxWgCtas + 1)));
   L->wg_part = reinterpret_cast<float*>(take(static_cast<size_t>(L->n_jobs) * kWgSlotFloats * 4));
   L->head_grid = static_cast<int>((L->n_pass * n_rays + kHeadWarps - 1) / kHeadWarps);
   L->direnc = reinterpret_cast<float*>(take(static_cast<size_t>(n_rays) * 28 * 4));
@@ -252,41 +246,132 @@ void make_train_layout(TrainLayout* L, uint8_t* base, int64_t n_rays, int n_samp
   L->bytes = off;
 }
 
-// Host image of the wgrad job table of a layout.
-void build_wgrad_jobs(const TrainLayout& L, WgradJob* jobs) {
-  for (int ps = 0; ps < L.n_pass; ++ps) {
-    const PassBufs& b = L.pass[ps];
-    const size_t lay = static_cast<size_t>(b.n_pad) * 512;
-    const long long chunks = b.n_pad / 64;
+// The wgrad plan of a layout: piece counts per (pass, layer) (always), and when `jobs` / `cta_first` are
+// given the host image of the piece table and of the per-CTA piece ranges.
+void job_operands(const TrainLayout& L, int ps, int k, const uint8_t** A, const uint8_t** B) {
+  const PassBufs& b = L.pass[ps];
+  const size_t lay = static_cast<size_t>(b.n_pad) * 512;
+  switch (k) {
+    case kJ1: *A = b.dpre; *B = b.enc; break;
+    case kJ5a: *A = b.dpre + 4 * lay; *B = b.enc; break;
+    case kJ5b: *A = b.dpre + 4 * lay; *B = b.act + 3 * lay; break;
+    case kJ9: *A = b.dd; *B = b.act + 7 * lay; break;
+    default: {
+      const int l = (k <= kJ4) ? k + 1 : k;            // kJ2..kJ4 -> layers 2..4, kJ6..kJ8 -> layers 6..8
+      *A = b.dpre + static_cast<size_t>(l - 1) * lay;
+      *B = b.act + static_cast<size_t>(l - 2) * lay;
+    }
+  }
+}
+
+void fill_piece(TrainLayout* L, WgradJob* jobs, int piece, int ps, int k, long long c0, long long c1, int step) {
+  if (!jobs) return;
+  int a_fb, b_fb;
+  job_shape(k, &a_fb, &b_fb);
+  const uint8_t *A = nullptr, *B = nullptr;
+  job_operands(*L, ps, k, &A, &B);
+  WgradJob& j = jobs[piece];
+  float* slot = L->wg_part + static_cast<size_t>(piece) * kWgSlotFloats;
+  j.a = A; j.b = B; j.a_fb = a_fb; j.b_fb = b_fb;
+  j.chunk0 = static_cast<int>(c0);
+  j.chunk1 = static_cast<int>(c1);
+  j.chunk_step = step;
+  j.out = slot;
+  j.bias_out = (k == kJ5b) ? nullptr : slot + 256 * 256;
+  j.dsig = (k == kJ9) ? L->pass[ps].dsigma : nullptr;
+  j.wsig_out = (k == kJ9) ? slot + 256 * 256 + 256 : nullptr;
+}
+
+void plan_wgrad(TrainLayout* L, int n_cta, WgradJob* jobs, int* cta_first) {
+  if (n_cta > kMaxWgCtas) n_cta = kMaxWgCtas;
+  long long total = 0;
+  long long work[2][kNumJobKinds];
+  for (int ps = 0; ps < L->n_pass; ++ps)
     for (int k = 0; k < kNumJobKinds; ++k) {
       int a_fb, b_fb;
       job_shape(k, &a_fb, &b_fb);
-      const uint8_t* A; const uint8_t* B;
-      switch (k) {
-        case kJ1: A = b.dpre; B = b.enc; break;
-        case kJ5a: A = b.dpre + 4 * lay; B = b.enc; break;
-        case kJ5b: A = b.dpre + 4 * lay; B = b.act + 3 * lay; break;
-        case kJ9: A = b.dd; B = b.act + 7 * lay; break;
-        default: {
-          const int l = (k <= kJ4) ? k + 1 : k;            // kJ2..kJ4 -> layers 2..4, kJ6..kJ8 -> layers 6..8
-          A = b.dpre + static_cast<size_t>(l - 1) * lay;
-          B = b.act + static_cast<size_t>(l - 2) * lay;
+      work[ps][k] = (L->pass[ps].n_pad / 64) * (a_fb + b_fb);
+      total += work[ps][k];
+    }
+  const int n_kinds = L->n_pass * kNumJobKinds;
+  if (env_switches().wg_plan == 1 && n_cta >= n_kinds) {
+    // ---- plan 1: whole CTAs per GEMM (largest-remainder apportionment of the SMs by bytes streamed); the
+    // CTAs of one GEMM take its chunks round-robin, so together they read ONE moving window of each operand
+    int n_of[2][kNumJobKinds];
+    double frac[2][kNumJobKinds];
+    int used = 0;
+    for (int ps = 0; ps < L->n_pass; ++ps)
+      for (int k = 0; k < kNumJobKinds; ++k) {
+        const double share = static_cast<double>(work[ps][k]) * n_cta / static_cast<double>(total);
+        int n = static_cast<int>(share);
+        if (n < 1) n = 1;
+        n_of[ps][k] = n;
+        frac[ps][k] = share - n;
+        used += n;
+      }
+    while (used < n_cta) {          // hand the remaining SMs to the GEMMs with the most work per CTA
+      int bp = 0, bk = 0;
+      double best = -1;
+      for (int ps = 0; ps < L->n_pass; ++ps)
+        for (int k = 0; k < kNumJobKinds; ++k) {
+          const double load = static_cast<double>(work[ps][k]) / n_of[ps][k];
+          if (load > best) { best = load; bp = ps; bk = k; }
+        }
+      ++n_of[bp][bk];
+      ++used;
+    }
+    (void)frac;
+    int piece = 0;
+    for (int ps = 0; ps < L->n_pass; ++ps)
+      for (int k = 0; k < kNumJobKinds; ++k) {
+        const long long chunks = L->pass[ps].n_pad / 64;
+        int g = n_of[ps][k];
+        if (g > chunks) g = static_cast<int>(chunks);
+        L->first_job[ps][k] = piece;
+        for (int j = 0; j < g; ++j) {
+          fill_piece(L, jobs, piece, ps, k, j, chunks, g);
+          if (cta_first) cta_first[piece] = piece;
+          ++piece;
+        }
+        L->n_split[ps][k] = g;
+      }
+    if (cta_first) cta_first[piece] = piece;
+    L->n_jobs = piece;
+    L->n_cta = piece;
+    return;
+  }
+  // ---- plan 0: the concatenation of all GEMMs cut into one equal-byte share per SM
+  int cta = 0, piece = 0;
+  long long done = 0;                                  // units handed out so far
+  if (cta_first) cta_first[0] = 0;
+  for (int ps = 0; ps < L->n_pass; ++ps)
+    for (int k = 0; k < kNumJobKinds; ++k) {
+      int a_fb, b_fb;
+      job_shape(k, &a_fb, &b_fb);
+      const long long unit = a_fb + b_fb, chunks = L->pass[ps].n_pad / 64;
+      L->first_job[ps][k] = piece;
+      long long c = 0;
+      while (c < chunks) {
+        const long long end = total * (cta + 1) / n_cta;
+        long long take_chunks = (end - done + unit - 1) / unit;       // chunks until this CTA's share is full
+        if (take_chunks < 1) take_chunks = 1;
+        if (take_chunks > chunks - c) take_chunks = chunks - c;
+        fill_piece(L, jobs, piece, ps, k, c, c + take_chunks, 1);
+        ++piece;
+        c += take_chunks;
+        done += take_chunks * unit;
+        while (cta < n_cta - 1 && done >= total * (cta + 1) / n_cta) {
+          ++cta;
+          if (cta_first) cta_first[cta] = piece;
         }
       }
-      const int ns = L.n_split[ps][k];
-      for (int sp = 0; sp < ns; ++sp) {
-        WgradJob& j = jobs[L.first_job[ps][k] + sp];
-        float* slot = L.wg_part + static_cast<size_t>(L.first_job[ps][k] + sp) * kWgSlotFloats;
-        j.a = A; j.b = B; j.a_fb = a_fb; j.b_fb = b_fb;
-        j.chunk0 = static_cast<int>(chunks * sp / ns);
-        j.chunk1 = static_cast<int>(chunks * (sp + 1) / ns);
-        j.out = slot;
-        j.bias_out = (k == kJ5b) ? nullptr : slot + 256 * 256;
-        j.dsig = (k == kJ9) ? b.dsigma : nullptr;
-        j.wsig_out = (k == kJ9) ? slot + 256 * 256 + 256 : nullptr;
-      }
+      L->n_split[ps][k] = piece - L->first_job[ps][k];
     }
+  if (cta_first) {
+    for (int i = cta + 1; i <= n_cta; ++i) cta_first[i] = piece;
   }
+  L->n_jobs = piece;
+  L->n_cta = n_cta;
 }
 
 // grow-only device arena for the *_host entry
@@ -458,6 +543,12 @@ int nerfb200_render_rays_host(const nerfb200_render_args* h, void* stream_v) {
     return fail(NERFB200_EINVAL, "render_rays_host: train_workspace / target / z_coarse are device-only%s");
   auto up = [&](const float* src, size_t count, size_t src_stride, size_t width) -> const float* {
     if (!src) return nullptr;
+    if (src_stride == width) {
+      // random inputs may already live on the device (drawn there by the caller): use them in place
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeDevice) return src;
+      (void)cudaGetLastError();
+    }
     float* dst = static_cast<float*>(ar.take(count * fl));
     if (src_stride == width) {
       cudaMemcpyAsync(dst, src, count * fl, cudaMemcpyHostToDevice, stream);
@@ -699,10 +790,13 @@ int nerfb200_train_workspace_init(void* workspace, size_t bytes, int64_t n_rays,
   // padding rows of the operand arrays must be zero (never written afterwards), counters zero
   CUDA_TRY(cudaMemsetAsync(workspace, 0, L.bytes, stream), "workspace memset");
   std::vector<WgradJob> jobs(kMaxWgJobs);
+  std::vector<int> cta_first(kMaxWgCtas + 1, 0);
   std::memset(jobs.data(), 0, sizeof(WgradJob) * kMaxWgJobs);
-  build_wgrad_jobs(L, jobs.data());
+  plan_wgrad(&L, d->sm_count, jobs.data(), cta_first.data());
   CUDA_TRY(cudaMemcpyAsync(L.jobs_dev, jobs.data(), sizeof(WgradJob) * kMaxWgJobs, cudaMemcpyHostToDevice, stream),
            "job table upload");
+  CUDA_TRY(cudaMemcpyAsync(L.cta_first_dev, cta_first.data(), sizeof(int) * (kMaxWgCtas + 1), cudaMemcpyHostToDevice, stream),
+           "cta table upload");
   CUDA_TRY(cudaStreamSynchronize(stream), "workspace init sync");
   return 0;
 }
@@ -810,35 +904,38 @@ int nerfb200_render_backward(const nerfb200_backward_args* b, void* stream_v) {
     g_launches++;
   }
   // 4. split-K wgrad (tcgen05)
-  wgrad_kernel<<<L.n_jobs, kWgThreads, kWgSmemTotal, stream>>>(L.jobs_dev, d->status);
+  wgrad_kernel<<<L.n_cta, kWgThreads, kWgSmemTotal, stream>>>(L.jobs_dev, L.cta_first_dev,
+                                                               static_cast<uint32_t>(env_switches().wg_copy),
+                                                               env_switches().wg_exp, d->status);
   g_launches++;
   // 5. partial sums -> gradient tensors (fixed order), 6. unfold W'
   ReduceTable tab;
   tab.n = 0;
   auto add = [&](const float* part, long long stride, int n_split, float* out, const float* mul, int rows, int cols,
-                 int part_ld, int out_ld, int out_col0) {
+                 int part_ld, int out_ld, int out_col0, int transposed = 0) {
     ReduceItem& it = tab.it[tab.n++];
     it.part = part; it.split_stride = stride; it.n_split = n_split; it.out = out; it.mul = mul;
     it.rows = rows; it.cols = cols; it.part_ld = part_ld; it.out_ld = out_ld; it.out_col0 = out_col0;
+    it.transposed = transposed;
   };
   for (int ps = 0; ps < L.n_pass; ++ps) {
     const float* linv = L.linv + ps * kLevels;       // level v: 0 = dd, v = 1..8 = dpre_{9-v}
     auto slot = [&](int kind) { return L.wg_part + static_cast<size_t>(L.first_job[ps][kind]) * kWgSlotFloats; };
     auto ns = [&](int kind) { return L.n_split[ps][kind]; };
     float* const* g = grads[ps];
-    add(slot(kJ1), kWgSlotFloats, ns(kJ1), g[0], linv + 8, 256, 63, 64, 63, 0);
+    add(slot(kJ1), kWgSlotFloats, ns(kJ1), g[0], linv + 8, 256, 63, 256, 63, 0, 1);
     add(slot(kJ1) + 65536, kWgSlotFloats, ns(kJ1), g[1], linv + 8, 1, 256, 256, 256, 0);
     const int hidden[6] = {kJ2, kJ3, kJ4, kJ6, kJ7, kJ8};
     const int layer[6] = {2, 3, 4, 6, 7, 8};
     for (int i = 0; i < 6; ++i) {
       const float* inv = linv + (9 - layer[i]);
-      add(slot(hidden[i]), kWgSlotFloats, ns(hidden[i]), g[2 * (layer[i] - 1)], inv, 256, 256, 256, 256, 0);
+      add(slot(hidden[i]), kWgSlotFloats, ns(hidden[i]), g[2 * (layer[i] - 1)], inv, 256, 256, 256, 256, 0, 1);
       add(slot(hidden[i]) + 65536, kWgSlotFloats, ns(hidden[i]), g[2 * (layer[i] - 1) + 1], inv, 1, 256, 256, 256, 0);
     }
-    add(slot(kJ5a), kWgSlotFloats, ns(kJ5a), g[8], linv + 4, 256, 63, 64, 319, 0);
-    add(slot(kJ5b), kWgSlotFloats, ns(kJ5b), g[8], linv + 4, 256, 256, 256, 319, 63);
+    add(slot(kJ5a), kWgSlotFloats, ns(kJ5a), g[8], linv + 4, 256, 63, 256, 319, 0, 1);
+    add(slot(kJ5b), kWgSlotFloats, ns(kJ5b), g[8], linv + 4, 256, 256, 256, 319, 63, 1);
     add(slot(kJ5a) + 65536, kWgSlotFloats, ns(kJ5a), g[9], linv + 4, 1, 256, 256, 256, 0);
-    add(slot(kJ9), kWgSlotFloats, ns(kJ9), L.gWp[ps], linv, 128, 256, 256, 256, 0);
+    add(slot(kJ9), kWgSlotFloats, ns(kJ9), L.gWp[ps], linv, 128, 256, 128, 256, 0, 1);
     add(slot(kJ9) + 65536, kWgSlotFloats, ns(kJ9), L.gbp[ps], linv, 1, 128, 128, 128, 0);
     add(slot(kJ9) + 65536 + 256, kWgSlotFloats, ns(kJ9), g[20], nullptr, 1, 256, 256, 256, 0);
     add(slot(kJ9) + 65536 + 256 + 256, kWgSlotFloats, ns(kJ9), g[21], nullptr, 1, 1, 1, 1, 0);
@@ -859,6 +956,35 @@ int nerfb200_render_backward(const nerfb200_backward_args* b, void* stream_v) {
   unfold_kernel<<<dim3((128 * 256 + (256 * 256 + 256 + 31) / 32 + 7) / 8, L.n_pass), 256, 0, stream>>>(up);
   g_launches++;
   CUDA_TRY(cudaGetLastError(), "render_backward launches");
+  return 0;
+}
+
+int nerfb200_adam_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                       float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int64_t step, void* stream) {
+  if (n_tensors < 0 || n_tensors > kAdamMaxTensors) return fail(NERFB200_EINVAL, "adam_step: at most 64 tensors per call%s");
+  if (n_tensors == 0) return 0;
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !numel || step < 1)
+    return fail(NERFB200_EINVAL, "adam_step: NULL argument / step < 1%s");
+  AdamParams a;
+  a.n_tensors = n_tensors;
+  int blocks = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    if (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i] || numel[i] < 0 || numel[i] > 0x7fffffff)
+      return fail(NERFB200_EINVAL, "adam_step: NULL tensor / bad size%s");
+    a.p[i] = params[i]; a.g[i] = grads[i]; a.m[i] = exp_avg[i]; a.v[i] = exp_avg_sq[i];
+    a.numel[i] = static_cast<int>(numel[i]);
+    a.block0[i] = blocks;
+    blocks += static_cast<int>((numel[i] + 1023) / 1024);
+  }
+  a.block0[n_tensors] = blocks;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+  a.bias1 = 1.f - std::pow(beta1, static_cast<float>(step));
+  a.bias2_sqrt = std::sqrt(1.f - std::pow(beta2, static_cast<float>(step)));
+  if (blocks == 0) return 0;
+  adam_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError(), "adam_step launch");
   return 0;
 }
 

@@ -369,6 +369,12 @@ constexpr int kStageBar0 = 3;          // named barriers 3..6: row groups 0..3 (
 constexpr uint32_t kStageBytes = 4 * 4096;
 __device__ __forceinline__ void stage_store(uint8_t* stage, int rg, int lane, int part, uint4 c0, uint4 c1,
                                             uint32_t chunk0, uint8_t* gdst) {
+#ifdef NERFB200_EXP_NOSTAGE       // experiment: no staging at all (results are NOT stored)
+  return;
+#endif
+#ifdef NERFB200_EXP_NOSTORE       // experiment: staging and barriers, but nothing handed to the copy engine
+  gdst = nullptr;
+#endif
   const bool issuer = (part == 0) && (lane == 0);
   if (issuer) bulk_wait_read();
   named_bar_sync(kStageBar0 + rg, 128);
@@ -434,24 +440,16 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
     static_assert(kColsPer / 4 == 16, "the hand-over assumes 16 epilogue warps (16 columns per K block per thread)");
     uint32_t r[4][16];
     uint32_t sgn_lo = 0, sgn_hi = 0;   // kSave: sign bits of the even / odd pre-activations, first in = top bit
-    // K block 0 is on the critical path "accumulator complete -> first MMA of the next layer": its 16
-    // columns are fetched alone, the other three loads are in flight while it is converted and stored
-#ifdef NERFB200_EXP_SPLIT_LD
-    tmem_ld16(c.tmem_row + kTmemD + c.part * 16, r[0]);
-    tmem_ld_wait();
-#pragma unroll
-    for (int kb = 1; kb < 4; ++kb) tmem_ld16(c.tmem_row + kTmemD + kb * 64 + c.part * 16, r[kb]);
-#else
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) tmem_ld16(c.tmem_row + kTmemD + kb * 64 + c.part * 16, r[kb]);
     tmem_ld_wait();
     if (!kStore && c.early) epi_release_accumulator(c);
-#endif
     NERFB200_TL_MARK(c.tl, 0, 3);
+    uint32_t hs[kSave ? 4 : 1][8];      // training mode: the layer's fp16 outputs, staged to HBM after the hand-over
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) {
       const int n0 = kb * 64 + c.part * 16;
-      uint32_t h[8];
+      uint32_t (&h)[8] = hs[kSave ? kb : 0];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const float4 b0 = (kb == 0) ? pb[2 * j] : *reinterpret_cast<const float4*>(bias + n0 + 8 * j);
@@ -486,27 +484,26 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
           h[4 * j + 2] = cvt_f16x2(v[4], v[5]); h[4 * j + 3] = cvt_f16x2(v[6], v[7]);
         }
       }
-      if (kStore) tmem_st8(c.tmem_row + kTmemA + n0 / 2, h);
-#ifdef NERFB200_EXP_SPLIT_LD
-      if (kb == 0) {      // every column of the accumulator is in registers from here on
-        tmem_ld_wait();
-        reg_fence16(r[1]); reg_fence16(r[2]); reg_fence16(r[3]);
-        if (!kStore && c.early) epi_release_accumulator(c);
-      }
-#endif
       if (kStore) {
+        tmem_st8(c.tmem_row + kTmemA + n0 / 2, h);
         if (kb == 3 && dir_row != nullptr) write_dir_row(c, dir_row);
         epi_signal_kb(c, kb, kb == 3 && dir_row != nullptr);
         NERFB200_TL_MARK(c.tl, 0, 40 + kb);
       }
-      if (kSave && c.save_act != nullptr) {
+    }
+    // training mode: the stores happen AFTER all four K blocks have been handed to the tensor core, i.e.
+    // behind the next layer's MMAs (staging per K block inside the loop paced the MMA stream: measured
+    // 6800 cycles per layer instead of 3350)
+    if (kSave && c.save_act != nullptr) {
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
         // tiled layout: this row group's 32 rows of column block kb are 4 KiB contiguous in HBM
         uint8_t* gdst = nullptr;
         if (c.save_g0 >= 0)
           gdst = c.save_act + static_cast<long long>(l) * c.save_n * 512 +
                  tiled_block_off(static_cast<unsigned long long>(c.save_g0 >> 6), kb, 4) + (c.save_g0 & 63) * 128;
-        stage_store(c.stage, (c.row >> 5), c.lane, c.part, make_uint4(h[0], h[1], h[2], h[3]),
-                    make_uint4(h[4], h[5], h[6], h[7]), 2u * c.part, gdst);
+        stage_store(c.stage, (c.row >> 5), c.lane, c.part, make_uint4(hs[kb][0], hs[kb][1], hs[kb][2], hs[kb][3]),
+                    make_uint4(hs[kb][4], hs[kb][5], hs[kb][6], hs[kb][7]), 2u * c.part, gdst);
       }
     }
     if (kSave && c.save_mask != nullptr && c.save_row >= 0)

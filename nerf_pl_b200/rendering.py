@@ -15,11 +15,20 @@ import torch
 from . import _lib
 from .nerf import _stream_ptr, nerf_forward_torch, packed_weights
 
-__all__ = ["render_rays", "render_rays_loss", "sample_pdf", "searchsorted", "volume_render"]
+__all__ = ["render_rays", "render_rays_host", "render_rays_loss", "sample_pdf", "searchsorted", "volume_render"]
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
+
+
+def _require_fp32(name: str, *tensors) -> None:
+    """The kernels compute in fp32 (the reference's dtype).  torchsearchsorted also
+    accepts float64 and keeps it; silently rounding such inputs would change results, so they are
+    rejected instead."""
+    for t in tensors:
+        if t is not None and t.dtype == torch.float64:
+            raise ValueError(f"nerf_pl_b200.{name} computes in float32; got a float64 tensor (convert it explicitly)")
 
 
 def _check_embeddings(embeddings: Sequence) -> None:
@@ -48,6 +57,7 @@ def searchsorted(a: torch.Tensor, v: torch.Tensor, out: Optional[torch.Tensor] =
         raise ValueError("side must be 'left' or 'right'")
     if not a.is_cuda:
         raise RuntimeError("nerf_pl_b200.searchsorted runs on CUDA tensors only (no CPU fallback)")
+    _require_fp32("searchsorted", a, v)
     lib = _lib.load()
     nrow = max(a.shape[0], v.shape[0])
     if out is None:
@@ -72,6 +82,7 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, N_importance: int, det
         raise ValueError("nerf_pl_b200.sample_pdf implements the reference default eps=1e-5")
     if not bins.is_cuda:
         raise RuntimeError("nerf_pl_b200.sample_pdf runs on CUDA tensors only (no CPU fallback)")
+    _require_fp32("sample_pdf", bins, weights, u)
     n_rays, n_w = weights.shape
     if bins.shape != (n_rays, n_w + 1):
         raise ValueError("bins must be (N_rays, N_samples_+1)")
@@ -98,6 +109,7 @@ def volume_render(sigmas: torch.Tensor, rgbs: Optional[torch.Tensor], z_vals: to
     Returns (weights, rgb | None, depth | None, opacity)."""
     if not sigmas.is_cuda:
         raise RuntimeError("nerf_pl_b200.volume_render runs on CUDA tensors only (no CPU fallback)")
+    _require_fp32("volume_render", sigmas, rgbs, z_vals, dirs, noise)
     n, S = sigmas.shape
     lib = _lib.load()
     dev = sigmas.device
@@ -251,6 +263,66 @@ def render_rays(models: List[torch.nn.Module],
             result["weights_fine"] = w_f
         result["weights_coarse"] = w_c
     return result
+
+
+@torch.no_grad()
+def render_rays_host(models: List[torch.nn.Module],
+                     embeddings: List[torch.nn.Module],
+                     rays: torch.Tensor,
+                     N_samples: int = 64,
+                     use_disp: bool = False,
+                     perturb: float = 0,
+                     noise_std: float = 1,
+                     N_importance: int = 0,
+                     chunk: int = 1024 * 32,
+                     white_back: bool = False,
+                     test_time: bool = False,
+                     *,
+                     out: Optional[Dict[str, torch.Tensor]] = None,
+                     match_reference_rng: bool = False) -> Dict[str, torch.Tensor]:
+    """render_rays for rays that live in HOST memory (the reference's eval loop moves every chunk with
+    ``.cuda()`` and the results back with ``.cpu()``, eval.py:117-123): ONE call into the C ABI
+    (``nerfb200_render_rays_host``) copies the rays to the models' device, renders, copies the result
+    tensors back and synchronises.  ``rays``: (N, 8) float32 CPU tensor (pinned memory makes the copies
+    asynchronous); returns CPU tensors (``out`` may supply pre-allocated, e.g. pinned, ones).
+    Inference only; the random inputs are drawn on the device."""
+    del chunk
+    if rays.is_cuda or rays.dim() != 2 or rays.shape[1] != 8 or rays.dtype != torch.float32:
+        raise ValueError("rays must be a (N_rays, 8) float32 CPU tensor")
+    _check_embeddings(embeddings)
+    if N_importance > 0 and len(models) < 2:
+        raise ValueError("N_importance > 0 needs a fine model (models[1])")
+    dev = next(models[0].parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("the models must live on a CUDA device (no CPU fallback)")
+    n, S_c, K = rays.shape[0], int(N_samples), int(N_importance)
+    rays = rays.contiguous()
+    with torch.cuda.device(dev):
+        pr, nc, ur, nf = _draw_randoms(n, S_c, K, float(perturb), float(noise_std), dev, match_reference_rng)
+        keys = ["opacity_coarse"] if test_time else ["rgb_coarse", "depth_coarse", "opacity_coarse"]
+        if K > 0:
+            keys += ["rgb_fine", "depth_fine", "opacity_fine"]
+        res = {}
+        for k in keys:
+            shape = (n, 3) if k.startswith("rgb") else (n,)
+            t = out[k] if out is not None and k in out else torch.empty(shape, dtype=torch.float32)
+            if t.is_cuda or t.shape != shape or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f"out[{k!r}] must be a contiguous float32 CPU tensor of shape {shape}")
+            res[k] = t
+        lib = _lib.load()
+        blob_c = packed_weights(models[0])
+        blob_f = packed_weights(models[1]) if K > 0 else None
+        args = _lib.RenderArgs(
+            rays=rays.data_ptr(), n_rays=n, ray_stride=rays.stride(0),
+            packed_coarse=blob_c.data_ptr(), packed_fine=_ptr(blob_f),
+            n_samples=S_c, n_importance=K, use_disp=int(bool(use_disp)), perturb=float(perturb),
+            noise_std=float(noise_std), white_back=int(bool(white_back)), test_time=int(bool(test_time)),
+            perturb_rand=_ptr(pr), noise_coarse=_ptr(nc), u_rand=_ptr(ur), noise_fine=_ptr(nf),
+            rgb_coarse=_ptr(res.get("rgb_coarse")), depth_coarse=_ptr(res.get("depth_coarse")),
+            opacity_coarse=_ptr(res.get("opacity_coarse")), rgb_fine=_ptr(res.get("rgb_fine")),
+            depth_fine=_ptr(res.get("depth_fine")), opacity_fine=_ptr(res.get("opacity_fine")))
+        _lib.check(lib.nerfb200_render_rays_host(ctypes.byref(args), _stream_ptr()), "nerfb200_render_rays_host")
+    return res
 
 
 def render_rays_loss(models: List[torch.nn.Module],

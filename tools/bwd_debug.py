@@ -166,13 +166,18 @@ def main():
         stat(f"[{tag}] dd", got, dd, None)
         Wp = w["dir_encoding.0.weight"][:, :256].astype(np.float64) @ w["xyz_encoding_final.weight"].astype(np.float64)
         dh = dd @ Wp + dsig[:, None] * w["sigma.weight"].astype(np.float64)
+        dh_m = dh.copy()          # second chain: float64 arithmetic on the DEVICE's ReLU masks (isolates mask flips)
+        masks = np.frombuffer(raw, np.uint32, npad * 8 * 8, P["mask"]).reshape(8, npad, 8)
         for l in range(7, -1, -1):
             dp = dh * (tape[f"h{l + 1}"] > 0)
+            dp_m = dh_m * (~decode_masks(masks[l], npad)[:nn])
             got = untile(raw[P["dpre"] + l * npad * 512:P["dpre"] + (l + 1) * npad * 512], npad, 256)[:nn]
             stat(f"[{tag}] dpre{l + 1}", got, dp, None)
+            stat(f"[{tag}] dpre{l + 1} same masks", got, dp_m, None)
             if l > 0:
                 W = w[f"xyz_encoding_{l + 1}.0.weight"].astype(np.float64)
                 dh = dp @ (W[:, 63:] if l == 4 else W)
+                dh_m = dp_m @ (W[:, 63:] if l == 4 else W)
     grads = {f"{tag}.{k}": p.grad.detach().cpu().numpy() for tag, m in zip(("coarse", "fine"), models)
              for k, p in m.named_parameters()}
     rows, (rel, cos) = og.grad_compare(grads, ref_grads)

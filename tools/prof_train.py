@@ -23,7 +23,7 @@ for s in (11, 12):
 emb = [nb.Embedding(3, 10), nb.Embedding(3, 4)]
 rays = torch.from_numpy(bench.blender_rays(n, 0)).to(dev)
 tgt = torch.rand(n, 3, device=dev)
-opt = torch.optim.Adam([p for m in models for p in m.parameters()], lr=5e-4, fused=True)
+opt = nb.FusedAdam([p for m in models for p in m.parameters()], lr=5e-4)
 
 
 def step():

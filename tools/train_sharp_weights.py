@@ -1,5 +1,5 @@
 """Train NeRF weights on a procedural scene with THIS repository's fused training step (forward + loss +
-hand-written sm_100a backward, torch Adam) and save them for parity tests (run on a B200 via gpurun).
+hand-written sm_100a backward and Adam update) and save them for parity tests (run on a B200 via gpurun).
 
     python tools/train_sharp_weights.py [steps] [out.npz]
 
@@ -53,7 +53,7 @@ def main():
     torch.manual_seed(1234)
     models = [nb.NeRF().to(dev), nb.NeRF().to(dev)]
     emb = [nb.Embedding(3, 10), nb.Embedding(3, 4)]
-    opt = torch.optim.Adam([p for m in models for p in m.parameters()], lr=5e-4, eps=1e-8, fused=True)
+    opt = nb.FusedAdam([p for m in models for p in m.parameters()], lr=5e-4, eps=1e-8)
     n_views = 64
     views = [torch.from_numpy(bench.blender_rays(16384, 7000 + v)).to(dev) for v in range(n_views)]
     targets = [ground_truth(v) for v in views]
