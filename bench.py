@@ -553,6 +553,12 @@ def run_b200(args):
                 out = nb.render_rays_loss(tm, emb, dev_rays[i % N_ROT], tgt[i % 4], N_SAMPLES, False, 1.0, 0.0, N_IMPORTANCE,
                                           1024 * 32, True, match_reference_rng=False)
                 out["loss"].backward()
+                if world > 1:      # data-parallel training as the reference does it (DDP, train.py:174-175):
+                    flat = torch._utils._flatten_dense_tensors([p.grad for p in params])    # one all-reduce of the
+                    dist.all_reduce(flat)                                                    # 4.77 MB of gradients
+                    flat.div_(world)
+                    for p, g in zip(params, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in params])):
+                        p.grad = g
                 opt.step()
                 return out["loss"]
             for i in range(max(args.warmup, 3)):
@@ -567,12 +573,17 @@ def run_b200(args):
             e1.record()
             barrier()
             t_ms = e0.elapsed_time(e1) / n_t
-            train = {"ms_per_step": t_ms, "value": BATCH * SAMPLES_PER_RAY / (t_ms * 1e-3), "unit": "ray-samples/s",
+            if world > 1:
+                tt = torch.tensor([t_ms], device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t_ms = float(tt)
+            train = {"ms_per_step": t_ms, "value": world * BATCH * SAMPLES_PER_RAY / (t_ms * 1e-3), "unit": "ray-samples/s",
                      "steps": n_t, "kernels_per_step": (lib.nerfb200_launch_count() - l0) / n_t,
                      "includes": "pack of both weight images, fused forward + MSE loss, compositing/head/chain/wgrad/"
                                  "reduce/unfold backward kernels, Adam update (nerfb200_adam_step): every kernel of the "
                                  "step is hand-written sm_100a code of this repository",
-                     "loss_first": float(first), "loss_last": float(last),
+                     "grad_allreduce": "NCCL all_reduce of the flattened gradients (4.77 MB) per step" if world > 1 else None,
+                     "loss_first": float(first.detach()), "loss_last": float(last.detach()),
                      "l2": "a step streams ~3.4 GB of activations (> L2): no flush needed"}
         except Exception as e:      # noqa: BLE001
             train = {"error": repr(e)}

@@ -158,7 +158,7 @@ int check_render_shapes(const nerfb200_render_args* a) {
 // numbers and the SM count, recomputed on every call (no state kept in the library).
 struct WgJobPlan { int ps, kind, split, n_split; };
 enum { kJ1 = 0, kJ2, kJ3, kJ4, kJ5a, kJ5b, kJ6, kJ7, kJ8, kJ9, kNumJobKinds };
-constexpr int kWgSlotFloats = 256 * 256 + 256 + 264;     // partial of one job: out, bias, wsig
+constexpr int kWgSlotFloats = 256 * 256 + 256;           // partial of one piece: out (transposed), bias
 constexpr int kMaxWgJobs = 1024;
 constexpr int kMaxWgCtas = 512;
 struct TrainLayout {
@@ -278,8 +278,6 @@ void fill_piece(TrainLayout* L, WgradJob* jobs, int piece, int ps, int k, long l
   j.chunk_step = step;
   j.out = slot;
   j.bias_out = (k == kJ5b) ? nullptr : slot + 256 * 256;
-  j.dsig = (k == kJ9) ? L->pass[ps].dsigma : nullptr;
-  j.wsig_out = (k == kJ9) ? slot + 256 * 256 + 256 : nullptr;
 }
 
 void plan_wgrad(TrainLayout* L, int n_cta, WgradJob* jobs, int* cta_first) {
@@ -917,6 +915,7 @@ int nerfb200_render_backward(const nerfb200_backward_args* b, void* stream_v) {
     it.part = part; it.split_stride = stride; it.n_split = n_split; it.out = out; it.mul = mul;
     it.rows = rows; it.cols = cols; it.part_ld = part_ld; it.out_ld = out_ld; it.out_col0 = out_col0;
     it.transposed = transposed;
+    it.by_warp = (n_split >= 64 && rows * cols <= 4096) ? 1 : 0;
   };
   for (int ps = 0; ps < L.n_pass; ++ps) {
     const float* linv = L.linv + ps * kLevels;       // level v: 0 = dd, v = 1..8 = dpre_{9-v}
@@ -937,8 +936,8 @@ int nerfb200_render_backward(const nerfb200_backward_args* b, void* stream_v) {
     add(slot(kJ5a) + 65536, kWgSlotFloats, ns(kJ5a), g[9], linv + 4, 1, 256, 256, 256, 0);
     add(slot(kJ9), kWgSlotFloats, ns(kJ9), L.gWp[ps], linv, 128, 256, 128, 256, 0, 1);
     add(slot(kJ9) + 65536, kWgSlotFloats, ns(kJ9), L.gbp[ps], linv, 1, 128, 128, 128, 0);
-    add(slot(kJ9) + 65536 + 256, kWgSlotFloats, ns(kJ9), g[20], nullptr, 1, 256, 256, 256, 0);
-    add(slot(kJ9) + 65536 + 256 + 256, kWgSlotFloats, ns(kJ9), g[21], nullptr, 1, 1, 1, 1, 0);
+    add(L.head_part[ps] + kHeadPartSigW, kHeadPartFloats, L.head_grid, g[20], nullptr, 1, 256, 256, 256, 0);
+    add(L.head_part[ps] + kHeadPartSigB, kHeadPartFloats, L.head_grid, g[21], nullptr, 1, 1, 1, 1, 0);
     add(L.head_part[ps] + kHeadPartRgbW, kHeadPartFloats, L.head_grid, g[22], nullptr, 1, 384, 384, 384, 0);
     add(L.head_part[ps] + kHeadPartRgbB, kHeadPartFloats, L.head_grid, g[23], nullptr, 1, 3, 3, 3, 0);
     add(L.dir_part[ps], 128 * 27, kDirSlices, g[18], nullptr, 128, 27, 27, 283, 256);

@@ -107,8 +107,10 @@ __device__ __forceinline__ void tl_val(Timeline* tl, int role, int tag, long lon
 
 struct RingState {
   uint32_t stage = 0, phase = 0;
+  uint32_t n = kStages;      // stages in use (the training-mode forward runs a 2-stage ring and stages its
+                             // activation stores through the third stage's 32 KiB)
   __device__ __forceinline__ void advance() {
-    if (++stage == kStages) { stage = 0; phase ^= 1; }
+    if (++stage == n) { stage = 0; phase ^= 1; }
   }
 };
 
@@ -296,6 +298,56 @@ __device__ __forceinline__ void mma_tile(RingState& rs, MmaPhases& ph, uint8_t* 
   else mma_tile_t<false, false>(rs, ph, smem, bars, tl, enc_off, enc_bar, enc_parity);
 }
 
+// ---- line-coalesced stores of an epilogue result (training mode / backward chain) -------------
+// The four warps that own the same 32 tile rows (column groups 0..3) assemble one [32 rows x 128 B]
+// block of the tiled layout (layout.h) in shared memory - each thread 16-byte chunks of its row,
+// already at their swizzled positions - and one of them hands the 4 KiB block to the TMA store
+// engine.  kBufs staging blocks per row group are used round-robin: a block is rewritten only after
+// the bulk store issued kBufs rounds earlier has finished reading it (cp.async.bulk.wait_group.read
+// kBufs - 1), so the copy engine's ~400-cycle read latency is off the warps' path for kBufs > 1.
+// Two named barriers per round: "the block is free" and "the block is complete".
+constexpr int kStageBar0 = 3;          // named barriers 3..6: row groups 0..3 (128 threads each)
+constexpr uint32_t kStageBufBytes = 4 * 4096;      // one buffer: 4 row groups x 4 KiB
+struct StageCtx {
+  uint8_t* base;        // this row group's block in buffer 0; buffer b is kStageBufBytes * b further
+  uint32_t buf;         // next buffer
+  int rg, lane, part;
+};
+template <int kBufs>
+__device__ __forceinline__ uint8_t* stage_begin(StageCtx& st) {
+  if (st.part == 0 && st.lane == 0) bulk_wait_read_n<kBufs - 1>();
+  named_bar_sync(kStageBar0 + st.rg, 128);
+  return st.base + st.buf * kStageBufBytes;
+}
+// gdst: the block's place in HBM (null = the rows are padding, nothing is stored)
+template <int kBufs>
+__device__ __forceinline__ void stage_end(StageCtx& st, uint8_t* block, uint8_t* gdst) {
+  fence_proxy_async();
+  named_bar_sync(kStageBar0 + st.rg, 128);
+#ifdef NERFB200_EXP_NOSTORE       // experiment: staging and barriers, but nothing handed to the copy engine
+  gdst = nullptr;
+#endif
+  if (st.part == 0 && st.lane == 0 && gdst != nullptr) {
+    bulk_s2g(gdst, smem_u32(block), 4096);
+    bulk_commit();
+  }
+  st.buf = (st.buf + 1 == kBufs) ? 0u : st.buf + 1;
+}
+// one round for two adjacent 16-byte chunks (chunk0, chunk0 + 1) per thread
+template <int kBufs>
+__device__ __forceinline__ void stage_store(StageCtx& st, uint4 c0, uint4 c1, uint32_t chunk0, uint8_t* gdst) {
+#ifdef NERFB200_EXP_NOSTAGE       // experiment: no staging at all (results are NOT stored)
+  return;
+#endif
+  uint8_t* block = stage_begin<kBufs>(st);
+  const uint32_t sw = static_cast<uint32_t>(st.lane & 7);      // == global row & 7 (row groups are 32-aligned)
+  uint8_t* row = block + st.lane * 128;
+  *reinterpret_cast<uint4*>(row + ((chunk0 ^ sw) << 4)) = c0;
+  *reinterpret_cast<uint4*>(row + (((chunk0 + 1u) ^ sw) << 4)) = c1;
+  stage_end<kBufs>(st, block, gdst);
+}
+constexpr int kFwdStageBufs = 2;       // training-mode forward: the third ring stage holds 2 x 16 KiB
+
 // --------------------------------------------------------------- epilogue
 struct EpiCtx {
   uint8_t* smem;
@@ -316,7 +368,7 @@ struct EpiCtx {
   long long save_n;                // padded rows per layer
   long long save_row;              // this thread's global sample row, -1 = padding row
   long long save_g0;               // global sample row of this thread's 32-row group (lane 0), -1 = padding group
-  uint8_t* stage;                  // this row group's 4 KiB staging block in shared memory (training mode)
+  StageCtx stage;                  // shared-memory staging of the stores (training mode)
   // Accumulator release.  false: d_free is signalled at tile start (the epilogue also wrote the
   // ENC tile).  true (render kernel: ENC comes from the helper warps): d_free is signalled as soon
   // as the LAST layer of a tile has been read out of tensor memory, so the next tile's first
@@ -356,38 +408,6 @@ __device__ __forceinline__ void epi_wait_d(EpiCtx& c) {
   mbar_wait(smem_u32(&c.bars->d_ready), c.d_phase, 5);
   c.d_phase ^= 1;
   tc_fence_after();
-}
-
-// ---- line-coalesced stores of an epilogue result (training mode / backward chain) -------------
-// The four warps that own the same 32 tile rows (column groups 0..3) assemble one [32 rows x 128 B]
-// block of the tiled layout (layout.h) in shared memory - each thread two 16-byte chunks of its
-// row, already at their swizzled positions - and one of them hands the 4 KiB block to the TMA store
-// engine.  Two named barriers per call: "the previous store has left the staging block" and "the
-// block is complete".  stage: this row group's 4 KiB staging block; gdst: the block's place in HBM
-// (null = rows are padding, nothing is stored).
-constexpr int kStageBar0 = 3;          // named barriers 3..6: row groups 0..3 (128 threads each)
-constexpr uint32_t kStageBytes = 4 * 4096;
-__device__ __forceinline__ void stage_store(uint8_t* stage, int rg, int lane, int part, uint4 c0, uint4 c1,
-                                            uint32_t chunk0, uint8_t* gdst) {
-#ifdef NERFB200_EXP_NOSTAGE       // experiment: no staging at all (results are NOT stored)
-  return;
-#endif
-#ifdef NERFB200_EXP_NOSTORE       // experiment: staging and barriers, but nothing handed to the copy engine
-  gdst = nullptr;
-#endif
-  const bool issuer = (part == 0) && (lane == 0);
-  if (issuer) bulk_wait_read();
-  named_bar_sync(kStageBar0 + rg, 128);
-  const uint32_t sw = static_cast<uint32_t>(lane & 7);         // == global row & 7 (row groups are 32-aligned)
-  uint8_t* row = stage + lane * 128;
-  *reinterpret_cast<uint4*>(row + ((chunk0 ^ sw) << 4)) = c0;
-  *reinterpret_cast<uint4*>(row + (((chunk0 + 1u) ^ sw) << 4)) = c1;
-  fence_proxy_async();
-  named_bar_sync(kStageBar0 + rg, 128);
-  if (issuer && gdst != nullptr) {
-    bulk_s2g(gdst, smem_u32(stage), 4096);
-    bulk_commit();
-  }
 }
 
 __device__ __forceinline__ void add_f32x2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
@@ -502,8 +522,8 @@ __device__ __forceinline__ void epi_hidden(EpiCtx& c, int l, const float* bias, 
         if (c.save_g0 >= 0)
           gdst = c.save_act + static_cast<long long>(l) * c.save_n * 512 +
                  tiled_block_off(static_cast<unsigned long long>(c.save_g0 >> 6), kb, 4) + (c.save_g0 & 63) * 128;
-        stage_store(c.stage, (c.row >> 5), c.lane, c.part, make_uint4(hs[kb][0], hs[kb][1], hs[kb][2], hs[kb][3]),
-                    make_uint4(hs[kb][4], hs[kb][5], hs[kb][6], hs[kb][7]), 2u * c.part, gdst);
+        stage_store<kFwdStageBufs>(c.stage, make_uint4(hs[kb][0], hs[kb][1], hs[kb][2], hs[kb][3]),
+                                   make_uint4(hs[kb][4], hs[kb][5], hs[kb][6], hs[kb][7]), 2u * c.part, gdst);
       }
     }
     if (kSave && c.save_mask != nullptr && c.save_row >= 0)
@@ -562,24 +582,16 @@ __device__ __forceinline__ void epi_dir(EpiCtx& c, const float* dbias, const flo
       if (c.save_g0 >= 0)
         gdst = c.save_d + tiled_block_off(static_cast<unsigned long long>(c.save_g0 >> 6), fb, 2) +
                (c.save_g0 & 63) * 128;
-      const bool mine = (c.part >> 1) == fb;
-      const bool issuer = (c.part == 0) && (c.lane == 0);
-      if (issuer) bulk_wait_read();
-      named_bar_sync(kStageBar0 + (c.row >> 5), 128);
-      if (mine) {
+      uint8_t* block = stage_begin<kFwdStageBufs>(c.stage);
+      if ((c.part >> 1) == fb) {
         const uint32_t sw = static_cast<uint32_t>(c.lane & 7);
-        uint8_t* row = c.stage + c.lane * 128;
+        uint8_t* row = block + c.lane * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           *reinterpret_cast<uint4*>(row + ((((c.part & 1) * 4u + q) ^ sw) << 4)) =
               make_uint4(dsave[4 * q], dsave[4 * q + 1], dsave[4 * q + 2], dsave[4 * q + 3]);
       }
-      fence_proxy_async();
-      named_bar_sync(kStageBar0 + (c.row >> 5), 128);
-      if (issuer && gdst != nullptr) {
-        bulk_s2g(gdst, smem_u32(c.stage), 4096);
-        bulk_commit();
-      }
+      stage_end<kFwdStageBufs>(c.stage, block, gdst);
     }
   }
 }

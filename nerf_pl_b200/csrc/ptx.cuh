@@ -93,6 +93,11 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, uint32_t smem_src, uint32_t
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk stores this thread has committed have finished READING shared memory (the source may be reused)
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the N most recently committed ones
+template <int N>
+__device__ __forceinline__ void bulk_wait_read_n() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");

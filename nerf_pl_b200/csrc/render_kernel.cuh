@@ -329,8 +329,7 @@ struct alignas(16) GroupState {
   float znew[2][kMaxImp];                   // u (sorted) then the new depths
 };
 
-struct alignas(128) RenderScratch {
-  alignas(128) uint8_t stage[4][4096];      // training mode: per row group, one [32 rows x 128 B] block on its way to HBM
+struct alignas(16) RenderScratch {
   Barriers bars;
   uint64_t enc_full[2];
   uint64_t out_full[2];
@@ -412,11 +411,13 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
   if (warp >= kEpiWarps && warp < kHelperWarp0) {
     if (warp == kProducerWarp && lane == 0) {
       RingState rs;
+      if (kSave) rs.n = 2;
       while (seq.next(tl))
         produce_tile(rs, smem, bars, tl.pass ? p.net_fine : p.net_coarse, tl.pass == 0 && coarse_sigma_only, false);
     } else if (warp == kMmaWarp && lane == 0) {
       {
       RingState rs;
+      if (kSave) rs.n = 2;
       MmaPhases ph;
       Timeline tlm{(blockIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
       while (seq.next(tl)) {
@@ -438,6 +439,9 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
     c.d_phase = 0;
     c.save_act = nullptr; c.save_mask = nullptr; c.save_d = nullptr; c.save_n = 0; c.save_row = -1;
     c.early = true;     // the accumulator is handed back as soon as a tile's last layer is read
+    // training mode: the weight ring runs with 2 stages, the third stage's 32 KiB stages the activation stores
+    c.stage.base = smem + kSmemRing + 2 * kSliceBytes256 + (warp & 3) * 4096;
+    c.stage.buf = 0; c.stage.rg = warp & 3; c.stage.lane = lane; c.stage.part = warp >> 2;
     Timeline tle{(blockIdx.x == 0 && threadIdx.x == 0) ? p.timeline : nullptr, {0, 0, 0}};
     c.tl = &tle;
     while (seq.next(tl)) {
@@ -454,7 +458,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
       c.save_mask = kSave ? p.tr[pass].mask : nullptr;
       c.save_d = kSave ? p.tr[pass].d : nullptr;
       c.save_n = kSave ? p.tr[pass].n_pad : 0;
-      c.stage = sc->stage[c.row >> 5];
+
       const GroupState& gs = sc->gs[tl.g % kGroupSlots];
       const int gr = tl.tile * 128 + c.row;
       const int r = (gr >= S) ? 1 : 0;       // rows past the group's 2 S samples (S < 64 k) are padding
@@ -469,7 +473,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_rays_kernel(const Re
         uint8_t* dst = p.tr[pass].enc + tiled_block_off(static_cast<unsigned long long>(c.save_g0 >> 6), 0, 1) +
                        (c.save_g0 & 63) * 128;
         bulk_s2g(dst, smem_u32(smem + (b ? kSmemEnc1 : kSmemEnc) + (c.row >> 5) * 4096), 4096);
-        bulk_commit();
+        bulk_commit();       // (the staging rounds' wait_group.read also covers this read; ENC is rewritten two tiles later)
       }
       float sig_part, rgb_part[3];
       epi_run_tile<kSave>(c, sigma_only, gs.dirbias[pass][r], nullptr, sig_part, rgb_part);

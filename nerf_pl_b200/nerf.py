@@ -63,6 +63,7 @@ class PackedWeights:
     def __init__(self) -> None:
         self.blob = None
         self.key = None
+        self.ptrs = None
 
     def get(self, model: nn.Module) -> torch.Tensor:
         params = nerf_parameters(model)
@@ -71,31 +72,37 @@ class PackedWeights:
             if p.requires_grad:
                 trainable = True
                 break
+        ptrs = tuple([p.data_ptr() for p in params])          # also changes with the device
         key = None
         if not trainable:
-            key = tuple([(p.data_ptr(), p._version) for p in params])   # data_ptr also changes with the device
+            key = (ptrs, tuple([p._version for p in params]))
             if self.blob is not None and key == self.key:
                 return self.blob
-        for p, shp in zip(params, _EXPECTED_SHAPES):
-            if tuple(p.shape) != shp:
-                raise ValueError(
-                    f"nerf_pl_b200 supports the reference's default NeRF(D=8, W=256, 63, 27, skips=[4]); "
-                    f"got a parameter of shape {tuple(p.shape)}, expected {shp}")
-            if not p.is_cuda or p.dtype != torch.float32:
-                raise ValueError("NeRF parameters must be float32 CUDA tensors")
         lib = _lib.load()
-        dev = params[0].device
-        if self.blob is None or self.blob.device != dev:
-            # the library wants 1024-byte alignment; torch's caching allocator guarantees 512
-            raw = torch.empty(lib.nerfb200_packed_bytes() + 1024, dtype=torch.uint8, device=dev)
-            off = (-raw.data_ptr()) % 1024
-            self.raw = raw
-            self.blob = raw[off:off + lib.nerfb200_packed_bytes()]
-        keep = [p.detach().contiguous() for p in params]
-        arr = (ctypes.c_void_p * 24)(*[ctypes.c_void_p(t.data_ptr()) for t in keep])
-        with torch.cuda.device(dev):
-            _lib.check(lib.nerfb200_pack_weights(arr, ctypes.c_void_p(self.blob.data_ptr()), _stream_ptr()),
-                       "nerfb200_pack_weights")
+        if ptrs != self.ptrs:            # first use / storage changed: validate, (re)allocate, rebuild the pointer table
+            for p, shp in zip(params, _EXPECTED_SHAPES):
+                if tuple(p.shape) != shp:
+                    raise ValueError(
+                        f"nerf_pl_b200 supports the reference's default NeRF(D=8, W=256, 63, 27, skips=[4]); "
+                        f"got a parameter of shape {tuple(p.shape)}, expected {shp}")
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise ValueError("NeRF parameters must be contiguous float32 CUDA tensors")
+            dev = params[0].device
+            if self.blob is None or self.blob.device != dev:
+                # the library wants 1024-byte alignment; torch's caching allocator guarantees 512
+                raw = torch.empty(lib.nerfb200_packed_bytes() + 1024, dtype=torch.uint8, device=dev)
+                off = (-raw.data_ptr()) % 1024
+                self.raw = raw
+                self.blob = raw[off:off + lib.nerfb200_packed_bytes()]
+            self.arr = (ctypes.c_void_p * 24)(*[ctypes.c_void_p(a) for a in ptrs])
+            self.blob_ptr = ctypes.c_void_p(self.blob.data_ptr())
+            self.ptrs = ptrs
+            self.dev = dev
+        if torch.cuda.current_device() == self.dev.index:
+            _lib.check(lib.nerfb200_pack_weights(self.arr, self.blob_ptr, _stream_ptr()), "nerfb200_pack_weights")
+        else:
+            with torch.cuda.device(self.dev):
+                _lib.check(lib.nerfb200_pack_weights(self.arr, self.blob_ptr, _stream_ptr()), "nerfb200_pack_weights")
         self.key = key
         return self.blob
 

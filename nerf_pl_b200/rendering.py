@@ -31,8 +31,13 @@ def _require_fp32(name: str, *tensors) -> None:
             raise ValueError(f"nerf_pl_b200.{name} computes in float32; got a float64 tensor (convert it explicitly)")
 
 
+_EMB_OK = set()
+
+
 def _check_embeddings(embeddings: Sequence) -> None:
     ex, ed = embeddings[0], embeddings[1]
+    if (id(ex), id(ed)) in _EMB_OK:          # validated before (reading freq_bands costs a host sync-free but slow .item())
+        return
     ok = (getattr(ex, "N_freqs", None) == 10 and getattr(ed, "N_freqs", None) == 4
           and getattr(ex, "in_channels", 3) == 3 and getattr(ed, "in_channels", 3) == 3)
     fb = getattr(ex, "freq_bands", None)
@@ -41,6 +46,8 @@ def _check_embeddings(embeddings: Sequence) -> None:
     if not ok:
         raise ValueError("nerf_pl_b200.render_rays supports the reference's embeddings "
                          "Embedding(3, 10) / Embedding(3, 4) with logscale=True")
+    if len(_EMB_OK) < 64:
+        _EMB_OK.add((id(ex), id(ed)))
 
 
 def searchsorted(a: torch.Tensor, v: torch.Tensor, out: Optional[torch.Tensor] = None,

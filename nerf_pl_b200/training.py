@@ -136,13 +136,17 @@ class FusedRenderFunction(torch.autograd.Function):
                 # seed restricted to one pass is not provided); take the gradient of the total loss
                 loss_grad = g4          # the kernel reads element 2 (address passed below)
                 use_target = target
-        grads = [torch.empty_like(p, memory_format=torch.contiguous_format) for p in params]
-        pc = (ctypes.c_void_p * 24)(*[ctypes.c_void_p(p.data_ptr()) for p in params[:24]])
-        gc = (ctypes.c_void_p * 24)(*[ctypes.c_void_p(t.data_ptr()) for t in grads[:24]])
+        # one allocation for all gradients (the kernels write every element), views per parameter
+        sizes, shapes = _param_sizes(params)
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        grads = [t.view(shp) for t, shp in zip(flat.split(sizes), shapes)]
+        base, offs = flat.data_ptr(), _offsets(sizes)
+        pc = (ctypes.c_void_p * 24)(*[p.data_ptr() for p in params[:24]])
+        gc = (ctypes.c_void_p * 24)(*[base + 4 * o for o in offs[:24]])
         pf = gf = None
         if K > 0:
-            pf = (ctypes.c_void_p * 24)(*[ctypes.c_void_p(p.data_ptr()) for p in params[24:48]])
-            gf = (ctypes.c_void_p * 24)(*[ctypes.c_void_p(t.data_ptr()) for t in grads[24:48]])
+            pf = (ctypes.c_void_p * 24)(*[p.data_ptr() for p in params[24:48]])
+            gf = (ctypes.c_void_p * 24)(*[base + 4 * o for o in offs[24:48]])
         rargs = _render_args(cfg, rays, pr, nc, ur, nf, out, blob_c, blob_f, ws, None, None)
         bargs = _lib.BackwardArgs(
             render=ctypes.pointer(rargs), params_coarse=pc, params_fine=pf,
@@ -159,14 +163,31 @@ class FusedRenderFunction(torch.autograd.Function):
         return (None, None, None, None, None, None, None, *grads)
 
 
+_SIZE_CACHE: Dict[int, tuple] = {}
+
+
+def _param_sizes(params):
+    key = len(params)
+    hit = _SIZE_CACHE.get(key)
+    if hit is None:
+        hit = ([p.numel() for p in params], [tuple(p.shape) for p in params])
+        _SIZE_CACHE[key] = hit
+    return hit
+
+
+def _offsets(sizes):
+    out, o = [], 0
+    for n in sizes:
+        out.append(o)
+        o += n
+    return out
+
+
 def _params_of(models, N_importance) -> List[torch.Tensor]:
     params = nerf_parameters(models[0])
     if N_importance > 0:
         params = params + nerf_parameters(models[1])
-    for p in params:
-        if not p.is_contiguous():
-            raise ValueError("NeRF parameters must be contiguous")
-    return params
+    return params          # shapes / contiguity are validated by packed_weights()
 
 
 def render_rays_train(models, rays, N_samples, use_disp, perturb, noise_std, N_importance, white_back,
