@@ -98,6 +98,46 @@ if os.path.exists(rp):
     cnt = {k: sass.count(k) for k in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTCBAR", "SYNCS.PHASECHK", "FADD2", "F2FP.RELU", "HMMA.")}
     out.append("\nSASS mnemonics in libnerf_pl_b200.so (cuobjdump): " + ", ".join(f"{k} x{v}" for k, v in cnt.items()) + "\n")
 
+# training-step capture: one --set full pass over the step's big kernels (tools/prof_train.py)
+tp = os.path.join(ROOT, "gpurun_out", f"prof_{tag}_train.ncu-rep")
+if os.path.exists(tp):
+    raw = subprocess.run(["ncu", "-i", tp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    cols = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM written"),
+            ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM % of peak"),
+            ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe % (elapsed)"),
+            ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
+            ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid")]
+    out.append(f"## Training step, 1024 rays ({os.path.basename(tp)}; ncu --set full --clock-control none, one step: "
+               f"fused forward in training mode + loss, then the backward kernels)\n")
+    out.append("| kernel | " + " | ".join(c[1] for c in cols) + " |\n|---|" + "---|" * len(cols))
+    kn = hdr.index("Kernel Name")
+    for r in rows[2:]:
+        cells = []
+        for key, _ in cols:
+            i = hdr.index(key)
+            cells.append(f"{r[i]} {units[i]}".strip())
+        out.append(f"| `{r[kn].split('(')[0]}` | " + " | ".join(cells) + " |")
+    out.append("")
+lt = os.path.join(ROOT, "gpurun_out", f"launches_{tag}_train.csv")
+if os.path.exists(lt):
+    rows = [r for r in csv.reader(open(lt)) if len(r) > 5 and r[0].strip('"').isdigit()]
+    per = defaultdict(lambda: [0, 0.0])
+    n_steps = max(1, sum(1 for r in rows if "adam_kernel" in r[4]))
+    for r in rows:
+        name = r[4].split("(")[0].strip()
+        if "at::" in name:
+            name = "torch fill / rand (zero_grad buffers, random draws)"
+        per[name][0] += 1
+        per[name][1] += float(r[-1])
+    total = sum(v[1] for v in per.values())
+    out.append(f"## Launch list of the training step ({os.path.basename(lt)}, {n_steps} steps incl. warm-up; gpu__time_duration, serialised)\n")
+    out.append("| kernel | launches / step | us / step | share |\n|---|---|---|---|")
+    for k, v in sorted(per.items(), key=lambda kv: -kv[1][1]):
+        out.append(f"| `{k}` | {v[0] / n_steps:.1f} | {v[1] / n_steps / 1e3:.1f} | {100 * v[1] / total:.1f}% |")
+    out.append(f"\nsum {total / n_steps / 1e3:.0f} us per step.\n")
+
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 dst = os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md")
 open(dst, "w").write(f"# ncu summary {tag}\n\n" + "\n".join(out) + "\n")

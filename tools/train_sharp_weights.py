@@ -10,8 +10,11 @@ the UNMODIFIED reference on the saved weights and the GPU tests hold the kernels
 
 The scene is analytic (no dataset on the box): three soft spheres with a position-dependent
 high-frequency colour pattern, white background; ground-truth pixel colours come from a 512-sample
-quadrature of the analytic field along each ray.  The recipe is the reference's Blender one
-(README.md:75-83: 64+64 samples, perturb 1, noise_std 0, batch 1024, Adam lr 5e-4; train.py:103-117).
+quadrature of the analytic field along each ray.  The recipe is the reference's (README.md:75-83,
+104-111: 64+64 samples, perturb 1, batch 1024, Adam lr 5e-4; train.py:103-117) with the LLFF setting
+noise_std 1: with noise_std 0 a default-initialised coarse network whose raw sigma starts negative
+everywhere never receives a gradient (relu'(sigma) = 0, models/rendering.py:155 - the known dead-density
+start of NeRF; a first run of this tool showed exactly that: mse_coarse stuck at 0.158 = white image).
 Deterministic seeds below.
 """
 import os
@@ -63,23 +66,27 @@ def main():
     for it in range(steps):
         v = it % n_views
         idx = torch.randint(0, views[v].shape[0], (1024,), device=dev, generator=gen)
-        out = nb.render_rays_loss(models, emb, views[v][idx], targets[v][idx], 64, False, 1.0, 0.0, 64, 32768, True,
+        out = nb.render_rays_loss(models, emb, views[v][idx], targets[v][idx], 64, False, 1.0, 1.0, 64, 32768, True,
                                   match_reference_rng=False)
         opt.zero_grad(set_to_none=True)
         out["loss"].backward()
         opt.step()
         if it % 50 == 0 or it == steps - 1:
-            curve.append((it, float(out["loss"].detach()), float(out["psnr"])))
+            curve.append((it, float(out["loss"].detach()), float(out["psnr"]), float(out["mse_coarse"])))
             if it % 500 == 0 or it == steps - 1:
-                print(f"step {it:5d} loss {curve[-1][1]:.5f} psnr_fine {curve[-1][2]:.2f} dB ({time.time() - t0:.1f} s)", flush=True)
+                print(f"step {it:5d} loss {curve[-1][1]:.5f} psnr_fine {curve[-1][2]:.2f} dB mse_coarse {curve[-1][3]:.5f} "
+                      f"({time.time() - t0:.1f} s)", flush=True)
     torch.cuda.synchronize()
     print(f"{steps} steps in {time.time() - t0:.1f} s")
     # held-out view through the inference path
     with torch.no_grad():
         hv = torch.from_numpy(bench.blender_rays(16384, 9999)).to(dev)
         res = nb.render_rays(models, emb, hv, 64, False, 0, 0, 64, 32768, True, test_time=True)
-        mse = float(((res["rgb_fine"] - ground_truth(hv)) ** 2).mean())
-    print(f"held-out view psnr {-10 * np.log10(mse):.2f} dB")
+        gt = ground_truth(hv)
+        mse = float(((res["rgb_fine"] - gt) ** 2).mean())
+        res_c = nb.render_rays(models, emb, hv, 64, False, 0, 0, 64, 32768, True, test_time=False)
+        mse_c = float(((res_c["rgb_coarse"] - gt) ** 2).mean())
+    print(f"held-out view psnr fine {-10 * np.log10(mse):.2f} dB, coarse {-10 * np.log10(mse_c):.2f} dB")
     store = {"loss_curve": np.array(curve, np.float32), "steps": steps, "heldout_psnr": np.float32(-10 * np.log10(mse))}
     for tag, m in zip(("coarse", "fine"), models):
         for k, p in m.state_dict().items():
