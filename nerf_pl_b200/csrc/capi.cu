@@ -54,7 +54,9 @@ struct EnvSwitches {
   int wg_plan = 1;        // wgrad plan: 0 = contiguous equal-byte shares, 1 = whole CTAs per GEMM, chunks interleaved
   int wg_copy = 32768;    // bytes per bulk copy of a wgrad operand chunk
   unsigned wg_exp = 0;    // wgrad timing experiments: bit 0 = no MMAs, bit 1 = no CUDA-core reductions
+  int no_zero_copy = 0;   // host entry: always stage through device memory (A/B of the mapped-memory fast path)
   EnvSwitches() {
+    if (const char* v = std::getenv("NERFB200_NO_ZERO_COPY")) no_zero_copy = std::atoi(v);
     if (const char* v = std::getenv("NERFB200_WG_EXP")) wg_exp = static_cast<unsigned>(std::atoi(v));
     if (const char* v = std::getenv("NERFB200_WG_PLAN")) wg_plan = std::atoi(v);
     if (const char* v = std::getenv("NERFB200_WG_COPY")) wg_copy = std::atoi(v);
@@ -393,6 +395,7 @@ struct Arena {
   }
 };
 Arena g_arena[64];
+std::mutex g_host_call_mu;
 std::mutex g_arena_mu;   // separate from g_mu: the host entry calls nerfb200_render_rays (device_info locks g_mu)
 
 }  // namespace
@@ -523,6 +526,76 @@ int nerfb200_render_rays_host(const nerfb200_render_args* h, void* stream_v) {
   if (rc) return rc;
   if (h->n_rays == 0) return 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (h->train_workspace || h->target || h->z_coarse)
+    return fail(NERFB200_EINVAL, "render_rays_host: train_workspace / target / z_coarse are device-only%s");
+  {
+    // Fast path: every host buffer is page-locked and mapped into the device's address space (cudaHostAlloc /
+    // cudaHostRegister; torch's pin_memory()).  The kernel then reads the rays and writes the <= 40 B of results
+    // per ray straight over PCIe - no staging copies, no copy-engine round trips (each small cudaMemcpyAsync
+    // costs ~8 us of latency on the stream; the bytes that cross the bus are the same) - and the call is
+    // "launch + synchronise".  Random inputs may be device tensors (drawn there by the caller) or mapped too.
+    bool all_mapped = true;
+    auto mapped = [&](const void* p, const void** dp) -> bool {
+      *dp = nullptr;
+      if (!p) return true;
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+      if ((attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) &&
+          attr.devicePointer != nullptr) {
+        *dp = attr.devicePointer;
+        return true;
+      }
+      return false;
+    };
+    nerfb200_render_args a = *h;
+    const void* dp = nullptr;
+#define NERFB200_MAP(field, type)                                          \
+    all_mapped = all_mapped && mapped(h->field, &dp);                      \
+    a.field = static_cast<type>(const_cast<void*>(dp));
+    NERFB200_MAP(rays, const float*)
+    NERFB200_MAP(perturb_rand, const float*)
+    NERFB200_MAP(noise_coarse, const float*)
+    NERFB200_MAP(u_rand, const float*)
+    NERFB200_MAP(noise_fine, const float*)
+    NERFB200_MAP(rgb_coarse, float*)
+    NERFB200_MAP(depth_coarse, float*)
+    NERFB200_MAP(opacity_coarse, float*)
+    NERFB200_MAP(rgb_fine, float*)
+    NERFB200_MAP(depth_fine, float*)
+    NERFB200_MAP(opacity_fine, float*)
+    NERFB200_MAP(z_fine, float*)
+    NERFB200_MAP(weights_coarse, float*)
+    NERFB200_MAP(weights_fine, float*)
+#undef NERFB200_MAP
+    if (all_mapped && !env_switches().no_zero_copy) {
+      int dev0 = 0;
+      CUDA_TRY(cudaGetDevice(&dev0), "cudaGetDevice");
+      static int* host_status[64] = {nullptr};
+      {
+        std::lock_guard<std::mutex> lk(g_arena_mu);
+        if (!host_status[dev0])
+          CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&host_status[dev0]), 256, cudaHostAllocMapped | cudaHostAllocPortable),
+                   "status cudaHostAlloc");
+      }
+      // one in-flight host call per device at a time shares the status word: serialise
+      std::lock_guard<std::mutex> lk(g_host_call_mu);
+      volatile int* hs = host_status[dev0];
+      *hs = 0;
+      int* dstatus = nullptr;
+      CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dstatus), host_status[dev0], 0), "status device pointer");
+      a.status = dstatus;
+      rc = nerfb200_render_rays(&a, stream);
+      if (rc) return rc;
+      CUDA_TRY(cudaStreamSynchronize(stream), "render_rays_host sync");
+      const int hstatus = *hs;
+      if (hstatus != 0) {
+        std::snprintf(g_err, sizeof(g_err), "render kernel reported device status %d", hstatus);
+        return NERFB200_EDEVICE;
+      }
+      if (h->status) *h->status = 0;
+      return 0;
+    }
+  }
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
   const size_t n = static_cast<size_t>(h->n_rays);
@@ -537,8 +610,6 @@ int nerfb200_render_rays_host(const nerfb200_render_args* h, void* stream_v) {
   ar.off = 0;
   nerfb200_render_args a = *h;
   a.ray_stride = 8;
-  if (h->train_workspace || h->target || h->z_coarse)
-    return fail(NERFB200_EINVAL, "render_rays_host: train_workspace / target / z_coarse are device-only%s");
   auto up = [&](const float* src, size_t count, size_t src_stride, size_t width) -> const float* {
     if (!src) return nullptr;
     if (src_stride == width) {

@@ -289,9 +289,10 @@ def render_rays_host(models: List[torch.nn.Module],
                      match_reference_rng: bool = False) -> Dict[str, torch.Tensor]:
     """render_rays for rays that live in HOST memory (the reference's eval loop moves every chunk with
     ``.cuda()`` and the results back with ``.cpu()``, eval.py:117-123): ONE call into the C ABI
-    (``nerfb200_render_rays_host``) copies the rays to the models' device, renders, copies the result
-    tensors back and synchronises.  ``rays``: (N, 8) float32 CPU tensor (pinned memory makes the copies
-    asynchronous); returns CPU tensors (``out`` may supply pre-allocated, e.g. pinned, ones).
+    (``nerfb200_render_rays_host``) renders them and returns with the results readable on the host.
+    ``rays``: (N, 8) float32 CPU tensor.  With pinned rays (and pinned ``out`` tensors, allocated here when
+    not supplied) the kernel reads the rays and writes the results over PCIe itself (mapped memory: no staging
+    copies); pageable buffers are staged through device memory with cudaMemcpyAsync.  Returns CPU tensors.
     Inference only; the random inputs are drawn on the device."""
     del chunk
     if rays.is_cuda or rays.dim() != 2 or rays.shape[1] != 8 or rays.dtype != torch.float32:
@@ -303,7 +304,9 @@ def render_rays_host(models: List[torch.nn.Module],
     if dev.type != "cuda":
         raise RuntimeError("the models must live on a CUDA device (no CPU fallback)")
     n, S_c, K = rays.shape[0], int(N_samples), int(N_importance)
-    rays = rays.contiguous()
+    if rays.stride(1) != 1 or rays.stride(0) < 8:
+        rays = rays.contiguous()          # a row stride (column slice of a wider tensor) is passed through
+    pinned = rays.is_pinned()       # results then come back in pinned memory too: the C entry's zero-copy path
     with torch.cuda.device(dev):
         pr, nc, ur, nf = _draw_randoms(n, S_c, K, float(perturb), float(noise_std), dev, match_reference_rng)
         keys = ["opacity_coarse"] if test_time else ["rgb_coarse", "depth_coarse", "opacity_coarse"]
@@ -312,7 +315,7 @@ def render_rays_host(models: List[torch.nn.Module],
         res = {}
         for k in keys:
             shape = (n, 3) if k.startswith("rgb") else (n,)
-            t = out[k] if out is not None and k in out else torch.empty(shape, dtype=torch.float32)
+            t = out[k] if out is not None and k in out else torch.empty(shape, dtype=torch.float32, pin_memory=pinned)
             if t.is_cuda or t.shape != shape or t.dtype != torch.float32 or not t.is_contiguous():
                 raise ValueError(f"out[{k!r}] must be a contiguous float32 CPU tensor of shape {shape}")
             res[k] = t

@@ -57,3 +57,23 @@ def load_grad_case(name):
     randoms = {k: z[k] for k in RANDOM_KEYS if k in z.files}
     ref = {k[4:]: z[k] for k in z.files if k.startswith("out_")}
     return z["rays"], z["target"], randoms, float(z["loss"]), ref, og.unpack_golden_grads(z)
+
+
+# Trained weights (tests/golden/trained_weights.npz: 8000 steps of this repository's own training step on a B200,
+# tools/train_sharp_weights.py) through the unmodified reference (make_golden.py TRAINED_CASES / TRAINED_GRAD).
+# name: (n_rays, ray seed, N_importance, perturb, noise_std, test_time)
+TRAINED_CASES = {
+    "trained_test": (192, 51, 64, 0.0, 0.0, True),
+    "trained_train": (128, 52, 64, 1.0, 0.0, False),
+    "trained_noise": (96, 53, 128, 1.0, 1.0, False),
+}
+TRAINED_GRAD = ("grad_trained", 64, 54, 64, 1.0, 0.0)
+
+
+def have_trained():
+    return os.path.exists(os.path.join(GOLDEN, "trained_weights.npz"))
+
+
+def trained_weights():
+    z = np.load(os.path.join(GOLDEN, "trained_weights.npz"))
+    return [{k[len(t) + 1:]: z[k] for k in z.files if k.startswith(t + ".")} for t in ("coarse", "fine")]

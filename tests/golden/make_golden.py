@@ -79,6 +79,85 @@ GRAD_CASES = {
 }
 
 
+# Trained weights (tests/golden/trained_weights.npz, written on a B200 by tools/train_sharp_weights.py with THIS
+# repository's training step; larger norms and high-frequency content than the random-init W_SEEDS) through the
+# unmodified reference: two renders and one training-step gradient.
+# name: (n_rays, ray seed, N_importance, perturb, noise_std, test_time)
+TRAINED_CASES = {
+    "trained_test": (192, 51, 64, 0.0, 0.0, True),
+    "trained_train": (128, 52, 64, 1.0, 0.0, False),
+    "trained_noise": (96, 53, 128, 1.0, 1.0, False),
+}
+TRAINED_GRAD = ("grad_trained", 64, 54, 64, 1.0, 0.0)     # name, n_rays, ray seed, N_importance, perturb, noise_std
+
+
+def load_trained_weights():
+    z = np.load(os.path.join(HERE, "trained_weights.npz"))
+    return [{k[len(t) + 1:]: z[k] for k in z.files if k.startswith(t + ".")} for t in ("coarse", "fine")]
+
+
+def trained_rays(n, seed):
+    """Blender-style rays (origin on a radius-4 sphere, looking at the scene the weights were trained on)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    return bench.blender_rays(n, seed)
+
+
+def make_trained_cases(NeRF, Embedding, render_rays, only):
+    if not os.path.exists(os.path.join(HERE, "trained_weights.npz")):
+        print("no trained_weights.npz: trained cases skipped")
+        return
+    ws = load_trained_weights()
+    emb = [Embedding(3, 10), Embedding(3, 4)]
+    S = 64
+    for name, (n, rseed, K, perturb, noise, tt) in TRAINED_CASES.items():
+        if only and name not in only:
+            continue
+        models = [ref_model(NeRF, w) for w in ws]
+        rays = trained_rays(n, rseed)
+        store = {"rays": rays}
+        torch.manual_seed(3000 + rseed)
+        if perturb > 0 or noise > 0:
+            g = torch.get_rng_state()
+            store["perturb_rand"] = torch.rand(n, S).numpy()
+            store["noise_coarse"] = torch.randn(n, S).numpy()
+            store["u_rand"] = torch.rand(n, K).numpy()
+            store["noise_fine"] = torch.randn(n, S + K).numpy()
+            torch.set_rng_state(g)
+        with torch.no_grad():
+            out = render_rays(models, emb, torch.from_numpy(rays), S, False, perturb, noise, K, 1024 * 32, True,
+                              test_time=tt)
+        for k, v in out.items():
+            store["out_" + k] = v.numpy()
+        np.savez_compressed(os.path.join(HERE, f"render_{name}.npz"), **store)
+        print(name, {k: (tuple(v.shape), float(v.mean())) for k, v in out.items()})
+    name, n, rseed, K, perturb, noise = TRAINED_GRAD
+    if only and name not in only:
+        return
+    models = [ref_model(NeRF, w).train() for w in ws]
+    rays = trained_rays(n, rseed)
+    target = np.random.RandomState(500 + rseed).uniform(0, 1, (n, 3)).astype(np.float32)
+    store = {"rays": rays, "target": target}
+    torch.manual_seed(2000 + rseed)
+    g = torch.get_rng_state()
+    store["perturb_rand"] = torch.rand(n, S).numpy()
+    store["noise_coarse"] = torch.randn(n, S).numpy()
+    store["u_rand"] = torch.rand(n, K).numpy()
+    store["noise_fine"] = torch.randn(n, S + K).numpy()
+    torch.set_rng_state(g)
+    out = render_rays(models, emb, torch.from_numpy(rays), S, False, perturb, noise, K, 1024 * 32, True, test_time=False)
+    tgt = torch.from_numpy(target)
+    loss = torch.nn.functional.mse_loss(out["rgb_coarse"], tgt) + torch.nn.functional.mse_loss(out["rgb_fine"], tgt)
+    loss.backward()
+    store["loss"] = np.float32(loss.item())
+    for k, v in out.items():
+        store["out_" + k] = v.detach().numpy()
+    grads = {f"{tag}.{key}": prm.grad.numpy() for tag, m in zip(("coarse", "fine"), models) for key, prm in m.named_parameters()}
+    store.update(pack_grads(grads))
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **store)
+    print(name, "loss", float(loss.item()))
+
+
 def pack_grads(grads):
     """48 fp32 gradient tensors -> per-tensor max-abs scale (fp32) + values / scale as fp16
     (relative precision 5e-4, far below the 5e-2 test tolerance; keeps the fixture ~2.4 MB)."""
@@ -135,6 +214,7 @@ def main():
     emb = [Embedding(3, 10), Embedding(3, 4)]
     only = sys.argv[1:]
     make_grad_cases(NeRF, Embedding, render_rays, only)
+    make_trained_cases(NeRF, Embedding, render_rays, only)
     for name, (n, kind, rseed, S, K, disp, perturb, noise, wb, tt) in CASES.items():
         if only and name not in only:
             continue

@@ -100,3 +100,29 @@ def test_training_step_gradients_match_reference(name, ws):
     assert rel < 2e-3 and cos > 0.99999, (rel, cos)
     for k, (r, c) in rows.items():
         assert r < 1e-2 and c > 0.9999, (k, r, c)
+
+
+@pytest.mark.skipif(not cases.have_trained(), reason="tests/golden/trained_weights.npz not generated")
+@pytest.mark.parametrize("name", list(cases.TRAINED_CASES))
+def test_trained_weights_render_matches_reference(name):
+    """The oracle on TRAINED weights (large norms, high-frequency content) against the unmodified reference."""
+    n, rseed, K, perturb, noise, tt = cases.TRAINED_CASES[name]
+    rays, randoms, ref = cases.load_case(name)
+    out = orc.render_rays(cases.trained_weights(), rays, 64, False, perturb, noise, K, True, tt, randoms or None)
+    assert set(out) == set(ref)
+    for k in ref:
+        mx, p999, mean = cases.error_stats(out[k], ref[k])
+        # depth under sigma noise: the ReLU kink at sigma + noise = 0 (DESIGN.md section 5 (iii))
+        assert mx < (5e-3 if (noise > 0 and k.startswith("depth")) else 5e-4), f"{name}/{k}: max {mx:.3e} mean {mean:.3e}"
+
+
+@pytest.mark.skipif(not cases.have_trained(), reason="tests/golden/trained_weights.npz not generated")
+def test_trained_weights_gradients_match_reference():
+    from oracle import nerf_oracle_grad as og
+    name, n, rseed, K, perturb, noise = cases.TRAINED_GRAD
+    rays, target, randoms, ref_loss, ref_out, ref_grads = cases.load_grad_case(name)
+    loss, out, grads = og.render_rays_loss_grad(cases.trained_weights(), rays, target, 64, False, perturb, noise, K, True,
+                                                randoms)
+    assert abs(loss - ref_loss) < 1e-4 * max(1.0, abs(ref_loss))
+    rows, (rel, cos) = og.grad_compare(grads, ref_grads)
+    assert rel < 5e-3 and cos > 0.9999, (rel, cos)
