@@ -39,6 +39,9 @@ const char* nerfb200_last_error(void);
  * the transposed 16-bit slices of the backward chain kernel. */
 size_t nerfb200_packed_bytes(void);
 int nerfb200_pack_weights(const float* const params[24], void* packed, void* stream);
+/* Both networks of a render (coarse, fine) in ONE launch: what a training step does after every optimiser update. */
+int nerfb200_pack_weights_pair(const float* const params_a[24], void* packed_a, const float* const params_b[24],
+                               void* packed_b, void* stream);
 
 /* ---- render_rays -----------------------------------------------------------------------
  * Replaces: models/rendering.py:58-244 render_rays(models, embeddings, rays, N_samples,
@@ -157,11 +160,14 @@ int nerfb200_adam_step(int32_t n_tensors, float* const* params, const float* con
                        float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
                        float weight_decay, int64_t step, void* stream);
 
-/* Same call with HOST buffers (pageable or pinned): copies rays (and the random inputs that
- * are non-NULL and not already device memory - they may be drawn on the device by the caller) to
- * the device, renders, copies the requested outputs back, synchronises.
- * The packed weight images stay device-resident.  This is the end-to-end entry the
- * reference's eval.py loop (eval.py:117-123 `.cuda()` ... `.cpu()`) maps to. */
+/* Same call with HOST buffers; returns with the requested outputs readable on the host (synchronises `stream`).
+ * The packed weight images stay device-resident.  This is the end-to-end entry the reference's eval.py loop
+ * (eval.py:117-123 `.cuda()` ... `.cpu()`) maps to.
+ *   - every buffer page-locked and mapped (cudaHostAlloc / cudaHostRegister, torch pin_memory()): the kernel reads
+ *     the rays and writes the results over PCIe itself; the call is launch + synchronise, no staging copies;
+ *   - otherwise (pageable memory): rays and the random inputs that are non-NULL and not already device memory are
+ *     staged with cudaMemcpyAsync, results are copied back the same way.
+ * Random inputs may be device pointers in both cases (drawn on the device by the caller). */
 int nerfb200_render_rays_host(const nerfb200_render_args* host_args, void* stream);
 
 /* ---- NeRF.forward ------------------------------------------------------------------------

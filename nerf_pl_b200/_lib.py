@@ -34,6 +34,7 @@ EXPORTS = [
     "nerfb200_last_error",
     "nerfb200_packed_bytes",
     "nerfb200_pack_weights",
+    "nerfb200_pack_weights_pair",
     "nerfb200_render_rays",
     "nerfb200_render_rays_host",
     "nerfb200_nerf_forward",
@@ -162,6 +163,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.nerfb200_last_error.restype = c_char_p
     lib.nerfb200_packed_bytes.restype = c_size_t
     lib.nerfb200_pack_weights.argtypes = [POINTER(c_void_p), c_void_p, c_void_p]
+    lib.nerfb200_pack_weights_pair.argtypes = [POINTER(c_void_p), c_void_p, POINTER(c_void_p), c_void_p, c_void_p]
     lib.nerfb200_render_rays.argtypes = [POINTER(RenderArgs), c_void_p]
     lib.nerfb200_render_rays_host.argtypes = [POINTER(RenderArgs), c_void_p]
     lib.nerfb200_nerf_forward.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p]
@@ -205,7 +207,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.nerfb200_check_status.restype = c_int32
     lib.nerfb200_launch_count.restype = c_int64
     lib.nerfb200_sm_count.restype = c_int32
-    for name in ("nerfb200_pack_weights", "nerfb200_render_rays", "nerfb200_render_rays_host",
+    for name in ("nerfb200_pack_weights", "nerfb200_pack_weights_pair", "nerfb200_render_rays", "nerfb200_render_rays_host",
                  "nerfb200_nerf_forward", "nerfb200_embed", "nerfb200_searchsorted",
                  "nerfb200_sample_pdf", "nerfb200_composite"):
         getattr(lib, name).restype = c_int32

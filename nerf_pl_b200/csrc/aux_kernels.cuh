@@ -16,8 +16,13 @@ struct PackParams {
   int bwd_bf16;                 // element type of the backward region: 1 = bf16, 0 = fp16
 };
 
+struct PackParams2 {
+  PackParams net[2];            // blockIdx.y selects the network: a training step packs both images in one launch
+};
+
 // One thread per fp16 element of the slice region, then the fp32 tail.
-__global__ void pack_weights_kernel(const PackParams pp) {
+__global__ void pack_weights_kernel(const __grid_constant__ PackParams2 pp2) {
+  const PackParams& pp = pp2.net[blockIdx.y];
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long n_half = kHalfRegionBytes / 2;
   if (idx < n_half) {

@@ -414,23 +414,44 @@ int nerfb200_sm_count(void) {
   return n;
 }
 
-int nerfb200_pack_weights(const float* const params[24], void* packed, void* stream) {
+static int fill_pack_params(PackParams* pp, const float* const params[24], void* packed) {
   if (!params || !packed) return fail(NERFB200_EINVAL, "pack_weights: NULL argument%s");
   if (reinterpret_cast<uintptr_t>(packed) & 15) return fail(NERFB200_EINVAL, "packed must be 16-byte aligned%s");
-  PackParams pp;
   for (int i = 0; i < kNumParams; ++i) {
     if (!params[i]) return fail(NERFB200_EINVAL, "pack_weights: NULL parameter tensor%s");
-    pp.p[i] = params[i];
+    pp->p[i] = params[i];
   }
-  pp.out = static_cast<uint8_t*>(packed);
-  pp.bwd_bf16 = kBwdBf16 ? 1 : 0;
+  pp->out = static_cast<uint8_t*>(packed);
+  pp->bwd_bf16 = kBwdBf16 ? 1 : 0;
+  return 0;
+}
+
+static int launch_pack(const PackParams2& pp2, int n_nets, void* stream) {
   const long long total = kHalfRegionBytes / 2 + kF32Count + static_cast<long long>(kNumSlicesBwd) * 256 * 64;
   const int threads = 256;
   const int blocks = static_cast<int>((total + threads - 1) / threads);
-  pack_weights_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(pp);
+  pack_weights_kernel<<<dim3(blocks, n_nets), threads, 0, static_cast<cudaStream_t>(stream)>>>(pp2);
   g_launches++;
   CUDA_TRY(cudaGetLastError(), "pack_weights launch");
   return 0;
+}
+
+int nerfb200_pack_weights(const float* const params[24], void* packed, void* stream) {
+  PackParams2 pp2;
+  int rc = fill_pack_params(&pp2.net[0], params, packed);
+  if (rc) return rc;
+  pp2.net[1] = pp2.net[0];
+  return launch_pack(pp2, 1, stream);
+}
+
+int nerfb200_pack_weights_pair(const float* const params_a[24], void* packed_a, const float* const params_b[24],
+                               void* packed_b, void* stream) {
+  PackParams2 pp2;
+  int rc = fill_pack_params(&pp2.net[0], params_a, packed_a);
+  if (rc) return rc;
+  rc = fill_pack_params(&pp2.net[1], params_b, packed_b);
+  if (rc) return rc;
+  return launch_pack(pp2, 2, stream);
 }
 
 int nerfb200_render_rays(const nerfb200_render_args* a, void* stream) {
@@ -933,7 +954,7 @@ int nerfb200_render_backward(const nerfb200_backward_args* b, void* stream_v) {
     hp.raysum[0] = L.raysum[0]; hp.raysum[1] = L.raysum[1];
     hp.direnc = L.direnc;
     hp.part[0] = L.head_part[0]; hp.part[1] = L.head_part[1];
-    head_bwd_kernel<<<L.head_grid, kHeadWarps * 32, 0, stream>>>(hp);
+    head_bwd_kernel<<<L.head_grid, kHeadWarps * 64, 0, stream>>>(hp);
     g_launches++;
     DirGradParams dp;
     dp.n_rays = L.n_rays;

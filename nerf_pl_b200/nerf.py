@@ -65,7 +65,8 @@ class PackedWeights:
         self.key = None
         self.ptrs = None
 
-    def get(self, model: nn.Module) -> torch.Tensor:
+    def prepare(self, model: nn.Module) -> bool:
+        """Everything except the pack launch; True if the image has to be (re)packed."""
         params = nerf_parameters(model)
         trainable = False
         for p in params:
@@ -77,7 +78,7 @@ class PackedWeights:
         if not trainable:
             key = (ptrs, tuple([p._version for p in params]))
             if self.blob is not None and key == self.key:
-                return self.blob
+                return False
         lib = _lib.load()
         if ptrs != self.ptrs:            # first use / storage changed: validate, (re)allocate, rebuild the pointer table
             for p, shp in zip(params, _EXPECTED_SHAPES):
@@ -98,12 +99,17 @@ class PackedWeights:
             self.blob_ptr = ctypes.c_void_p(self.blob.data_ptr())
             self.ptrs = ptrs
             self.dev = dev
-        if torch.cuda.current_device() == self.dev.index:
-            _lib.check(lib.nerfb200_pack_weights(self.arr, self.blob_ptr, _stream_ptr()), "nerfb200_pack_weights")
-        else:
-            with torch.cuda.device(self.dev):
-                _lib.check(lib.nerfb200_pack_weights(self.arr, self.blob_ptr, _stream_ptr()), "nerfb200_pack_weights")
         self.key = key
+        return True
+
+    def get(self, model: nn.Module) -> torch.Tensor:
+        if self.prepare(model):
+            lib = _lib.load()
+            if torch.cuda.current_device() == self.dev.index:
+                _lib.check(lib.nerfb200_pack_weights(self.arr, self.blob_ptr, _stream_ptr()), "nerfb200_pack_weights")
+            else:
+                with torch.cuda.device(self.dev):
+                    _lib.check(lib.nerfb200_pack_weights(self.arr, self.blob_ptr, _stream_ptr()), "nerfb200_pack_weights")
         return self.blob
 
 
@@ -122,6 +128,36 @@ def packed_weights(model: nn.Module) -> torch.Tensor:
         cache = PackedWeights()
         model.__dict__["_nerfb200_packed"] = cache
     return cache.get(model)
+
+
+def _cache_of(model: nn.Module) -> PackedWeights:
+    cache = model.__dict__.get("_nerfb200_packed")
+    if cache is None:
+        cache = PackedWeights()
+        model.__dict__["_nerfb200_packed"] = cache
+    return cache
+
+
+def packed_weights_pair(coarse: nn.Module, fine: nn.Module):
+    """Packed images of both networks of a render; when both need (re)packing - every training step - ONE launch
+    (``nerfb200_pack_weights_pair``) does it."""
+    ca, cb = _cache_of(coarse), _cache_of(fine)
+    if ca is cb:
+        blob = ca.get(coarse)
+        return blob, blob
+    na, nb_ = ca.prepare(coarse), cb.prepare(fine)
+    if na or nb_:
+        lib = _lib.load()
+        with torch.cuda.device(ca.dev):
+            if na and nb_ and ca.dev == cb.dev:
+                _lib.check(lib.nerfb200_pack_weights_pair(ca.arr, ca.blob_ptr, cb.arr, cb.blob_ptr, _stream_ptr()),
+                           "nerfb200_pack_weights_pair")
+            else:
+                for need, c in ((na, ca), (nb_, cb)):
+                    if need:
+                        with torch.cuda.device(c.dev):
+                            _lib.check(lib.nerfb200_pack_weights(c.arr, c.blob_ptr, _stream_ptr()), "nerfb200_pack_weights")
+    return ca.blob, cb.blob
 
 
 class Embedding(nn.Module):

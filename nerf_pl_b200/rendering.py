@@ -142,6 +142,10 @@ def _draw_randoms(n: int, S_c: int, K: int, perturb: float, noise_std: float, de
     same numbers.  With ``match_rng`` the unused randn draws (noise_std == 0) are still made, as
     the reference does."""
     pr = nc = ur = nf = None
+    if perturb > 0 and K > 0 and not match_rng and noise_std <= 0:
+        # no promise about the draw order: both uniform tensors from ONE generator launch
+        flat = torch.rand(n * (S_c + K), device=device)
+        return flat[:n * S_c].view(n, S_c), None, flat[n * S_c:].view(n, K), None
     if perturb > 0:
         pr = torch.rand(n, S_c, device=device)
     if noise_std > 0 or match_rng:

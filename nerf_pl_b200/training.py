@@ -22,7 +22,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import _lib
-from .nerf import _stream_ptr, nerf_parameters, packed_weights
+from .nerf import _stream_ptr, nerf_parameters, packed_weights, packed_weights_pair
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -98,8 +98,10 @@ class FusedRenderFunction(torch.autograd.Function):
             out += [torch.empty(n, 3, **f32), torch.empty(n, **f32), torch.empty(n, **f32)]
         loss_out = torch.empty(4, **f32) if target is not None else None
         lib = _lib.load()
-        blob_c = packed_weights(models[0])
-        blob_f = packed_weights(models[1]) if K > 0 else None
+        if K > 0:
+            blob_c, blob_f = packed_weights_pair(models[0], models[1])      # one launch for both images
+        else:
+            blob_c, blob_f = packed_weights(models[0]), None
         ws = TrainWorkspace.acquire(dev, n, S_c, K)
         args = _render_args(cfg, rays, pr, nc, ur, nf, out, blob_c, blob_f, ws, target, loss_out)
         with torch.cuda.device(dev):
