@@ -11,7 +11,8 @@ rays per GPU per step, perturb=1, noise_std=0, white_back, coarse rgb computed (
 
 One JSON line on stdout (rank 0):
   value      device-timed whole-job ray-samples/s of the render_rays forward, batch resident in HBM.
-             A "step" = one render_rays pass over one batch (incl. drawing its random numbers); for
+             A "step" = one render_rays pass over one batch (its stratified-sampling random numbers are
+             Philox draws inside the kernel: randoms="kernel"); for
              N>1 every step ends with ONE NCCL all-gather of the rendered batch (north_star).  The K
              timed steps are captured in one CUDA graph (no host in the timed region) and bracketed
              by two events; every step reads a different copy of the packed weights and a different
@@ -411,8 +412,8 @@ def run_b200(args):
 
     def step(i, rays=None, randoms=None):
         out = nb.render_rays(model_sets[i % N_ROT], emb, dev_rays[i % N_ROT] if rays is None else rays, N_SAMPLES, False,
-                             1.0, 0.0, N_IMPORTANCE, 1024 * 32, True, test_time=False, randoms=randoms,
-                             match_reference_rng=False)
+                             1.0, 0.0, N_IMPORTANCE, 1024 * 32, True, test_time=False,
+                             randoms="kernel" if randoms is None else randoms)
         if world > 1:      # north_star: the rendered batch is exchanged with ONE all-gather at the end
             packed = out["rgb_coarse"].new_empty(BATCH, 10)
             torch.cat((out["rgb_coarse"], out["depth_coarse"][:, None], out["opacity_coarse"][:, None],
@@ -476,13 +477,11 @@ def run_b200(args):
         if graphed:
             launches = K                               # replayed nodes do not pass through the library's counter
 
-        # ---- kernel-only (roofline): pre-drawn randoms, the render kernel is the only node of a step
-        rnd = {"perturb_rand": torch.rand(BATCH, N_SAMPLES, device=dev),
-               "u_rand": torch.rand(BATCH, N_IMPORTANCE, device=dev)}
-
+        # ---- kernel-only (roofline): the render kernel is the only node of a step (as in `value`: the uniform
+        # numbers are Philox draws inside the kernel)
         def kstep(i):
             nb.render_rays(model_sets[i % N_ROT], emb, dev_rays[i % N_ROT], N_SAMPLES, False, 1.0, 0.0, N_IMPORTANCE,
-                           1024 * 32, True, test_time=False, randoms=rnd)
+                           1024 * 32, True, test_time=False, randoms={"seed": 1000 + i})
         krun, _ = timed_graph(kstep, K)
         krun()
         kern_total, _ = time_region(krun)
@@ -508,7 +507,7 @@ def run_b200(args):
 
         def e2e_step(i):
             out = nb.render_rays_host(model_sets[i % N_ROT], emb, host_rays[i % N_ROT], N_SAMPLES, False, 1.0, 0.0,
-                                      N_IMPORTANCE, 1024 * 32, True, test_time=False, out=host_res)
+                                      N_IMPORTANCE, 1024 * 32, True, test_time=False, out=host_res, randoms="kernel")
             if world > 1:
                 dist.all_gather_into_tensor(gather_buf, packed_dev)
                 torch.cuda.current_stream().synchronize()
@@ -551,7 +550,7 @@ def run_b200(args):
             def tstep(i):
                 opt.zero_grad(set_to_none=True)
                 out = nb.render_rays_loss(tm, emb, dev_rays[i % N_ROT], tgt[i % 4], N_SAMPLES, False, 1.0, 0.0, N_IMPORTANCE,
-                                          1024 * 32, True, match_reference_rng=False)
+                                          1024 * 32, True, randoms="kernel")
                 out["loss"].backward()
                 if world > 1:      # data-parallel training as the reference does it (DDP, train.py:174-175):
                     flat = torch._utils._flatten_dense_tensors([p.grad for p in params])    # one all-reduce of the

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define NERFB200_ABI_VERSION 2
+#define NERFB200_ABI_VERSION 3
 
 #define NERFB200_EINVAL (-1)      /* bad argument value / null pointer            */
 #define NERFB200_EUNSUPPORTED (-2) /* shape outside what the fused kernel supports */
@@ -111,6 +111,15 @@ typedef struct nerfb200_render_args {
    * deterministic). */
   const float* target;
   float* loss_out;
+  /* Uniform random inputs drawn INSIDE the kernel (rng_in_kernel != 0): perturb_rand / u_rand may then be NULL and
+   * are ignored; element (ray r, index i) of stream s (0 = perturb_rand, 1 = u_rand) is word i & 3 of
+   * Philox4x32-10(counter = {r, i >> 2, s, 0}, key = {rng_seed lo, hi}) mapped to [0,1) as (x >> 8) * 2^-24 -
+   * counter-based, so the numbers do not depend on the launch shape and a host replica reproduces them
+   * (tests/philox.py).  The reference draws these with torch.rand from the global generator
+   * (models/rendering.py:203, :39); the tensor inputs remain the way to replay a seeded torch stream.  The Gaussian
+   * noise inputs (noise_std > 0) are always tensors. */
+  uint64_t rng_seed;
+  int32_t rng_in_kernel;
 } nerfb200_render_args;
 
 int nerfb200_render_rays(const nerfb200_render_args* args, void* stream);

@@ -99,6 +99,8 @@ class RenderArgs(ctypes.Structure):
         ("train_workspace", c_void_p),
         ("target", c_void_p),
         ("loss_out", c_void_p),
+        ("rng_seed", ctypes.c_uint64),
+        ("rng_in_kernel", c_int32),
     ]
 
 
@@ -224,7 +226,7 @@ def load() -> ctypes.CDLL:
                     "(nerf_pl_b200 has no CPU fallback)")
             lib = ctypes.CDLL(LIB_PATH)
             _declare(lib)
-            if lib.nerfb200_abi_version() != 2:
+            if lib.nerfb200_abi_version() != 3:
                 raise RuntimeError("libnerf_pl_b200.so ABI version mismatch")
             _lib = lib
     return _lib

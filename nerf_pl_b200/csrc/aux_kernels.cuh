@@ -417,47 +417,6 @@ __global__ void to_uint8_kernel(const float* __restrict__ src, long long n, uint
   }
 }
 
-// ------------------------------------------------ backward glue: ReLU mask + transpose
-// dpre[s][c] = dh[s][c] * (act[s][c] > 0), written row-major (S, C) for the dgrad GEMM and
-// transposed (C, S) for the wgrad GEMM in one pass (fp16).  64 x 64 tiles through shared memory.
-__global__ void __launch_bounds__(256) relu_bwd_transpose_kernel(const __half* __restrict__ dh,
-                                                                 const __half* __restrict__ act, long long S, int C,
-                                                                 __half* __restrict__ dpre, __half* __restrict__ dpre_t) {
-  __shared__ __half tile[64][66];
-  const long long s0 = static_cast<long long>(blockIdx.x) * 64;
-  const int c0 = blockIdx.y * 64;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
-  for (int r = ty; r < 64; r += 8) {
-    const long long srow = s0 + r;
-    if (srow < S) {
-      const long long off = srow * C + c0 + 2 * tx;
-      const __half2 g = *reinterpret_cast<const __half2*>(dh + off);
-      const __half2 a = *reinterpret_cast<const __half2*>(act + off);
-      __half2 v;
-      v.x = (__half2float(a.x) > 0.f) ? g.x : __float2half(0.f);
-      v.y = (__half2float(a.y) > 0.f) ? g.y : __float2half(0.f);
-      *reinterpret_cast<__half2*>(dpre + off) = v;
-      tile[r][2 * tx] = v.x;
-      tile[r][2 * tx + 1] = v.y;
-    } else {
-      tile[r][2 * tx] = __float2half(0.f);
-      tile[r][2 * tx + 1] = __float2half(0.f);
-    }
-  }
-  __syncthreads();
-  for (int c = ty; c < 64; c += 8) {
-    const long long scol = s0 + 2 * tx;
-    if (scol + 1 < S) {
-      __half2 v;
-      v.x = tile[2 * tx][c];
-      v.y = tile[2 * tx + 1][c];
-      *reinterpret_cast<__half2*>(dpre_t + static_cast<long long>(c0 + c) * S + scol) = v;
-    } else if (scol < S) {
-      dpre_t[static_cast<long long>(c0 + c) * S + scol] = tile[2 * tx][c];
-    }
-  }
-}
-
 // ------------------------------------------------ loss / metric epilogue (losses.py:9-14, metrics.py:4-13)
 // out[0] = mean((rgb_coarse - t)^2), out[1] = mean((rgb_fine - t)^2) (0 if rgb_fine is null),
 // out[2] = out[0] + out[1] (MSELoss.forward), out[3] = -10 log10(mse of the finest available)  (psnr).

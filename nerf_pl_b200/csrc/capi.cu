@@ -140,7 +140,7 @@ int check_render_shapes(const nerfb200_render_args* a) {
     if (!a->rgb_fine || !a->depth_fine || !a->opacity_fine)
       return fail(NERFB200_EINVAL, "fine outputs are NULL with N_importance>0%s");
   }
-  if (a->perturb > 0.f) {
+  if (a->perturb > 0.f && !a->rng_in_kernel) {
     if (!a->perturb_rand) return fail(NERFB200_EINVAL, "perturb>0 needs perturb_rand%s");
     if (a->n_importance > 0 && !a->u_rand) return fail(NERFB200_EINVAL, "perturb>0 needs u_rand%s");
   }
@@ -491,6 +491,8 @@ int nerfb200_render_rays(const nerfb200_render_args* a, void* stream) {
   p.weights_fine = a->weights_fine;
   p.status = a->status ? a->status : d->status;
   p.z_coarse = a->z_coarse;
+  p.rng_seed = a->rng_seed;
+  p.rng_in_kernel = a->rng_in_kernel;
   p.train = 0;
   p.target = nullptr; p.loss_part = nullptr; p.loss_out = nullptr; p.loss_counter = nullptr;
   std::memset(p.tr, 0, sizeof(p.tr));

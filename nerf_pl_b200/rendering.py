@@ -160,6 +160,44 @@ def _draw_randoms(n: int, S_c: int, K: int, perturb: float, noise_std: float, de
     return pr, nc, ur, nf
 
 
+_KERNEL_RNG_CALLS = 0
+
+
+def _resolve_randoms(randoms, n, S_c, K, perturb, noise_std, dev, match_rng):
+    """-> (perturb_rand, noise_coarse, u_rand, noise_fine, kernel_seed | None).
+
+    ``randoms`` is None (draw with torch as the reference does), a dict of pre-drawn tensors, the string
+    ``"kernel"`` or ``{"seed": int}``: the two uniform inputs are then generated inside the render kernel
+    (Philox4x32-10 keyed by the seed, include/nerf_pl_b200.h ``rng_in_kernel``) - no generator launch, no (N, S)
+    tensors.  ``"kernel"`` derives the seed from ``torch.initial_seed()`` and a per-process call counter
+    (deterministic under ``torch.manual_seed``; a CUDA graph replays the captured seed).  The Gaussian noise
+    inputs (``noise_std > 0``) are tensors in every mode."""
+    global _KERNEL_RNG_CALLS
+    seed = None
+    if isinstance(randoms, str):
+        if randoms != "kernel":
+            raise ValueError("randoms must be None, a dict of tensors, {'seed': int} or 'kernel'")
+        _KERNEL_RNG_CALLS += 1
+        seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _KERNEL_RNG_CALLS * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+        randoms = {}
+    elif randoms is not None and "seed" in randoms:
+        seed = int(randoms["seed"]) & 0xFFFFFFFFFFFFFFFF
+    if randoms is None:
+        pr, nc, ur, nf = _draw_randoms(n, S_c, K, perturb, noise_std, dev, match_rng)
+    else:
+        pr, nc = randoms.get("perturb_rand"), randoms.get("noise_coarse")
+        ur, nf = randoms.get("u_rand"), randoms.get("noise_fine")
+        if seed is not None:
+            pr = ur = None
+            if noise_std > 0:
+                if nc is None:
+                    nc = torch.randn(n, S_c, device=dev)
+                if nf is None and K > 0:
+                    nf = torch.randn(n, S_c + K, device=dev)
+    pr, nc, ur, nf = [t.to(torch.float32).contiguous() if t is not None else None for t in (pr, nc, ur, nf)]
+    return pr, nc, ur, nf, seed
+
+
 def render_rays(models: List[torch.nn.Module],
                 embeddings: List[torch.nn.Module],
                 rays: torch.Tensor,
@@ -186,7 +224,8 @@ def render_rays(models: List[torch.nn.Module],
 
     ``chunk`` is accepted and ignored (nothing is materialised per point, so there is nothing to
     chunk).  Keyword-only extensions: ``randoms`` supplies pre-drawn ``perturb_rand``,
-    ``noise_coarse``, ``u_rand``, ``noise_fine`` tensors; ``extras=True`` adds ``z_vals_fine``,
+    ``noise_coarse``, ``u_rand``, ``noise_fine`` tensors, or ``"kernel"`` / ``{"seed": s}`` to draw the uniform
+    numbers inside the kernel (``_resolve_randoms``); ``extras=True`` adds ``z_vals_fine``,
     ``weights_coarse``, ``weights_fine`` to the result.  When a gradient graph is needed the
     result comes from ``nerf_pl_b200.training.FusedRenderFunction`` (fused forward with activation
     capture + hand-written backward); ``autograd_impl="torch"`` selects the plain torch-op
@@ -213,19 +252,16 @@ def render_rays(models: List[torch.nn.Module],
     perturb = float(perturb)
     noise_std = float(noise_std)
 
-    if randoms is None:
-        pr, nc, ur, nf = _draw_randoms(n, S_c, K, perturb, noise_std, dev, match_reference_rng)
-    else:
-        pr, nc = randoms.get("perturb_rand"), randoms.get("noise_coarse")
-        ur, nf = randoms.get("u_rand"), randoms.get("noise_fine")
-    keep = [t.to(torch.float32).contiguous() if t is not None else None for t in (pr, nc, ur, nf)]
-    pr, nc, ur, nf = keep
+    pr, nc, ur, nf, seed = _resolve_randoms(randoms, n, S_c, K, perturb, noise_std, dev, match_reference_rng)
+    if seed is not None and needs_graph and (autograd_impl == "torch" or test_time):
+        raise ValueError("in-kernel random numbers are not available on the torch-autograd path")
 
     if needs_graph and extras:
         raise ValueError("extras=True is an inference-only option (no gradient graph is built for the extra tensors)")
     if needs_graph and autograd_impl == "fused" and not test_time and n > 0:
         from .training import render_rays_train
-        return render_rays_train(models, rays_c, S_c, use_disp, perturb, noise_std, K, white_back, pr, nc, ur, nf)
+        return render_rays_train(models, rays_c, S_c, use_disp, perturb, noise_std, K, white_back, pr, nc, ur, nf,
+                                 rng_seed=seed)
 
     f32 = dict(dtype=torch.float32, device=dev)
     coarse_rgb = not test_time
@@ -256,7 +292,7 @@ def render_rays(models: List[torch.nn.Module],
         opacity_coarse=_ptr(out["opacity_coarse"]), rgb_fine=_ptr(out["rgb_fine"]),
         depth_fine=_ptr(out["depth_fine"]), opacity_fine=_ptr(out["opacity_fine"]),
         z_fine=_ptr(z_fine), weights_coarse=_ptr(w_c), weights_fine=_ptr(w_f),
-        status=None, max_ctas=0)
+        status=None, max_ctas=0, rng_seed=seed or 0, rng_in_kernel=int(seed is not None))
     if torch.cuda.current_device() == dev.index:
         _lib.check(lib.nerfb200_render_rays(ctypes.byref(args), _stream_ptr()), "nerfb200_render_rays")
     else:
@@ -290,6 +326,7 @@ def render_rays_host(models: List[torch.nn.Module],
                      test_time: bool = False,
                      *,
                      out: Optional[Dict[str, torch.Tensor]] = None,
+                     randoms=None,
                      match_reference_rng: bool = False) -> Dict[str, torch.Tensor]:
     """render_rays for rays that live in HOST memory (the reference's eval loop moves every chunk with
     ``.cuda()`` and the results back with ``.cpu()``, eval.py:117-123): ONE call into the C ABI
@@ -312,7 +349,8 @@ def render_rays_host(models: List[torch.nn.Module],
         rays = rays.contiguous()          # a row stride (column slice of a wider tensor) is passed through
     pinned = rays.is_pinned()       # results then come back in pinned memory too: the C entry's zero-copy path
     with torch.cuda.device(dev):
-        pr, nc, ur, nf = _draw_randoms(n, S_c, K, float(perturb), float(noise_std), dev, match_reference_rng)
+        pr, nc, ur, nf, seed = _resolve_randoms(randoms, n, S_c, K, float(perturb), float(noise_std), dev,
+                                                match_reference_rng)
         keys = ["opacity_coarse"] if test_time else ["rgb_coarse", "depth_coarse", "opacity_coarse"]
         if K > 0:
             keys += ["rgb_fine", "depth_fine", "opacity_fine"]
@@ -334,7 +372,8 @@ def render_rays_host(models: List[torch.nn.Module],
             perturb_rand=_ptr(pr), noise_coarse=_ptr(nc), u_rand=_ptr(ur), noise_fine=_ptr(nf),
             rgb_coarse=_ptr(res.get("rgb_coarse")), depth_coarse=_ptr(res.get("depth_coarse")),
             opacity_coarse=_ptr(res.get("opacity_coarse")), rgb_fine=_ptr(res.get("rgb_fine")),
-            depth_fine=_ptr(res.get("depth_fine")), opacity_fine=_ptr(res.get("opacity_fine")))
+            depth_fine=_ptr(res.get("depth_fine")), opacity_fine=_ptr(res.get("opacity_fine")),
+            rng_seed=seed or 0, rng_in_kernel=int(seed is not None))
         _lib.check(lib.nerfb200_render_rays_host(ctypes.byref(args), _stream_ptr()), "nerfb200_render_rays_host")
     return res
 
@@ -371,15 +410,11 @@ def render_rays_loss(models: List[torch.nn.Module],
     if n == 0:
         raise ValueError("empty ray batch")
     rays_c = rays.detach().to(torch.float32).contiguous()
-    if randoms is None:
-        pr, nc, ur, nf = _draw_randoms(n, S_c, K, float(perturb), float(noise_std), rays.device, match_reference_rng)
-    else:
-        pr, nc = randoms.get("perturb_rand"), randoms.get("noise_coarse")
-        ur, nf = randoms.get("u_rand"), randoms.get("noise_fine")
-    pr, nc, ur, nf = [t.to(torch.float32).contiguous() if t is not None else None for t in (pr, nc, ur, nf)]
+    pr, nc, ur, nf, seed = _resolve_randoms(randoms, n, S_c, K, float(perturb), float(noise_std), rays.device,
+                                            match_reference_rng)
     from .training import render_rays_train
     return render_rays_train(models, rays_c, S_c, use_disp, float(perturb), float(noise_std), K, white_back,
-                             pr, nc, ur, nf, target=rgbs)
+                             pr, nc, ur, nf, target=rgbs, rng_seed=seed)
 
 
 # ---------------------------------------------------------------------------------------------

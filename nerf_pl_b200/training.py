@@ -80,7 +80,8 @@ def _render_args(cfg, rays, pr, nc, ur, nf, out, blob_c, blob_f, ws, target, los
         rgb_fine=_ptr(out[3]) if K > 0 else None, depth_fine=_ptr(out[4]) if K > 0 else None,
         opacity_fine=_ptr(out[5]) if K > 0 else None,
         z_fine=None, weights_coarse=None, weights_fine=None, status=None, max_ctas=0, z_coarse=None,
-        train_workspace=ws.buf.data_ptr(), target=_ptr(target), loss_out=_ptr(loss_out))
+        train_workspace=ws.buf.data_ptr(), target=_ptr(target), loss_out=_ptr(loss_out),
+        rng_seed=cfg.get("rng_seed") or 0, rng_in_kernel=int(cfg.get("rng_seed") is not None))
 
 
 class FusedRenderFunction(torch.autograd.Function):
@@ -193,14 +194,15 @@ def _params_of(models, N_importance) -> List[torch.Tensor]:
 
 
 def render_rays_train(models, rays, N_samples, use_disp, perturb, noise_std, N_importance, white_back,
-                      pr, nc, ur, nf, target: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                      pr, nc, ur, nf, target: Optional[torch.Tensor] = None,
+                      rng_seed: Optional[int] = None) -> Dict[str, torch.Tensor]:
     """Differentiable render_rays (test_time=False) through FusedRenderFunction.  With ``target``
     (n,3) the result also carries ``loss`` (losses.py:9-14 MSELoss of the batch), ``psnr``
     (metrics.py:4-13, of the finest pass), ``mse_coarse`` and ``mse_fine`` computed by the same
     launch; ``loss.backward()`` then seeds the backward inside the kernels."""
     cfg = dict(models=list(models), N_samples=int(N_samples), N_importance=int(N_importance),
                use_disp=bool(use_disp), perturb=float(perturb), noise_std=float(noise_std),
-               white_back=bool(white_back))
+               white_back=bool(white_back), rng_seed=rng_seed)
     params = _params_of(models, N_importance)
     if target is not None:
         target = target.detach().to(torch.float32).contiguous()

@@ -39,14 +39,32 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_basics(lib):
-    assert lib.nerfb200_abi_version() == 2
+    assert lib.nerfb200_abi_version() == 3
     # layout.h: 30 x 32 KiB + 5 x 16 KiB fp16 slices + fp32 tail, rounded to 1 KiB, + 30 backward slices
     fwd = 30 * 32768 + 5 * 16384 + 4 * (9 * 256 + 256 + 4 + 384 + 4 + 28 * 128)
     assert lib.nerfb200_packed_bytes() == (fwd + 1023) // 1024 * 1024 + 30 * 32768
     assert lib.nerfb200_launch_count() >= 0
     # the Python mirrors of the argument structs have the C sizes (x86-64 / aarch64 LP64 layout)
-    assert ctypes.sizeof(_lib.RenderArgs) == 8 * 5 + 4 * 2 + 4 + 4 * 2 + 4 * 2 + 4 + 8 * 14 + 8 + 8 * 4
+    assert ctypes.sizeof(_lib.RenderArgs) == 8 * 5 + 4 * 2 + 4 + 4 * 2 + 4 * 2 + 4 + 8 * 14 + 8 + 8 * 4 + 8 + 8
     assert ctypes.sizeof(_lib.BackwardArgs) == 8 * 13
+
+
+def test_struct_mirrors_match_the_header(tmp_path):
+    """sizeof / offsetof of the argument structs as gcc lays out include/nerf_pl_b200.h == the ctypes mirrors."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "nerf_pl_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(nerfb200_render_args), '
+                   'sizeof(nerfb200_backward_args), offsetof(nerfb200_render_args, rng_seed), '
+                   'offsetof(nerfb200_render_args, rng_in_kernel), offsetof(nerfb200_render_args, train_workspace), '
+                   'offsetof(nerfb200_render_args, perturb_rand));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    R = _lib.RenderArgs
+    assert got == [ctypes.sizeof(R), ctypes.sizeof(_lib.BackwardArgs), R.rng_seed.offset, R.rng_in_kernel.offset,
+                   R.train_workspace.offset, R.perturb_rand.offset]
 
 
 def test_training_workspace_layout(lib):

@@ -344,6 +344,43 @@ def test_host_buffer_entry_matches_device_path(models, emb, dev):
         assert got[k] is outs[k] and torch.equal(got[k], v.cpu()), k
 
 
+def test_in_kernel_random_numbers(models, emb, ws, dev):
+    """rng_in_kernel (randoms={'seed': s}): the kernel's Philox numbers are exactly those of the host replica
+    (tests/philox.py, itself pinned to the published known-answer vectors): feeding the replica's arrays as TENSORS
+    gives bit-identical results, and the oracle on the same numbers agrees within the float tolerance."""
+    from tests import philox
+    n, seed = 333, 0x1234_5678_9ABC_DEF0
+    rays = orc.make_rays(n, 17)
+    r = torch.from_numpy(rays).to(dev)
+    for K, tt in ((64, False), (128, True)):
+        rnd = philox.randoms(seed, n, 64, K)
+        with torch.no_grad():
+            a = nb.render_rays(models, emb, r, 64, False, 1.0, 0.0, K, 32768, True, test_time=tt, randoms={"seed": seed},
+                               extras=True)
+            b = nb.render_rays(models, emb, r, 64, False, 1.0, 0.0, K, 32768, True, test_time=tt, randoms=to_dev(rnd, dev),
+                               extras=True)
+        torch.cuda.synchronize()
+        assert set(a) == set(b)
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+        ref = orc.render_rays(ws, rays, 64, False, 1.0, 0.0, K, True, tt, rnd)
+        for k, v in ref.items():
+            assert cases.error_stats(a[k].cpu().numpy(), v)[0] < tol_for(k), k
+    # 'kernel': a fresh seed per call, deterministic under torch.manual_seed
+    with torch.no_grad():
+        torch.manual_seed(5)
+        x1 = nb.render_rays(models, emb, r, 64, False, 1.0, 0.0, 64, 32768, True, randoms="kernel")["rgb_fine"]
+        x2 = nb.render_rays(models, emb, r, 64, False, 1.0, 0.0, 64, 32768, True, randoms="kernel")["rgb_fine"]
+    assert not torch.equal(x1, x2)
+    # the host entry takes the same option (no device tensors at all: rays and results are host memory)
+    got = nb.render_rays_host(models, emb, torch.from_numpy(rays).pin_memory(), 64, False, 1.0, 0.0, 64, 32768, True,
+                              randoms={"seed": seed})
+    with torch.no_grad():
+        dev_res = nb.render_rays(models, emb, r, 64, False, 1.0, 0.0, 64, 32768, True, randoms={"seed": seed})
+    for k in got:
+        assert torch.equal(got[k], dev_res[k].cpu()), k
+
+
 def test_weight_cache_tracks_parameter_updates(ws, emb, dev):
     m = []
     for w in ws:                  # pseudo-trained weights: non-zero opacity, so colours matter
