@@ -410,16 +410,34 @@ def run_b200(args):
     dev_rays = [r.to(dev) for r in host_rays]
     gather_buf = torch.empty(world * BATCH, 10, device=dev) if world > 1 else None
 
+    ag_stream = torch.cuda.Stream() if world > 1 else None
+    packed_ring = [torch.empty(BATCH, 10, device=dev) for _ in range(4)] if world > 1 else None
+    overlap = {"on": world > 1 and os.environ.get("NERFB200_BENCH_AG_OVERLAP", "1") != "0", "pending": False}
+
     def step(i, rays=None, randoms=None):
         out = nb.render_rays(model_sets[i % N_ROT], emb, dev_rays[i % N_ROT] if rays is None else rays, N_SAMPLES, False,
                              1.0, 0.0, N_IMPORTANCE, 1024 * 32, True, test_time=False,
                              randoms="kernel" if randoms is None else randoms)
-        if world > 1:      # north_star: the rendered batch is exchanged with ONE all-gather at the end
-            packed = out["rgb_coarse"].new_empty(BATCH, 10)
+        if world > 1:      # north_star: the rendered batch is exchanged with ONE all-gather at the end of the step
+            packed = packed_ring[i % 4]
             torch.cat((out["rgb_coarse"], out["depth_coarse"][:, None], out["opacity_coarse"][:, None],
                        out["rgb_fine"], out["depth_fine"][:, None], out["opacity_fine"][:, None]), 1, out=packed)
-            dist.all_gather_into_tensor(gather_buf, packed)
+            if overlap["on"]:
+                # the collective of step i runs on its own stream, behind the tail of the next step's render kernel
+                # (the persistent render CTAs own all shared memory of their SM: NCCL's CTAs are placed as SMs
+                # drain); join_collectives() closes the timed region
+                ag_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(ag_stream):
+                    dist.all_gather_into_tensor(gather_buf, packed)
+                overlap["pending"] = True
+            else:
+                dist.all_gather_into_tensor(gather_buf, packed)
         return out
+
+    def join_collectives():
+        if overlap["pending"]:
+            torch.cuda.current_stream().wait_stream(ag_stream)
+            overlap["pending"] = False
 
     def barrier():
         if world > 1:
@@ -429,25 +447,37 @@ def run_b200(args):
     def timed_graph(fn, n_steps):
         """Capture n_steps calls of fn(i) in one CUDA graph; returns (replay callable, True) or the
         eager loop (callable, False) if capture is not possible on this box."""
-        try:
-            g = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                fn(0)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            with torch.cuda.graph(g):
-                for i in range(n_steps):
-                    fn(i)
-            return g.replay, True
-        except Exception as e:      # noqa: BLE001
-            print("CUDA graph capture unavailable, timing the eager loop:", repr(e), file=sys.stderr)
-            torch.cuda.synchronize()
+        for attempt in range(2 if overlap["on"] else 1):
+            try:
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    fn(0)
+                    join_collectives()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    for i in range(n_steps):
+                        fn(i)
+                    join_collectives()
+                return g.replay, True
+            except Exception as e:      # noqa: BLE001
+                print("CUDA graph capture failed (%s): %r" % ("collective on its own stream" if overlap["on"] else
+                                                              "in-stream", e), file=sys.stderr)
+                overlap["pending"] = False
+                torch.cuda.synchronize()
+                if overlap["on"]:
+                    overlap["on"] = False       # retry with the collective in the capture stream
+                    continue
+                break
+        print("timing the eager loop", file=sys.stderr)
+        if True:
 
             def loop():
                 for i in range(n_steps):
                     fn(i)
+                join_collectives()
             return loop, False
 
     def time_region(run):
@@ -651,7 +681,10 @@ def run_b200(args):
             "parity": parity,
             "train": train,
             "image_800": img,
-            "collective": ("NCCL all_gather_into_tensor, %d B per rank per step" % (BATCH * 40)) if world > 1 else None,
+            "collective": (("NCCL all_gather_into_tensor, %d B per rank per step" % (BATCH * 40)) +
+                           (", enqueued on its own stream inside the graph: the collective of step i runs behind the tail "
+                            "of step i+1's render kernel; the last one is joined before the closing event"
+                            if overlap["on"] else ", in the step's stream")) if world > 1 else None,
             "wall_s_timed_region": t_wall,
         }
         emit(line)

@@ -500,12 +500,15 @@ struct ChainEpi {
 //   kFirst: add the rank-1 sigma-head term;  kStore: hand the result to the next step (TMEM A operand)
 //   ratio = scale of the produced level / scale of the consumed level (a power of two)
 //   kProbe: no HBM stores; returns the largest |value| (in units of the produced level's scale)
+//   mw: this step's 64 ReLU sign bits (loaded one step earlier); next_mask: where the NEXT step's bits are (or null).
+//   The load is issued here, as soon as the accumulator is drained, and first used one step later: its HBM / L2
+//   latency hides behind this step's conversion and staging (it used to be issued at the top of the step it was
+//   needed in, where the wait for it - the top stall of the r02 capture, 6.8 % of all samples - delayed the
+//   d_ready wait of every step).
 template <bool kFirst, bool kStore, bool kProbe>
-__device__ __forceinline__ float epi_chain_step(ChainEpi& c, int out_idx, const uint2* __restrict__ mask, float dsig,
-                                                const float* wsig, float ratio) {
-  // masks, off the critical path (fetched while the step's MMAs run): after << i the sign flag of
-  // pair i of K block kb sits in the top bit of byte 3 - kb (even elements in ylo, odd in yhi)
-  const uint2 mw = __ldg(mask + (static_cast<long long>(out_idx) * c.n_pad + c.g) * 4 + c.part);
+__device__ __forceinline__ float epi_chain_step(ChainEpi& c, int out_idx, uint2& mw, const uint2* __restrict__ next_mask,
+                                                float dsig, const float* wsig, float ratio) {
+  // after << i the sign flag of pair i of K block kb sits in the top bit of byte 3 - kb (even elements in ylo, odd in yhi)
   uint32_t ylo[8], yhi[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { ylo[i] = mw.x << i; yhi[i] = mw.y << i; }
@@ -516,6 +519,7 @@ __device__ __forceinline__ float epi_chain_step(ChainEpi& c, int out_idx, const 
   uint32_t r[4][16];
 #pragma unroll
   for (int kb = 0; kb < 4; ++kb) tmem_ld16(c.tmem_row + kTmemD + kb * 64 + c.part * 16, r[kb]);
+  if (next_mask != nullptr) mw = __ldg(next_mask);
   tmem_ld_wait();
   if (!kStore) {      // last step: the next tile may overwrite the accumulator
     tc_fence_before();
@@ -570,7 +574,7 @@ __device__ __forceinline__ float epi_chain_step(ChainEpi& c, int out_idx, const 
 }
 
 template <bool kProbe>
-__global__ void __launch_bounds__(kThreads, 1) chain_bwd_kernel(const ChainParams p) {
+__global__ void __maxnreg__(112) chain_bwd_kernel(const ChainParams p) {   // 576 threads x 112 registers = 63 Ki (ptxas stops at 96 + spills under __launch_bounds__)
   extern __shared__ __align__(1024) uint8_t smem[];
   ChainScratch* sc = reinterpret_cast<ChainScratch*>(smem + kChScratch);
   Barriers* bars = &sc->bars;
@@ -693,6 +697,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_bwd_kernel(const ChainParam
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&bars->d_free));
+    uint2 mw = make_uint2(0u, 0u);      // ReLU sign bits of the step about to run (software-pipelined loads)
     float amx[2][8];      // probe mode only: per pass and level, in un-scaled units
 #pragma unroll
     for (int i = 0; i < 8; ++i) { amx[0][i] = 0.f; amx[1][i] = 0.f; }
@@ -709,18 +714,32 @@ __global__ void __launch_bounds__(kThreads, 1) chain_bwd_kernel(const ChainParam
       const float dsig = pb.dsigma[c.g] * sc_in;
       const float* wsig = wsig_s + ps * 256;
       float sc_out = ls[1];
-      float m = epi_chain_step<true, true, kProbe>(c, 7, pb.mask, dsig, wsig, sc_out / sc_in);
+      auto mask_at = [&](const PassBufs& q, long long g, int idx) {
+        return q.mask + (static_cast<long long>(idx) * q.n_pad + g) * 4 + c.part;
+      };
+      if (t == static_cast<long long>(blockIdx.x)) mw = __ldg(mask_at(pb, c.g, 7));      // first tile: not prefetched
+      float m = epi_chain_step<true, true, kProbe>(c, 7, mw, mask_at(pb, c.g, 6), dsig, wsig, sc_out / sc_in);
       if (kProbe) amx[ps][0] = fmaxf(amx[ps][0], m / sc_out);
 #pragma unroll 1
       for (int s = 1; s < 7; ++s) {
         sc_in = sc_out;
         sc_out = ls[s + 1];
-        m = epi_chain_step<false, true, kProbe>(c, 7 - s, pb.mask, 0.f, nullptr, sc_out / sc_in);
+        m = epi_chain_step<false, true, kProbe>(c, 7 - s, mw, mask_at(pb, c.g, 6 - s), 0.f, nullptr, sc_out / sc_in);
         if (kProbe) amx[ps][s] = fmaxf(amx[ps][s], m / sc_out);
       }
       sc_in = sc_out;
       sc_out = ls[8];
-      m = epi_chain_step<false, false, kProbe>(c, 0, pb.mask, 0.f, nullptr, sc_out / sc_in);
+      // the last step prefetches the first mask of this CTA's next tile
+      const uint2* nxt = nullptr;
+      {
+        const long long t2 = t + gridDim.x;
+        if (t2 < total) {
+          const int ps2 = (t2 >= p.tiles[0]) ? 1 : 0;
+          const long long tile2 = t2 - (ps2 ? p.tiles[0] : 0);
+          nxt = mask_at(p.pass[ps2], tile2 * 128 + c.row, 7);
+        }
+      }
+      m = epi_chain_step<false, false, kProbe>(c, 0, mw, nxt, 0.f, nullptr, sc_out / sc_in);
       if (kProbe) amx[ps][7] = fmaxf(amx[ps][7], m / sc_out);
     }
     if (!kProbe) bulk_wait_all();
