@@ -654,6 +654,40 @@ def run_b200(args):
                       "bar": "rgb_fine within 1e-3 abs (north_star)"}
         except Exception as e:      # noqa: BLE001
             parity = {"error": repr(e)}
+        # ---- the same check on TRAINED weights (tests/golden/trained_weights.npz: 8000 steps of this repository's own
+        # training step; sharp density, large norms - where the fp16 MLP's error is largest), 1024 rays, reference only
+        parity_trained = None
+        tw_path = os.path.join(ROOT, "tests", "golden", "trained_weights.npz")
+        if host.kind == "reference" and os.path.exists(tw_path):
+            try:
+                z = np.load(tw_path)
+                tws = [{k[len(t) + 1:]: z[k] for k in z.files if k.startswith(t + ".")} for t in ("coarse", "fine")]
+                n_tr = 1024
+                rays_np = blender_rays(n_tr, 777)
+                rnd_np = host.replay_randoms(n_tr, 99)
+                for m, w in zip(host.models, tws):
+                    m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+                ref = host.render(rays_np, rnd_np, 99)
+                for m, w in zip(host.models, host.ws):
+                    m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+                tm_ = []
+                for w in tws:
+                    m = nb.NeRF()
+                    m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+                    tm_.append(m.to(dev).eval().requires_grad_(False))
+                with torch.no_grad():
+                    got = nb.render_rays(tm_, emb, torch.from_numpy(rays_np).to(dev), N_SAMPLES, False, 1.0, 0.0,
+                                         N_IMPORTANCE, 1024 * 32, True, test_time=False,
+                                         randoms={k: torch.from_numpy(v).to(dev) for k, v in rnd_np.items()})
+                dif = np.abs(got["rgb_fine"].cpu().numpy().astype(np.float64) - ref["rgb_fine"]).max(-1)
+                mse = float(((got["rgb_fine"].cpu().numpy().astype(np.float64) - ref["rgb_fine"]) ** 2).mean())
+                parity_trained = {"rgb_fine_max_abs": float(dif.max()), "rgb_fine_p99": float(np.percentile(dif, 99)),
+                                  "rgb_fine_p90": float(np.percentile(dif, 90)), "rgb_fine_mean": float(dif.mean()),
+                                  "rays_over_1e-3": int((dif > 1e-3).sum()), "n_rays": n_tr,
+                                  "psnr_db": float(-10 * np.log10(max(mse, 1e-30))), "against": "reference",
+                                  "note": "per-ray max over channels; the tail is the fp16 format's (DESIGN.md section 5)"}
+            except Exception as e:      # noqa: BLE001
+                parity_trained = {"error": repr(e)}
         n_cpu = BATCH if host.kind == "reference" else 256
         cpu_v, cpu_t = host.time_forward(n_cpu, 3)
         cpu_train = host.time_train_step(256, 2) if host.kind == "reference" else None
@@ -679,6 +713,7 @@ def run_b200(args):
                                        f"{os.cpu_count()} host threads (fastest setting probed)",
                              "train_step_s_256_rays": cpu_train},
             "parity": parity,
+            "parity_trained_weights": parity_trained,
             "train": train,
             "image_800": img,
             "collective": (("NCCL all_gather_into_tensor, %d B per rank per step" % (BATCH * 40)) +

