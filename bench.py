@@ -724,7 +724,35 @@ def run_b200(args):
         }
         emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without relying on interpreter / C++ teardown: at N = 8 (r02, NVLS communicator, collectives captured
+        # in CUDA graphs) the process printed its line and then sat in teardown until the box's limit killed it.
+        # Order: drop the graphs that hold NCCL nodes, drain the device, give destroy_process_group a bounded
+        # chance, run the atexit hooks (bounded), exit.  The result line is already on the original stdout.
+        run = krun = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        _bounded(dist.destroy_process_group, 15.0)
+        _hard_exit(0)
+
+
+def _bounded(fn, seconds):
+    """Run fn() on a daemon thread, wait at most `seconds`; True if it finished."""
+    t = threading.Thread(target=fn, daemon=True)
+    t.start()
+    t.join(seconds)
+    return not t.is_alive()
+
+
+def _hard_exit(code):
+    import atexit
+    _bounded(atexit._run_exitfuncs, 10.0)
+    try:
+        sys.stdout.flush()
+        sys.stderr.flush()
+    except Exception:      # noqa: BLE001
+        pass
+    os._exit(code)
 
 
 _JSON_FD = None
