@@ -726,14 +726,19 @@ def run_b200(args):
     if world > 1:
         # Leave without relying on interpreter / C++ teardown: at N = 8 (r02, NVLS communicator, collectives captured
         # in CUDA graphs) the process printed its line and then sat in teardown until the box's limit killed it.
-        # Order: drop the graphs that hold NCCL nodes, drain the device, give destroy_process_group a bounded
-        # chance, run the atexit hooks (bounded), exit.  The result line is already on the original stdout.
-        run = krun = None
+        # Order: drop the graphs that hold NCCL nodes (their destruction releases NCCL's graph registrations), drain
+        # the device, give destroy_process_group a bounded chance (it releases the GIL), then leave with os._exit -
+        # through the atexit hooks only if the process group is really gone (torch registers an exit-time NCCL abort
+        # that could block on a half-destroyed group).  The result line is already on the original stdout.  Last
+        # resort, independent of the GIL: faulthandler's watchdog thread ends the process after 90 s.
+        import faulthandler
         import gc
+        faulthandler.dump_traceback_later(90, exit=True)
+        run = krun = None
         gc.collect()
         torch.cuda.synchronize()
-        _bounded(dist.destroy_process_group, 15.0)
-        _hard_exit(0)
+        clean = _bounded(dist.destroy_process_group, 20.0)
+        _hard_exit(0, run_atexit=clean)
 
 
 def _bounded(fn, seconds):
@@ -744,9 +749,10 @@ def _bounded(fn, seconds):
     return not t.is_alive()
 
 
-def _hard_exit(code):
+def _hard_exit(code, run_atexit=True):
     import atexit
-    _bounded(atexit._run_exitfuncs, 10.0)
+    if run_atexit:
+        _bounded(atexit._run_exitfuncs, 10.0)
     try:
         sys.stdout.flush()
         sys.stderr.flush()

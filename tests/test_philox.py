@@ -24,3 +24,27 @@ def test_uniform_mapping():
     assert np.abs(hist - 1 / 16).max() < 2e-3
     # rows are independent of the launch shape: ray r of a 2048-ray call == ray r of a call that starts at r
     np.testing.assert_array_equal(philox.uniform(20260923, 3, 128, 1, ray0=77), u[77:80])
+
+
+def test_kernel_rng_option_resolves_without_tensors():
+    """randoms='kernel' / {'seed': s} (nerf_pl_b200/rendering.py _resolve_randoms): no tensors are drawn for the uniform
+    inputs, the seed is deterministic under torch.manual_seed and differs from call to call."""
+    import torch
+
+    from nerf_pl_b200 import rendering
+    dev = torch.device("cpu")
+    pr, nc, ur, nf, seed = rendering._resolve_randoms({"seed": 2 ** 64 + 5}, 8, 64, 64, 1.0, 0.0, dev, True)
+    assert (pr, nc, ur, nf) == (None, None, None, None) and seed == 5
+    torch.manual_seed(123)
+    rendering._KERNEL_RNG_CALLS = 0
+    a = [rendering._resolve_randoms("kernel", 8, 64, 64, 1.0, 0.0, dev, True)[4] for _ in range(3)]
+    torch.manual_seed(123)
+    rendering._KERNEL_RNG_CALLS = 0
+    b = [rendering._resolve_randoms("kernel", 8, 64, 64, 1.0, 0.0, dev, True)[4] for _ in range(3)]
+    assert a == b and len(set(a)) == 3 and all(0 <= s < 2 ** 64 for s in a)
+    # the Gaussian inputs stay tensors
+    pr, nc, ur, nf, seed = rendering._resolve_randoms({"seed": 1}, 4, 64, 64, 1.0, 1.0, dev, True)
+    assert pr is None and ur is None and nc.shape == (4, 64) and nf.shape == (4, 128)
+    import pytest
+    with pytest.raises(ValueError):
+        rendering._resolve_randoms("philox", 4, 64, 64, 1.0, 0.0, dev, True)
