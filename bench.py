@@ -733,6 +733,7 @@ def run_b200(args):
         # resort, independent of the GIL: faulthandler's watchdog thread ends the process after 90 s.
         import faulthandler
         import gc
+        _bounded(barrier, 120.0)       # the other ranks wait here for rank 0's host-side legs: teardown starts together
         faulthandler.dump_traceback_later(90, exit=True)
         run = krun = None
         gc.collect()
