@@ -733,27 +733,33 @@ def run_b200(args):
         # resort, independent of the GIL: faulthandler's watchdog thread ends the process after 90 s.
         import faulthandler
         import gc
-        _bounded(barrier, 120.0)       # the other ranks wait here for rank 0's host-side legs: teardown starts together
+        _bounded(barrier, 120.0, dev)  # the other ranks wait here for rank 0's host-side legs: teardown starts together
         faulthandler.dump_traceback_later(90, exit=True)
         run = krun = None
         gc.collect()
         torch.cuda.synchronize()
-        clean = _bounded(dist.destroy_process_group, 20.0)
-        _hard_exit(0, run_atexit=clean)
+        clean = _bounded(dist.destroy_process_group, 20.0, dev)
+        _hard_exit(0, run_atexit=clean, device=dev)
 
 
-def _bounded(fn, seconds):
-    """Run fn() on a daemon thread, wait at most `seconds`; True if it finished."""
-    t = threading.Thread(target=fn, daemon=True)
+def _bounded(fn, seconds, device=None):
+    """Run fn() on a daemon thread, wait at most `seconds`; True if it finished.  `device`: the CUDA device to make
+    current in that thread first (the current device is thread-local; a fresh thread would otherwise touch device 0)."""
+    def target():
+        if device is not None:
+            import torch
+            torch.cuda.set_device(device)
+        fn()
+    t = threading.Thread(target=target, daemon=True)
     t.start()
     t.join(seconds)
     return not t.is_alive()
 
 
-def _hard_exit(code, run_atexit=True):
+def _hard_exit(code, run_atexit=True, device=None):
     import atexit
     if run_atexit:
-        _bounded(atexit._run_exitfuncs, 10.0)
+        _bounded(atexit._run_exitfuncs, 10.0, device)
     try:
         sys.stdout.flush()
         sys.stderr.flush()
