@@ -730,11 +730,11 @@ def run_b200(args):
         # the device, give destroy_process_group a bounded chance (it releases the GIL), then leave with os._exit -
         # through the atexit hooks only if the process group is really gone (torch registers an exit-time NCCL abort
         # that could block on a half-destroyed group).  The result line is already on the original stdout.  Last
-        # resort, independent of the GIL: faulthandler's watchdog thread ends the process after 90 s.
+        # resort, independent of the GIL: faulthandler's watchdog thread ends the process 240 s after this point.
         import faulthandler
         import gc
-        _bounded(barrier, 120.0, dev)  # the other ranks wait here for rank 0's host-side legs: teardown starts together
-        faulthandler.dump_traceback_later(90, exit=True)
+        faulthandler.dump_traceback_later(240, exit=True)
+        barrier()                      # the other ranks wait here for rank 0's host-side legs: teardown starts together
         run = krun = None
         gc.collect()
         torch.cuda.synchronize()
