@@ -34,7 +34,7 @@ if os.path.exists(lp):
     rr = [float(r[-1]) for r in rows if "render_rays_kernel" in r[4]]
     if rr:
         out.append(f"\nrender_rays_kernel: {len(rr)} launches, mean {sum(rr) / len(rr) / 1e3:.1f} us "
-                   f"(1024 rays x 192 samples each; excludes the 256 MiB L2-flush fill between bench steps).\n")
+                   f"(1024 rays x 192 samples each; ncu's clock, cold caches, serialised launches).\n")
 
 # bench-shaped launch (1024 rays): DRAM traffic per launch for bench.py's roofline.traffic
 bp = os.path.join(ROOT, "gpurun_out", f"prof_{tag}_bench1024.ncu-rep")
