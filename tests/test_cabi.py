@@ -202,3 +202,15 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_integration_md_stub_matches_the_struct():
+    """The ctypes stub printed in INTEGRATION.md section 4 is the struct the library takes (names, order, size)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = txt[txt.index("class RenderArgs(ctypes.Structure):"):txt.index("packed = torch.empty(lib.nerfb200_packed_bytes()")]
+    assert re.findall(r'\("(\w+)", ctypes\.c_\w+\)', block) == [f[0] for f in _lib.RenderArgs._fields_]
+    ns = {}
+    exec("import ctypes\n" + block, ns)
+    assert ctypes.sizeof(ns["RenderArgs"]) == ctypes.sizeof(_lib.RenderArgs)
